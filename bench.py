@@ -1,0 +1,510 @@
+#!/usr/bin/env python
+"""bench.py — single-batch DeepSeek decode throughput on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this engine (libdsk.so), one rank per GPU
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (oracle/_ref)
+
+A "step" is one fixed 128-token greedy completion (the reference's `-n 128 -t 0`, src/main.cpp:324-335) after a
+16-token prompt has hydrated the KV cache.  `value` is decode-only tok/s with everything resident in HBM (device
+argmax feeds the next token inside one CUDA graph per token, CUDA-event timed); `e2e` is the same completion driven
+through the reference-shaped host call `dsk_forward(token, pos, OUTPUT_LOGITS, host_logits)` per token: control words
+go host->device, the vocab-sized logits come device->host, and the host samples (argmax) — copies inside the timed
+region.  Weights are synthetic (no checkpoints exist offline): N(0,1)/sqrt(fan_in) quantised like convert.py (f8e5m2)
+or random valid K-quant blocks, generated on the GPU and handed to dsk_upload_tensor(src_on_device=1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(REPO, "deepseek.cpp_b200"))
+
+GEN_TOKENS = 128
+PROMPT_LEN = 16
+
+# shapes: HF configs of the DeepSeek family; K-quants need 256-multiples
+WORKLOADS = {
+    "v2lite": dict(arch="DeepseekV2ForCausalLM", dim=2048, hidden_dim=10944, n_layers=27, n_heads=16, vocab_size=102400,
+                   qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, kv_lora_rank=512, q_lora_rank=0,
+                   first_k_dense_replace=1, n_shared_experts=2, n_routed_experts=64, n_active_routed=6,
+                   moe_intermediate_size=1408, routed_scaling_factor=1.0, n_group=1, topk_group=1, norm_topk_prob=0,
+                   scoring_sigmoid=0, topk_method=0),
+    "v2": dict(arch="DeepseekV2ForCausalLM", dim=5120, hidden_dim=12288, n_layers=60, n_heads=128, vocab_size=102400,
+               qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, kv_lora_rank=512, q_lora_rank=1536,
+               first_k_dense_replace=1, n_shared_experts=2, n_routed_experts=160, n_active_routed=6,
+               moe_intermediate_size=1536, routed_scaling_factor=16.0, n_group=8, topk_group=3, norm_topk_prob=0,
+               scoring_sigmoid=0, topk_method=1),
+    "v3": dict(arch="DeepseekV3ForCausalLM", dim=7168, hidden_dim=18432, n_layers=61, n_heads=128, vocab_size=129280,
+               qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128, kv_lora_rank=512, q_lora_rank=1536,
+               first_k_dense_replace=3, n_shared_experts=1, n_routed_experts=256, n_active_routed=8,
+               moe_intermediate_size=2048, routed_scaling_factor=2.5, n_group=8, topk_group=4, norm_topk_prob=1,
+               scoring_sigmoid=1, topk_method=1),
+}
+QUANT_IDS = {"fp32": 0, "fp16": 1, "f8e5m2": 2, "q2_k": 3, "q3_k": 4}
+KBYTES = {"q2_k": 84, "q3_k": 110}
+
+
+def workload_cfg(name: str, quant: str, n_layers=None, max_seq_len=1024):
+    w = dict(WORKLOADS[name])
+    if quant in KBYTES:
+        up = lambda v: (v + 255) // 256 * 256
+        w["moe_intermediate_size"] = up(w["moe_intermediate_size"])
+        w["hidden_dim"] = up(w["hidden_dim"])
+    if n_layers:
+        w["n_layers"] = n_layers
+    w["max_seq_len"] = max_seq_len
+    w["quant"] = quant
+    return w
+
+
+def tensor_plan(w):
+    """(name, rows, cols, n_experts) for every quantised tensor + F32 extras, in .dseek naming (src/model.cpp:766-871)."""
+    dim, nh = w["dim"], w["n_heads"]
+    hd = w["qk_nope_head_dim"] + w["qk_rope_head_dim"]
+    mi, E, ns = w["moe_intermediate_size"], w["n_routed_experts"], w["n_shared_experts"]
+    plan, f32 = [("model.embed", w["vocab_size"], dim, 0), ("model.output", w["vocab_size"], dim, 0)], [("model.norm.weight", dim)]
+    for l in range(w["n_layers"]):
+        p = f"model.layers.{l}."
+        f32 += [(p + "attn.norm.weight", dim), (p + "mlp.norm.weight", dim), (p + "attn.kv_a_norm.weight", w["kv_lora_rank"])]
+        if w["q_lora_rank"] > 0:
+            f32.append((p + "attn.q_a_norm.weight", w["q_lora_rank"]))
+            plan += [(p + "attn.wq_a", w["q_lora_rank"], dim, 0), (p + "attn.wq_b", nh * hd, w["q_lora_rank"], 0)]
+        else:
+            plan.append((p + "attn.wq", nh * hd, dim, 0))
+        plan += [(p + "attn.wkv_a", w["kv_lora_rank"] + w["qk_rope_head_dim"], dim, 0),
+                 (p + "attn.wkv_b", nh * (w["qk_nope_head_dim"] + w["v_head_dim"]), w["kv_lora_rank"], 0),
+                 (p + "attn.wo", dim, nh * w["v_head_dim"], 0)]
+        if E > 0 and l >= w["first_k_dense_replace"]:
+            f32.append((p + "moegate.weight", E * dim))
+            if w["arch"] == "DeepseekV3ForCausalLM":
+                f32.append((p + "moegate.bias", E))
+            plan += [(p + "mlp.w1", mi, dim, E), (p + "mlp.w2", dim, mi, E), (p + "mlp.w3", mi, dim, E)]
+            if ns > 0:
+                plan += [(p + "shared_mlp.w1", ns * mi, dim, 0), (p + "shared_mlp.w2", dim, ns * mi, 0),
+                         (p + "shared_mlp.w3", ns * mi, dim, 0)]
+        else:
+            plan += [(p + "mlp.w1", w["hidden_dim"], dim, 0), (p + "mlp.w2", dim, w["hidden_dim"], 0),
+                     (p + "mlp.w3", w["hidden_dim"], dim, 0)]
+    return plan, f32
+
+
+def make_config(dsk, w):
+    c = dsk.Config()
+    for k in ("dim", "hidden_dim", "n_layers", "n_heads", "vocab_size", "max_seq_len", "first_k_dense_replace",
+              "n_shared_experts", "n_routed_experts", "n_active_routed", "moe_intermediate_size", "n_group", "topk_group",
+              "norm_topk_prob", "scoring_sigmoid", "topk_method", "kv_lora_rank", "q_lora_rank", "qk_nope_head_dim",
+              "qk_rope_head_dim", "v_head_dim"):
+        setattr(c, k, int(w[k]))
+    c.rope_theta, c.norm_eps, c.act_silu = 10000.0, 1e-6, 1
+    c.routed_scaling_factor = float(w["routed_scaling_factor"])
+    c.is_v3 = 1 if w["arch"] == "DeepseekV3ForCausalLM" else 0
+    c.quant = QUANT_IDS[w["quant"]]
+    c.bs0, c.bs1 = (128, 128) if w["quant"] == "f8e5m2" else (0, 0)
+    c.original_max_position = 4096
+    return c
+
+
+def mint_on_gpu(dsk, w, rank, n_ranks, device):
+    """Random-init weights of the named architecture, generated on the GPU."""
+    import torch
+    torch.manual_seed(1234)
+    dev = torch.device("cuda", device)
+    m = dsk.Model(make_config(dsk, w), rank, n_ranks, device)
+    quant = w["quant"]
+    plan, f32 = tensor_plan(w)
+    E = w["n_routed_experts"]
+    per = -(-E // n_ranks) if E else 0
+    for name, n in f32:
+        if name.endswith("moegate.weight"):
+            t = torch.randn(n, device=dev) * (w["dim"] ** -0.5) * 4.0
+        elif name.endswith("moegate.bias"):
+            t = 0.01 * torch.randn(n, device=dev)
+        else:
+            t = 1.0 + 0.1 * torch.randn(n, device=dev)
+        t = t.float().contiguous()
+        m.upload_device(name, "F32", (n,), t.data_ptr(), t.numel() * 4)
+    for name, rows, cols, ne in plan:
+        lead = max(1, ne)
+        if quant == "f8e5m2":
+            chunks_q, chunks_s = [], []
+            for e0 in range(0, lead, 16):
+                e1 = min(lead, e0 + 16)
+                if ne and n_ranks > 1 and (e1 <= rank * per or e0 >= (rank + 1) * per):
+                    # another rank's experts: the library drops them anyway; skip the randn, keep shapes
+                    chunks_q.append(torch.zeros(e1 - e0, rows, cols, dtype=torch.uint8, device=dev))
+                    chunks_s.append(torch.ones(e1 - e0, -(-rows // 128), -(-cols // 128), device=dev))
+                    continue
+                x = torch.randn(e1 - e0, rows, cols, device=dev) * (cols ** -0.5 if name != "model.embed" else 1.0)
+                Rp, Cp = -(-rows // 128) * 128, -(-cols // 128) * 128
+                xp = torch.zeros(e1 - e0, Rp, Cp, device=dev)
+                xp[:, :rows, :cols] = x
+                blk = xp.view(e1 - e0, Rp // 128, 128, Cp // 128, 128)
+                amax = blk.abs().amax(dim=(2, 4))
+                scale = 57344.0 / amax.clamp(min=1e-12)                       # convert.py:216-244
+                q = (blk * scale[:, :, None, :, None]).clamp(-57344.0, 57344.0).to(torch.float8_e5m2)
+                chunks_q.append(q.view(e1 - e0, Rp, Cp)[:, :rows, :cols].contiguous().view(torch.uint8))
+                chunks_s.append(scale.float().reciprocal())
+                del x, xp, blk, q
+            q = torch.cat(chunks_q).contiguous()
+            s = torch.cat(chunks_s).float().contiguous()
+            shape = (ne, rows, cols) if ne else (rows, cols)
+            m.upload_device(name + ".weight", "F8_E5M2", shape, q.data_ptr(), q.numel())
+            m.upload_device(name + ".scale", "F32", s.shape, s.data_ptr(), s.numel() * 4)
+            del q, s, chunks_q, chunks_s
+        elif quant in KBYTES:
+            bb, nb = KBYTES[quant], cols // 256
+            q = torch.randint(0, 256, (lead, rows, nb, bb), dtype=torch.uint8, device=dev)
+            d = np.float16(0.1 / np.sqrt(cols))
+            if quant == "q2_k":
+                q[..., 80:82] = torch.from_numpy(np.frombuffer(d.tobytes(), np.uint8).copy()).to(dev)
+                q[..., 82:84] = torch.from_numpy(np.frombuffer(np.float16(d * 1.5).tobytes(), np.uint8).copy()).to(dev)
+            else:
+                q[..., 108:110] = torch.from_numpy(np.frombuffer(np.float16(d / 8).tobytes(), np.uint8).copy()).to(dev)
+            shape = (ne, rows, nb * bb) if ne else (rows, nb * bb)
+            m.upload_device(name + ".weight", "U8", shape, q.data_ptr(), q.numel())
+            del q
+        else:
+            x = torch.randn(lead, rows, cols, device=dev) * (cols ** -0.5 if name != "model.embed" else 1.0)
+            if quant == "fp16":
+                x = x.half()
+            x = x.contiguous()
+            m.upload_device(name + ".weight", "F16" if quant == "fp16" else "F32", x.shape, x.data_ptr(),
+                            x.numel() * x.element_size())
+            del x
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    m.finalize()
+    return m
+
+
+def prompt_ids(vocab):
+    return [(7919 * (i + 1)) % vocab for i in range(PROMPT_LEN)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle/_ref = the unmodified reference compiled in the build container)
+# ----------------------------------------------------------------------------------------------------
+def mint_cpu_truncated(w, dirname, n_layers):
+    """Layer-truncated checkpoint of the workload's shapes for the CPU legs: pooled N(0,1) values cast like convert.py."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import dseek
+    rng = np.random.default_rng(1234)
+    wt = dict(w)
+    wt["n_layers"] = n_layers
+    plan, f32 = tensor_plan(wt)
+    quant = w["quant"]
+    import torch
+    pool = torch.randn(1 << 24)
+    if quant == "f8e5m2":
+        pool8 = (pool * (57344.0 / 6.0)).clamp(-57344, 57344).to(torch.float8_e5m2).view(torch.uint8).numpy()
+    os.makedirs(dirname, exist_ok=True)
+    md = {"arch": w["arch"], "use_mla": "0", "quant": quant, "dim": w["dim"], "hidden_dim": w["hidden_dim"], "n_layers": n_layers,
+          "n_heads": w["n_heads"], "vocab_size": w["vocab_size"], "max_seq_len": w["max_seq_len"], "bos_token_id": 0,
+          "eos_token_id": 1, "rope_theta": 10000.0, "norm_eps": 1e-6, "norm_type": "rmsnorm", "act_type": "silu",
+          "first_k_dense_replace": w["first_k_dense_replace"], "kv_lora_rank": w["kv_lora_rank"], "q_lora_rank": w["q_lora_rank"],
+          "qk_nope_head_dim": w["qk_nope_head_dim"], "qk_rope_head_dim": w["qk_rope_head_dim"], "v_head_dim": w["v_head_dim"],
+          "n_shared_experts": w["n_shared_experts"], "n_routed_experts": w["n_routed_experts"],
+          "n_active_routed": w["n_active_routed"], "moe_intermediate_size": w["moe_intermediate_size"],
+          "routed_scaling_factor": w["routed_scaling_factor"], "n_group": w["n_group"],
+          "norm_topk_prob": "True" if w["norm_topk_prob"] else "False",
+          "scoring_func": "sigmoid" if w["scoring_sigmoid"] else "softmax", "topk_group": w["topk_group"],
+          "topk_method": "group_limited_greedy" if w["topk_method"] else "greedy", "rope_scaling_beta_fast": 32,
+          "rope_scaling_beta_slow": 1, "rope_scaling_factor": 40.0, "rope_scaling_mscale": 1.0,
+          "rope_scaling_mscale_all_dim": 1.0, "rope_scaling_original_max_position_embeddings": 4096}
+    if quant == "f8e5m2":
+        md["quantization_block_size_0"] = 128
+        md["quantization_block_size_1"] = 128
+    T = {"tokenizer.tokens": ("U8", np.frombuffer(b"\0".join(b"t%d" % i for i in range(w["vocab_size"])) + b"\0", np.uint8).copy())}
+    for name, n in f32:
+        if name.endswith("moegate.weight"):
+            a = (rng.standard_normal(n, dtype=np.float32) * w["dim"] ** -0.5 * 4.0).reshape(w["n_routed_experts"], w["dim"])
+        elif name.endswith("moegate.bias"):
+            a = (0.01 * rng.standard_normal(n)).astype(np.float32)
+        else:
+            a = (1.0 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        T[name] = ("F32", a)
+    for name, rows, cols, ne in plan:
+        lead = max(1, ne)
+        shape = (ne, rows, cols) if ne else (rows, cols)
+        numel = lead * rows * cols
+        if quant == "f8e5m2":
+            off = int(rng.integers(0, pool8.size))
+            a = np.resize(np.roll(pool8, -off), numel).reshape(shape)
+            T[name + ".weight"] = ("F8_E5M2", a)
+            sshape = ((ne,) if ne else ()) + (-(-rows // 128), -(-cols // 128))
+            sc = 6.0 / 57344.0 * (1.0 if name == "model.embed" else cols ** -0.5)
+            T[name + ".scale"] = ("F32", np.full(sshape, sc, np.float32))
+        elif quant in KBYTES:
+            bb, nb = KBYTES[quant], cols // 256
+            a = rng.integers(0, 256, size=(lead * rows, nb, bb), dtype=np.uint8)
+            d = np.float16(0.1 / np.sqrt(cols))
+            if quant == "q2_k":
+                a[:, :, 80:82] = np.frombuffer(d.tobytes(), np.uint8)
+                a[:, :, 82:84] = np.frombuffer(np.float16(d * 1.5).tobytes(), np.uint8)
+            else:
+                a[:, :, 108:110] = np.frombuffer(np.float16(d / 8).tobytes(), np.uint8)
+            T[name + ".weight"] = ("U8", a.reshape(((ne,) if ne else ()) + (rows, nb * bb)))
+        else:
+            a = np.resize(pool.numpy(), numel).reshape(shape) * np.float32(cols ** -0.5)
+            T[name + ".weight"] = ("F16", a.astype(np.float16)) if quant == "fp16" else ("F32", a.astype(np.float32))
+    dseek.write_shard(os.path.join(dirname, "shard_000.dseek"), T, md)
+
+
+def cpu_reference_leg(w, steps, warmup, tokens_per_step=8):
+    """Times the UNMODIFIED reference (oracle/_ref/libdsref.so) on this box's host cores, on a bounded sample:
+    a 3-layer truncation (first dense layer + 2 MoE layers + LM head) of the workload's shapes, per-block timings
+    extrapolated to the full depth.  Returns (tok/s, description dict)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import oracle as O
+    if O.ref_lib() is None:
+        O.port_lib()
+        raise RuntimeError("oracle/_ref/libdsref.so is not present")
+    nl_full, fk = w["n_layers"], w["first_k_dense_replace"]
+    n_trunc = min(nl_full, fk + 2)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    d = tempfile.mkdtemp(prefix="dsk_ref_", dir=base)
+    try:
+        mint_cpu_truncated(w, d, n_trunc)
+        cores = os.cpu_count() or 1
+        best = None
+        for threads in sorted({max(1, cores // 2), cores}):
+            O.ref_lib().ref_set_num_threads(threads)
+            s = O.RefSession(d, 0)
+            pr = prompt_ids(w["vocab_size"])[:4]
+            for p, t in enumerate(pr):
+                s.forward(t, p, True)
+            pos = len(pr)
+            per_tok = []
+            for it in range((warmup + steps) * tokens_per_step):
+                tok = s.argmax()
+                t0 = time.perf_counter(); s.forward(tok, pos, True); t_f = time.perf_counter() - t0
+                tb = []
+                for l in range(n_trunc):
+                    t0 = time.perf_counter(); s.block(l, pos, 0, pos, pos + 1); tb.append(time.perf_counter() - t0)
+                pos += 1
+                if it >= warmup * tokens_per_step:
+                    t_dense = float(np.mean(tb[:fk])) if fk else 0.0
+                    t_moe = float(np.mean(tb[fk:])) if n_trunc > fk else 0.0
+                    t_rest = max(0.0, t_f - sum(tb))
+                    per_tok.append(t_rest + fk * t_dense + (nl_full - fk) * t_moe)
+            s.close()
+            tps = 1.0 / float(np.mean(per_tok))
+            if best is None or tps > best[0]:
+                best = (tps, threads)
+        return best[0], {"kind": "reference", "cores": best[1], "host_cpus": cores,
+                         "sample": f"{n_trunc}-layer truncation ({fk} dense + {n_trunc - fk} MoE + LM head) of the workload's shapes, "
+                                   f"{steps * tokens_per_step} decoded tokens, per-block times extrapolated to {nl_full} layers; "
+                                   f"unmodified reference (-O3 -ffast-math -fopenmp -mavx2), best of OMP threads {{cores/2, cores}}"}
+    finally:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DSK_WORKLOAD", "v2lite"))
+    ap.add_argument("--quant", default=os.environ.get("DSK_QUANT", "f8e5m2"))
+    ap.add_argument("--n-layers", type=int, default=int(os.environ.get("DSK_LAYERS", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = workload_cfg(a.workload, a.quant, a.n_layers or None)
+    wl_name = f"DeepSeek-{a.workload.upper()}-shaped {a.quant} single-batch decode, {PROMPT_LEN}-token prompt + {GEN_TOKENS}-token greedy completion"
+    base = {"metric": "tok/s single-batch decode (128-tok gen)", "unit": "tok/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"f8e5m2": "f8e5m2 weights x f32 activations", "q2_k": "u2 x i8 integer dot (Q2_K x Q8_K), f32 accumulate",
+                      "q3_k": "u3 x i8 integer dot (Q3_K x Q8_K), f32 accumulate", "fp16": "f16 weights x f32", "fp32": "f32"}[a.quant],
+            "data": "synthetic (random-init weights of the named architecture; no checkpoints offline)",
+            "config": {"workload": wl_name, "layers": w["n_layers"], "tokens_per_step": GEN_TOKENS,
+                       "parallelism": f"experts sharded over {a.gpus} GPU(s), rest replicated" if a.gpus > 1 else "1 GPU",
+                       "l2": "weights streamed per token (GBs) exceed the 126 MB L2; no flush needed"}}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        try:
+            tps, desc = cpu_reference_leg(w, max(1, a.steps), max(1, a.warmup))
+        except Exception as e:  # the oracle always exists in this tier; this only trips if _ref did not travel
+            print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+            return 0
+        out = dict(base)
+        out.update({"impl": "reference", "value": tps, "ms_per_step": GEN_TOKENS / tps * 1e3, "n_gpus": a.gpus,
+                    "cpu_baseline": dict(desc, value=tps, unit="tok/s"),
+                    "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0, "dtype": "reference CPU path (AVX2/F16C, OpenMP)"})
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import dsk
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dsk.init(local_rank)
+    m = mint_on_gpu(dsk, w, rank, world, local_rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(dsk.Model.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(uid, 0)
+        m.comm_init(bytes(uid.cpu().numpy().tobytes()))
+
+    vocab = w["vocab_size"]
+    pr = prompt_ids(vocab)
+
+    def hydrate():
+        for p, t in enumerate(pr):
+            last = p + 1 == len(pr)
+            _, am = m.forward(t, p, dsk.OUTPUT_LOGITS if last else dsk.HYDRATE_KV_CACHE, want_logits=False)
+        return am
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident decode, CUDA events inside dsk_decode_greedy --------------------------
+    for _ in range(a.warmup):
+        hydrate()
+        m.decode_greedy(PROMPT_LEN, GEN_TOKENS)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(a.steps):
+        hydrate()
+        barrier()
+        toks, ms = m.decode_greedy(PROMPT_LEN, GEN_TOKENS)
+        dev_ms += ms
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clk = clocks.stop() if clocks else None
+    if dist is not None:
+        t = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = a.steps * GEN_TOKENS / (dev_ms / 1e3)
+
+    # ---- e2e: reference-shaped host loop, host buffers, copies inside the timed region -------------
+    def host_completion():
+        am = hydrate()
+        t0 = time.perf_counter()
+        pos = PROMPT_LEN
+        for _ in range(GEN_TOKENS):
+            logits, _ = m.forward(am, pos)            # H2D control words, D2H vocab logits, sync
+            am = int(np.argmax(logits))               # host sampler (Sampler::sample_argmax)
+            pos += 1
+        return time.perf_counter() - t0
+    for _ in range(max(1, a.warmup // 2)):
+        host_completion()
+    barrier()
+    e2e_s = sum(host_completion() for _ in range(a.steps))
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = a.steps * GEN_TOKENS / e2e_s
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline: whole-token algorithmic bytes vs measured HBM peak + the dominant kernel alone ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    abytes = m.active_bytes_per_token()
+    achieved = abytes * value / 1e9 / a.gpus
+    kern = {}
+    try:
+        hd = w["qk_nope_head_dim"] + w["qk_rope_head_dim"]
+        for label, (d_, n_) in {"lm_head": (w["vocab_size"], w["dim"]), "wq": (w["n_heads"] * hd, w["dim"]),
+                                 "expert_w1": (w["moe_intermediate_size"], w["dim"])}.items():
+            n_mats = max(2, int(300e6 // (d_ * n_)) + 1)
+            ms_k, b_k = dsk.bench_gemv(a.quant, d_, n_, n_mats=min(n_mats, 64), warmup=3, iters=20)
+            kern[label] = {"rows": d_, "cols": n_, "us": ms_k * 1e3, "GB/s": b_k / (ms_k / 1e3) / 1e9, "frac": b_k / (ms_k / 1e3) / 1e9 / peak}
+    except Exception as e:
+        kern = {"error": str(e)[:120]}
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "gemv_kernel<Q> (all launches of one token; achieved = algorithmic bytes/token x tok/s, i.e. every "
+                      "non-GEMV kernel and launch gap is charged to it)",
+            "algorithmic_bytes_per_token": abytes, "peak_source": peak_src, "isolated_kernels": kern}
+
+    out = dict(base)
+    out.update({"value": value, "ms_per_step": dev_ms / a.steps, "wall_s": wall,
+                "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": GEN_TOKENS * 48, "d2h_bytes_per_step": GEN_TOKENS * vocab * 4},
+                "gpu_launches": m.launches_per_forward(dsk.OUTPUT_LOGITS) * GEN_TOKENS * a.steps,
+                "launches_per_token": m.launches_per_forward(dsk.OUTPUT_LOGITS),
+                "roofline": roof, "clocks": clk, "resident_gb": m.resident_bytes() / 1e9, "sample_tokens": toks[:8].tolist()})
+    if a.gpus == 1 and not a.no_cpu_baseline:
+        try:
+            tps, desc = cpu_reference_leg(w, 2, 1)
+            out["cpu_baseline"] = dict(desc, value=tps, unit="tok/s")
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "reference", "sample": f"failed: {str(e)[:150]}"}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

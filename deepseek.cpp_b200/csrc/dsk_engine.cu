@@ -1,0 +1,1124 @@
+// dsk_engine.cu — C-ABI (include/dsk.h) over the sm_100a kernels: device model, state, the per-token
+// launch sequence (one CUDA graph per token), expert-shard placement and the NCCL partial-sum all-reduce.
+//
+// Replaces, behind the reference's call surface (all /root/reference @ 8db9e56):
+//   Model::forward -> _forward_cpu        src/model.cpp:874-883, src/infer.cpp:1265-1317   dsk_forward
+//   Block::block   -> _block_cpu          src/model.cpp:290-322, src/infer.cpp:810-932     dsk_block_forward
+//   BlockMHA::_attention_impl             src/infer.cpp:934-1049                           enqueue_layer (attention part)
+//   Model::_copy_embedding                src/infer.cpp:1217-1263                          dsk_copy_embedding
+//   Model::Model / Block ctors (binding)  src/model.cpp:149-515, 756-871                   dsk_upload_tensor / finalize
+//   InferenceState                        src/model.cpp:677-754                            dsk_state_*
+// There is no CPU fallback: every entry point fails if no CUDA device is bound.
+
+#include "../../include/dsk.h"
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "dsk_kernels.cuh"
+
+using namespace dsk;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(-2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CKN(call)                                                                                  \
+  do {                                                                                             \
+    ncclResult_t e_ = (call);                                                                      \
+    if (e_ != ncclSuccess) return fail(-3, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int g_device = -1;
+static int g_sm_count = 148;
+static bool g_attrs_set = false;
+
+// ---------------------------------------------------------------------------------------------------
+// device tensors
+// ---------------------------------------------------------------------------------------------------
+struct DTensor {
+  bool present = false;
+  int quant = 0;
+  int total_experts = 0;       // 0 = plain matrix
+  int expert_first = 0, expert_count = 0;
+  int rows = 0, cols = 0;
+  uint8_t* w = nullptr;
+  float* scale = nullptr;
+  size_t row_bytes = 0;        // device bytes per row
+  size_t expert_bytes = 0;     // device bytes per expert
+  size_t scale_expert = 0;     // scale floats per expert
+};
+
+struct Layer {
+  float *rms_att = nullptr, *rms_ffn = nullptr, *rms_q_a = nullptr, *rms_kv_a = nullptr;
+  DTensor wq, wq_a, wq_b, wkv_a, wkv_b, wo, w1, w2, w3, sw1, sw2, sw3;
+  float *gate = nullptr, *gate_bias = nullptr;
+  bool is_moe = false;
+  __half *kcache = nullptr, *vcache = nullptr;
+};
+
+struct dsk_model {
+  dsk_config c;
+  int head_dim = 0;
+  int rank = 0, n_ranks = 1;
+  int expert_first = 0, expert_count = 0;
+  std::vector<Layer> layers;
+  DTensor embed, wcls;
+  bool has_wcls = false;
+  float* rms_final = nullptr;
+  size_t resident = 0;
+  ncclComm_t comm = nullptr;
+  std::vector<void*> allocs;
+};
+
+struct dsk_state {
+  dsk_model* m = nullptr;
+  float *x = nullptr, *xb2 = nullptr, *hbk = nullptr, *hbs = nullptr, *q_a = nullptr, *q = nullptr, *kv_a = nullptr,
+        *kv_b = nullptr, *moe_logits = nullptr, *act_w = nullptr, *logits = nullptr, *partial = nullptr;
+  int* act = nullptr;
+  Ctrl* ctrl = nullptr;       // device
+  Ctrl* h_ctrl = nullptr;     // pinned host mirror
+  int* token_log = nullptr;   // device
+  int* step = nullptr;        // device
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [mode][from_argmax]
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int last_pos = -1;
+  size_t token_log_cap = 0;
+};
+
+static size_t disk_row_bytes(int quant, int cols) {
+  switch (quant) {
+    case DSK_F32: return (size_t)cols * 4;
+    case DSK_F16: return (size_t)cols * 2;
+    case DSK_F8E5M2: return (size_t)cols;
+    case DSK_Q2_K: return (size_t)(cols / 256) * kQ2Bytes;
+    case DSK_Q3_K: return (size_t)(cols / 256) * kQ3Disk;
+  }
+  return 0;
+}
+static size_t dev_row_bytes(int quant, int cols) {
+  if (quant == DSK_Q3_K) return (size_t)(cols / 256) * kQ3Bytes;
+  return disk_row_bytes(quant, cols);
+}
+static int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------------
+// process / device
+// ---------------------------------------------------------------------------------------------------
+template <int Q>
+static cudaError_t set_attrs_q() {
+  cudaError_t e = cudaFuncSetAttribute(gemv_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(moe_down_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
+extern "C" int dsk_abi_version(void) { return DSK_ABI_VERSION; }
+extern "C" const char* dsk_last_error(void) { return g_err; }
+
+extern "C" int dsk_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(-1, "no CUDA device available (%s) — libdsk has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(-1, "device %d out of range (have %d)", device, n);
+  CK(cudaSetDevice(device));
+  g_device = device;
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, device));
+  g_sm_count = p.multiProcessorCount;
+  if (!g_attrs_set) {
+    CK(set_attrs_q<Q_F32>());
+    CK(set_attrs_q<Q_F16>());
+    CK(set_attrs_q<Q_F8>());
+    CK(set_attrs_q<Q_Q2K>());
+    CK(set_attrs_q<Q_Q3K>());
+    CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    g_attrs_set = true;
+  }
+  return 0;
+}
+static int need_device() {
+  if (g_device < 0) return fail(-1, "dsk_init() has not bound a CUDA device — libdsk has no CPU fallback");
+  return 0;
+}
+extern "C" int dsk_sync(void) {
+  if (need_device()) return -1;
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+extern "C" int dsk_device_info(char* name128, int* sm_count, size_t* hbm_bytes) {
+  if (need_device()) return -1;
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, g_device));
+  if (name128) { strncpy(name128, p.name, 127); name128[127] = 0; }
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (hbm_bytes) *hbm_bytes = p.totalGlobalMem;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------------
+static int dmalloc(dsk_model* m, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  m->allocs.push_back(*p);
+  m->resident += bytes;
+  return 0;
+}
+
+extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ranks) {
+  if (need_device()) return nullptr;
+  if (!cfg || n_ranks < 1 || rank < 0 || rank >= n_ranks) { fail(-1, "bad arguments"); return nullptr; }
+  if (cfg->n_routed_experts > 256) { fail(-1, "n_routed_experts > 256 unsupported (src/infer.cpp:527)"); return nullptr; }
+  if (cfg->n_active_routed + 1 > kMaxJobs) { fail(-1, "n_active_routed > %d unsupported", kMaxJobs - 1); return nullptr; }
+  dsk_model* m = new dsk_model();
+  m->c = *cfg;
+  m->head_dim = cfg->qk_nope_head_dim + cfg->qk_rope_head_dim;
+  m->rank = rank;
+  m->n_ranks = n_ranks;
+  const int E = cfg->n_routed_experts;
+  const int per = E > 0 ? cdiv(E, n_ranks) : 0;
+  m->expert_first = std::min(E, rank * per);
+  m->expert_count = std::max(0, std::min(per, E - m->expert_first));
+  m->layers.resize(cfg->n_layers);
+  for (int l = 0; l < cfg->n_layers; l++) {
+    Layer& L = m->layers[l];
+    L.is_moe = E > 0 && l >= cfg->first_k_dense_replace;
+    const size_t kb = (size_t)cfg->max_seq_len * cfg->n_heads * m->head_dim * sizeof(__half);
+    const size_t vb = (size_t)cfg->max_seq_len * cfg->n_heads * cfg->v_head_dim * sizeof(__half);
+    if (cudaMalloc(&L.kcache, kb) != cudaSuccess || cudaMalloc(&L.vcache, vb) != cudaSuccess) {
+      fail(-2, "KV cache allocation failed (layer %d, %zu bytes)", l, kb + vb);
+      delete m;
+      return nullptr;
+    }
+    m->allocs.push_back(L.kcache);
+    m->allocs.push_back(L.vcache);
+    cudaMemset(L.kcache, 0, kb);
+    cudaMemset(L.vcache, 0, vb);
+  }
+  return m;
+}
+
+extern "C" void dsk_model_destroy(dsk_model* m) {
+  if (!m) return;
+  if (m->comm) ncclCommDestroy(m->comm);
+  for (void* p : m->allocs) cudaFree(p);
+  delete m;
+}
+
+// expected logical shape of a weight by its role
+struct Role { DTensor* t; int rows, cols; bool expert; };
+
+static bool parse_layer_name(const char* name, int* layer, std::string* rest) {
+  const char* pre = "model.layers.";
+  size_t n = strlen(pre);
+  if (strncmp(name, pre, n) != 0) return false;
+  char* end = nullptr;
+  long l = strtol(name + n, &end, 10);
+  if (end == name + n || *end != '.') return false;
+  *layer = (int)l;
+  *rest = std::string(end + 1);
+  return true;
+}
+
+static int upload_f32(dsk_model* m, float** dst, size_t n_expected, const void* data, size_t nbytes, int on_dev,
+                      const char* name) {
+  if (nbytes != n_expected * 4) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, n_expected * 4, nbytes);
+  if (dmalloc(m, (void**)dst, nbytes)) return -2;
+  CK(cudaMemcpy(*dst, data, nbytes, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expert, bool is_scale, const void* data,
+                         size_t nbytes, int on_dev, const char* name) {
+  const dsk_config& c = m->c;
+  const int E = expert ? c.n_routed_experts : 0;
+  const int first = expert ? m->expert_first : 0;
+  const int count = expert ? m->expert_count : 1;
+  if (is_scale) {
+    const size_t per = (size_t)cdiv(rows, c.bs0) * cdiv(cols, c.bs1);
+    const size_t tot = per * (expert ? E : 1);
+    if (nbytes != tot * 4) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, tot * 4, nbytes);
+    t.scale_expert = per;
+    const size_t local = per * count;
+    if (dmalloc(m, (void**)&t.scale, local * 4)) return -2;
+    if (local)
+      CK(cudaMemcpy(t.scale, (const char*)data + (size_t)first * per * 4, local * 4,
+                    on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return 0;
+  }
+  const int q = c.quant;
+  if ((q == DSK_Q2_K || q == DSK_Q3_K) && cols % 256 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 256", name, cols);
+  if ((q == DSK_F16 || q == DSK_F8E5M2) && cols % 16 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 16", name, cols);
+  if (q == DSK_F32 && cols % 4 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 4", name, cols);
+  const size_t drb = disk_row_bytes(q, cols), vrb = dev_row_bytes(q, cols);
+  const size_t tot = drb * rows * (expert ? E : 1);
+  if (nbytes != tot) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, tot, nbytes);
+  t.present = true;
+  t.quant = q;
+  t.total_experts = E;
+  t.expert_first = first;
+  t.expert_count = count;
+  t.rows = rows;
+  t.cols = cols;
+  t.row_bytes = vrb;
+  t.expert_bytes = vrb * rows;
+  const size_t local_disk = drb * rows * count, local_dev = vrb * rows * count;
+  if (dmalloc(m, (void**)&t.w, local_dev + 16)) return -2;
+  const char* src = (const char*)data + (size_t)first * drb * rows;
+  if (local_disk == 0) return 0;
+  if (q == DSK_Q3_K) {
+    // stage the 110-byte disk blocks, repack to 112-byte aligned blocks on the device
+    const unsigned char* dsrc = (const unsigned char*)src;
+    void* staging = nullptr;
+    if (!on_dev) {
+      CK(cudaMalloc(&staging, local_disk));
+      CK(cudaMemcpy(staging, src, local_disk, cudaMemcpyHostToDevice));
+      dsrc = (const unsigned char*)staging;
+    }
+    const size_t nblocks = local_disk / kQ3Disk;
+    q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256>>>(dsrc, t.w, nblocks);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    if (staging) cudaFree(staging);
+  } else {
+    CK(cudaMemcpy(t.w, src, local_disk, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, const int64_t shape[4], const void* data,
+                                 size_t nbytes, int src_on_device) {
+  if (need_device()) return -1;
+  if (!m || !name || !data) return fail(-1, "bad arguments");
+  (void)dtype; (void)shape;
+  const dsk_config& c = m->c;
+  const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size;
+  std::string nm(name);
+  if (nm == "tokenizer.tokens") return 0;  // host-side only
+  if (nm == "model.embed.weight") return upload_weight(m, m->embed, c.vocab_size, c.dim, false, false, data, nbytes, src_on_device, name);
+  if (nm == "model.embed.scale") return upload_weight(m, m->embed, c.vocab_size, c.dim, false, true, data, nbytes, src_on_device, name);
+  if (nm == "model.output.weight") { m->has_wcls = true; return upload_weight(m, m->wcls, c.vocab_size, c.dim, false, false, data, nbytes, src_on_device, name); }
+  if (nm == "model.output.scale") return upload_weight(m, m->wcls, c.vocab_size, c.dim, false, true, data, nbytes, src_on_device, name);
+  if (nm == "model.norm.weight") return upload_f32(m, &m->rms_final, c.dim, data, nbytes, src_on_device, name);
+  int l = -1;
+  std::string rest;
+  if (!parse_layer_name(name, &l, &rest) || l < 0 || l >= c.n_layers) return fail(-4, "unknown tensor name %s", name);
+  Layer& L = m->layers[l];
+  if (rest == "attn.norm.weight") return upload_f32(m, &L.rms_att, c.dim, data, nbytes, src_on_device, name);
+  if (rest == "mlp.norm.weight") return upload_f32(m, &L.rms_ffn, c.dim, data, nbytes, src_on_device, name);
+  if (rest == "attn.kv_a_norm.weight") return upload_f32(m, &L.rms_kv_a, c.kv_lora_rank, data, nbytes, src_on_device, name);
+  if (rest == "attn.q_a_norm.weight") return upload_f32(m, &L.rms_q_a, c.q_lora_rank, data, nbytes, src_on_device, name);
+  if (rest == "moegate.weight") return upload_f32(m, &L.gate, (size_t)c.n_routed_experts * c.dim, data, nbytes, src_on_device, name);
+  if (rest == "moegate.bias") return upload_f32(m, &L.gate_bias, c.n_routed_experts, data, nbytes, src_on_device, name);
+  const size_t dot = rest.rfind('.');
+  if (dot == std::string::npos) return fail(-4, "unknown tensor name %s", name);
+  const std::string base = rest.substr(0, dot), kind = rest.substr(dot + 1);
+  const bool is_scale = kind == "scale";
+  if (!is_scale && kind != "weight") return fail(-4, "unknown tensor name %s", name);
+  const int sh = c.n_shared_experts * mi;
+  Role r{nullptr, 0, 0, false};
+  if (base == "attn.wq") r = {&L.wq, c.n_heads * hd, c.dim, false};
+  else if (base == "attn.wq_a") r = {&L.wq_a, c.q_lora_rank, c.dim, false};
+  else if (base == "attn.wq_b") r = {&L.wq_b, c.n_heads * hd, c.q_lora_rank, false};
+  else if (base == "attn.wkv_a") r = {&L.wkv_a, c.kv_lora_rank + c.qk_rope_head_dim, c.dim, false};
+  else if (base == "attn.wkv_b") r = {&L.wkv_b, c.n_heads * (nope + c.v_head_dim), c.kv_lora_rank, false};
+  else if (base == "attn.wo") r = {&L.wo, c.dim, c.n_heads * c.v_head_dim, false};
+  else if (base == "mlp.w1") r = L.is_moe ? Role{&L.w1, mi, c.dim, true} : Role{&L.w1, c.hidden_dim, c.dim, false};
+  else if (base == "mlp.w2") r = L.is_moe ? Role{&L.w2, c.dim, mi, true} : Role{&L.w2, c.dim, c.hidden_dim, false};
+  else if (base == "mlp.w3") r = L.is_moe ? Role{&L.w3, mi, c.dim, true} : Role{&L.w3, c.hidden_dim, c.dim, false};
+  else if (base == "shared_mlp.w1") r = {&L.sw1, sh, c.dim, false};
+  else if (base == "shared_mlp.w2") r = {&L.sw2, c.dim, sh, false};
+  else if (base == "shared_mlp.w3") r = {&L.sw3, sh, c.dim, false};
+  else return fail(-4, "unknown tensor name %s (MLA-mode tensors are not part of this path)", name);
+  return upload_weight(m, *r.t, r.rows, r.cols, r.expert, is_scale, data, nbytes, src_on_device, name);
+}
+
+extern "C" int dsk_model_finalize(dsk_model* m) {
+  if (need_device()) return -1;
+  if (!m) return fail(-1, "null model");
+  const dsk_config& c = m->c;
+  const bool f8 = c.quant == DSK_F8E5M2;
+  auto need = [&](const DTensor& t, const char* what, int l) -> int {
+    if (!t.present) return fail(-5, "missing tensor %s (layer %d)", what, l);
+    if (f8 && !t.scale) return fail(-5, "missing scale for %s (layer %d)", what, l);
+    return 0;
+  };
+  if (need(m->embed, "model.embed", -1)) return -5;
+  if (!m->rms_final) return fail(-5, "missing model.norm.weight");
+  if (!m->has_wcls) m->wcls = m->embed;  // tied embeddings (src/model.cpp:852-855)
+  for (int l = 0; l < c.n_layers; l++) {
+    Layer& L = m->layers[l];
+    if (!L.rms_att || !L.rms_ffn || !L.rms_kv_a) return fail(-5, "missing norm weights (layer %d)", l);
+    if (c.q_lora_rank > 0) {
+      if (!L.rms_q_a) return fail(-5, "missing q_a_norm (layer %d)", l);
+      if (need(L.wq_a, "attn.wq_a", l) || need(L.wq_b, "attn.wq_b", l)) return -5;
+    } else if (need(L.wq, "attn.wq", l)) return -5;
+    if (need(L.wkv_a, "attn.wkv_a", l) || need(L.wkv_b, "attn.wkv_b", l) || need(L.wo, "attn.wo", l)) return -5;
+    if (need(L.w1, "mlp.w1", l) || need(L.w2, "mlp.w2", l) || need(L.w3, "mlp.w3", l)) return -5;
+    if (L.is_moe) {
+      if (!L.gate) return fail(-5, "missing moegate.weight (layer %d)", l);
+      if (c.is_v3 && !L.gate_bias) return fail(-5, "missing moegate.bias (layer %d)", l);
+      if (c.n_shared_experts > 0 && (need(L.sw1, "shared_mlp.w1", l) || need(L.sw2, "shared_mlp.w2", l) || need(L.sw3, "shared_mlp.w3", l)))
+        return -5;
+    }
+  }
+  return 0;
+}
+
+extern "C" size_t dsk_model_resident_bytes(const dsk_model* m) { return m ? m->resident : 0; }
+
+// Algorithmic weight bytes per decoded token: sum over executed GEMVs of rows*cols*bpw,
+// bpw = 4 / 2 / 1+4/(bs0*bs1) / 84/256 / 110/256, plus the F32 gate, gate bias and norm weights.
+extern "C" double dsk_model_active_bytes_per_token(const dsk_model* m) {
+  if (!m) return 0;
+  const dsk_config& c = m->c;
+  double bpw = 4;
+  switch (c.quant) {
+    case DSK_F16: bpw = 2; break;
+    case DSK_F8E5M2: bpw = 1.0 + 4.0 / ((double)c.bs0 * c.bs1); break;
+    case DSK_Q2_K: bpw = 84.0 / 256; break;
+    case DSK_Q3_K: bpw = 110.0 / 256; break;
+    default: break;
+  }
+  const double hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, dim = c.dim;
+  double total = 0;
+  for (int l = 0; l < c.n_layers; l++) {
+    double w = 0;
+    if (c.q_lora_rank > 0) w += (double)c.q_lora_rank * dim + (double)c.n_heads * hd * c.q_lora_rank;
+    else w += (double)c.n_heads * hd * dim;
+    w += (double)(c.kv_lora_rank + c.qk_rope_head_dim) * dim;
+    w += (double)c.n_heads * (nope + c.v_head_dim) * c.kv_lora_rank;
+    w += dim * c.n_heads * c.v_head_dim;
+    double f32 = 2 * dim + c.kv_lora_rank + c.q_lora_rank;  // norm weights
+    if (m->layers[l].is_moe) {
+      w += 3.0 * c.n_active_routed * mi * dim + 3.0 * c.n_shared_experts * mi * dim;
+      f32 += (double)c.n_routed_experts * dim + (c.is_v3 ? c.n_routed_experts : 0);
+    } else {
+      w += 3.0 * c.hidden_dim * dim;
+    }
+    total += w * bpw + f32 * 4;
+  }
+  total += dim * bpw;                          // embedding row
+  total += (double)c.vocab_size * dim * bpw;   // LM head
+  total += dim * 4;                            // final norm
+  return total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// state
+// ---------------------------------------------------------------------------------------------------
+extern "C" dsk_state* dsk_state_create(dsk_model* m) {
+  if (need_device() || !m) return nullptr;
+  const dsk_config& c = m->c;
+  dsk_state* s = new dsk_state();
+  s->m = m;
+  auto fa = [&](float** p, size_t n) { cudaMalloc((void**)p, std::max<size_t>(n, 4) * 4); cudaMemset(*p, 0, std::max<size_t>(n, 4) * 4); };
+  const int mi = c.moe_intermediate_size;
+  fa(&s->x, c.dim);
+  fa(&s->xb2, std::max(c.dim, c.n_heads * c.v_head_dim));
+  fa(&s->hbk, (size_t)std::max(1, c.n_active_routed) * std::max(1, mi));
+  fa(&s->hbs, std::max(c.hidden_dim, c.n_shared_experts * mi));
+  fa(&s->q_a, std::max(1, c.q_lora_rank));
+  fa(&s->q, (size_t)c.n_heads * m->head_dim);
+  fa(&s->kv_a, c.kv_lora_rank + c.qk_rope_head_dim);
+  fa(&s->kv_b, (size_t)c.n_heads * (c.qk_nope_head_dim + c.v_head_dim));
+  fa(&s->moe_logits, std::max(1, c.n_routed_experts));
+  fa(&s->act_w, 16);
+  fa(&s->logits, c.vocab_size);
+  fa(&s->partial, c.dim);
+  cudaMalloc((void**)&s->act, 16 * sizeof(int));
+  cudaMemset(s->act, 0, 16 * sizeof(int));
+  cudaMalloc((void**)&s->ctrl, sizeof(Ctrl));
+  cudaMemset(s->ctrl, 0, sizeof(Ctrl));
+  cudaMallocHost((void**)&s->h_ctrl, sizeof(Ctrl));
+  memset(s->h_ctrl, 0, sizeof(Ctrl));
+  s->token_log_cap = 1 << 16;
+  cudaMalloc((void**)&s->token_log, s->token_log_cap * sizeof(int));
+  cudaMalloc((void**)&s->step, sizeof(int));
+  cudaMemset(s->step, 0, sizeof(int));
+  cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&s->ev0);
+  cudaEventCreate(&s->ev1);
+  if (cudaGetLastError() != cudaSuccess) { fail(-2, "state allocation failed"); return nullptr; }
+  return s;
+}
+
+extern "C" void dsk_state_destroy(dsk_state* s) {
+  if (!s) return;
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (s->graph[a][b]) cudaGraphExecDestroy(s->graph[a][b]);
+  float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->kv_a, s->kv_b, s->moe_logits, s->act_w, s->logits, s->partial};
+  for (float* b : bufs) cudaFree(b);
+  cudaFree(s->act); cudaFree(s->ctrl); cudaFreeHost(s->h_ctrl); cudaFree(s->token_log); cudaFree(s->step);
+  cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
+  cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+static float* state_buf(dsk_state* s, const char* name, size_t* cap) {
+  const dsk_config& c = s->m->c;
+  std::string k(name);
+  if (k == "x") { *cap = c.dim; return s->x; }
+  if (k == "xb2") { *cap = std::max(c.dim, c.n_heads * c.v_head_dim); return s->xb2; }
+  if (k == "hb") { *cap = std::max(c.hidden_dim, c.n_shared_experts * c.moe_intermediate_size); return s->hbs; }
+  if (k == "hb_routed") { *cap = (size_t)c.n_active_routed * c.moe_intermediate_size; return s->hbk; }
+  if (k == "q_a") { *cap = c.q_lora_rank; return s->q_a; }
+  if (k == "q") { *cap = (size_t)c.n_heads * s->m->head_dim; return s->q; }
+  if (k == "kv_a") { *cap = c.kv_lora_rank + c.qk_rope_head_dim; return s->kv_a; }
+  if (k == "kv_b") { *cap = (size_t)c.n_heads * (c.qk_nope_head_dim + c.v_head_dim); return s->kv_b; }
+  if (k == "moe_weights") { *cap = c.n_routed_experts; return s->moe_logits; }
+  if (k == "active_experts_weights") { *cap = c.n_active_routed; return s->act_w; }
+  if (k == "logits") { *cap = c.vocab_size; return s->logits; }
+  return nullptr;
+}
+extern "C" int dsk_state_read(dsk_state* s, const char* buffer, float* dst, size_t n) {
+  if (need_device() || !s) return -1;
+  size_t cap = 0;
+  float* p = state_buf(s, buffer, &cap);
+  if (!p) return fail(-4, "unknown state buffer %s", buffer);
+  if (n > cap) return fail(-4, "state buffer %s holds %zu floats, asked %zu", buffer, cap, n);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpy(dst, p, n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int dsk_state_write(dsk_state* s, const char* buffer, const float* src, size_t n) {
+  if (need_device() || !s) return -1;
+  size_t cap = 0;
+  float* p = state_buf(s, buffer, &cap);
+  if (!p) return fail(-4, "unknown state buffer %s", buffer);
+  if (n > cap) return fail(-4, "state buffer %s holds %zu floats, asked %zu", buffer, cap, n);
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpy(p, src, n * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int dsk_state_read_i32(dsk_state* s, const char* buffer, int32_t* dst, size_t n) {
+  if (need_device() || !s) return -1;
+  if (std::string(buffer) != "active_experts") return fail(-4, "unknown int buffer %s", buffer);
+  if (n > 16) return fail(-4, "active_experts holds at most 16 ints");
+  CK(cudaStreamSynchronize(s->stream));
+  CK(cudaMemcpy(dst, s->act, n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+static int kv_ptr(dsk_model* m, int layer, int which, __half** p, size_t* cap) {
+  if (!m || layer < 0 || layer >= m->c.n_layers) return fail(-4, "bad layer");
+  Layer& L = m->layers[layer];
+  *p = which == 0 ? L.kcache : L.vcache;
+  *cap = (size_t)m->c.max_seq_len * m->c.n_heads * (which == 0 ? m->head_dim : m->c.v_head_dim);
+  return 0;
+}
+extern "C" int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, size_t n) {
+  if (need_device()) return -1;
+  __half* p; size_t cap;
+  if (kv_ptr(m, layer, which, &p, &cap)) return -4;
+  if (n > cap) return fail(-4, "kv cache holds %zu halfs", cap);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(dst, p, n * 2, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int dsk_kv_write(dsk_model* m, int layer, int which, const uint16_t* src, size_t n) {
+  if (need_device()) return -1;
+  __half* p; size_t cap;
+  if (kv_ptr(m, layer, which, &p, &cap)) return -4;
+  if (n > cap) return fail(-4, "kv cache holds %zu halfs", cap);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(p, src, n * 2, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------------
+static int g_launch_count = 0;
+
+static void plan_rows(GemvArgs& a, int total_rows) {
+  a.total_rows = total_rows;
+  int rpc = cdiv(total_rows, g_sm_count * 4);
+  rpc = std::max(kWarps, cdiv(rpc, kWarps) * kWarps);
+  a.rows_per_cta = rpc;
+}
+
+template <int Q>
+static cudaError_t launch_gemv_q(const GemvArgs& a, cudaStream_t st) {
+  const int grid = cdiv(a.total_rows, a.rows_per_cta);
+  gemv_kernel<Q><<<grid, kThreads, stage_smem_bytes<Q>(a.n), st>>>(a);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+static cudaError_t launch_gemv(int quant, const GemvArgs& a, cudaStream_t st) {
+  switch (quant) {
+    case DSK_F32: return launch_gemv_q<Q_F32>(a, st);
+    case DSK_F16: return launch_gemv_q<Q_F16>(a, st);
+    case DSK_F8E5M2: return launch_gemv_q<Q_F8>(a, st);
+    case DSK_Q2_K: return launch_gemv_q<Q_Q2K>(a, st);
+    default: return launch_gemv_q<Q_Q3K>(a, st);
+  }
+}
+template <int Q>
+static cudaError_t launch_down_q(const DownArgs& a, cudaStream_t st) {
+  const int grid = cdiv(a.dim, a.rows_per_cta);
+  moe_down_kernel<Q><<<grid, kThreads, down_smem_bytes<Q>(a.K, a.mi, a.sh), st>>>(a);
+  g_launch_count++;
+  return cudaGetLastError();
+}
+static cudaError_t launch_down(int quant, const DownArgs& a, cudaStream_t st) {
+  switch (quant) {
+    case DSK_F32: return launch_down_q<Q_F32>(a, st);
+    case DSK_F16: return launch_down_q<Q_F16>(a, st);
+    case DSK_F8E5M2: return launch_down_q<Q_F8>(a, st);
+    case DSK_Q2_K: return launch_down_q<Q_Q2K>(a, st);
+    default: return launch_down_q<Q_Q3K>(a, st);
+  }
+}
+
+static GemvJob plain_job(const DTensor& t, float* out) {
+  GemvJob j{};
+  j.w = t.w; j.scale = t.scale; j.out = out; j.rows = t.rows; j.expert_slot = -1;
+  return j;
+}
+
+static GemvArgs base_args(const dsk_model* m, const dsk_state* s, const float* in, const float* norm_w, int n) {
+  GemvArgs a{};
+  const dsk_config& c = m->c;
+  a.in = in; a.norm_w = norm_w; a.eps = c.norm_eps; a.n = n;
+  a.bs0 = c.bs0 > 0 ? c.bs0 : 1; a.bs1 = c.bs1 > 0 ? c.bs1 : 1;
+  a.act_silu = c.act_silu;
+  a.active_experts = s->act;
+  a.expert_first = m->expert_first; a.expert_count = m->expert_count;
+  a.ctrl = s->ctrl; a.ctrl_rw = s->ctrl;
+  a.epi = EPI_STORE;
+  return a;
+}
+
+#define CKL(call)                                                                                   \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return fail(-2, "launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// One transformer block: Block::_block_cpu (src/infer.cpp:810-932) + BlockMHA::_attention_impl (934-1049).
+static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
+  const dsk_config& c = m->c;
+  Layer& L = m->layers[l];
+  const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant;
+  // S1: xb = rmsnorm(x) fused; q (or q_a) and kv_a in one launch            infer.cpp:823, 942-954
+  {
+    GemvArgs a = base_args(m, s, s->x, L.rms_att, c.dim);
+    if (c.q_lora_rank > 0) a.job[0] = plain_job(L.wq_a, s->q_a); else a.job[0] = plain_job(L.wq, s->q);
+    a.job[1] = plain_job(L.wkv_a, s->kv_a);
+    a.njobs = 2;
+    plan_rows(a, a.job[0].rows + a.job[1].rows);
+    CKL(launch_gemv(q, a, st));
+  }
+  if (c.q_lora_rank > 0) {  // q = wq_b . rmsnorm(q_a)                          infer.cpp:944-950
+    GemvArgs a = base_args(m, s, s->q_a, L.rms_q_a, c.q_lora_rank);
+    a.job[0] = plain_job(L.wq_b, s->q);
+    a.njobs = 1;
+    plan_rows(a, a.job[0].rows);
+    CKL(launch_gemv(q, a, st));
+  }
+  // S2: kv_b = wkv_b . rmsnorm(kv_a[:kv_lora]); epilogue writes fp16 K(nope)/V cache row   infer.cpp:974-1002
+  {
+    GemvArgs a = base_args(m, s, s->kv_a, L.rms_kv_a, c.kv_lora_rank);
+    a.job[0] = plain_job(L.wkv_b, s->kv_b);
+    a.njobs = 1;
+    a.epi = EPI_KVB;
+    a.kcache = L.kcache; a.vcache = L.vcache; a.n_heads = c.n_heads; a.nope = nope; a.vh = c.v_head_dim; a.hd = hd;
+    plan_rows(a, a.job[0].rows);
+    CKL(launch_gemv(q, a, st));
+  }
+  // S3: RoPE(q_pe, k_pe) + sink re-rotation + attention over the fp16 cache               infer.cpp:956-1045
+  {
+    AttnArgs a{};
+    a.q = s->q; a.kv_a = s->kv_a; a.kcache = L.kcache; a.vcache = L.vcache; a.out = s->xb2; a.ctrl = s->ctrl;
+    a.n_heads = c.n_heads; a.hd = hd; a.nope = nope; a.rope = c.qk_rope_head_dim; a.vh = c.v_head_dim;
+    a.kv_lora = c.kv_lora_rank; a.theta = c.rope_theta; a.is_v3 = c.is_v3; a.max_seq = c.max_seq_len; a.do_prologue = 1;
+    attn_kernel<<<c.n_heads, kThreads, attn_smem_bytes(hd, c.v_head_dim, c.max_seq_len), st>>>(a);
+    g_launch_count++;
+    CKL(cudaGetLastError());
+  }
+  // S4: x += wo . xb2                                                                     infer.cpp:1048, 832-834
+  {
+    GemvArgs a = base_args(m, s, s->xb2, nullptr, c.n_heads * c.v_head_dim);
+    a.job[0] = plain_job(L.wo, s->x);
+    a.njobs = 1;
+    a.epi = EPI_RESID;
+    plan_rows(a, a.job[0].rows);
+    CKL(launch_gemv(q, a, st));
+  }
+  if (L.is_moe) {
+    // gate logits (F32 weights in every quant)                                           infer.cpp:847
+    {
+      GemvArgs a = base_args(m, s, s->x, L.rms_ffn, c.dim);
+      GemvJob j{};
+      j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
+      a.job[0] = j;
+      a.njobs = 1;
+      plan_rows(a, j.rows);
+      CKL(launch_gemv(DSK_F32, a, st));
+    }
+    {  // moe_gate                                                                        infer.cpp:848-852
+      GateArgs g{};
+      g.x = s->moe_logits; g.bias = L.gate_bias; g.active = s->act; g.weights = s->act_w;
+      g.E = c.n_routed_experts; g.K = c.n_active_routed; g.norm_topk_prob = c.norm_topk_prob; g.sigmoid = c.scoring_sigmoid;
+      g.method = c.topk_method; g.n_group = std::max(1, c.n_group); g.topk_group = c.topk_group; g.scale = c.routed_scaling_factor;
+      gate_topk_kernel<<<1, 256, 0, st>>>(g);
+      g_launch_count++;
+      CKL(cudaGetLastError());
+    }
+    // routed + shared up/gate projections with fused act(h1)*h3                           infer.cpp:853-870, 879-897
+    const int sh = c.n_shared_experts * mi;
+    {
+      GemvArgs a = base_args(m, s, s->x, L.rms_ffn, c.dim);
+      int nj = 0, rows = 0;
+      for (int k = 0; k < c.n_active_routed; k++) {
+        GemvJob j{};
+        j.w = L.w1.w; j.scale = L.w1.scale; j.w_b = L.w3.w; j.scale_b = L.w3.scale;
+        j.out = s->hbk + (size_t)k * mi; j.rows = mi; j.expert_slot = k;
+        j.w_stride = (long long)L.w1.expert_bytes; j.s_stride = (long long)L.w1.scale_expert;
+        a.job[nj++] = j; rows += mi;
+      }
+      if (sh > 0) {
+        GemvJob j = plain_job(L.sw1, s->hbs);
+        j.w_b = L.sw3.w; j.scale_b = L.sw3.scale;
+        a.job[nj++] = j; rows += sh;
+      }
+      a.njobs = nj;
+      a.epi = EPI_GLU;
+      plan_rows(a, rows);
+      CKL(launch_gemv(q, a, st));
+    }
+    // down projections + weighted accumulate into the residual stream                     infer.cpp:873-877, 899-903
+    {
+      DownArgs d{};
+      d.w2 = L.w2.w; d.s2 = L.w2.scale; d.w_stride = (long long)L.w2.expert_bytes; d.s_stride = (long long)L.w2.scale_expert;
+      d.sw2 = sh > 0 ? L.sw2.w : nullptr; d.ss2 = sh > 0 ? L.sw2.scale : nullptr;
+      d.hb = s->hbk; d.hb_shared = s->hbs; d.active = s->act; d.weights = s->act_w;
+      d.K = c.n_active_routed; d.mi = mi; d.sh = sh; d.dim = c.dim;
+      d.bs0 = c.bs0 > 0 ? c.bs0 : 1; d.bs1 = c.bs1 > 0 ? c.bs1 : 1;
+      d.expert_first = m->expert_first; d.expert_count = m->expert_count;
+      d.x = s->x;
+      d.partial = m->n_ranks > 1 ? s->partial : nullptr;
+      d.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
+      d.rows_per_cta = std::max(kWarps, cdiv(cdiv(c.dim, g_sm_count * 2), kWarps) * kWarps);
+      CKL(launch_down(q, d, st));
+      if (m->n_ranks > 1) {
+        if (!m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
+        CKN(ncclAllReduce(s->partial, s->partial, c.dim, ncclFloat, ncclSum, m->comm, st));
+        add_vec_kernel<<<cdiv(c.dim, 256), 256, 0, st>>>(s->x, s->partial, c.dim);
+        g_launch_count += 2;
+        CKL(cudaGetLastError());
+      }
+    }
+  } else {
+    // dense FFN                                                                          infer.cpp:905-931
+    {
+      GemvArgs a = base_args(m, s, s->x, L.rms_ffn, c.dim);
+      GemvJob j = plain_job(L.w1, s->hbs);
+      j.w_b = L.w3.w; j.scale_b = L.w3.scale;
+      a.job[0] = j;
+      a.njobs = 1;
+      a.epi = EPI_GLU;
+      plan_rows(a, j.rows);
+      CKL(launch_gemv(q, a, st));
+    }
+    {
+      DownArgs d{};
+      d.sw2 = L.w2.w; d.ss2 = L.w2.scale;
+      d.hb = s->hbk; d.hb_shared = s->hbs; d.active = s->act; d.weights = s->act_w;
+      d.K = 0; d.mi = 0; d.sh = c.hidden_dim; d.dim = c.dim;
+      d.bs0 = c.bs0 > 0 ? c.bs0 : 1; d.bs1 = c.bs1 > 0 ? c.bs1 : 1;
+      d.x = s->x; d.partial = nullptr; d.add_shared = 1;
+      d.rows_per_cta = std::max(kWarps, cdiv(cdiv(c.dim, g_sm_count * 2), kWarps) * kWarps);
+      CKL(launch_down(q, d, st));
+    }
+  }
+  return 0;
+}
+
+static int enqueue_embed(dsk_model* m, dsk_state* s, int from_argmax, cudaStream_t st) {
+  const dsk_config& c = m->c;
+  EmbedArgs e{};
+  e.table = m->embed.w; e.scale = m->embed.scale; e.x = s->x; e.ctrl = s->ctrl;
+  e.quant = c.quant; e.dim = c.dim; e.bs0 = c.bs0 > 0 ? c.bs0 : 1; e.bs1 = c.bs1 > 0 ? c.bs1 : 1;
+  e.from_argmax = from_argmax; e.original_max = c.original_max_position;
+  e.token_log = s->token_log; e.step = s->step;
+  embed_kernel<<<1, 256, 0, st>>>(e);
+  g_launch_count++;
+  CKL(cudaGetLastError());
+  return 0;
+}
+
+// Model::_forward_cpu (src/infer.cpp:1265-1317) as one launch sequence
+static int enqueue_forward(dsk_model* m, dsk_state* s, int mode, int from_argmax, cudaStream_t st) {
+  const dsk_config& c = m->c;
+  if (enqueue_embed(m, s, from_argmax, st)) return -2;
+  for (int l = 0; l < c.n_layers; l++)
+    if (enqueue_layer(m, s, l, st)) return -2;
+  if (mode == DSK_HYDRATE_KV_CACHE) return 0;
+  // final RMSNorm fused into the LM-head prologue; fused argmax (Sampler::sample_argmax)   infer.cpp:1292-1316
+  GemvArgs a = base_args(m, s, s->x, m->rms_final, c.dim);
+  a.job[0] = plain_job(m->wcls, s->logits);
+  a.njobs = 1;
+  a.epi = EPI_LOGITS;
+  plan_rows(a, a.job[0].rows);
+  CKL(launch_gemv(c.quant, a, st));
+  return 0;
+}
+
+static int get_graph(dsk_model* m, dsk_state* s, int mode, int from_argmax, cudaGraphExec_t* out) {
+  cudaGraphExec_t& g = s->graph[mode][from_argmax];
+  if (!g) {
+    cudaGraph_t graph;
+    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_forward(m, s, mode, from_argmax, s->stream);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(-2, "graph capture failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&g, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  *out = g;
+  return 0;
+}
+
+static void fill_ctrl(Ctrl* h, const dsk_config& c, int token, int pos) {
+  // src/infer.cpp:1274-1277
+  const int omp = c.original_max_position;
+  h->token = token;
+  h->pos = pos;
+  h->kv_sink = pos >= omp ? 2 : 0;
+  h->kv_pos = h->kv_sink + (pos - h->kv_sink) % (omp - h->kv_sink);
+  h->kv_len = pos >= omp ? omp : pos + 1;
+  h->argmax_key = 0ull;
+}
+
+extern "C" int dsk_forward(dsk_model* m, dsk_state* s, int token, int pos, int mode, float* host_logits, int* argmax) {
+  if (need_device()) return -1;
+  if (!m || !s) return fail(-1, "null model/state");
+  const dsk_config& c = m->c;
+  if (token < 0 || token >= c.vocab_size) return fail(-4, "token %d out of range", token);
+  if (pos < 0) return fail(-4, "negative pos");
+  mode = mode ? 1 : 0;
+  fill_ctrl(s->h_ctrl, c, token, pos);
+  if (s->h_ctrl->kv_pos >= c.max_seq_len || s->h_ctrl->kv_len > c.max_seq_len)
+    return fail(-4, "pos %d does not fit the KV cache (max_seq_len %d; the reference would overrun it)", pos, c.max_seq_len);
+  cudaGraphExec_t g;
+  if (get_graph(m, s, mode, 0, &g)) return -2;
+  CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+  CK(cudaGraphLaunch(g, s->stream));
+  if (mode && host_logits) CK(cudaMemcpyAsync(host_logits, s->logits, (size_t)c.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (mode && argmax) CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (mode && argmax) *argmax = (int)(0xFFFFFFFFu - (unsigned)(s->h_ctrl->argmax_key & 0xFFFFFFFFull));
+  s->last_pos = pos;
+  return 0;
+}
+
+extern "C" int dsk_copy_embedding(dsk_model* m, dsk_state* s, int token) {
+  if (need_device()) return -1;
+  if (!m || !s) return fail(-1, "null model/state");
+  fill_ctrl(s->h_ctrl, m->c, token, 0);
+  CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+  if (enqueue_embed(m, s, 0, s->stream)) return -2;
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int dsk_block_forward(dsk_model* m, dsk_state* s, int layer, int pos, int kv_sink, int kv_pos, int kv_len) {
+  if (need_device()) return -1;
+  if (!m || !s) return fail(-1, "null model/state");
+  if (layer < 0 || layer >= m->c.n_layers) return fail(-4, "bad layer %d", layer);
+  Ctrl* h = s->h_ctrl;
+  h->token = 0; h->pos = pos; h->kv_sink = kv_sink; h->kv_pos = kv_pos; h->kv_len = kv_len; h->argmax_key = 0;
+  CK(cudaMemcpyAsync(s->ctrl, h, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+  if (enqueue_layer(m, s, layer, s->stream)) return -2;
+  CK(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int n_steps, int32_t* out_tokens,
+                                 float* elapsed_ms) {
+  if (need_device()) return -1;
+  if (!m || !s) return fail(-1, "null model/state");
+  if (s->last_pos < 0 || start_pos != s->last_pos + 1)
+    return fail(-4, "dsk_decode_greedy: start_pos %d must follow the last forward (pos %d)", start_pos, s->last_pos);
+  if ((size_t)n_steps > s->token_log_cap) return fail(-4, "n_steps too large");
+  const dsk_config& c = m->c;
+  if (c.original_max_position > c.max_seq_len && start_pos + n_steps > c.max_seq_len)
+    return fail(-4, "decode would run past the KV cache (%d)", c.max_seq_len);
+  cudaGraphExec_t g;
+  if (get_graph(m, s, 1, 1, &g)) return -2;
+  CK(cudaMemsetAsync(s->step, 0, sizeof(int), s->stream));
+  CK(cudaEventRecord(s->ev0, s->stream));
+  for (int i = 0; i < n_steps; i++) CK(cudaGraphLaunch(g, s->stream));
+  CK(cudaEventRecord(s->ev1, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+  if (out_tokens) CK(cudaMemcpy(out_tokens, s->token_log, (size_t)n_steps * 4, cudaMemcpyDeviceToHost));
+  s->last_pos = start_pos + n_steps - 1;
+  return 0;
+}
+
+extern "C" int dsk_launches_per_forward(const dsk_model* m, int mode) {
+  if (!m) return 0;
+  const dsk_config& c = m->c;
+  int n = 1;  // embed
+  for (int l = 0; l < c.n_layers; l++) {
+    n += 4 + (c.q_lora_rank > 0 ? 1 : 0);
+    if (m->layers[l].is_moe) n += 4 + (m->n_ranks > 1 ? 2 : 0); else n += 2;
+  }
+  if (mode) n += 1;
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dsk_comm_unique_id(void* out128) {
+  ncclUniqueId id;
+  CKN(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+  return 0;
+}
+extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
+  if (need_device()) return -1;
+  if (!m) return fail(-1, "null model");
+  if (m->n_ranks == 1) return 0;
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id128, 128);
+  CKN(ncclCommInitRank(&m->comm, m->n_ranks, id, m->rank));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel-level test hooks
+// ---------------------------------------------------------------------------------------------------
+struct Tmp {
+  std::vector<void*> p;
+  ~Tmp() { for (void* q : p) cudaFree(q); }
+  template <typename T> T* up(const T* host, size_t n) {
+    T* d = nullptr;
+    if (cudaMalloc((void**)&d, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) return nullptr;
+    p.push_back(d);
+    if (host && n) cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+  }
+};
+
+extern "C" int dsk_gemv(int quant, int d, int n, const void* w, const float* scale, int bs0, int bs1, const float* x,
+                        float* out) {
+  if (need_device()) return -1;
+  if (quant < 0 || quant > 4) return fail(-4, "bad quant");
+  if ((quant >= DSK_Q2_K && n % 256) || (quant == DSK_F8E5M2 && n % 16) || (quant == DSK_F16 && n % 16) || (quant == DSK_F32 && n % 4))
+    return fail(-4, "n=%d not supported for quant %d (src/infer.cpp:169,246; src/quant.cpp:617)", n, quant);
+  Tmp t;
+  const size_t drb = disk_row_bytes(quant, n), vrb = dev_row_bytes(quant, n);
+  uint8_t* dw = t.up<uint8_t>(nullptr, vrb * d + 16);
+  if (quant == DSK_Q3_K) {
+    uint8_t* st = t.up<uint8_t>((const uint8_t*)w, drb * d);
+    const size_t nblocks = drb * d / kQ3Disk;
+    q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256>>>(st, dw, nblocks);
+  } else {
+    CK(cudaMemcpy(dw, w, drb * d, cudaMemcpyHostToDevice));
+  }
+  float* ds = scale ? t.up<float>(scale, (size_t)cdiv(d, bs0) * cdiv(n, bs1)) : nullptr;
+  float* dx = t.up<float>(x, n);
+  float* dout = t.up<float>(nullptr, d);
+  GemvArgs a{};
+  a.in = dx; a.n = n; a.bs0 = bs0 > 0 ? bs0 : 1; a.bs1 = bs1 > 0 ? bs1 : 1; a.epi = EPI_STORE; a.njobs = 1;
+  GemvJob j{};
+  j.w = dw; j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
+  a.job[0] = j;
+  plan_rows(a, d);
+  CKL(launch_gemv(quant, a, 0));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dout, (size_t)d * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_quantize_q8k(const float* x, int k, void* out) {
+  if (need_device()) return -1;
+  if (k <= 0 || k % 256) return fail(-4, "k must be a positive multiple of 256 (src/quant.cpp:617)");
+  Tmp t;
+  float* dx = t.up<float>(x, k);
+  unsigned char* dout = t.up<unsigned char>(nullptr, (size_t)k / 256 * 292);
+  q8k_export_kernel<<<1, kThreads, stage_smem_bytes<Q_Q2K>(k)>>>(dx, k, dout);
+  CKL(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dout, (size_t)k / 256 * 292, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_dequantize_row(int quant, const void* blocks, int k, float* out) {
+  if (need_device()) return -1;
+  if ((quant != DSK_Q2_K && quant != DSK_Q3_K) || k % 256) return fail(-4, "bad arguments");
+  Tmp t;
+  const size_t drb = disk_row_bytes(quant, k), vrb = dev_row_bytes(quant, k);
+  uint8_t* dw = t.up<uint8_t>(nullptr, vrb + 16);
+  if (quant == DSK_Q3_K) {
+    uint8_t* st = t.up<uint8_t>((const uint8_t*)blocks, drb);
+    q3k_repack_kernel<<<(unsigned)((k / 256 + 7) / 8), 256>>>(st, dw, k / 256);
+  } else {
+    CK(cudaMemcpy(dw, blocks, drb, cudaMemcpyHostToDevice));
+  }
+  float* dx = t.up<float>(nullptr, k);
+  Ctrl* ctrl = t.up<Ctrl>(nullptr, 1);
+  CK(cudaMemset(ctrl, 0, sizeof(Ctrl)));
+  EmbedArgs e{};
+  e.table = dw; e.x = dx; e.ctrl = ctrl; e.quant = quant; e.dim = k; e.bs0 = 1; e.bs1 = 1; e.original_max = 1 << 30;
+  embed_kernel<<<1, 256>>>(e);
+  CKL(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dx, (size_t)k * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_rmsnorm(const float* x, const float* w, int n, float eps, float* out) {
+  if (need_device()) return -1;
+  Tmp t;
+  float *dx = t.up<float>(x, n), *dw = t.up<float>(w, n), *dout = t.up<float>(nullptr, n);
+  rmsnorm_kernel<<<1, 256>>>(dout, dx, dw, n, eps);
+  CKL(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_rope(float* vec, int d, int head_dim, int pos, float theta, int v3) {
+  if (need_device()) return -1;
+  if (d % 2 || d > 2048) return fail(-4, "bad d");
+  Tmp t;
+  float* dv = t.up<float>(vec, d);
+  rope_test_kernel<<<1, 1024, (size_t)d * 4>>>(dv, d, head_dim, pos, theta, v3);
+  CKL(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(vec, dv, (size_t)d * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_moe_gate(float* logits, const float* bias, int n_routed, int n_active, int norm_topk_prob,
+                            float routed_scaling_factor, int scoring_sigmoid, int topk_method, int n_group, int topk_group,
+                            int32_t* active_experts, float* weights) {
+  if (need_device()) return -1;
+  if (n_routed > 256 || n_active > 16) return fail(-4, "E <= 256 (src/infer.cpp:527), K <= 16");
+  Tmp t;
+  float* dx = t.up<float>(logits, n_routed);
+  float* db = bias ? t.up<float>(bias, n_routed) : nullptr;
+  int* da = t.up<int>(nullptr, 16);
+  float* dwt = t.up<float>(nullptr, 16);
+  GateArgs g{};
+  g.x = dx; g.bias = db; g.active = da; g.weights = dwt; g.E = n_routed; g.K = n_active; g.norm_topk_prob = norm_topk_prob;
+  g.sigmoid = scoring_sigmoid; g.method = topk_method; g.n_group = std::max(1, n_group); g.topk_group = topk_group;
+  g.scale = routed_scaling_factor;
+  gate_topk_kernel<<<1, 256>>>(g);
+  CKL(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(logits, dx, (size_t)n_routed * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(active_experts, da, (size_t)n_active * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(weights, dwt, (size_t)n_active * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_attn(const float* q, const uint16_t* kcache, const uint16_t* vcache, int n_heads, int head_dim,
+                        int v_head_dim, int kv_len, float* out) {
+  if (need_device()) return -1;
+  Tmp t;
+  float* dq = t.up<float>(q, (size_t)n_heads * head_dim);
+  uint16_t* dk = t.up<uint16_t>(kcache, (size_t)kv_len * n_heads * head_dim);
+  uint16_t* dv = t.up<uint16_t>(vcache, (size_t)kv_len * n_heads * v_head_dim);
+  float* dout = t.up<float>(nullptr, (size_t)n_heads * v_head_dim);
+  AttnArgs a{};
+  a.q = dq; a.kcache = (__half*)dk; a.vcache = (__half*)dv; a.out = dout; a.ctrl = nullptr;
+  a.n_heads = n_heads; a.hd = head_dim; a.nope = head_dim; a.rope = 0; a.vh = v_head_dim; a.do_prologue = 0;
+  a.kv_len_fixed = kv_len; a.max_seq = kv_len;
+  attn_kernel<<<n_heads, kThreads, attn_smem_bytes(head_dim, v_head_dim, kv_len)>>>(a);
+  CKL(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, dout, (size_t)n_heads * v_head_dim * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// measurement hook
+// ---------------------------------------------------------------------------------------------------
+__global__ void fill_pattern_kernel(uint32_t* p, size_t n_words, uint32_t seed, uint32_t and_mask, uint32_t or_mask) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n_words; i += stride) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    p[i] = (x & and_mask) | or_mask;
+  }
+}
+
+extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, int iters, float* avg_ms,
+                              double* bytes_per_launch) {
+  if (need_device()) return -1;
+  if (quant < 0 || quant > 4 || n_mats < 1) return fail(-4, "bad arguments");
+  Tmp t;
+  const size_t vrb = dev_row_bytes(quant, n);
+  const size_t mat = (vrb * d + 255) & ~(size_t)255;
+  uint8_t* w = t.up<uint8_t>(nullptr, mat * n_mats + 256);
+  if (!w) return fail(-2, "allocation of %zu bytes failed", mat * n_mats);
+  // finite synthetic payload: f8/f16 exponent bits kept small; K-quant bytes arbitrary (d/dmin patched by mask)
+  uint32_t and_mask = 0xFFFFFFFFu, or_mask = 0;
+  if (quant == DSK_F8E5M2) and_mask = 0xBFBFBFBFu;       // clear the top exponent bit of every byte
+  if (quant == DSK_F16) and_mask = 0xBFFFBFFFu;
+  if (quant == DSK_F32) { and_mask = 0xBFFFFFFFu; }
+  if (quant >= DSK_Q2_K) and_mask = 0x3F3F3F3Fu;          // keeps the fp16 d/dmin fields finite wherever they fall
+  fill_pattern_kernel<<<1024, 256>>>((uint32_t*)w, mat * n_mats / 4, 12345u, and_mask, or_mask);
+  const int srows = cdiv(d, 128), scols = cdiv(n, 128);
+  std::vector<float> hs((size_t)srows * scols, 1e-3f);
+  float* ds = quant == DSK_F8E5M2 ? t.up<float>(hs.data(), hs.size()) : nullptr;
+  std::vector<float> hx(n, 0.5f);
+  float* dx = t.up<float>(hx.data(), n);
+  float* dout = t.up<float>(nullptr, d);
+  GemvArgs a{};
+  a.in = dx; a.n = n; a.bs0 = 128; a.bs1 = 128; a.epi = EPI_STORE; a.njobs = 1;
+  GemvJob j{};
+  j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
+  plan_rows(a, d);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < warmup + iters; i++) {
+    if (i == warmup) CK(cudaEventRecord(e0, 0));
+    j.w = w + (size_t)(i % n_mats) * mat;
+    a.job[0] = j;
+    CKL(launch_gemv(quant, a, 0));
+  }
+  CK(cudaEventRecord(e1, 0));
+  CK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (avg_ms) *avg_ms = ms / iters;
+  double bpw = quant == DSK_F32 ? 4 : quant == DSK_F16 ? 2 : quant == DSK_F8E5M2 ? 1.0 + 4.0 / 16384 : quant == DSK_Q2_K ? 84.0 / 256 : 110.0 / 256;
+  if (bytes_per_launch) *bytes_per_launch = (double)d * n * bpw;
+  return 0;
+}

@@ -1,0 +1,144 @@
+/* include/dsk.h — C-ABI of the B200-native single-batch DeepSeek decoder (libdsk.so).
+ *
+ * This is the drop-in boundary for the reference's decode hot path.  The reference
+ * (andrewkchan/deepseek.cpp @ 8db9e56) has no FFI: its boundary is the link-time seam between
+ * src/model.cpp (dispatch) and src/infer.cpp (backend TU) plus `enum class Device` (src/model.h:36-38).
+ * Each entry point below names the reference interface it replaces; INTEGRATION.md shows the
+ * `Device::CUDA` binding a maintainer would add on the reference side.
+ *
+ * Conventions: plain C types only; every call returns 0 on success and a negative code on failure
+ * (dsk_last_error() has the text); one caller thread per model (like the reference, not re-entrant);
+ * there is NO CPU fallback — without a CUDA device every call fails loudly.
+ */
+#ifndef DSK_H
+#define DSK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSK_ABI_VERSION 1
+
+/* Quant: src/codec.h:79-85 (same numbering) */
+enum { DSK_F32 = 0, DSK_F16 = 1, DSK_F8E5M2 = 2, DSK_Q2_K = 3, DSK_Q3_K = 4 };
+/* CodecDType subset used by .dseek payloads: src/codec.h:62-72 */
+enum { DSK_DT_F32 = 0, DSK_DT_F16 = 1, DSK_DT_F8E5M2 = 3, DSK_DT_U8 = 8 };
+/* InferenceMode: src/model.h:40-43 */
+enum { DSK_HYDRATE_KV_CACHE = 0, DSK_OUTPUT_LOGITS = 1 };
+/* TopKMethod / ScoringFunc: src/model.h:25-34 */
+enum { DSK_TOPK_GREEDY = 0, DSK_TOPK_GROUP_LIMITED_GREEDY = 1 };
+
+/* Config: src/model.h:47-96 (fields the MHA-mode decode path reads; filled from .dseek metadata,
+ * src/model.cpp:22-127). */
+typedef struct dsk_config {
+  int dim, hidden_dim, n_layers, n_heads, vocab_size, max_seq_len;
+  float rope_theta, norm_eps;
+  int act_silu;              /* 1 = SiLU, 0 = GELU (ActivationType) */
+  int first_k_dense_replace;
+  int n_shared_experts, n_routed_experts, n_active_routed, moe_intermediate_size;
+  float routed_scaling_factor;
+  int n_group, norm_topk_prob, scoring_sigmoid, topk_group, topk_method;
+  int is_v3;                 /* has_moegate_bias: gate bias + interleaved RoPE (src/infer.cpp:958) */
+  int kv_lora_rank, q_lora_rank, qk_nope_head_dim, qk_rope_head_dim, v_head_dim;
+  int quant;                 /* DSK_* weight quant */
+  int bs0, bs1;              /* f8e5m2 scale block (128,128) */
+  int original_max_position; /* rope_scaling_original_max_position_embeddings (sinks, src/infer.cpp:1274) */
+} dsk_config;
+
+typedef struct dsk_model dsk_model;
+typedef struct dsk_state dsk_state;
+
+/* ---- process / device -------------------------------------------------------------------------- */
+int dsk_abi_version(void);
+const char* dsk_last_error(void);
+/* Binds the calling process to CUDA device `device` (one process per GPU). */
+int dsk_init(int device);
+int dsk_sync(void);
+/* Device facts for logs/bench: name (<=128 chars), SM count, HBM bytes. */
+int dsk_device_info(char* name128, int* sm_count, size_t* hbm_bytes);
+
+/* ---- model: replaces Model::Model weight binding (src/model.cpp:756-871) + device upload -------- */
+/* rank/n_ranks: expert-shard placement — routed expert e lives on rank e / ceil(E/n_ranks); everything
+ * else is replicated. */
+dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ranks);
+void dsk_model_destroy(dsk_model* m);
+/* Upload one .dseek tensor by its on-disk name (src/model.cpp:766-871), raw payload bytes exactly as
+ * stored (K-quants: U8 block rows).  Expert stacks (E, rows, cols): only this rank's slice is kept.
+ * `src_on_device` != 0 means `data` is already a device pointer (GPU-side minting). */
+int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, const int64_t shape[4], const void* data,
+                      size_t nbytes, int src_on_device);
+/* Checks every tensor the config requires is present (check_tensor, src/model.cpp:129-136). */
+int dsk_model_finalize(dsk_model* m);
+/* Bytes of weights resident on this GPU / algorithmic weight bytes streamed per decoded token
+ * (replaces Model::active_bytes, src/model.cpp:885-901, which under-counts). */
+size_t dsk_model_resident_bytes(const dsk_model* m);
+double dsk_model_active_bytes_per_token(const dsk_model* m);
+
+/* ---- state: replaces InferenceState (src/model.h:101-179) -------------------------------------- */
+dsk_state* dsk_state_create(dsk_model* m);
+void dsk_state_destroy(dsk_state* s);
+/* Named buffer access for parity taps: "x","xb2","hb","q","kv_a","kv_b","moe_weights",
+ * "active_experts_weights","logits" (float) and "active_experts" (int32, via the _i32 variant). */
+int dsk_state_read(dsk_state* s, const char* buffer, float* dst, size_t n);
+int dsk_state_write(dsk_state* s, const char* buffer, const float* src, size_t n);
+int dsk_state_read_i32(dsk_state* s, const char* buffer, int32_t* dst, size_t n);
+/* fp16 KV cache rows of one layer (BlockMHA::key_cache/value_cache, src/model.h:344-347). which: 0 K, 1 V. */
+int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, size_t n_halfs);
+int dsk_kv_write(dsk_model* m, int layer, int which, const uint16_t* src, size_t n_halfs);
+
+/* ---- forward ----------------------------------------------------------------------------------- */
+/* Model::forward(state, token, pos, mode) — src/model.cpp:874-883 -> _forward_cpu src/infer.cpp:1265-1317.
+ * host_logits (vocab floats, nullable) receives s.logits(); argmax (nullable) receives
+ * Sampler::sample_argmax (src/sampler.cpp:28-39) computed on device. */
+int dsk_forward(dsk_model* m, dsk_state* s, int token, int pos, int mode, float* host_logits, int* argmax);
+/* Model::_copy_embedding — src/infer.cpp:1217-1263. */
+int dsk_copy_embedding(dsk_model* m, dsk_state* s, int token);
+/* Block::block(state, pos, kv_sink, kv_pos, kv_len) — src/model.cpp:290-322 -> _block_cpu src/infer.cpp:810-932. */
+int dsk_block_forward(dsk_model* m, dsk_state* s, int layer, int pos, int kv_sink, int kv_pos, int kv_len);
+/* Device-resident greedy decode (run_completion's sample->forward loop, src/main.cpp:324-335, -t 0):
+ * starting from the logits already in `s`, generates n_steps tokens with on-device argmax feeding the
+ * next forward; no host round trip per token.  out_tokens (n_steps ints, nullable).  Returns the device
+ * time of the loop in milliseconds through *elapsed_ms (CUDA events), nullable. */
+int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int n_steps, int32_t* out_tokens,
+                      float* elapsed_ms);
+/* Number of kernels one forward launches (for bench.py's gpu_launches) */
+int dsk_launches_per_forward(const dsk_model* m, int mode);
+
+/* ---- multi-GPU: one NCCL all-reduce of the MoE partial sum per MoE layer ---------- */
+/* nccl_unique_id: 128 bytes from dsk_comm_unique_id() on rank 0, broadcast by the launcher. */
+int dsk_comm_unique_id(void* out128);
+int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128);
+
+/* ---- kernel-level test hooks (mirror the statics reached by the reference's tests) -------------- */
+/* matmul / matmul_unscaled — src/infer.cpp:381-421.  w: raw payload (host), scale nullable. */
+int dsk_gemv(int quant, int d, int n, const void* w, const float* scale, int bs0, int bs1, const float* x,
+             float* out);
+/* quantize_row_q8_K_ref — src/quant.cpp:616-653.  out: k/256 block_q8_K (292 B each). */
+int dsk_quantize_q8k(const float* x, int k, void* out);
+/* dequantize_row_q{2,3}_K — src/quant.cpp:217-247, 384-432 (through the embedding-row kernel). */
+int dsk_dequantize_row(int quant, const void* blocks, int k, float* out);
+/* rmsnorm — src/infer.cpp:601-611 */
+int dsk_rmsnorm(const float* x, const float* w, int n, float eps, float* out);
+/* rope / rope_v3 — src/infer.cpp:648-685 (fp32) */
+int dsk_rope(float* vec, int d, int head_dim, int pos, float theta, int v3);
+/* moe_gate — src/infer.cpp:493-599.  logits (E) in/out (post-softmax/sigmoid+bias scores). */
+int dsk_moe_gate(float* logits, const float* bias, int n_routed, int n_active, int norm_topk_prob,
+                 float routed_scaling_factor, int scoring_sigmoid, int topk_method, int n_group, int topk_group,
+                 int32_t* active_experts, float* weights);
+/* attn over all heads — src/infer.cpp:728-762 / mha_cpu 1143-1164.  kcache/vcache fp16 (kv_len rows). */
+int dsk_attn(const float* q, const uint16_t* kcache, const uint16_t* vcache, int n_heads, int head_dim,
+             int v_head_dim, int kv_len, float* out);
+
+/* ---- measurement hook (bench.py roofline): times `iters` back-to-back launches of the GEMV kernel on a
+ * (d x n) matrix of synthetic weights resident in HBM, CUDA events on the launching stream, after `warmup`
+ * launches.  n_mats >= 1 distinct matrices are cycled so consecutive launches never re-read L2-resident data.
+ * Returns average milliseconds per launch and the algorithmic bytes per launch. */
+int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, int iters, float* avg_ms, double* bytes_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSK_H */

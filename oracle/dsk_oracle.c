@@ -83,8 +83,10 @@ static inline int nearest_int(float fval) {
 
 /* quantize_row_q8_K_ref: src/quant.cpp:616-653.
  * Bit-exactness note: the reference is built with -ffast-math (Makefile:31); its object code computes
- * iscale = -127.f/max as a true division and d = 1/iscale as written (checked against libdsref.so by
- * tests/test_oracle_vs_ref.py::test_q8k_bit_exact). */
+ * iscale = -127.f/max as a true division but folds `d = 1/iscale` into `max * (-1/127.f)` (one vmulss by a
+ * constant) — measured: 3000/3000 random blocks match that form, 2171/3000 match the literal 1/iscale.
+ * The restatement (and the CUDA kernel) follow the compiled form; tests/test_oracle.py::test_q8k_bit_exact
+ * pins it byte-for-byte against libdsref.so. */
 void ork_quantize_row_q8_K(const float* x, ork_block_q8_K* y, long k) {
   const long nb = k / ORK_QK_K;
   for (long i = 0; i < nb; i++) {
@@ -111,7 +113,7 @@ void ork_quantize_row_q8_K(const float* x, ork_block_q8_K* y, long k) {
       for (int ii = 0; ii < 16; ++ii) sum += y[i].qs[j * 16 + ii];
       y[i].bsums[j] = (int16_t)sum;
     }
-    y[i].d = 1 / iscale;
+    y[i].d = max * (-1.0f / 127.0f);
     x += ORK_QK_K;
   }
 }

@@ -1,0 +1,178 @@
+"""GPU parity, tier T1: every kernel fed the oracle's exact inputs, through the C-ABI hooks.
+Checker = the unmodified reference (oracle/_ref) when present, else the plain-C port; plus committed goldens."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dsk():
+    import dsk as d
+    d.init(0)
+    return d
+
+
+@pytest.fixture(scope="module")
+def chk():
+    return O.Ops("ref") if O.ref_lib() is not None else O.Ops("port")
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return np.load(os.path.join(golden_dir, "ops.npz"))
+
+
+def test_q8k_bit_exact(dsk, chk, ops):
+    """quantize_row_q8_K_ref: byte-identical blocks (integer path -> bit-exact bar)."""
+    got = dsk.quantize_q8k(ops["q8k_x"]).reshape(-1, 292)
+    exp = ops["q8k_blocks"].reshape(-1, 292)
+    for b in range(exp.shape[0]):
+        nz = ops["q8k_x"][b * 256:(b + 1) * 256].any()
+        assert np.array_equal(got[b, :260], exp[b, :260])
+        assert not nz or np.array_equal(got[b], exp[b])
+    rng = np.random.default_rng(11)
+    for t in range(40):
+        n = int(rng.choice([256, 512, 1536, 2048, 7168]))
+        x = (rng.standard_normal(n) * 10 ** rng.uniform(-4, 4)).astype(np.float32)
+        if t % 7 == 0:
+            x[:256] = 0
+        if t % 5 == 0:  # exact +/- ties on the block maximum: the first one must win
+            x[300 % n] = 99.0 * 10 ** 3
+            x[(301) % n] = -99.0 * 10 ** 3
+        a, b = chk.quantize_q8k(x).reshape(-1, 292), dsk.quantize_q8k(x).reshape(-1, 292)
+        for i in range(a.shape[0]):
+            if x[i * 256:(i + 1) * 256].any():
+                assert np.array_equal(a[i], b[i]), (t, i)
+            else:
+                assert np.array_equal(a[i, :260], b[i, :260])
+
+
+@pytest.mark.parametrize("quant,d,n,tol", [
+    ("fp32", 64, 2048, 2e-6), ("fp16", 40, 256, 2e-6), ("fp16", 300, 2048, 2e-6),
+    ("f8e5m2", 200, 384, 2e-6), ("f8e5m2", 3072, 2048, 2e-6), ("f8e5m2", 2048, 1408, 2e-6), ("f8e5m2", 576, 512, 2e-6),
+    ("q2_k", 24, 768, 2e-6), ("q2_k", 1000, 2048, 2e-6), ("q2_k", 512, 512, 2e-6), ("q2_k", 130, 11008, 2e-6),
+    ("q3_k", 24, 768, 2e-6), ("q3_k", 1000, 2048, 2e-6), ("q3_k", 512, 256, 2e-6), ("q3_k", 64, 7168, 2e-6)])
+def test_gemv_vs_oracle(dsk, chk, quant, d, n, tol):
+    """_matmul x5 (src/infer.cpp:121-379): fp32 re-association only (integer dots exact) -> rel-L2 <= 2e-6."""
+    import mint
+    rng = np.random.default_rng(d * 31 + n)
+    w = (rng.standard_normal((d, n)) * n ** -0.5).astype(np.float32)
+    x = rng.standard_normal(n).astype(np.float32)
+    scale = None
+    if quant == "fp16":
+        wq = w.astype(np.float16)
+    elif quant == "f8e5m2":
+        wq, scale = mint.f8e5m2_blockwise(w)
+    elif quant in ("q2_k", "q3_k"):
+        wq = mint.kquant_rows(w, quant, d * n > 300000, rng)
+    else:
+        wq = w
+    got = dsk.gemv(quant, wq, x, d, n, scale)
+    exp = chk.matmul(x, wq, quant, d, n, scale)
+    assert rel_l2(got, exp) < tol
+    assert np.max(np.abs(got - exp)) < 1e-4 * max(1.0, np.max(np.abs(exp)))
+
+
+def test_gemv_golden(dsk, ops):
+    for quant in ("q2_k", "q3_k"):
+        w, x = ops[f"{quant}_w"], ops[f"{quant}_x"]
+        assert rel_l2(dsk.gemv(quant, w, x, w.shape[0], x.size), ops[f"{quant}_out"]) < 2e-6
+        assert np.allclose(dsk.dequantize_row(quant, w[0], x.size), ops[f"{quant}_deq_row0"], rtol=1e-6, atol=1e-8)
+    assert rel_l2(dsk.gemv("f8e5m2", ops["f8_w"], ops["f8_x"], 200, 384, ops["f8_scale"]), ops["f8_out"]) < 2e-6
+    assert rel_l2(dsk.gemv("fp16", ops["f16_w"], ops["f16_x"], 40, 256), ops["f16_out"]) < 2e-6
+    assert rel_l2(dsk.gemv("fp32", ops["f32_w"], ops["f16_x"], 40, 256), ops["f32_out"]) < 1e-5
+
+
+def test_gemv_rejects_bad_shapes(dsk):
+    """Same preconditions as the reference's asserts (src/infer.cpp:169,246; src/quant.cpp:617)."""
+    with pytest.raises(dsk.DskError):
+        dsk.gemv("q2_k", np.zeros((2, 84), np.uint8), np.zeros(200, np.float32), 2, 200)
+    with pytest.raises(dsk.DskError):
+        dsk.gemv("f8e5m2", np.zeros((2, 24), np.uint8), np.zeros(24, np.float32), 2, 24)
+
+
+def test_rmsnorm_rope_silu(dsk, chk, ops):
+    rng = np.random.default_rng(3)
+    for n in (512, 1536, 2048, 7168):
+        x, w = rng.standard_normal(n).astype(np.float32) * 3, (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        assert rel_l2(dsk.rmsnorm(x, w, 1e-6), chk.rmsnorm(x, w, 1e-6)) < 1e-6
+    for v3 in (False, True):
+        for pos in (0, 1, 37, 1234, 4095):
+            v = rng.standard_normal(64).astype(np.float32)
+            assert np.allclose(dsk.rope(v, 64, pos, 1e4, v3), chk.rope(v, 64, pos, 1e4, v3), rtol=1e-4, atol=3e-5), (v3, pos)
+    assert np.allclose(dsk.rope(ops["rope_x"], 64, 1234, 1e4, False), ops["rope_v2_p1234"], rtol=1e-4, atol=3e-5)
+    assert np.allclose(dsk.rope(ops["rope_x"], 64, 1234, 1e4, True), ops["rope_v3_p1234"], rtol=1e-4, atol=3e-5)
+
+
+@pytest.mark.parametrize("name,cfg", [("v2lite", (6, 0, 1.0, 0, 0, 1, 1)), ("v2", (6, 0, 16.0, 0, 1, 8, 3)),
+                                      ("v3", (8, 1, 2.5, 1, 1, 8, 4))])
+def test_moe_gate(dsk, chk, ops, name, cfg):
+    """moe_gate (src/infer.cpp:493-599): identical expert ids (index work -> exact), weights to 2e-6."""
+    K, norm, scale, sig, method, ng, tg = cfg
+    bias = ops[f"gate_{name}_bias"] if f"gate_{name}_bias" in ops else None
+    idx, w, sc = dsk.moe_gate(ops[f"gate_{name}_logits"], bias, K, norm, scale, sig, method, ng, tg)
+    assert idx.tolist() == ops[f"gate_{name}_idx"].tolist()
+    assert np.allclose(w, ops[f"gate_{name}_w"], rtol=5e-6)
+    assert np.allclose(sc, ops[f"gate_{name}_scores"], rtol=5e-6, atol=1e-9)
+    rng = np.random.default_rng(17)
+    E = ops[f"gate_{name}_logits"].size
+    for t in range(25):
+        lg = (rng.standard_normal(E) * rng.uniform(0.5, 4)).astype(np.float32)
+        if t % 4 == 0:
+            lg[5] = lg[9] = lg[E - 1] = lg.max() + 1  # exact ties: lowest index must win
+        b = (0.01 * rng.standard_normal(E)).astype(np.float32) if sig else None
+        if sig and t % 3 == 0:
+            b -= 1.0  # negative scores: exercises the group-limited "x[j] > x[-1] == 0" rule
+        i1, w1, _ = dsk.moe_gate(lg, b, K, norm, scale, sig, method, ng, tg)
+        i2, w2, _ = chk.moe_gate(lg, b, K, norm, scale, sig, method, ng, tg)
+        assert i1.tolist() == i2.tolist(), t
+        assert np.allclose(w1, w2, rtol=5e-6, atol=1e-9)
+
+
+def test_attn(dsk, chk, ops):
+    nh, hd, vh, T = 3, 48, 32, 37
+    got = dsk.attn(ops["attn_q"], ops["attn_k"], ops["attn_v"], nh, hd, vh, T)
+    assert rel_l2(got, ops["attn_out"]) < 2e-6
+    rng = np.random.default_rng(23)
+    for (nh, hd, vh, T) in ((16, 192, 128, 1), (16, 192, 128, 150), (4, 96, 64, 700), (128, 192, 128, 33)):
+        q = rng.standard_normal(nh * hd).astype(np.float32)
+        kc = rng.standard_normal(T * nh * hd).astype(np.float16).view(np.uint16)
+        vc = rng.standard_normal(T * nh * vh).astype(np.float16).view(np.uint16)
+        got = dsk.attn(q, kc, vc, nh, hd, vh, T)
+        exp = np.concatenate([chk.attn(q[h * hd:(h + 1) * hd], kc[h * hd:], vc[h * vh:], hd, vh, nh, T) for h in range(nh)])
+        assert rel_l2(got, exp) < 5e-6, (nh, hd, vh, T)
+
+
+def test_full_size_properties(dsk):
+    """BASELINE-size shapes where the CPU oracle would take too long: size-independent properties.
+    Linearity gemv(W, a*x + y) == a*gemv(W,x) + gemv(W,y) does not hold through Q8_K rounding, so K-quants use
+    scale-equivariance by powers of two (exact: Q8_K scales are exactly doubled) and sampled rows vs the port."""
+    rng = np.random.default_rng(99)
+    P = O.Ops("port")
+    d, n = 102400, 2048  # V2-Lite LM head
+    w8 = rng.integers(0, 120, size=(d, n), dtype=np.uint8)  # finite, positive-exponent-safe f8 bytes
+    w8 |= (rng.integers(0, 2, size=(d, n), dtype=np.uint8) << 7)
+    sc = rng.uniform(0.5, 1.5, size=(d // 128, n // 128)).astype(np.float32) * 1e-4
+    x = rng.standard_normal(n).astype(np.float32)
+    y = dsk.gemv("f8e5m2", w8, x, d, n, sc)
+    y2 = dsk.gemv("f8e5m2", w8, x * 4.0, d, n, sc)
+    assert np.array_equal(y2, y * 4.0)                       # power-of-two equivariance is exact in fp32
+    rows = rng.choice(d, 64, replace=False)
+    for r in rows[:16]:
+        exp = P.matmul(x, w8[r:r + 1], "f8e5m2", 1, n, sc[r // 128:r // 128 + 1])
+        assert abs(y[r] - exp[0]) <= 2e-6 * max(1.0, abs(exp[0])) + 1e-6
+    wq = rng.integers(0, 256, size=(d // 8, n // 256 * 84), dtype=np.uint8)
+    blk = wq.reshape(d // 8, n // 256, 84)
+    blk[:, :, 80:82] = np.frombuffer(np.float16(0.01).tobytes(), np.uint8)
+    blk[:, :, 82:84] = np.frombuffer(np.float16(0.02).tobytes(), np.uint8)
+    yq = dsk.gemv("q2_k", wq, x, d // 8, n)
+    assert np.array_equal(dsk.gemv("q2_k", wq, x * 2.0, d // 8, n), yq * 2.0)
+    for r in rows[:16] % (d // 8):
+        exp = P.matmul(x, wq[r:r + 1], "q2_k", 1, n)
+        assert abs(yq[r] - exp[0]) <= 3e-6 * max(1.0, abs(exp[0]))

@@ -1,0 +1,219 @@
+"""CPU suite: pins the oracle restatement against the committed golden vectors and (when oracle/_ref is built)
+against the unmodified reference itself; checks host logic and that libdsk.so exports the declared C-ABI."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle as O
+from conftest import rel_l2
+
+P = O.Ops("port")
+HAVE_REF = O.ref_lib() is not None
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref/libdsref.so not built")
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "kat.json")))
+
+
+@pytest.fixture(scope="module")
+def ops(golden_dir):
+    return np.load(os.path.join(golden_dir, "ops.npz"))
+
+
+# ---- known answers carried by the reference's own tests (src/test.cpp:128-186) --------------------
+def test_testcpp_matmul_kat(kat):
+    x = np.array(kat["testcpp_x"], np.float32)
+    w = np.array(kat["testcpp_w"], np.float32)
+    exp = np.array(kat["testcpp_expect_f32_f16"])
+    assert np.allclose(P.matmul(x, w, "fp32", 2, 16), exp, atol=1e-4)                       # test.cpp:150-153
+    assert np.allclose(P.matmul(x, w.astype(np.float16), "fp16", 2, 16), exp, atol=1e-3)    # test.cpp:156-160
+    w8 = (w.astype(np.float16).view(np.uint16) >> 8).astype(np.uint8)
+    got = P.matmul(x, w8, "f8e5m2", 2, 16)
+    assert np.allclose(got, exp, atol=3.78e-1)                                               # test.cpp:163-166
+    assert np.allclose(got, kat["testcpp_ref_f8"], rtol=1e-6)
+    L = O.port_lib()
+    for v in (1.0, -1.5, 0.109375):                                                          # test.cpp:129-131
+        h = L.ork_float_to_half(v)
+        assert L.ork_f8e5m2_to_float(h >> 8) == v
+
+
+def test_survey_kats(kat):
+    assert np.allclose(P.rmsnorm(kat["rmsnorm_in"], kat["rmsnorm_w"], kat["rmsnorm_eps"]), kat["rmsnorm_out"], rtol=1e-6)
+    assert np.allclose(P.rope(kat["rope_in"], 8, kat["rope_pos"], kat["rope_theta"], False), kat["rope_v2_out"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(P.rope(kat["rope_in"], 8, kat["rope_pos"], kat["rope_theta"], True), kat["rope_v3_out"], rtol=1e-5, atol=1e-6)
+    i, w, _ = P.moe_gate(kat["gate_logits"], None, 3, False, 2.0, False, 0, 1, 1)
+    assert i.tolist() == kat["gate_softmax_greedy"]["idx"] and np.allclose(w, kat["gate_softmax_greedy"]["w"], rtol=1e-6)
+    i, w, _ = P.moe_gate(kat["gate_logits"], None, 3, True, 1.0, True, 1, 4, 1)
+    assert i.tolist() == kat["gate_sigmoid_group"]["idx"] and np.allclose(w, kat["gate_sigmoid_group"]["w"], rtol=1e-6)
+    assert abs(P.silu(1.5) - kat["silu_1p5"]) < 1e-6
+
+
+# ---- golden op vectors (generated from the unmodified reference, tests/golden/make_golden.py) -----
+def test_q8k_golden_bit_exact(ops):
+    got = P.quantize_q8k(ops["q8k_x"]).reshape(-1, 292)
+    exp = ops["q8k_blocks"].reshape(-1, 292)
+    for b in range(exp.shape[0]):
+        nz = ops["q8k_x"][b * 256:(b + 1) * 256].any()
+        # the reference leaves bsums of an all-zero block uninitialised (src/quant.cpp:630-635)
+        assert np.array_equal(got[b, :260], exp[b, :260]) and (not nz or np.array_equal(got[b], exp[b]))
+
+
+@pytest.mark.parametrize("quant", ["q2_k", "q3_k"])
+def test_kquant_gemv_and_dequant_golden(ops, quant):
+    w, x = ops[f"{quant}_w"], ops[f"{quant}_x"]
+    got = P.matmul(x, w, quant, w.shape[0], x.size)
+    assert rel_l2(got, ops[f"{quant}_out"]) < 2e-6
+    assert np.array_equal(P.dequantize(w[0], quant, x.size), ops[f"{quant}_deq_row0"]) or \
+        np.allclose(P.dequantize(w[0], quant, x.size), ops[f"{quant}_deq_row0"], rtol=1e-6, atol=1e-8)
+
+
+def test_dense_gemv_golden(ops):
+    assert rel_l2(P.matmul(ops["f8_x"], ops["f8_w"], "f8e5m2", 200, 384, ops["f8_scale"]), ops["f8_out"]) < 1e-6
+    assert rel_l2(P.matmul(ops["f16_x"], ops["f16_w"], "fp16", 40, 256), ops["f16_out"]) < 1e-6
+    assert rel_l2(P.matmul(ops["f16_x"], ops["f32_w"], "fp32", 40, 256), ops["f32_out"]) < 1e-5
+
+
+@pytest.mark.parametrize("name,cfg", [("v2lite", (6, 0, 1.0, 0, 0, 1, 1)), ("v2", (6, 0, 16.0, 0, 1, 8, 3)),
+                                      ("v3", (8, 1, 2.5, 1, 1, 8, 4))])
+def test_gate_golden(ops, name, cfg):
+    K, norm, scale, sig, method, ng, tg = cfg
+    bias = ops[f"gate_{name}_bias"] if f"gate_{name}_bias" in ops else None
+    idx, w, sc = P.moe_gate(ops[f"gate_{name}_logits"], bias, K, norm, scale, sig, method, ng, tg)
+    assert idx.tolist() == ops[f"gate_{name}_idx"].tolist()
+    assert np.allclose(w, ops[f"gate_{name}_w"], rtol=2e-6)
+    assert np.allclose(sc, ops[f"gate_{name}_scores"], rtol=2e-6, atol=1e-9)
+
+
+def test_rope_attn_golden(ops):
+    assert np.allclose(P.rope(ops["rope_x"], 64, 1234, 1e4, False), ops["rope_v2_p1234"], rtol=1e-4, atol=2e-5)
+    assert np.allclose(P.rope(ops["rope_x"], 64, 1234, 1e4, True), ops["rope_v3_p1234"], rtol=1e-4, atol=2e-5)
+    for v3, key in ((False, "rope16_v2_p1"), (True, "rope16_v3_p1")):
+        got = P.rope_f16(ops["rope16_x"], 64, 1, 1e4, v3).view(np.float16).astype(np.float32)
+        exp = ops[key].view(np.float16).astype(np.float32)
+        assert np.max(np.abs(got - exp)) <= 2e-3  # at most one fp16 ulp
+    nh, hd, vh, T = 3, 48, 32, 37
+    got = np.concatenate([P.attn(ops["attn_q"][h * hd:(h + 1) * hd], ops["attn_k"][h * hd:], ops["attn_v"][h * vh:], hd, vh, nh, T)
+                          for h in range(nh)])
+    assert rel_l2(got, ops["attn_out"]) < 1e-6
+
+
+def test_e2e_golden_port(golden_dir, tmp_path):
+    """End-to-end teacher-forced logits of the port vs the reference's (committed), on checkpoints that can be
+    minted without the reference (random valid Q2_K blocks / torch f8 cast)."""
+    import mint
+    g = np.load(os.path.join(golden_dir, "e2e.npz"))
+    for preset, quant, tol in (("tiny_v3", "q2_k", 5e-2), ("tiny_v2lite", "f8e5m2", 1e-3)):
+        d = str(tmp_path / f"{preset}_{quant}")
+        mint.mint(d, preset, quant, fast=True, seed=77)
+        s = O.PortSession(d)
+        for p, t in enumerate(g[f"{preset}_{quant}_tokens"]):
+            s.forward(int(t), p)
+            exp = g[f"{preset}_{quant}_logits"][p]
+            assert rel_l2(s.buffer("logits"), exp) < tol, (preset, quant, p)
+
+
+# ---- port vs the unmodified reference, live (build container and GPU box both carry oracle/_ref) ----
+@needs_ref
+def test_q8k_bit_exact_vs_ref():
+    R = O.Ops("ref")
+    rng = np.random.default_rng(5)
+    for t in range(100):
+        x = (rng.standard_normal(1024) * 10 ** rng.uniform(-4, 4)).astype(np.float32)
+        a, b = R.quantize_q8k(x).reshape(-1, 292), P.quantize_q8k(x).reshape(-1, 292)
+        assert np.array_equal(a, b)
+
+
+@needs_ref
+@pytest.mark.parametrize("quant,tol", [("fp32", 1e-5), ("fp16", 1e-6), ("f8e5m2", 1e-6), ("q2_k", 2e-6), ("q3_k", 2e-6)])
+def test_gemv_vs_ref(quant, tol):
+    import mint
+    R = O.Ops("ref")
+    rng = np.random.default_rng(6)
+    d, n = 96, 1024
+    w = (rng.standard_normal((d, n)) * n ** -0.5).astype(np.float32)
+    x = rng.standard_normal(n).astype(np.float32)
+    scale = None
+    if quant == "fp16":
+        wq = w.astype(np.float16)
+    elif quant == "f8e5m2":
+        wq, scale = mint.f8e5m2_blockwise(w)
+    elif quant in ("q2_k", "q3_k"):
+        wq = mint.kquant_rows(w, quant, False, rng)
+    else:
+        wq = w
+    assert rel_l2(P.matmul(x, wq, quant, d, n, scale), R.matmul(x, wq, quant, d, n, scale)) < tol
+
+
+@needs_ref
+@pytest.mark.parametrize("preset", ["tiny_v2lite", "tiny_v2", "tiny_v3"])
+@pytest.mark.parametrize("quant,tol", [("fp32", 1e-3), ("f8e5m2", 1e-3), ("q3_k", 5e-2)])
+def test_forward_port_vs_ref(ckpt, preset, quant, tol):
+    d = ckpt(preset, quant)
+    r, p = O.RefSession(d), O.PortSession(d)
+    for pos, tok in enumerate([0, 9, 400, 33, 1001]):
+        r.forward(tok, pos)
+        p.forward(tok, pos)
+        assert rel_l2(p.buffer("logits"), r.buffer("logits")) < tol
+    r.close()
+
+
+@needs_ref
+def test_sink_ring_port_vs_ref(ckpt):
+    """pos >= original_max_position: 2 sinks kept, ring overwrite, sink keys re-rotated (src/infer.cpp:1271-1277, 1008-1020)."""
+    d = ckpt("tiny_v2lite", "fp32", original_max_position=8)
+    r, p = O.RefSession(d), O.PortSession(d)
+    for pos in range(14):
+        r.forward(pos * 7 % 1024, pos)
+        p.forward(pos * 7 % 1024, pos)
+        assert rel_l2(p.buffer("logits"), r.buffer("logits")) < 1e-3, pos
+    r.close()
+
+
+# ---- host logic -------------------------------------------------------------------------------------
+def test_dseek_roundtrip_and_config(ckpt):
+    import dseek
+    import dsk
+    d = ckpt("tiny_v3", "q2_k")
+    md, T = dseek.read_dir(d)
+    c = dsk.Config.from_metadata(md)
+    assert (c.dim, c.n_layers, c.is_v3, c.scoring_sigmoid, c.topk_method, c.quant) == (512, 3, 1, 1, 1, 3)
+    assert T["model.layers.1.mlp.w1.weight"].shape == (16, 256, 512 // 256 * 84)
+    assert T["model.layers.1.moegate.bias"].shape == (16,)
+    c2 = dsk.Config.from_metadata(md, context=64)
+    assert c2.max_seq_len == 64
+    oc = O.config_from_metadata(md)
+    for k in ("dim", "n_heads", "kv_lora_rank", "q_lora_rank", "n_group", "topk_group", "original_max_position"):
+        assert getattr(c, k) == oc[k]
+
+
+def test_cabi_exports_every_declared_symbol(repo):
+    """libdsk.so must load on a GPU-less machine and export exactly what include/dsk.h declares."""
+    import dsk
+    hdr = open(os.path.join(repo, "include", "dsk.h")).read()
+    names = sorted(set(re.findall(r"\b(dsk_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    L = ctypes.CDLL(dsk.build())
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.dsk_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device every compute entry point must fail loudly (no silent CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import dsk
+    with pytest.raises(dsk.DskError):
+        dsk.init(0)
+    L = dsk.lib()
+    out = np.zeros(4, np.float32)
+    assert L.dsk_rmsnorm(out.ctypes.data_as(dsk.f32p), out.ctypes.data_as(dsk.f32p), 4, ctypes.c_float(1e-5),
+                         out.ctypes.data_as(dsk.f32p)) != 0
+    assert b"no CPU fallback" in L.dsk_last_error()
