@@ -183,6 +183,14 @@ def mint_on_gpu(dsk, w, rank, n_ranks, device):
     return m
 
 
+T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (stdout carries exactly one JSON line)"""
+    print(f"[bench +{time.time() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def prompt_ids(vocab):
     return [(7919 * (i + 1)) % vocab for i in range(PROMPT_LEN)]
 
@@ -306,10 +314,12 @@ def cpu_reference_leg(w, steps, warmup, tokens_per_step=8):
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
     d = tempfile.mkdtemp(prefix="dsk_ref_", dir=base)
     try:
+        log(f"cpu reference: minting {n_trunc}-layer truncated checkpoint in {d}")
         mint_cpu_truncated(w, d, n_trunc)
         cores = os.cpu_count() or 1
         best = None
-        for threads in sorted({max(1, cores // 2), cores}):
+        for threads in sorted({min(cores, 16), min(cores, 32), max(1, cores // 2)}):
+            log(f"cpu reference: {threads} threads")
             O.ref_lib().ref_set_num_threads(threads)
             s = O.RefSession(d, 0)
             pr = prompt_ids(w["vocab_size"])[:4]
@@ -336,7 +346,7 @@ def cpu_reference_leg(w, steps, warmup, tokens_per_step=8):
         return best[0], {"kind": "reference", "cores": best[1], "host_cpus": cores,
                          "sample": f"{n_trunc}-layer truncation ({fk} dense + {n_trunc - fk} MoE + LM head) of the workload's shapes, "
                                    f"{steps * tokens_per_step} decoded tokens, per-block times extrapolated to {nl_full} layers; "
-                                   f"unmodified reference (-O3 -ffast-math -fopenmp -mavx2), best of OMP threads {{cores/2, cores}}"}
+                                   f"unmodified reference (-O3 -ffast-math -fopenmp -mavx2), best of OMP threads {{16, 32, cores/2}}"}
     finally:
         import shutil
         shutil.rmtree(d, ignore_errors=True)
@@ -392,7 +402,9 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dsk.init(local_rank)
+    log(f"rank {rank}/{world}: minting {a.workload}/{a.quant} on the GPU")
     m = mint_on_gpu(dsk, w, rank, world, local_rank)
+    log(f"minted: {m.resident_bytes() / 1e9:.2f} GB resident, {m.active_bytes_per_token() / 1e9:.3f} GB/token algorithmic")
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -418,6 +430,7 @@ def main():
     for _ in range(a.warmup):
         hydrate()
         m.decode_greedy(PROMPT_LEN, GEN_TOKENS)
+    log("warm-up done; timing device-resident decode")
     clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t_wall0 = time.perf_counter()
@@ -435,6 +448,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
     value = a.steps * GEN_TOKENS / (dev_ms / 1e3)
+    log(f"value {value:.1f} tok/s ({dev_ms / a.steps / GEN_TOKENS:.3f} ms/token); timing host-driven e2e")
 
     # ---- e2e: reference-shaped host loop, host buffers, copies inside the timed region -------------
     def host_completion():
@@ -455,6 +469,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e = a.steps * GEN_TOKENS / e2e_s
+    log(f"e2e {e2e:.1f} tok/s; isolated kernels + CPU baseline next")
 
     if rank != 0:
         if dist is not None:

@@ -13,7 +13,8 @@
 #include "../../include/dsk.h"
 
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed lazily (see NcclApi)
 
 #include <cmath>
 #include <cstdarg>
@@ -47,8 +48,36 @@ static int fail(int code, const char* fmt, ...) {
 #define CKN(call)                                                                                  \
   do {                                                                                             \
     ncclResult_t e_ = (call);                                                                      \
-    if (e_ != ncclSuccess) return fail(-3, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(e_), __FILE__, __LINE__); \
+    if (e_ != ncclSuccess) return fail(-3, "%s failed: %s (%s:%d)", #call, g_nccl.GetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
+
+// NCCL is bound at run time, not link time: a Python host usually has torch's bundled libnccl.so.2 loaded (or
+// loads it later); hard-linking the system copy makes the two clash on the shared soname.  dlopen() returns the
+// copy already in the process, else the system one.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.h) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(-3, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
+    return fail(-3, "libnccl.so.2 lacks a required symbol");
+  g_nccl.h = h;
+  return 0;
+}
 
 static int g_device = -1;
 static int g_sm_count = 148;
@@ -87,6 +116,7 @@ struct dsk_model {
   DTensor embed, wcls;
   bool has_wcls = false;
   float* rms_final = nullptr;
+  float* rope_freq = nullptr;  // qk_rope_head_dim/2 floats, tabulated on the host (src/infer.cpp:655)
   size_t resident = 0;
   ncclComm_t comm = nullptr;
   std::vector<void*> allocs;
@@ -189,6 +219,13 @@ static int dmalloc(dsk_model* m, void** p, size_t bytes) {
   return 0;
 }
 
+// freq_j = 1.0f / powf(theta, j / head_dim) for even j (src/infer.cpp:655, 675) — host libm, like the reference
+static std::vector<float> rope_table(int rot, float theta) {
+  std::vector<float> f(rot / 2);
+  for (int t = 0; t < rot / 2; t++) f[t] = 1.0f / powf(theta, (float)(2 * t) / (float)rot);
+  return f;
+}
+
 extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ranks) {
   if (need_device()) return nullptr;
   if (!cfg || n_ranks < 1 || rank < 0 || rank >= n_ranks) { fail(-1, "bad arguments"); return nullptr; }
@@ -203,6 +240,12 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
   const int per = E > 0 ? cdiv(E, n_ranks) : 0;
   m->expert_first = std::min(E, rank * per);
   m->expert_count = std::max(0, std::min(per, E - m->expert_first));
+  {
+    std::vector<float> fr = rope_table(cfg->qk_rope_head_dim, cfg->rope_theta);
+    if (cudaMalloc(&m->rope_freq, std::max<size_t>(fr.size(), 1) * 4) != cudaSuccess) { fail(-2, "alloc failed"); delete m; return nullptr; }
+    m->allocs.push_back(m->rope_freq);
+    if (!fr.empty()) cudaMemcpy(m->rope_freq, fr.data(), fr.size() * 4, cudaMemcpyHostToDevice);
+  }
   m->layers.resize(cfg->n_layers);
   for (int l = 0; l < cfg->n_layers; l++) {
     Layer& L = m->layers[l];
@@ -224,7 +267,7 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
 
 extern "C" void dsk_model_destroy(dsk_model* m) {
   if (!m) return;
-  if (m->comm) ncclCommDestroy(m->comm);
+  if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
 }
@@ -654,7 +697,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     AttnArgs a{};
     a.q = s->q; a.kv_a = s->kv_a; a.kcache = L.kcache; a.vcache = L.vcache; a.out = s->xb2; a.ctrl = s->ctrl;
     a.n_heads = c.n_heads; a.hd = hd; a.nope = nope; a.rope = c.qk_rope_head_dim; a.vh = c.v_head_dim;
-    a.kv_lora = c.kv_lora_rank; a.theta = c.rope_theta; a.is_v3 = c.is_v3; a.max_seq = c.max_seq_len; a.do_prologue = 1;
+    a.kv_lora = c.kv_lora_rank; a.rope_freq = m->rope_freq; a.is_v3 = c.is_v3; a.max_seq = c.max_seq_len; a.do_prologue = 1;
     attn_kernel<<<c.n_heads, kThreads, attn_smem_bytes(hd, c.v_head_dim, c.max_seq_len), st>>>(a);
     g_launch_count++;
     CKL(cudaGetLastError());
@@ -726,7 +769,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       CKL(launch_down(q, d, st));
       if (m->n_ranks > 1) {
         if (!m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
-        CKN(ncclAllReduce(s->partial, s->partial, c.dim, ncclFloat, ncclSum, m->comm, st));
+        CKN(g_nccl.AllReduce(s->partial, s->partial, c.dim, ncclFloat, ncclSum, m->comm, st));
         add_vec_kernel<<<cdiv(c.dim, 256), 256, 0, st>>>(s->x, s->partial, c.dim);
         g_launch_count += 2;
         CKL(cudaGetLastError());
@@ -898,8 +941,9 @@ extern "C" int dsk_launches_per_forward(const dsk_model* m, int mode) {
 // multi-GPU
 // ---------------------------------------------------------------------------------------------------
 extern "C" int dsk_comm_unique_id(void* out128) {
+  if (nccl_load()) return -3;
   ncclUniqueId id;
-  CKN(ncclGetUniqueId(&id));
+  CKN(g_nccl.GetUniqueId(&id));
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   memcpy(out128, &id, 128);
   return 0;
@@ -908,9 +952,10 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
   if (need_device()) return -1;
   if (!m) return fail(-1, "null model");
   if (m->n_ranks == 1) return 0;
+  if (nccl_load()) return -3;
   ncclUniqueId id;
   memcpy(&id, nccl_unique_id128, 128);
-  CKN(ncclCommInitRank(&m->comm, m->n_ranks, id, m->rank));
+  CKN(g_nccl.CommInitRank(&m->comm, m->n_ranks, id, m->rank));
   return 0;
 }
 
@@ -1013,7 +1058,9 @@ extern "C" int dsk_rope(float* vec, int d, int head_dim, int pos, float theta, i
   if (d % 2 || d > 2048) return fail(-4, "bad d");
   Tmp t;
   float* dv = t.up<float>(vec, d);
-  rope_test_kernel<<<1, 1024, (size_t)d * 4>>>(dv, d, head_dim, pos, theta, v3);
+  std::vector<float> fr = rope_table(head_dim, theta);
+  float* df = t.up<float>(fr.data(), fr.size());
+  rope_test_kernel<<<1, 1024, (size_t)d * 4>>>(dv, d, head_dim, pos, df, v3);
   CKL(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(vec, dv, (size_t)d * 4, cudaMemcpyDeviceToHost));

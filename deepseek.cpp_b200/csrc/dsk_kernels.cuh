@@ -596,11 +596,12 @@ __global__ void add_vec_kernel(float* x, const float* p, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// RoPE helpers (src/infer.cpp:648-724).  i = even index within the rotary dims.
+// RoPE helpers (src/infer.cpp:648-724).  freq[t] = 1/powf(theta, 2t/rot) is tabulated on the HOST with libm's
+// powf — the same function the reference calls — because the angle pos*freq amplifies a 1-ulp difference in freq
+// by `pos` (CUDA's powf is only 4-ulp accurate).  cosf/sinf here are CUDA's full-range-reduction versions.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rope_cs(int i, int rot, int pos, float theta, float& c, float& s) {
-  const float freq = 1.0f / powf(theta, (float)i / (float)rot);
-  const float val = (float)pos * freq;
+__device__ __forceinline__ void rope_cs(const float* __restrict__ freq, int t, int pos, float& c, float& s) {
+  const float val = (float)pos * freq[t];
   c = cosf(val);
   s = sinf(val);
 }
@@ -617,7 +618,7 @@ struct AttnArgs {
   float* out;          // n_heads*vh
   const Ctrl* ctrl;
   int n_heads, hd, nope, rope, vh, kv_lora;
-  float theta;
+  const float* rope_freq;  // rope/2 host-tabulated frequencies
   int is_v3;
   int max_seq;
   int do_prologue;     // 0 for the dsk_attn test hook (plain attn over a given cache)
@@ -642,14 +643,14 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const __grid_constant__ 
   if (a.do_prologue) {
     const int half_r = a.rope >> 1;
     if (tid < half_r) {                       // q_pe
-      float c, s; rope_cs(2 * tid, a.rope, pos, a.theta, c, s);
+      float c, s; rope_cs(a.rope_freq, tid, pos, c, s);
       const float v0 = qh[a.nope + 2 * tid], v1 = qh[a.nope + 2 * tid + 1];
       const float r0 = v0 * c - v1 * s, r1 = v0 * s + v1 * c;
       if (a.is_v3) { qs[a.nope + 2 * tid] = r0; qs[a.nope + 2 * tid + 1] = r1; }
       else { qs[a.nope + tid] = r0; qs[a.nope + tid + half_r] = r1; }
     } else if (tid >= 64 && tid < 64 + half_r) {  // k_pe -> cache row kv_pos of this head
       const int t = tid - 64;
-      float c, s; rope_cs(2 * t, a.rope, pos, a.theta, c, s);
+      float c, s; rope_cs(a.rope_freq, t, pos, c, s);
       const float v0 = a.kv_a[a.kv_lora + 2 * t], v1 = a.kv_a[a.kv_lora + 2 * t + 1];
       const float r0 = v0 * c - v1 * s, r1 = v0 * s + v1 * c;
       __half* kr = a.kcache + (size_t)kv_pos * kstride + (size_t)h * a.hd + a.nope;
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(kThreads) attn_kernel(const __grid_constant__ 
       else { kr[t] = __float2half_rn(r0); kr[t + half_r] = __float2half_rn(r1); }
     } else if (tid >= 128 && tid < 128 + half_r * kv_sink && kv_sink > 0) {  // sink re-rotation by one position
       const int t = (tid - 128) % half_r, r = (tid - 128) / half_r;
-      float c, s; rope_cs(2 * t, a.rope, 1, a.theta, c, s);
+      float c, s; rope_cs(a.rope_freq, t, 1, c, s);
       __half* kr = a.kcache + (size_t)r * kstride + (size_t)h * a.hd + a.nope;
       const float v0 = __half2float(kr[2 * t]), v1 = __half2float(kr[2 * t + 1]);
       stage[2 * (r * half_r + t)] = v0 * c - v1 * s;     // staged: the V2 layout permutes, so read all first
@@ -931,11 +932,11 @@ __global__ void __launch_bounds__(kThreads) q8k_export_kernel(const float* in, i
 }
 
 // standalone rope for the dsk_rope test hook
-__global__ void rope_test_kernel(float* vec, int d, int head_dim, int pos, float theta, int v3) {
+__global__ void rope_test_kernel(float* vec, int d, int head_dim, int pos, const float* freq, int v3) {
   extern __shared__ float buf[];
   const int t = threadIdx.x;
   if (2 * t < d) {
-    float c, s; rope_cs((2 * t) % head_dim, head_dim, pos, theta, c, s);
+    float c, s; rope_cs(freq, ((2 * t) % head_dim) / 2, pos, c, s);
     const float v0 = vec[2 * t], v1 = vec[2 * t + 1];
     if (v3) { buf[2 * t] = v0 * c - v1 * s; buf[2 * t + 1] = v0 * s + v1 * c; }
     else { buf[t] = v0 * c - v1 * s; buf[t + d / 2] = v0 * s + v1 * c; }

@@ -7,6 +7,7 @@
 #include "dsk_oracle.h"
 
 #include <float.h>
+#include <omp.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -608,3 +609,6 @@ int ork_argmax(const float* logits, int n) {
   for (int i = 0; i < n; ++i) if (logits[i] > max_val) { max_val = logits[i]; argmax = i; }
   return argmax;
 }
+
+/* host thread control for the checkers (tests cap it: the reference forks one parallel region per 128-row band) */
+void ork_set_num_threads(int n) { omp_set_num_threads(n); }

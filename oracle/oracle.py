@@ -21,6 +21,11 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
+# The reference opens one OpenMP parallel region per 128-row scale band (src/infer.cpp:255-258); on a 128-thread
+# host that fork-join cost dominates small models.  Checker runs default to a modest team, passive waiting.
+DEFAULT_THREADS = int(os.environ.get("DSK_ORACLE_THREADS", str(min(16, os.cpu_count() or 1))))
+os.environ.setdefault("OMP_NUM_THREADS", str(DEFAULT_THREADS))
+os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
 sys.path.insert(0, os.path.join(REPO, "deepseek.cpp_b200"))
 import dseek  # noqa: E402
 
@@ -115,6 +120,7 @@ def ref_lib():
         L.ref_vec_dot_q2_K.argtypes = [C.c_int, f32p, C.c_void_p, C.c_void_p]
         L.ref_vec_dot_q3_K.argtypes = [C.c_int, f32p, C.c_void_p, C.c_void_p]
         L.ref_set_num_threads.argtypes = [C.c_int]
+        L.ref_set_num_threads(DEFAULT_THREADS)
         _ref = L
     return _ref
 
@@ -190,6 +196,8 @@ def port_lib():
         L.ork_block.argtypes = [C.POINTER(OrkModel), C.POINTER(OrkState)] + [C.c_int] * 5
         L.ork_forward.argtypes = [C.POINTER(OrkModel), C.POINTER(OrkState), C.c_int, C.c_int, C.c_int]
         L.ork_argmax.argtypes = [f32p, C.c_int]
+        L.ork_set_num_threads.argtypes = [C.c_int]
+        L.ork_set_num_threads(DEFAULT_THREADS)
         _port = L
     return _port
 
