@@ -157,11 +157,15 @@ static int cdiv(int a, int b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------------------------------------------
 // process / device
 // ---------------------------------------------------------------------------------------------------
+static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+static constexpr size_t kSmemBudget = 200 * 1024;
+static bool g_use_pdl = true;
+
 template <int Q>
 static cudaError_t set_attrs_q() {
-  cudaError_t e = cudaFuncSetAttribute(gemv_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(gemv_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(moe_down_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return cudaFuncSetAttribute(moe_down_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
 }
 
 extern "C" int dsk_abi_version(void) { return DSK_ABI_VERSION; }
@@ -184,8 +188,9 @@ extern "C" int dsk_init(int device) {
     CK(set_attrs_q<Q_F8>());
     CK(set_attrs_q<Q_Q2K>());
     CK(set_attrs_q<Q_Q3K>());
-    CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    g_use_pdl = getenv("DSK_NO_PDL") == nullptr;
     g_attrs_set = true;
   }
   return 0;
@@ -596,43 +601,77 @@ extern "C" int dsk_kv_write(dsk_model* m, int layer, int which, const uint16_t* 
 // ---------------------------------------------------------------------------------------------------
 static int g_launch_count = 0;
 
-static void plan_rows(GemvArgs& a, int total_rows) {
-  a.total_rows = total_rows;
-  int rpc = cdiv(total_rows, g_sm_count * 4);
-  rpc = std::max(kWarps, cdiv(rpc, kWarps) * kWarps);
-  a.rows_per_cta = rpc;
+// Every kernel is launched with the programmatic-stream-serialization attribute: inside the token's CUDA graph this
+// becomes a programmatic dependency edge, so kernel N+1 is scheduled while kernel N drains, issues its TMA weight
+// prefetch, and blocks in griddepcontrol.wait until N has completed (all kernels call wait before touching state).
+template <typename Arg>
+static cudaError_t launch_k(void (*kern)(Arg), int grid, int block, size_t smem, cudaStream_t st, const Arg& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  g_launch_count++;
+  return cudaLaunchKernelEx(&cfg, kern, arg);
 }
 
-template <int Q>
-static cudaError_t launch_gemv_q(const GemvArgs& a, cudaStream_t st) {
-  const int grid = cdiv(a.total_rows, a.rows_per_cta);
-  gemv_kernel<Q><<<grid, kThreads, stage_smem_bytes<Q>(a.n), st>>>(a);
-  g_launch_count++;
-  return cudaGetLastError();
+static size_t row_bytes_q(int quant, int n) { return dev_row_bytes(quant, n); }
+static size_t xvec_bytes_q(int quant, int n) {
+  return (quant == DSK_Q2_K || quant == DSK_Q3_K) ? xvec_bytes<Q_Q2K>(n) : xvec_bytes<Q_F32>(n);
 }
-static cudaError_t launch_gemv(int quant, const GemvArgs& a, cudaStream_t st) {
+
+// Tile plan: rows per CTA (power of two, 4..32), rows per warp pass, CTA ranges per job, dynamic smem bytes.
+struct GemvPlan { int grid; size_t smem; };
+static GemvPlan plan_gemv(GemvArgs& a, int quant) {
+  const size_t rb = row_bytes_q(quant, a.n), xb = xvec_bytes_q(quant, a.n);
+  const int parts = a.epi == EPI_GLU ? 2 : 1;
+  int total_rows = 0;
+  for (int j = 0; j < a.njobs; j++) total_rows += a.job[j].rows;
+  int rpc = 32;
+  while (rpc > 4 && kSmemHdr + xb + align_up((size_t)rpc * rb, 128) * parts > kSmemBudget) rpc >>= 1;
+  while (rpc > 8 && (size_t)rpc * rb * parts > 64 * 1024) rpc >>= 1;            // keep >= 2-3 CTAs per SM resident
+  while (rpc > 8 && cdiv(total_rows, rpc) < 2 * g_sm_count) rpc >>= 1;           // small matrices: spread over the SMs
+  a.rows_per_cta = rpc;
+  const bool kq = quant == DSK_Q2_K || quant == DSK_Q3_K;
+  a.rpass = kq ? 1 : (rpc >= 32 ? 4 : (rpc >= 16 ? 2 : 1));
+  int cta = 0;
+  for (int j = 0; j < a.njobs; j++) { a.cta_begin[j] = cta; cta += cdiv(a.job[j].rows, rpc); }
+  for (int j = a.njobs; j <= kMaxJobs; j++) a.cta_begin[j] = cta;
+  return GemvPlan{cta, kSmemHdr + xb + align_up((size_t)rpc * rb, 128) * parts + 128};
+}
+
+static cudaError_t launch_gemv(int quant, GemvArgs& a, cudaStream_t st) {
+  const GemvPlan p = plan_gemv(a, quant);
   switch (quant) {
-    case DSK_F32: return launch_gemv_q<Q_F32>(a, st);
-    case DSK_F16: return launch_gemv_q<Q_F16>(a, st);
-    case DSK_F8E5M2: return launch_gemv_q<Q_F8>(a, st);
-    case DSK_Q2_K: return launch_gemv_q<Q_Q2K>(a, st);
-    default: return launch_gemv_q<Q_Q3K>(a, st);
+    case DSK_F32: return launch_k(gemv_kernel<Q_F32>, p.grid, kThreads, p.smem, st, a);
+    case DSK_F16: return launch_k(gemv_kernel<Q_F16>, p.grid, kThreads, p.smem, st, a);
+    case DSK_F8E5M2: return launch_k(gemv_kernel<Q_F8>, p.grid, kThreads, p.smem, st, a);
+    case DSK_Q2_K: return launch_k(gemv_kernel<Q_Q2K>, p.grid, kThreads, p.smem, st, a);
+    default: return launch_k(gemv_kernel<Q_Q3K>, p.grid, kThreads, p.smem, st, a);
   }
 }
-template <int Q>
-static cudaError_t launch_down_q(const DownArgs& a, cudaStream_t st) {
-  const int grid = cdiv(a.dim, a.rows_per_cta);
-  moe_down_kernel<Q><<<grid, kThreads, down_smem_bytes<Q>(a.K, a.mi, a.sh), st>>>(a);
-  g_launch_count++;
-  return cudaGetLastError();
-}
-static cudaError_t launch_down(int quant, const DownArgs& a, cudaStream_t st) {
+
+static cudaError_t launch_down(int quant, DownArgs& d, cudaStream_t st) {
+  const size_t rb_mi = row_bytes_q(quant, d.mi), rb_sh = row_bytes_q(quant, d.sh);
+  size_t xb = 0;
+  for (int k = 0; k <= d.K; k++) { const int n = k < d.K ? d.mi : d.sh; if (n) xb += xvec_bytes_q(quant, n); }
+  int rpc = 8;
+  auto need = [&](int r) { return kSmemHdr + xb + align_up((size_t)r * rb_mi, 128) * d.K + align_up((size_t)r * rb_sh, 128) + 128; };
+  while (rpc > 1 && need(rpc) > kSmemBudget + 20 * 1024) rpc >>= 1;
+  d.rows_per_cta = rpc;
+  const int grid = cdiv(d.dim, rpc);
+  const size_t smem = need(rpc);
   switch (quant) {
-    case DSK_F32: return launch_down_q<Q_F32>(a, st);
-    case DSK_F16: return launch_down_q<Q_F16>(a, st);
-    case DSK_F8E5M2: return launch_down_q<Q_F8>(a, st);
-    case DSK_Q2_K: return launch_down_q<Q_Q2K>(a, st);
-    default: return launch_down_q<Q_Q3K>(a, st);
+    case DSK_F32: return launch_k(moe_down_kernel<Q_F32>, grid, kThreads, smem, st, d);
+    case DSK_F16: return launch_k(moe_down_kernel<Q_F16>, grid, kThreads, smem, st, d);
+    case DSK_F8E5M2: return launch_k(moe_down_kernel<Q_F8>, grid, kThreads, smem, st, d);
+    case DSK_Q2_K: return launch_k(moe_down_kernel<Q_Q2K>, grid, kThreads, smem, st, d);
+    default: return launch_k(moe_down_kernel<Q_Q3K>, grid, kThreads, smem, st, d);
   }
 }
 
@@ -672,14 +711,12 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     if (c.q_lora_rank > 0) a.job[0] = plain_job(L.wq_a, s->q_a); else a.job[0] = plain_job(L.wq, s->q);
     a.job[1] = plain_job(L.wkv_a, s->kv_a);
     a.njobs = 2;
-    plan_rows(a, a.job[0].rows + a.job[1].rows);
     CKL(launch_gemv(q, a, st));
   }
   if (c.q_lora_rank > 0) {  // q = wq_b . rmsnorm(q_a)                          infer.cpp:944-950
     GemvArgs a = base_args(m, s, s->q_a, L.rms_q_a, c.q_lora_rank);
     a.job[0] = plain_job(L.wq_b, s->q);
     a.njobs = 1;
-    plan_rows(a, a.job[0].rows);
     CKL(launch_gemv(q, a, st));
   }
   // S2: kv_b = wkv_b . rmsnorm(kv_a[:kv_lora]); epilogue writes fp16 K(nope)/V cache row   infer.cpp:974-1002
@@ -689,7 +726,6 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     a.njobs = 1;
     a.epi = EPI_KVB;
     a.kcache = L.kcache; a.vcache = L.vcache; a.n_heads = c.n_heads; a.nope = nope; a.vh = c.v_head_dim; a.hd = hd;
-    plan_rows(a, a.job[0].rows);
     CKL(launch_gemv(q, a, st));
   }
   // S3: RoPE(q_pe, k_pe) + sink re-rotation + attention over the fp16 cache               infer.cpp:956-1045
@@ -698,9 +734,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     a.q = s->q; a.kv_a = s->kv_a; a.kcache = L.kcache; a.vcache = L.vcache; a.out = s->xb2; a.ctrl = s->ctrl;
     a.n_heads = c.n_heads; a.hd = hd; a.nope = nope; a.rope = c.qk_rope_head_dim; a.vh = c.v_head_dim;
     a.kv_lora = c.kv_lora_rank; a.rope_freq = m->rope_freq; a.is_v3 = c.is_v3; a.max_seq = c.max_seq_len; a.do_prologue = 1;
-    attn_kernel<<<c.n_heads, kThreads, attn_smem_bytes(hd, c.v_head_dim, c.max_seq_len), st>>>(a);
-    g_launch_count++;
-    CKL(cudaGetLastError());
+    CKL(launch_k(attn_kernel, c.n_heads, kThreads, attn_smem_bytes(hd, c.v_head_dim, c.max_seq_len), st, a));
   }
   // S4: x += wo . xb2                                                                     infer.cpp:1048, 832-834
   {
@@ -708,7 +742,6 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     a.job[0] = plain_job(L.wo, s->x);
     a.njobs = 1;
     a.epi = EPI_RESID;
-    plan_rows(a, a.job[0].rows);
     CKL(launch_gemv(q, a, st));
   }
   if (L.is_moe) {
@@ -719,7 +752,6 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
       a.job[0] = j;
       a.njobs = 1;
-      plan_rows(a, j.rows);
       CKL(launch_gemv(DSK_F32, a, st));
     }
     {  // moe_gate                                                                        infer.cpp:848-852
@@ -727,9 +759,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       g.x = s->moe_logits; g.bias = L.gate_bias; g.active = s->act; g.weights = s->act_w;
       g.E = c.n_routed_experts; g.K = c.n_active_routed; g.norm_topk_prob = c.norm_topk_prob; g.sigmoid = c.scoring_sigmoid;
       g.method = c.topk_method; g.n_group = std::max(1, c.n_group); g.topk_group = c.topk_group; g.scale = c.routed_scaling_factor;
-      gate_topk_kernel<<<1, 256, 0, st>>>(g);
-      g_launch_count++;
-      CKL(cudaGetLastError());
+      CKL(launch_k(gate_topk_kernel, 1, 256, 0, st, g));
     }
     // routed + shared up/gate projections with fused act(h1)*h3                           infer.cpp:853-870, 879-897
     const int sh = c.n_shared_experts * mi;
@@ -750,7 +780,6 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       }
       a.njobs = nj;
       a.epi = EPI_GLU;
-      plan_rows(a, rows);
       CKL(launch_gemv(q, a, st));
     }
     // down projections + weighted accumulate into the residual stream                     infer.cpp:873-877, 899-903
@@ -765,12 +794,11 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       d.x = s->x;
       d.partial = m->n_ranks > 1 ? s->partial : nullptr;
       d.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
-      d.rows_per_cta = std::max(kWarps, cdiv(cdiv(c.dim, g_sm_count * 2), kWarps) * kWarps);
       CKL(launch_down(q, d, st));
       if (m->n_ranks > 1) {
         if (!m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
         CKN(g_nccl.AllReduce(s->partial, s->partial, c.dim, ncclFloat, ncclSum, m->comm, st));
-        add_vec_kernel<<<cdiv(c.dim, 256), 256, 0, st>>>(s->x, s->partial, c.dim);
+        add_vec_kernel<<<cdiv(c.dim, 256), 256, 0, st>>>(s->x, s->partial, c.dim);  // follows a NCCL kernel: plain edge
         g_launch_count += 2;
         CKL(cudaGetLastError());
       }
@@ -784,7 +812,6 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       a.job[0] = j;
       a.njobs = 1;
       a.epi = EPI_GLU;
-      plan_rows(a, j.rows);
       CKL(launch_gemv(q, a, st));
     }
     {
@@ -794,7 +821,6 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       d.K = 0; d.mi = 0; d.sh = c.hidden_dim; d.dim = c.dim;
       d.bs0 = c.bs0 > 0 ? c.bs0 : 1; d.bs1 = c.bs1 > 0 ? c.bs1 : 1;
       d.x = s->x; d.partial = nullptr; d.add_shared = 1;
-      d.rows_per_cta = std::max(kWarps, cdiv(cdiv(c.dim, g_sm_count * 2), kWarps) * kWarps);
       CKL(launch_down(q, d, st));
     }
   }
@@ -808,9 +834,7 @@ static int enqueue_embed(dsk_model* m, dsk_state* s, int from_argmax, cudaStream
   e.quant = c.quant; e.dim = c.dim; e.bs0 = c.bs0 > 0 ? c.bs0 : 1; e.bs1 = c.bs1 > 0 ? c.bs1 : 1;
   e.from_argmax = from_argmax; e.original_max = c.original_max_position;
   e.token_log = s->token_log; e.step = s->step;
-  embed_kernel<<<1, 256, 0, st>>>(e);
-  g_launch_count++;
-  CKL(cudaGetLastError());
+  CKL(launch_k(embed_kernel, 1, 256, 0, st, e));
   return 0;
 }
 
@@ -826,7 +850,6 @@ static int enqueue_forward(dsk_model* m, dsk_state* s, int mode, int from_argmax
   a.job[0] = plain_job(m->wcls, s->logits);
   a.njobs = 1;
   a.epi = EPI_LOGITS;
-  plan_rows(a, a.job[0].rows);
   CKL(launch_gemv(c.quant, a, st));
   return 0;
 }
@@ -998,7 +1021,6 @@ extern "C" int dsk_gemv(int quant, int d, int n, const void* w, const float* sca
   GemvJob j{};
   j.w = dw; j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
   a.job[0] = j;
-  plan_rows(a, d);
   CKL(launch_gemv(quant, a, 0));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, dout, (size_t)d * 4, cudaMemcpyDeviceToHost));
@@ -1011,7 +1033,7 @@ extern "C" int dsk_quantize_q8k(const float* x, int k, void* out) {
   Tmp t;
   float* dx = t.up<float>(x, k);
   unsigned char* dout = t.up<unsigned char>(nullptr, (size_t)k / 256 * 292);
-  q8k_export_kernel<<<1, kThreads, stage_smem_bytes<Q_Q2K>(k)>>>(dx, k, dout);
+  q8k_export_kernel<<<1, kThreads, 512 + xvec_bytes<Q_Q2K>(k)>>>(dx, k, dout);
   CKL(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, dout, (size_t)k / 256 * 292, cudaMemcpyDeviceToHost));
@@ -1148,7 +1170,6 @@ extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, i
   a.in = dx; a.n = n; a.bs0 = 128; a.bs1 = 128; a.epi = EPI_STORE; a.njobs = 1;
   GemvJob j{};
   j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
-  plan_rows(a, d);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));

@@ -88,6 +88,41 @@ __device__ __forceinline__ uint32_t ldg_stream32(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
+// ---- sm_100a async machinery: 1-D TMA bulk copies (UBLKCP) completing on an mbarrier, PDL, explicit LDS ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// cp.async.bulk global -> shared, completion counted in bytes on `bar` (src/dst 16-byte aligned, size % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+// Programmatic dependent launch: let the next kernel of the graph start (and prefetch its weights) while this one
+// runs; griddepcontrol.wait blocks until every prerequisite grid has completed and flushed its writes.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+  return r;
+}
 __device__ __forceinline__ float h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 // f8e5m2 byte = top byte of an fp16 (src/codec.h:40-48): two bytes -> half2 -> float2
 __device__ __forceinline__ float2 f8x2_lo(uint32_t w) {
@@ -195,77 +230,75 @@ __device__ __forceinline__ void stage_input_q8(const float* __restrict__ in, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// Row dot products: one warp, one weight row; returns this lane's partial (caller warp-reduces).
+// Row dot products over weight tiles staged in SHARED memory by TMA.  One warp owns NACC rows that share
+// one activation vector: the activation chunk is read once into registers and reused for every row.
 // ------------------------------------------------------------------------------------------------
-// F8E5M2 block-scaled row (src/infer.cpp:238-313): sum over 16-wide chunks, scale applied per chunk.
-__device__ __forceinline__ float dot_f8(const uint8_t* __restrict__ w, const float* __restrict__ srow, int bs1, int n,
-                                        const float* xs, int lane) {
-  float acc = 0.f;
-  const int nch = n >> 4;
-#pragma unroll 4
-  for (int c = lane; c < nch; c += 32) {
-    const uint4 wv = ldg_stream(w + (size_t)c * 16);
-    const float4* xp = reinterpret_cast<const float4*>(xs + c * 16);
-    const float4 x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+template <int Q> struct QTraits;
+template <> struct QTraits<Q_F32> { static constexpr bool kq = false; static constexpr int epc = 4;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)n * 4; } };
+template <> struct QTraits<Q_F16> { static constexpr bool kq = false; static constexpr int epc = 8;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)n * 2; } };
+template <> struct QTraits<Q_F8>  { static constexpr bool kq = false; static constexpr int epc = 16; static __host__ __device__ size_t row_bytes(int n) { return (size_t)n; } };
+template <> struct QTraits<Q_Q2K> { static constexpr bool kq = true;  static constexpr int epc = 0;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)(n >> 8) * kQ2Bytes; } };
+template <> struct QTraits<Q_Q3K> { static constexpr bool kq = true;  static constexpr int epc = 0;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)(n >> 8) * kQ3Bytes; } };
+
+// 16 weight bytes x EPC activations -> partial dot (F32: src/infer.cpp:121-157, F16: 161-233, F8E5M2: 238-313)
+template <int Q>
+__device__ __forceinline__ float chunk_dot(const uint4& wv, const float* xv) {
+  float p = 0.f;
+  if constexpr (Q == Q_F8) {
     float2 a;
-    float p = 0.f;
-    a = f8x2_lo(wv.x); p = fmaf(a.x, x0.x, p); p = fmaf(a.y, x0.y, p);
-    a = f8x2_hi(wv.x); p = fmaf(a.x, x0.z, p); p = fmaf(a.y, x0.w, p);
-    a = f8x2_lo(wv.y); p = fmaf(a.x, x1.x, p); p = fmaf(a.y, x1.y, p);
-    a = f8x2_hi(wv.y); p = fmaf(a.x, x1.z, p); p = fmaf(a.y, x1.w, p);
-    a = f8x2_lo(wv.z); p = fmaf(a.x, x2.x, p); p = fmaf(a.y, x2.y, p);
-    a = f8x2_hi(wv.z); p = fmaf(a.x, x2.z, p); p = fmaf(a.y, x2.w, p);
-    a = f8x2_lo(wv.w); p = fmaf(a.x, x3.x, p); p = fmaf(a.y, x3.y, p);
-    a = f8x2_hi(wv.w); p = fmaf(a.x, x3.z, p); p = fmaf(a.y, x3.w, p);
-    const float s = srow ? srow[(c * 16) / bs1] : 1.0f;
-    acc = fmaf(p, s, acc);
-  }
-  return acc;
-}
-// F16 row (src/infer.cpp:161-233)
-__device__ __forceinline__ float dot_f16(const uint8_t* __restrict__ w, const float* __restrict__ srow, int bs1, int n,
-                                         const float* xs, int lane) {
-  float acc = 0.f;
-  const int nch = n >> 3;
-#pragma unroll 4
-  for (int c = lane; c < nch; c += 32) {
-    const uint4 wv = ldg_stream(w + (size_t)c * 16);
-    const float4* xp = reinterpret_cast<const float4*>(xs + c * 8);
-    const float4 x0 = xp[0], x1 = xp[1];
+    a = f8x2_lo(wv.x); p = fmaf(a.x, xv[0], p);  p = fmaf(a.y, xv[1], p);
+    a = f8x2_hi(wv.x); p = fmaf(a.x, xv[2], p);  p = fmaf(a.y, xv[3], p);
+    a = f8x2_lo(wv.y); p = fmaf(a.x, xv[4], p);  p = fmaf(a.y, xv[5], p);
+    a = f8x2_hi(wv.y); p = fmaf(a.x, xv[6], p);  p = fmaf(a.y, xv[7], p);
+    a = f8x2_lo(wv.z); p = fmaf(a.x, xv[8], p);  p = fmaf(a.y, xv[9], p);
+    a = f8x2_hi(wv.z); p = fmaf(a.x, xv[10], p); p = fmaf(a.y, xv[11], p);
+    a = f8x2_lo(wv.w); p = fmaf(a.x, xv[12], p); p = fmaf(a.y, xv[13], p);
+    a = f8x2_hi(wv.w); p = fmaf(a.x, xv[14], p); p = fmaf(a.y, xv[15], p);
+  } else if constexpr (Q == Q_F16) {
     float2 a;
-    float p = 0.f;
-    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.x)); p = fmaf(a.x, x0.x, p); p = fmaf(a.y, x0.y, p);
-    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.y)); p = fmaf(a.x, x0.z, p); p = fmaf(a.y, x0.w, p);
-    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.z)); p = fmaf(a.x, x1.x, p); p = fmaf(a.y, x1.y, p);
-    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.w)); p = fmaf(a.x, x1.z, p); p = fmaf(a.y, x1.w, p);
-    const float s = srow ? srow[(c * 8) / bs1] : 1.0f;
-    acc = fmaf(p, s, acc);
+    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.x)); p = fmaf(a.x, xv[0], p); p = fmaf(a.y, xv[1], p);
+    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.y)); p = fmaf(a.x, xv[2], p); p = fmaf(a.y, xv[3], p);
+    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.z)); p = fmaf(a.x, xv[4], p); p = fmaf(a.y, xv[5], p);
+    a = __half22float2(*reinterpret_cast<const __half2*>(&wv.w)); p = fmaf(a.x, xv[6], p); p = fmaf(a.y, xv[7], p);
+  } else {
+    p = __uint_as_float(wv.x) * xv[0];
+    p = fmaf(__uint_as_float(wv.y), xv[1], p);
+    p = fmaf(__uint_as_float(wv.z), xv[2], p);
+    p = fmaf(__uint_as_float(wv.w), xv[3], p);
   }
-  return acc;
-}
-// F32 row (src/infer.cpp:121-157) — used by the MoE gate in every quant
-__device__ __forceinline__ float dot_f32(const uint8_t* __restrict__ w, const float* __restrict__ srow, int bs1, int n,
-                                         const float* xs, int lane) {
-  float acc = 0.f;
-  const int nch = n >> 2;
-#pragma unroll 4
-  for (int c = lane; c < nch; c += 32) {
-    const uint4 wv = ldg_stream(w + (size_t)c * 16);
-    const float4 x0 = *reinterpret_cast<const float4*>(xs + c * 4);
-    float p = __uint_as_float(wv.x) * x0.x;
-    p = fmaf(__uint_as_float(wv.y), x0.y, p);
-    p = fmaf(__uint_as_float(wv.z), x0.z, p);
-    p = fmaf(__uint_as_float(wv.w), x0.w, p);
-    const float s = srow ? srow[(c * 4) / bs1] : 1.0f;
-    acc = fmaf(p, s, acc);
-  }
-  return acc;
+  return p;
 }
 
-// Q2_K x Q8_K row (ggml_vec_dot_q2_K_q8_K, src/quant.cpp:666-783).  A lane owns a quarter block
-// (h = 128-half, c = 16-byte half of the 32 qs bytes): 4 sub-blocks j = 8h+2s+c, s = 0..3.
-// Integer part exact (dp4a); per-block fp32 combine as the reference: d_y*d*isum - d_y*dmin*summs.
-__device__ __forceinline__ float dot_q2k(const uint8_t* __restrict__ wrow, int nb, const Q8Smem& q8, int lane) {
+// wa[i]: shared address of row i; sr[i]: its f8 scale row (global, nullable); xs: shared address of the fp32 activations
+template <int Q, int NACC>
+__device__ __forceinline__ void dot_dense(const uint32_t (&wa)[NACC], const float* const (&sr)[NACC], int bs1, int n,
+                                          uint32_t xs, int lane, float (&acc)[NACC]) {
+  constexpr int EPC = QTraits<Q>::epc;
+  const int nch = n / EPC;
+#pragma unroll 2
+  for (int c = lane; c < nch; c += 32) {
+    float xv[EPC];
+#pragma unroll
+    for (int q = 0; q < EPC / 4; q++) {
+      const uint4 t = lds128(xs + (uint32_t)(c * EPC + q * 4) * 4u);
+      xv[4 * q] = __uint_as_float(t.x); xv[4 * q + 1] = __uint_as_float(t.y);
+      xv[4 * q + 2] = __uint_as_float(t.z); xv[4 * q + 3] = __uint_as_float(t.w);
+    }
+    const int sidx = (c * EPC) / bs1;
+#pragma unroll
+    for (int r = 0; r < NACC; r++) {
+      const uint4 wv = lds128(wa[r] + (uint32_t)c * 16u);
+      const float p = chunk_dot<Q>(wv, xv);
+      const float s = sr[r] ? __ldg(sr[r] + sidx) : 1.0f;
+      acc[r] = fmaf(p, s, acc[r]);
+    }
+  }
+}
+
+// Q2_K x Q8_K row (ggml_vec_dot_q2_K_q8_K, src/quant.cpp:666-783) from a shared-memory tile.  A lane owns a quarter
+// block (h = 128-half, c = 16-byte half of the 32 qs bytes): 4 sub-blocks j = 8h+2s+c, s = 0..3.  Integer part
+// exact (dp4a); per-block fp32 combine as the reference: d_y*d*isum - d_y*dmin*summs.
+__device__ __forceinline__ float dot_q2k(uint32_t wrow, int nb, const Q8Smem& q8, int lane) {
   float acc = 0.f;
   const int nqb = nb * 4;
   for (int base = 0; base < nqb; base += 32) {
@@ -273,11 +306,11 @@ __device__ __forceinline__ float dot_q2k(const uint8_t* __restrict__ wrow, int n
     const bool act = qb < nqb;
     const int b = qb >> 2, h = (qb >> 1) & 1, c = qb & 1;
     int isum = 0, summs = 0;
-    const uint8_t* blk = wrow + (size_t)b * kQ2Bytes;
+    const uint32_t blk = wrow + (uint32_t)b * kQ2Bytes;
     if (act) {
-      const uint8_t* qp = blk + 16 + 32 * h + 16 * c;
-      const uint32_t q0 = ldg_stream32(qp), q1 = ldg_stream32(qp + 4), q2 = ldg_stream32(qp + 8), q3 = ldg_stream32(qp + 12);
-      const uint32_t sA = ldg_stream32(blk + 8 * h), sB = ldg_stream32(blk + 8 * h + 4);
+      const uint32_t qp = blk + 16 + 32 * h + 16 * c;
+      const uint32_t q0 = lds32(qp), q1 = lds32(qp + 4), q2 = lds32(qp + 8), q3 = lds32(qp + 12);
+      const uint32_t sA = lds32(blk + 8 * h), sB = lds32(blk + 8 * h + 4);
       const int8_t* y = q8.qs + b * 256 + 128 * h + 16 * c;
       const short* bs = q8.bsums + b * 16 + 8 * h + c;
 #pragma unroll
@@ -298,7 +331,7 @@ __device__ __forceinline__ float dot_q2k(const uint8_t* __restrict__ wrow, int n
     summs += __shfl_xor_sync(0xffffffffu, summs, 1);
     summs += __shfl_xor_sync(0xffffffffu, summs, 2);
     if (act && (lane & 3) == 0) {
-      const uint32_t dm = ldg_stream32(blk + 80);
+      const uint32_t dm = lds32(blk + 80);
       const float yd = q8.d[b];
       const float dall = yd * h2f((uint16_t)(dm & 0xffff));
       const float dmin = yd * h2f((uint16_t)(dm >> 16));
@@ -310,7 +343,7 @@ __device__ __forceinline__ float dot_q2k(const uint8_t* __restrict__ wrow, int n
 
 // Q3_K x Q8_K row (ggml_vec_dot_q3_K_q8_K, src/quant.cpp:434-614) on 112-byte repacked blocks
 // [hmask 32 | qs 64 | scales 12 | d 2 | pad 2].  q = (low2 | hbit<<2) - 4  =>  dot = dp4a(low2|hbit<<2, y) - 4*bsum.
-__device__ __forceinline__ float dot_q3k(const uint8_t* __restrict__ wrow, int nb, const Q8Smem& q8, int lane) {
+__device__ __forceinline__ float dot_q3k(uint32_t wrow, int nb, const Q8Smem& q8, int lane) {
   float acc = 0.f;
   const int nqb = nb * 4;
   for (int base = 0; base < nqb; base += 32) {
@@ -318,11 +351,11 @@ __device__ __forceinline__ float dot_q3k(const uint8_t* __restrict__ wrow, int n
     const bool act = qb < nqb;
     const int b = qb >> 2, h = (qb >> 1) & 1, c = qb & 1;
     int isum = 0;
-    const uint8_t* blk = wrow + (size_t)b * kQ3Bytes;
+    const uint32_t blk = wrow + (uint32_t)b * kQ3Bytes;
     if (act) {
-      const uint4 hm = ldg_stream(blk + 16 * c);
-      const uint4 qq = ldg_stream(blk + 32 + 32 * h + 16 * c);
-      const uint32_t s0 = ldg_stream32(blk + 96), s1 = ldg_stream32(blk + 100), s2 = ldg_stream32(blk + 104);
+      const uint4 hm = lds128(blk + 16 * c);
+      const uint4 qq = lds128(blk + 32 + 32 * h + 16 * c);
+      const uint32_t s0 = lds32(blk + 96), s1 = lds32(blk + 100), s2 = lds32(blk + 104);
       const int8_t* y = q8.qs + b * 256 + 128 * h + 16 * c;
       const short* bs = q8.bsums + b * 16 + 8 * h + c;
 #pragma unroll
@@ -347,35 +380,38 @@ __device__ __forceinline__ float dot_q3k(const uint8_t* __restrict__ wrow, int n
     isum += __shfl_xor_sync(0xffffffffu, isum, 1);
     isum += __shfl_xor_sync(0xffffffffu, isum, 2);
     if (act && (lane & 3) == 0) {
-      const uint32_t dw = ldg_stream32(blk + 108);
+      const uint32_t dw = lds32(blk + 108);
       acc += (h2f((uint16_t)(dw & 0xffff)) * q8.d[b]) * (float)isum;
     }
   }
   return acc;
 }
 
-template <int Q> struct QTraits;
-template <> struct QTraits<Q_F32> { static constexpr bool kq = false; static __host__ __device__ size_t row_bytes(int n) { return (size_t)n * 4; } };
-template <> struct QTraits<Q_F16> { static constexpr bool kq = false; static __host__ __device__ size_t row_bytes(int n) { return (size_t)n * 2; } };
-template <> struct QTraits<Q_F8>  { static constexpr bool kq = false; static __host__ __device__ size_t row_bytes(int n) { return (size_t)n; } };
-template <> struct QTraits<Q_Q2K> { static constexpr bool kq = true;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)(n >> 8) * kQ2Bytes; } };
-template <> struct QTraits<Q_Q3K> { static constexpr bool kq = true;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)(n >> 8) * kQ3Bytes; } };
-
-template <int Q>
-__device__ __forceinline__ float row_dot(const uint8_t* w, const float* srow, int bs1, int n, const float* xs,
-                                         const Q8Smem& q8, int lane) {
-  if constexpr (Q == Q_F32) return dot_f32(w, srow, bs1, n, xs, lane);
-  else if constexpr (Q == Q_F16) return dot_f16(w, srow, bs1, n, xs, lane);
-  else if constexpr (Q == Q_F8) return dot_f8(w, srow, bs1, n, xs, lane);
-  else if constexpr (Q == Q_Q2K) return dot_q2k(w, n >> 8, q8, lane);
-  else return dot_q3k(w, n >> 8, q8, lane);
+// NACC rows sharing one activation vector -> NACC warp-reduced dot products (valid in every lane)
+template <int Q, int NACC>
+__device__ __forceinline__ void rows_dot(const uint32_t (&wa)[NACC], const float* const (&sr)[NACC], int bs1, int n,
+                                         uint32_t xs, const Q8Smem& q8, int lane, float (&out)[NACC]) {
+#pragma unroll
+  for (int r = 0; r < NACC; r++) out[r] = 0.f;
+  if constexpr (QTraits<Q>::kq) {
+#pragma unroll
+    for (int r = 0; r < NACC; r++) out[r] = (Q == Q_Q2K) ? dot_q2k(wa[r], n >> 8, q8, lane) : dot_q3k(wa[r], n >> 8, q8, lane);
+  } else {
+    dot_dense<Q, NACC>(wa, sr, bs1, n, xs, lane, out);
+  }
+#pragma unroll
+  for (int r = 0; r < NACC; r++) out[r] = warp_sum(out[r]);
 }
 
-// carve the dynamic shared memory: [red 64 floats][xs n floats]  or  [red][q8 qs n][d nb][bsums nb*16]
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// bytes of the staged activation vector (fp32, or Q8_K: n int8 + n/256 floats + n/256*16 shorts)
 template <int Q>
-__device__ __forceinline__ void carve_smem(unsigned char* smem, int n, float*& red, float*& xs, Q8Smem& q8) {
-  red = reinterpret_cast<float*>(smem);
-  unsigned char* p = smem + 256;
+__host__ __device__ inline size_t xvec_bytes(int n) {
+  if (QTraits<Q>::kq) return align_up((size_t)n + (size_t)(n >> 8) * 36, 128);
+  return align_up((size_t)n * 4, 128);
+}
+template <int Q>
+__device__ __forceinline__ void carve_x(unsigned char* p, int n, float*& xs, Q8Smem& q8) {
   if constexpr (QTraits<Q>::kq) {
     q8.qs = reinterpret_cast<int8_t*>(p);
     q8.d = reinterpret_cast<float*>(p + n);
@@ -386,15 +422,15 @@ __device__ __forceinline__ void carve_smem(unsigned char* smem, int n, float*& r
     q8.qs = nullptr; q8.d = nullptr; q8.bsums = nullptr;
   }
 }
-template <int Q>
-inline size_t stage_smem_bytes(int n) {
-  if (QTraits<Q>::kq) return 256 + (size_t)n + (size_t)(n >> 8) * 4 + (size_t)(n >> 8) * 32 + 16;
-  return 256 + (size_t)n * 4;
-}
+constexpr int kSmemHdr = 384;  // [0,16) two mbarriers, [64,320) reduction scratch
 
 // ------------------------------------------------------------------------------------------------
-// gemv_kernel: up to kMaxJobs weight matrices sharing ONE input vector; rows of all jobs form one
-// virtual row space split evenly over CTAs; one warp per row.
+// gemv_kernel: up to kMaxJobs weight matrices sharing ONE input vector.  Each CTA owns `rows_per_cta` consecutive
+// rows of one job: that slice of the weight matrix (and of the paired `up` matrix for EPI_GLU) is pulled into
+// shared memory with 1-D TMA bulk copies — issued BEFORE the programmatic-dependency wait whenever the address
+// does not depend on the previous kernel (everything except routed experts), so weight streaming overlaps the
+// tail of the producer kernel.  After the wait the CTA stages the activation vector (RMSNorm / Q8_K fused),
+// waits for its tile, and each warp reduces `rpass` rows at a time out of shared memory.
 // ------------------------------------------------------------------------------------------------
 struct GemvJob {
   const uint8_t* w;      // (rows, cols) row-major payload; for expert stacks: base of the local slice
@@ -416,89 +452,140 @@ struct GemvArgs {
   int njobs;
   int epi;
   int rows_per_cta;
-  int total_rows;
+  int rpass;             // rows a warp reduces at once (1, 2 or 4)
   int bs0, bs1;
   int act_silu;
-  const int* active_experts;  // device list of routed expert ids (EPI with expert_slot >= 0)
+  const int* active_experts;  // device list of routed expert ids (jobs with expert_slot >= 0)
   int expert_first, expert_count;  // this rank's expert range [first, first+count)
   const Ctrl* ctrl;
   // EPI_KVB: kv_b rows -> fp16 K(nope)/V cache row kv_pos  (src/infer.cpp:979-1002)
   __half* kcache; __half* vcache; int n_heads, nope, vh, hd;
   // EPI_LOGITS
   Ctrl* ctrl_rw;
+  int cta_begin[kMaxJobs + 1];
   GemvJob job[kMaxJobs];
 };
 
-template <int Q>
-__global__ void __launch_bounds__(kThreads) gemv_kernel(const __grid_constant__ GemvArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  float *red, *xs;
-  Q8Smem q8;
-  carve_smem<Q>(smem, a.n, red, xs, q8);
-  if constexpr (QTraits<Q>::kq) stage_input_q8(a.in, a.n, a.norm_w, a.eps, q8, red);
-  else stage_input_f32(a.in, a.n, a.norm_w, a.eps, xs, red);
-
+template <int Q, int R, bool GLU>
+__device__ __forceinline__ void gemv_rows(const GemvArgs& a, const GemvJob& jb, int r0, int nrows, uint32_t tile,
+                                          uint32_t part_stride, const float* sc, const float* scb, uint32_t xs,
+                                          const Q8Smem& q8, unsigned long long& best) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = blockIdx.x * a.rows_per_cta;
-  const int row1 = min(row0 + a.rows_per_cta, a.total_rows);
-  const size_t rb = QTraits<Q>::row_bytes(a.n);
-  const int ncb = a.bs1 > 0 ? (a.n + a.bs1 - 1) / a.bs1 : 0;
-  unsigned long long best = 0ull;
-
-  for (int vr = row0 + warp; vr < row1; vr += kWarps) {
-    // virtual row -> (job, local row)
-    int j = 0, r = vr;
-    while (j + 1 < a.njobs && r >= a.job[j].rows) { r -= a.job[j].rows; j++; }
-    const GemvJob& jb = a.job[j];
-    const uint8_t* w = jb.w;
-    const float* sc = jb.scale;
-    const uint8_t* wb = jb.w_b;
-    const float* scb = jb.scale_b;
-    if (jb.expert_slot >= 0) {
-      const int e = a.active_experts[jb.expert_slot] - a.expert_first;
-      if (e < 0 || e >= a.expert_count) continue;  // expert lives on another rank
-      w += (size_t)e * jb.w_stride;
-      if (sc) sc += (size_t)e * jb.s_stride;
-      if (wb) wb += (size_t)e * jb.w_stride;
-      if (scb) scb += (size_t)e * jb.s_stride;
+  const uint32_t rb = (uint32_t)QTraits<Q>::row_bytes(a.n);
+  const int ncb = (a.n + a.bs1 - 1) / a.bs1;
+  constexpr int NACC = R * (GLU ? 2 : 1);
+  for (int g = warp * R; g < nrows; g += kWarps * R) {
+    uint32_t wa[NACC];
+    const float* sr[NACC];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int lr = min(g + i, nrows - 1);  // ragged tail: recompute the last row, never store it twice
+      wa[i] = tile + (uint32_t)lr * rb;
+      sr[i] = sc ? sc + (size_t)((r0 + lr) / a.bs0) * ncb : nullptr;
+      if constexpr (GLU) {
+        wa[R + i] = tile + part_stride + (uint32_t)lr * rb;
+        sr[R + i] = scb ? scb + (size_t)((r0 + lr) / a.bs0) * ncb : nullptr;
+      }
     }
-    const float* srow = sc ? sc + (size_t)(r / a.bs0) * ncb : nullptr;
-    float v = row_dot<Q>(w + (size_t)r * rb, srow, a.bs1, a.n, xs, q8, lane);
-    v = warp_sum(v);
-    if (a.epi == EPI_GLU) {
-      const float* srowb = scb ? scb + (size_t)(r / a.bs0) * ncb : nullptr;
-      float u = row_dot<Q>(wb + (size_t)r * rb, srowb, a.bs1, a.n, xs, q8, lane);
-      u = warp_sum(u);
-      v = (a.act_silu ? silu_f(v) : gelu_f(v)) * u;
-    }
+    float v[NACC];
+    rows_dot<Q, NACC>(wa, sr, a.bs1, a.n, xs, q8, lane, v);
     if (lane == 0) {
-      switch (a.epi) {
-        case EPI_RESID: jb.out[r] = jb.out[r] + v; break;
-        case EPI_KVB: {
-          jb.out[r] = v;
-          const int per = a.nope + a.vh, hh = r / per, i = r - hh * per;
-          const int kv_pos = a.ctrl->kv_pos;
-          if (i < a.nope) a.kcache[(size_t)kv_pos * a.n_heads * a.hd + hh * a.hd + i] = __float2half_rn(v);
-          else a.vcache[(size_t)kv_pos * a.n_heads * a.vh + hh * a.vh + (i - a.nope)] = __float2half_rn(v);
-          break;
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        if (g + i >= nrows) break;
+        const int r = r0 + g + i;
+        float val = v[i];
+        if constexpr (GLU) val = (a.act_silu ? silu_f(val) : gelu_f(val)) * v[R + i];
+        switch (a.epi) {
+          case EPI_RESID: jb.out[r] = jb.out[r] + val; break;
+          case EPI_KVB: {
+            jb.out[r] = val;
+            const int per = a.nope + a.vh, hh = r / per, ii = r - hh * per;
+            const int kv_pos = a.ctrl->kv_pos;
+            if (ii < a.nope) a.kcache[(size_t)kv_pos * a.n_heads * a.hd + hh * a.hd + ii] = __float2half_rn(val);
+            else a.vcache[(size_t)kv_pos * a.n_heads * a.vh + hh * a.vh + (ii - a.nope)] = __float2half_rn(val);
+            break;
+          }
+          case EPI_LOGITS: {
+            jb.out[r] = val;
+            const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+            if (key > best) best = key;
+            break;
+          }
+          default: jb.out[r] = val; break;
         }
-        case EPI_LOGITS: {
-          jb.out[r] = v;
-          unsigned long long key = ((unsigned long long)orderable(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
-          if (key > best) best = key;
-          break;
-        }
-        default: jb.out[r] = v; break;
       }
     }
   }
-  if (a.epi == EPI_LOGITS && lane == 0 && best) atomicMax(&a.ctrl_rw->argmax_key, best);
+}
+
+template <int Q>
+__global__ void __launch_bounds__(kThreads) gemv_kernel(const __grid_constant__ GemvArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t bar = smem_u32(smem);
+  float* red = reinterpret_cast<float*>(smem + 64);
+  float* xsp;
+  Q8Smem q8;
+  carve_x<Q>(smem + kSmemHdr, a.n, xsp, q8);
+  const uint32_t tile = smem_u32(smem + kSmemHdr + xvec_bytes<Q>(a.n));
+  const bool glu = a.epi == EPI_GLU;
+
+  int j = 0;
+  while (j + 1 < a.njobs && (int)blockIdx.x >= a.cta_begin[j + 1]) j++;
+  const GemvJob& jb = a.job[j];
+  const int r0 = ((int)blockIdx.x - a.cta_begin[j]) * a.rows_per_cta;
+  const int nrows = min(a.rows_per_cta, jb.rows - r0);
+  const size_t rb = QTraits<Q>::row_bytes(a.n);
+  const uint32_t part_bytes = (uint32_t)align_up((size_t)nrows * rb, 16);
+  const uint32_t part_stride = (uint32_t)align_up((size_t)a.rows_per_cta * rb, 128);
+
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_proxy_async(); }
+  __syncthreads();
+  const bool dyn = jb.expert_slot >= 0;
+  if (!dyn && threadIdx.x == 0) {   // static weights: stream them in before the dependency resolves
+    mbar_expect_tx(bar, part_bytes * (glu ? 2u : 1u));
+    bulk_g2s(tile, jb.w + (size_t)r0 * rb, part_bytes, bar);
+    if (glu) bulk_g2s(tile + part_stride, jb.w_b + (size_t)r0 * rb, part_bytes, bar);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const float* sc = jb.scale;
+  const float* scb = jb.scale_b;
+  if (dyn) {
+    const int e = a.active_experts[jb.expert_slot] - a.expert_first;
+    if (e < 0 || e >= a.expert_count) return;  // expert lives on another rank
+    if (sc) sc += (size_t)e * jb.s_stride;
+    if (scb) scb += (size_t)e * jb.s_stride;
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, part_bytes * (glu ? 2u : 1u));
+      bulk_g2s(tile, jb.w + (size_t)e * jb.w_stride + (size_t)r0 * rb, part_bytes, bar);
+      if (glu) bulk_g2s(tile + part_stride, jb.w_b + (size_t)e * jb.w_stride + (size_t)r0 * rb, part_bytes, bar);
+    }
+  }
+  if constexpr (QTraits<Q>::kq) stage_input_q8(a.in, a.n, a.norm_w, a.eps, q8, red);
+  else stage_input_f32(a.in, a.n, a.norm_w, a.eps, xsp, red);
+  mbar_wait(bar, 0);
+
+  const uint32_t xs = QTraits<Q>::kq ? 0u : smem_u32(xsp);
+  unsigned long long best = 0ull;
+  if (glu) {
+    if (a.rpass >= 2) gemv_rows<Q, 2, true>(a, jb, r0, nrows, tile, part_stride, sc, scb, xs, q8, best);
+    else gemv_rows<Q, 1, true>(a, jb, r0, nrows, tile, part_stride, sc, scb, xs, q8, best);
+  } else {
+    if (a.rpass >= 4) gemv_rows<Q, 4, false>(a, jb, r0, nrows, tile, part_stride, sc, scb, xs, q8, best);
+    else if (a.rpass >= 2) gemv_rows<Q, 2, false>(a, jb, r0, nrows, tile, part_stride, sc, scb, xs, q8, best);
+    else gemv_rows<Q, 1, false>(a, jb, r0, nrows, tile, part_stride, sc, scb, xs, q8, best);
+  }
+  if (a.epi == EPI_LOGITS && (threadIdx.x & 31) == 0 && best) atomicMax(&a.ctrl_rw->argmax_key, best);
 }
 
 // ------------------------------------------------------------------------------------------------
 // moe_down_kernel: x[i] += sum_k w_k * (w2[e_k][i,:] . hb_k) + shared_w2[i,:] . hb_shared
 // (src/infer.cpp:873-877, 899-903; dense layers: K = 0 and the "shared" matrix is the dense w2, 926-930).
-// Each CTA stages all K+1 input vectors; one warp per output row; accumulate order = reference order.
+// Each CTA owns `rows_per_cta` output rows: the shared/dense slice is TMA-prefetched before the dependency wait,
+// the K routed slices right after it (their address needs the gate's top-K).  One warp per output row walks the
+// K+1 segments in the reference's accumulation order.
 // ------------------------------------------------------------------------------------------------
 struct DownArgs {
   const uint8_t* w2; const float* s2; long long w_stride, s_stride;  // routed stack (local slice)
@@ -517,80 +604,94 @@ struct DownArgs {
 
 template <int Q>
 __global__ void __launch_bounds__(kThreads) moe_down_kernel(const __grid_constant__ DownArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  float* red = reinterpret_cast<float*>(smem);
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t bar_s = smem_u32(smem), bar_r = smem_u32(smem) + 8;
+  float* red = reinterpret_cast<float*>(smem + 64);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // stage K routed inputs + the shared input, each as its own vector
+  const int row0 = blockIdx.x * a.rows_per_cta;
+  const int nrows = min(a.rows_per_cta, a.dim - row0);
+  const size_t rb_mi = QTraits<Q>::row_bytes(a.mi), rb_sh = QTraits<Q>::row_bytes(a.sh);
+  const bool use_shared = a.sw2 != nullptr && a.add_shared;
+  // shared memory: [hdr][x_0 .. x_{K-1}][x_shared][tile_0 .. tile_{K-1}][tile_shared]
+  unsigned char* p = smem + kSmemHdr;
   float* xs[kMaxJobs];
   Q8Smem q8[kMaxJobs];
-  unsigned char* p = smem + 256;
   for (int k = 0; k <= a.K; k++) {
     const int n = k < a.K ? a.mi : a.sh;
-    if (n == 0) { xs[k] = nullptr; continue; }
-    if constexpr (QTraits<Q>::kq) {
-      q8[k].qs = reinterpret_cast<int8_t*>(p);
-      q8[k].d = reinterpret_cast<float*>(p + n);
-      q8[k].bsums = reinterpret_cast<short*>(p + n + (n >> 8) * 4);
-      p += ((size_t)n + (n >> 8) * 36 + 15) & ~(size_t)15;
-      xs[k] = nullptr;
-    } else {
-      xs[k] = reinterpret_cast<float*>(p);
-      p += (size_t)n * 4;
+    carve_x<Q>(p, n, xs[k], q8[k]);
+    p += n ? xvec_bytes<Q>(n) : 0;
+  }
+  const uint32_t tiles = smem_u32(p);
+  const uint32_t stride_mi = (uint32_t)align_up((size_t)a.rows_per_cta * rb_mi, 128);
+  const uint32_t tile_sh = tiles + (uint32_t)a.K * stride_mi;
+
+  if (threadIdx.x == 0) { mbar_init(bar_s, 1); mbar_init(bar_r, 1); fence_proxy_async(); }
+  __syncthreads();
+  if (use_shared && threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)align_up((size_t)nrows * rb_sh, 16);
+    mbar_expect_tx(bar_s, bytes);
+    bulk_g2s(tile_sh, a.sw2 + (size_t)row0 * rb_sh, bytes, bar_s);
+  }
+  pdl_launch_dependents();
+  pdl_wait();
+
+  int nlocal = 0;
+  for (int k = 0; k < a.K; k++) {
+    const int e = a.active[k] - a.expert_first;
+    if (e >= 0 && e < a.expert_count) nlocal++;
+  }
+  if (nlocal && threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)align_up((size_t)nrows * rb_mi, 16);
+    mbar_expect_tx(bar_r, bytes * (uint32_t)nlocal);
+    for (int k = 0; k < a.K; k++) {
+      const int e = a.active[k] - a.expert_first;
+      if (e < 0 || e >= a.expert_count) continue;
+      bulk_g2s(tiles + (uint32_t)k * stride_mi, a.w2 + (size_t)e * a.w_stride + (size_t)row0 * rb_mi, bytes, bar_r);
     }
   }
   for (int k = 0; k <= a.K; k++) {
     const int n = k < a.K ? a.mi : a.sh;
     if (n == 0) continue;
-    const float* src = k < a.K ? a.hb + (size_t)k * a.mi : a.hb_shared;
     if (k < a.K) {
       const int e = a.active[k] - a.expert_first;
       if (e < 0 || e >= a.expert_count) continue;
-    }
+    } else if (!use_shared) continue;
+    const float* src = k < a.K ? a.hb + (size_t)k * a.mi : a.hb_shared;
     if constexpr (QTraits<Q>::kq) stage_input_q8(src, n, nullptr, 0.f, q8[k], red);
     else stage_input_f32(src, n, nullptr, 0.f, xs[k], red);
   }
   __syncthreads();
-  const int row0 = blockIdx.x * a.rows_per_cta;
-  const int row1 = min(row0 + a.rows_per_cta, a.dim);
-  const size_t rb_mi = QTraits<Q>::row_bytes(a.mi), rb_sh = QTraits<Q>::row_bytes(a.sh);
-  const int ncb_mi = a.bs1 > 0 ? (a.mi + a.bs1 - 1) / a.bs1 : 0;
-  const int ncb_sh = a.bs1 > 0 ? (a.sh + a.bs1 - 1) / a.bs1 : 0;
-  const int nrb = a.bs0 > 0 ? (a.dim + a.bs0 - 1) / a.bs0 : 0;
-  (void)nrb;
-  for (int i = row0 + warp; i < row1; i += kWarps) {
+  if (nlocal) mbar_wait(bar_r, 0);
+  if (use_shared) mbar_wait(bar_s, 0);
+
+  const int ncb_mi = (a.mi + a.bs1 - 1) / a.bs1, ncb_sh = (a.sh + a.bs1 - 1) / a.bs1;
+  for (int li = warp; li < nrows; li += kWarps) {
+    const int i = row0 + li;
     float acc = a.partial ? 0.f : a.x[i];
     for (int k = 0; k < a.K; k++) {
       const int e = a.active[k] - a.expert_first;
       if (e < 0 || e >= a.expert_count) continue;
-      const uint8_t* w = a.w2 + (size_t)e * a.w_stride + (size_t)i * rb_mi;
-      const float* srow = a.s2 ? a.s2 + (size_t)e * a.s_stride + (size_t)(i / a.bs0) * ncb_mi : nullptr;
-      float v = row_dot<Q>(w, srow, a.bs1, a.mi, xs[k], q8[k], lane);
-      v = warp_sum(v);
-      acc = fmaf(v, a.weights[k], acc);
+      const uint32_t wa[1] = {tiles + (uint32_t)k * stride_mi + (uint32_t)li * (uint32_t)rb_mi};
+      const float* const sr[1] = {a.s2 ? a.s2 + (size_t)e * a.s_stride + (size_t)(i / a.bs0) * ncb_mi : nullptr};
+      float v[1];
+      rows_dot<Q, 1>(wa, sr, a.bs1, a.mi, QTraits<Q>::kq ? 0u : smem_u32(xs[k]), q8[k], lane, v);
+      acc = fmaf(v[0], a.weights[k], acc);
     }
-    if (a.sw2 && a.add_shared) {
-      const float* srow = a.ss2 ? a.ss2 + (size_t)(i / a.bs0) * ncb_sh : nullptr;
-      float v = row_dot<Q>(a.sw2 + (size_t)i * rb_sh, srow, a.bs1, a.sh, xs[a.K], q8[a.K], lane);
-      v = warp_sum(v);
-      acc += v;
+    if (use_shared) {
+      const uint32_t wa[1] = {tile_sh + (uint32_t)li * (uint32_t)rb_sh};
+      const float* const sr[1] = {a.ss2 ? a.ss2 + (size_t)(i / a.bs0) * ncb_sh : nullptr};
+      float v[1];
+      rows_dot<Q, 1>(wa, sr, a.bs1, a.sh, QTraits<Q>::kq ? 0u : smem_u32(xs[a.K]), q8[a.K], lane, v);
+      acc += v[0];
     }
     if (lane == 0) { if (a.partial) a.partial[i] = acc; else a.x[i] = acc; }
   }
 }
 
-template <int Q>
-inline size_t down_smem_bytes(int K, int mi, int sh) {
-  size_t s = 256;
-  for (int k = 0; k <= K; k++) {
-    int n = k < K ? mi : sh;
-    if (QTraits<Q>::kq) s += ((size_t)n + (n >> 8) * 36 + 15) & ~(size_t)15;
-    else s += (size_t)n * 4;
-  }
-  return s + 16;
-}
-
 // x += partial (after the all-reduce)
 __global__ void add_vec_kernel(float* x, const float* p, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] += p[i];
 }
@@ -626,12 +727,14 @@ struct AttnArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) attn_kernel(const __grid_constant__ AttnArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   float* red = reinterpret_cast<float*>(smem);
   float* stage = reinterpret_cast<float*>(smem + 256);        // 512 floats: sink re-rotation staging
   float* qs = reinterpret_cast<float*>(smem + 256 + 2048);    // hd
   float* att = qs + ((a.hd + 3) & ~3);                        // kv_len, then kThreads partials
   const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int pos = a.ctrl ? a.ctrl->pos : 0;
   const int kv_pos = a.ctrl ? a.ctrl->kv_pos : 0;
   const int kv_len = a.ctrl ? a.ctrl->kv_len : a.kv_len_fixed;
@@ -760,6 +863,8 @@ __global__ void __launch_bounds__(256) gate_topk_kernel(const __grid_constant__ 
   __shared__ unsigned char mask[256];  // 1 = not selectable
   __shared__ int sel[16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   float v = tid < a.E ? a.x[tid] : -3.402823466e38f;
   if (a.sigmoid) {
     v = 1.0f / (1.0f + expf(-v));
@@ -830,6 +935,8 @@ struct EmbedArgs {
 
 __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ EmbedArgs a) {
   __shared__ int s_token;
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x == 0) {
     Ctrl* c = a.ctrl;
     int token = c->token;
@@ -915,7 +1022,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(float* out, const float* i
 
 // standalone Q8_K quantiser for the dsk_quantize_q8k test hook: writes reference-layout block_q8_K (292 B)
 __global__ void __launch_bounds__(kThreads) q8k_export_kernel(const float* in, int n, unsigned char* out) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   float* red = reinterpret_cast<float*>(smem);
   Q8Smem q8;
   q8.qs = reinterpret_cast<int8_t*>(smem + 256);
