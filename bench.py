@@ -363,6 +363,7 @@ def main():
     ap.add_argument("--quant", default=os.environ.get("DSK_QUANT", "f8e5m2"))
     ap.add_argument("--n-layers", type=int, default=int(os.environ.get("DSK_LAYERS", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-token", action="store_true", help="print a per-launch event profile of one token to stderr")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -425,6 +426,11 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if a.profile_token and rank == 0:
+        hydrate()
+        m.profile_token(pr[0], PROMPT_LEN)
+        print(m.profile_token(pr[1], PROMPT_LEN + 1), file=sys.stderr, flush=True)
 
     # ---- value: device-resident decode, CUDA events inside dsk_decode_greedy --------------------------
     for _ in range(a.warmup):

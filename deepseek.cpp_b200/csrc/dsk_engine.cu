@@ -604,8 +604,22 @@ static int g_launch_count = 0;
 // Every kernel is launched with the programmatic-stream-serialization attribute: inside the token's CUDA graph this
 // becomes a programmatic dependency edge, so kernel N+1 is scheduled while kernel N drains, issues its TMA weight
 // prefetch, and blocks in griddepcontrol.wait until N has completed (all kernels call wait before touching state).
+struct ProfRec { const char* name; int grid; size_t smem; cudaEvent_t e0, e1; };
+static std::vector<ProfRec>* g_prof = nullptr;   // non-null while dsk_profile_token() records
+static const char* g_prof_tag = "";
+
 template <typename Arg>
 static cudaError_t launch_k(void (*kern)(Arg), int grid, int block, size_t smem, cudaStream_t st, const Arg& arg) {
+  if (g_prof) {
+    ProfRec r{g_prof_tag, grid, smem, nullptr, nullptr};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+    void* args[] = {(void*)&arg};
+    cudaError_t er = cudaLaunchKernel((const void*)kern, dim3((unsigned)grid), dim3((unsigned)block), args, smem, st);
+    cudaEventRecord(r.e1, st);
+    g_prof->push_back(r);
+    return er;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
@@ -711,12 +725,14 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     if (c.q_lora_rank > 0) a.job[0] = plain_job(L.wq_a, s->q_a); else a.job[0] = plain_job(L.wq, s->q);
     a.job[1] = plain_job(L.wkv_a, s->kv_a);
     a.njobs = 2;
+    g_prof_tag = "S1 q+kv_a gemv";
     CKL(launch_gemv(q, a, st));
   }
   if (c.q_lora_rank > 0) {  // q = wq_b . rmsnorm(q_a)                          infer.cpp:944-950
     GemvArgs a = base_args(m, s, s->q_a, L.rms_q_a, c.q_lora_rank);
     a.job[0] = plain_job(L.wq_b, s->q);
     a.njobs = 1;
+    g_prof_tag = "S1b wq_b gemv";
     CKL(launch_gemv(q, a, st));
   }
   // S2: kv_b = wkv_b . rmsnorm(kv_a[:kv_lora]); epilogue writes fp16 K(nope)/V cache row   infer.cpp:974-1002
@@ -725,6 +741,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     a.job[0] = plain_job(L.wkv_b, s->kv_b);
     a.njobs = 1;
     a.epi = EPI_KVB;
+    g_prof_tag = "S2 kv_b gemv+cache";
     a.kcache = L.kcache; a.vcache = L.vcache; a.n_heads = c.n_heads; a.nope = nope; a.vh = c.v_head_dim; a.hd = hd;
     CKL(launch_gemv(q, a, st));
   }
@@ -734,6 +751,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     a.q = s->q; a.kv_a = s->kv_a; a.kcache = L.kcache; a.vcache = L.vcache; a.out = s->xb2; a.ctrl = s->ctrl;
     a.n_heads = c.n_heads; a.hd = hd; a.nope = nope; a.rope = c.qk_rope_head_dim; a.vh = c.v_head_dim;
     a.kv_lora = c.kv_lora_rank; a.rope_freq = m->rope_freq; a.is_v3 = c.is_v3; a.max_seq = c.max_seq_len; a.do_prologue = 1;
+    g_prof_tag = "S3 rope+attn";
     CKL(launch_k(attn_kernel, c.n_heads, kThreads, attn_smem_bytes(hd, c.v_head_dim, c.max_seq_len), st, a));
   }
   // S4: x += wo . xb2                                                                     infer.cpp:1048, 832-834
@@ -742,6 +760,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
     a.job[0] = plain_job(L.wo, s->x);
     a.njobs = 1;
     a.epi = EPI_RESID;
+    g_prof_tag = "S4 wo gemv+resid";
     CKL(launch_gemv(q, a, st));
   }
   if (L.is_moe) {
@@ -752,6 +771,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
       a.job[0] = j;
       a.njobs = 1;
+      g_prof_tag = "gate gemv f32";
       CKL(launch_gemv(DSK_F32, a, st));
     }
     {  // moe_gate                                                                        infer.cpp:848-852
@@ -759,6 +779,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       g.x = s->moe_logits; g.bias = L.gate_bias; g.active = s->act; g.weights = s->act_w;
       g.E = c.n_routed_experts; g.K = c.n_active_routed; g.norm_topk_prob = c.norm_topk_prob; g.sigmoid = c.scoring_sigmoid;
       g.method = c.topk_method; g.n_group = std::max(1, c.n_group); g.topk_group = c.topk_group; g.scale = c.routed_scaling_factor;
+      g_prof_tag = "gate topk";
       CKL(launch_k(gate_topk_kernel, 1, 256, 0, st, g));
     }
     // routed + shared up/gate projections with fused act(h1)*h3                           infer.cpp:853-870, 879-897
@@ -780,6 +801,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       }
       a.njobs = nj;
       a.epi = EPI_GLU;
+      g_prof_tag = "S56 experts glu";
       CKL(launch_gemv(q, a, st));
     }
     // down projections + weighted accumulate into the residual stream                     infer.cpp:873-877, 899-903
@@ -794,6 +816,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       d.x = s->x;
       d.partial = m->n_ranks > 1 ? s->partial : nullptr;
       d.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
+      g_prof_tag = "S7 moe down";
       CKL(launch_down(q, d, st));
       if (m->n_ranks > 1) {
         if (!m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
@@ -812,6 +835,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       a.job[0] = j;
       a.njobs = 1;
       a.epi = EPI_GLU;
+      g_prof_tag = "dense glu";
       CKL(launch_gemv(q, a, st));
     }
     {
@@ -821,6 +845,7 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
       d.K = 0; d.mi = 0; d.sh = c.hidden_dim; d.dim = c.dim;
       d.bs0 = c.bs0 > 0 ? c.bs0 : 1; d.bs1 = c.bs1 > 0 ? c.bs1 : 1;
       d.x = s->x; d.partial = nullptr; d.add_shared = 1;
+      g_prof_tag = "dense down";
       CKL(launch_down(q, d, st));
     }
   }
@@ -834,6 +859,7 @@ static int enqueue_embed(dsk_model* m, dsk_state* s, int from_argmax, cudaStream
   e.quant = c.quant; e.dim = c.dim; e.bs0 = c.bs0 > 0 ? c.bs0 : 1; e.bs1 = c.bs1 > 0 ? c.bs1 : 1;
   e.from_argmax = from_argmax; e.original_max = c.original_max_position;
   e.token_log = s->token_log; e.step = s->step;
+  g_prof_tag = "embed";
   CKL(launch_k(embed_kernel, 1, 256, 0, st, e));
   return 0;
 }
@@ -850,6 +876,7 @@ static int enqueue_forward(dsk_model* m, dsk_state* s, int mode, int from_argmax
   a.job[0] = plain_job(m->wcls, s->logits);
   a.njobs = 1;
   a.epi = EPI_LOGITS;
+  g_prof_tag = "lm_head+argmax";
   CKL(launch_gemv(c.quant, a, st));
   return 0;
 }
@@ -1188,5 +1215,43 @@ extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, i
   if (avg_ms) *avg_ms = ms / iters;
   double bpw = quant == DSK_F32 ? 4 : quant == DSK_F16 ? 2 : quant == DSK_F8E5M2 ? 1.0 + 4.0 / 16384 : quant == DSK_Q2_K ? 84.0 / 256 : 110.0 / 256;
   if (bytes_per_launch) *bytes_per_launch = (double)d * n * bpw;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-launch profile of one token (un-graphed, CUDA events around every launch; includes launch gaps)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos, char* out, size_t cap) {
+  if (need_device()) return -1;
+  if (!m || !s || !out) return fail(-1, "bad arguments");
+  std::vector<ProfRec> recs;
+  fill_ctrl(s->h_ctrl, m->c, token, pos);
+  CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
+  g_prof = &recs;
+  int rc = enqueue_forward(m, s, 1, 0, s->stream);
+  g_prof = nullptr;
+  CK(cudaStreamSynchronize(s->stream));
+  if (rc) return rc;
+  std::map<std::string, std::pair<int, double>> agg;
+  size_t off = 0;
+  double total = 0;
+  for (auto& r : recs) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    char key[128];
+    snprintf(key, sizeof(key), "%-22s grid=%5d smem=%6zu", r.name, r.grid, r.smem);
+    agg[key].first++;
+    agg[key].second += ms * 1e3;
+    total += ms * 1e3;
+  }
+  for (auto& kv : agg) {
+    int n = snprintf(out + off, cap - off, "%s n=%3d avg=%8.2f us sum=%9.1f us\n", kv.first.c_str(), kv.second.first,
+                     kv.second.second / kv.second.first, kv.second.second);
+    if (n < 0 || (size_t)n >= cap - off) break;
+    off += n;
+  }
+  snprintf(out + off, cap - off, "total %.1f us over %zu launches\n", total, recs.size());
+  s->last_pos = pos;
   return 0;
 }

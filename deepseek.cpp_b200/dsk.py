@@ -123,6 +123,7 @@ def lib():
         L.dsk_copy_embedding.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dsk_block_forward.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 5
         L.dsk_decode_greedy.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, f32p]
+        L.dsk_profile_token.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]
         L.dsk_launches_per_forward.argtypes = [C.c_void_p, C.c_int]
         L.dsk_comm_unique_id.argtypes = [C.c_void_p]
         L.dsk_comm_init.argtypes = [C.c_void_p, C.c_void_p]
@@ -276,6 +277,11 @@ class Model:
     def set_kv_cache(self, layer: int, which: int, data: np.ndarray):
         a = np.ascontiguousarray(data, dtype=np.uint16)
         _ck(self.L.dsk_kv_write(self.h, layer, which, a.ctypes.data_as(u16p), a.size))
+
+    def profile_token(self, token: int, pos: int) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        _ck(self.L.dsk_profile_token(self.h, self.s, token, pos, buf, len(buf)))
+        return buf.value.decode()
 
     def resident_bytes(self) -> int:
         return self.L.dsk_model_resident_bytes(self.h)

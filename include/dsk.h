@@ -138,6 +138,10 @@ int dsk_attn(const float* q, const uint16_t* kcache, const uint16_t* vcache, int
  * Returns average milliseconds per launch and the algorithmic bytes per launch. */
 int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, int iters, float* avg_ms, double* bytes_per_launch);
 
+/* Per-launch profile of one token: runs the forward un-graphed with CUDA events around every launch and writes a
+ * text table (kernel, grid, smem, count, avg/sum microseconds) into `out`. */
+int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos, char* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif
