@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "dsk_kernels.cuh"
+#include "dsk_mega.cuh"
 
 using namespace dsk;
 
@@ -125,7 +126,7 @@ struct dsk_model {
 struct dsk_state {
   dsk_model* m = nullptr;
   float *x = nullptr, *xb2 = nullptr, *hbk = nullptr, *hbs = nullptr, *q_a = nullptr, *q = nullptr, *kv_a = nullptr,
-        *kv_b = nullptr, *moe_logits = nullptr, *act_w = nullptr, *logits = nullptr, *partial = nullptr;
+        *kv_b = nullptr, *moe_logits = nullptr, *moe_scores = nullptr, *act_w = nullptr, *logits = nullptr, *partial = nullptr;
   int* act = nullptr;
   Ctrl* ctrl = nullptr;       // device
   Ctrl* h_ctrl = nullptr;     // pinned host mirror
@@ -136,6 +137,14 @@ struct dsk_state {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int last_pos = -1;
   size_t token_log_cap = 0;
+  // persistent interpreter
+  Program* prog = nullptr;              // device
+  float* att_scratch = nullptr;
+  unsigned int* sync_words = nullptr;   // [0] arrivals counter, [1] base
+  int n_stages = 0;
+  size_t mega_smem = 0;
+  std::vector<int> layer_begin, layer_end;  // stage ranges per layer
+  std::vector<int> cut_after;           // multi-GPU: stage indices followed by the partial-sum all-reduce
 };
 
 static size_t disk_row_bytes(int quant, int cols) {
@@ -160,6 +169,8 @@ static int cdiv(int a, int b) { return (a + b - 1) / b; }
 static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 static constexpr size_t kSmemBudget = 200 * 1024;
 static bool g_use_pdl = true;
+enum { ENG_MEGA = 0, ENG_STAGE = 1, ENG_V2 = 2 };
+static int g_engine = ENG_MEGA;
 
 template <int Q>
 static cudaError_t set_attrs_q() {
@@ -191,6 +202,16 @@ extern "C" int dsk_init(int device) {
     CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     g_use_pdl = getenv("DSK_NO_PDL") == nullptr;
+    if (const char* en = getenv("DSK_ENGINE")) {
+      if (!strcmp(en, "stage")) g_engine = ENG_STAGE;
+      else if (!strcmp(en, "v2")) g_engine = ENG_V2;
+      else g_engine = ENG_MEGA;
+    }
+    CK(cudaFuncSetAttribute(decode_kernel<Q_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_Q2K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_Q3K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
     g_attrs_set = true;
   }
   return 0;
@@ -479,6 +500,8 @@ extern "C" double dsk_model_active_bytes_per_token(const dsk_model* m) {
 // ---------------------------------------------------------------------------------------------------
 // state
 // ---------------------------------------------------------------------------------------------------
+static int build_program(dsk_model* m, dsk_state* s);
+
 extern "C" dsk_state* dsk_state_create(dsk_model* m) {
   if (need_device() || !m) return nullptr;
   const dsk_config& c = m->c;
@@ -495,6 +518,7 @@ extern "C" dsk_state* dsk_state_create(dsk_model* m) {
   fa(&s->kv_a, c.kv_lora_rank + c.qk_rope_head_dim);
   fa(&s->kv_b, (size_t)c.n_heads * (c.qk_nope_head_dim + c.v_head_dim));
   fa(&s->moe_logits, std::max(1, c.n_routed_experts));
+  fa(&s->moe_scores, std::max(1, c.n_routed_experts));
   fa(&s->act_w, 16);
   fa(&s->logits, c.vocab_size);
   fa(&s->partial, c.dim);
@@ -512,14 +536,16 @@ extern "C" dsk_state* dsk_state_create(dsk_model* m) {
   cudaEventCreate(&s->ev0);
   cudaEventCreate(&s->ev1);
   if (cudaGetLastError() != cudaSuccess) { fail(-2, "state allocation failed"); return nullptr; }
+  if (build_program(m, s)) { return nullptr; }
   return s;
 }
 
 extern "C" void dsk_state_destroy(dsk_state* s) {
   if (!s) return;
   for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (s->graph[a][b]) cudaGraphExecDestroy(s->graph[a][b]);
-  float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->kv_a, s->kv_b, s->moe_logits, s->act_w, s->logits, s->partial};
+  float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->kv_a, s->kv_b, s->moe_logits, s->moe_scores, s->act_w, s->logits, s->partial};
   for (float* b : bufs) cudaFree(b);
+  cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words);
   cudaFree(s->act); cudaFree(s->ctrl); cudaFreeHost(s->h_ctrl); cudaFree(s->token_log); cudaFree(s->step);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   cudaStreamDestroy(s->stream);
@@ -537,7 +563,7 @@ static float* state_buf(dsk_state* s, const char* name, size_t* cap) {
   if (k == "q") { *cap = (size_t)c.n_heads * s->m->head_dim; return s->q; }
   if (k == "kv_a") { *cap = c.kv_lora_rank + c.qk_rope_head_dim; return s->kv_a; }
   if (k == "kv_b") { *cap = (size_t)c.n_heads * (c.qk_nope_head_dim + c.v_head_dim); return s->kv_b; }
-  if (k == "moe_weights") { *cap = c.n_routed_experts; return s->moe_logits; }
+  if (k == "moe_weights") { *cap = c.n_routed_experts; return g_engine == ENG_V2 ? s->moe_logits : s->moe_scores; }
   if (k == "active_experts_weights") { *cap = c.n_active_routed; return s->act_w; }
   if (k == "logits") { *cap = c.vocab_size; return s->logits; }
   return nullptr;
@@ -852,6 +878,261 @@ static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// persistent interpreter: build the per-state program (stages, tile plans, column pieces)
+// ---------------------------------------------------------------------------------------------------
+static int granules(int quant, int n) {
+  switch (quant) { case DSK_F32: return n / 4; case DSK_F16: return n / 8; case DSK_F8E5M2: return n / 16; default: return n / 256; }
+}
+static bool kq_quant(int q) { return q == DSK_Q2_K || q == DSK_Q3_K; }
+
+static void plan_gemv_stage(Stage& st, int quant, int G) {
+  const size_t rb = dev_row_bytes(quant, st.n);
+  const int parts = st.epi == EPI_GLU ? 2 : 1;
+  int total_rows = 0;
+  for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
+  int RT = 32;
+  while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)kSlotData) RT >>= 1;
+  int min_rt = 1;
+  if (quant == DSK_Q2_K) { const int nb = st.n / 256; min_rt = (nb % 4 == 0) ? 1 : (nb % 2 == 0 ? 2 : 4); }  // 16-byte TMA source alignment
+  while (RT > std::max(min_rt, 4) && cdiv(total_rows, RT) < G) RT >>= 1;   // at least one tile per CTA when possible
+  RT = std::max(RT, min_rt);
+  st.rows_per_tile = RT;
+  const bool kq = kq_quant(quant);
+  int R = kq ? 1 : (RT >= 32 ? 4 : (RT >= 16 ? 2 : 1));
+  if (parts == 2) R = std::min(R, 2);
+  st.rpass = R;
+  const int groups = cdiv(RT, R), gran = granules(quant, st.n);
+  int csplit = groups >= 8 ? 1 : 8 / groups;
+  csplit = std::max(1, std::min(csplit, std::max(1, gran / 2)));
+  csplit = std::min(csplit, 8);
+  st.npieces = csplit;
+  for (int cs = 0; cs < csplit; cs++) st.piece[cs] = Piece{0, (int)((long long)cs * gran / csplit), (int)((long long)(cs + 1) * gran / csplit), 0};
+  int t = 0;
+  st.has_dyn = 0;
+  for (int j = 0; j < st.njobs; j++) { st.job[j].tile_begin = t; t += cdiv(st.job[j].rows, RT); if (st.job[j].expert_slot >= 0) st.has_dyn = 1; }
+  st.ntiles = t;
+}
+
+static int plan_down_stage(Stage& st, int quant, int dim) {
+  const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
+  int RT = 8;
+  auto bytes = [&](int r) { return align_up((size_t)r * rb_mi, 128) * st.K + align_up((size_t)r * rb_sh, 128); };
+  while (RT > 1 && bytes(RT) > (size_t)kSlotData) RT >>= 1;
+  if (bytes(RT) > (size_t)kSlotData) return fail(-4, "down-projection row (%zu bytes) does not fit a ring slot", bytes(1));
+  if (quant == DSK_Q2_K) {
+    auto ok = [&](int n) { const int nb = n / 256; return n == 0 || (RT * nb) % 4 == 0; };
+    if (!ok(st.mi) || !ok(st.sh)) return fail(-4, "Q2_K down projection: tile rows x blocks not 16-byte aligned");
+  }
+  st.rows_per_tile = RT;
+  st.seg_stride = (int)align_up((size_t)RT * rb_mi, 128);
+  st.ntiles = cdiv(dim, RT);
+  const int g_mi = st.mi ? granules(quant, st.mi) : 0, g_sh = st.sh ? granules(quant, st.sh) : 0;
+  const long long total = (long long)g_mi * st.K + g_sh;
+  const int want = std::max(1, cdiv(16, RT));
+  const long long L = std::max<long long>(1, cdiv((int)total, want));
+  int np = 0;
+  for (int k = 0; k <= st.K; k++) {
+    const int g = k < st.K ? g_mi : g_sh;
+    if (g == 0) continue;
+    int cs = (int)std::max<long long>(1, (g + L / 2) / L);
+    cs = std::min(cs, g);
+    while (np + cs + (st.K - k) > kMaxPieces && cs > 1) cs--;
+    for (int c = 0; c < cs; c++) st.piece[np++] = Piece{k, (int)((long long)c * g / cs), (int)((long long)(c + 1) * g / cs), 0};
+  }
+  st.npieces = np;
+  return 0;
+}
+
+static MJob mjob(const DTensor& t, float* out) {
+  MJob j{};
+  j.w = t.w; j.scale = t.scale; j.out = out; j.rows = t.rows; j.expert_slot = -1;
+  return j;
+}
+
+static int build_program(dsk_model* m, dsk_state* s) {
+  const dsk_config& c = m->c;
+  const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
+  std::vector<Stage> S;
+  auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {
+    Stage st{};
+    st.kind = ST_GEMV; st.quant = quant; st.epi = epi; st.in = in; st.norm_w = norm_w; st.n = n; st.layer = layer;
+    return st;
+  };
+  s->layer_begin.assign(c.n_layers, 0);
+  s->layer_end.assign(c.n_layers, 0);
+  { Stage st{}; st.kind = ST_EMBED; st.quant = q; S.push_back(st); }
+  for (int l = 0; l < c.n_layers; l++) {
+    Layer& L = m->layers[l];
+    s->layer_begin[l] = (int)S.size();
+    {  // S1
+      Stage st = gemv(q, s->x, L.rms_att, c.dim, EPI_STORE, l);
+      st.job[0] = c.q_lora_rank > 0 ? mjob(L.wq_a, s->q_a) : mjob(L.wq, s->q);
+      st.job[1] = mjob(L.wkv_a, s->kv_a);
+      st.njobs = 2;
+      plan_gemv_stage(st, q, G);
+      S.push_back(st);
+    }
+    if (c.q_lora_rank > 0) {
+      Stage st = gemv(q, s->q_a, L.rms_q_a, c.q_lora_rank, EPI_STORE, l);
+      st.job[0] = mjob(L.wq_b, s->q); st.njobs = 1;
+      plan_gemv_stage(st, q, G);
+      S.push_back(st);
+    }
+    {  // S2
+      Stage st = gemv(q, s->kv_a, L.rms_kv_a, c.kv_lora_rank, EPI_KVB, l);
+      st.job[0] = mjob(L.wkv_b, s->kv_b); st.njobs = 1; st.kcache = L.kcache; st.vcache = L.vcache;
+      plan_gemv_stage(st, q, G);
+      S.push_back(st);
+    }
+    { Stage st{}; st.kind = ST_ATTN; st.quant = q; st.layer = l; st.kcache = L.kcache; st.vcache = L.vcache; S.push_back(st); }
+    {  // S4
+      Stage st = gemv(q, s->xb2, nullptr, c.n_heads * c.v_head_dim, EPI_RESID, l);
+      st.job[0] = mjob(L.wo, s->x); st.njobs = 1;
+      plan_gemv_stage(st, q, G);
+      S.push_back(st);
+    }
+    if (L.is_moe) {
+      const int sh = c.n_shared_experts * mi;
+      {  // S5 gate logits (F32 weights in every quant)
+        Stage st = gemv(DSK_F32, s->x, L.rms_ffn, c.dim, EPI_STORE, l);
+        MJob j{}; j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
+        st.job[0] = j; st.njobs = 1;
+        plan_gemv_stage(st, DSK_F32, G);
+        S.push_back(st);
+      }
+      {  // S56: routing + shared (static, first: streams before the routing is known) + routed experts
+        Stage st = gemv(q, s->x, L.rms_ffn, c.dim, EPI_GLU, l);
+        st.need_topk = 1; st.gate_logits = s->moe_logits; st.gate_bias = L.gate_bias;
+        int nj = 0;
+        if (sh > 0) { MJob j = mjob(L.sw1, s->hbs); j.w_b = L.sw3.w; j.scale_b = L.sw3.scale; st.job[nj++] = j; }
+        for (int k = 0; k < c.n_active_routed; k++) {
+          MJob j{};
+          j.w = L.w1.w; j.scale = L.w1.scale; j.w_b = L.w3.w; j.scale_b = L.w3.scale;
+          j.out = s->hbk + (size_t)k * mi; j.rows = mi; j.expert_slot = k;
+          j.w_stride = (long long)L.w1.expert_bytes; j.s_stride = (long long)L.w1.scale_expert;
+          st.job[nj++] = j;
+        }
+        st.njobs = nj;
+        plan_gemv_stage(st, q, G);
+        S.push_back(st);
+      }
+      {  // S7
+        Stage st{};
+        st.kind = ST_DOWN; st.quant = q; st.layer = l;
+        st.w2 = L.w2.w; st.s2 = L.w2.scale; st.w2_stride = (long long)L.w2.expert_bytes; st.s2_stride = (long long)L.w2.scale_expert;
+        st.sw2 = sh > 0 ? L.sw2.w : nullptr; st.ss2 = sh > 0 ? L.sw2.scale : nullptr;
+        st.K = c.n_active_routed; st.mi = mi; st.sh = sh;
+        st.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
+        if (plan_down_stage(st, q, c.dim)) return -4;
+        S.push_back(st);
+        if (m->n_ranks > 1) s->cut_after.push_back((int)S.size() - 1);
+      }
+    } else {
+      {
+        Stage st = gemv(q, s->x, L.rms_ffn, c.dim, EPI_GLU, l);
+        MJob j = mjob(L.w1, s->hbs); j.w_b = L.w3.w; j.scale_b = L.w3.scale;
+        st.job[0] = j; st.njobs = 1;
+        plan_gemv_stage(st, q, G);
+        S.push_back(st);
+      }
+      {
+        Stage st{};
+        st.kind = ST_DOWN; st.quant = q; st.layer = l;
+        st.sw2 = L.w2.w; st.ss2 = L.w2.scale; st.K = 0; st.mi = 0; st.sh = c.hidden_dim; st.add_shared = 1;
+        if (plan_down_stage(st, q, c.dim)) return -4;
+        S.push_back(st);
+      }
+    }
+    s->layer_end[l] = (int)S.size();
+  }
+  {  // LM head + argmax
+    Stage st = gemv(q, s->x, m->rms_final, c.dim, EPI_LOGITS, -1);
+    st.job[0] = mjob(m->wcls, s->logits); st.njobs = 1;
+    plan_gemv_stage(st, q, G);
+    S.push_back(st);
+  }
+  // shared-memory budget: activation region = max over stages, the rest is ring slots
+  size_t xreg = 8192;
+  for (const Stage& st : S) {
+    if (st.kind == ST_GEMV) xreg = std::max(xreg, xvec_bytes_q(st.quant, st.n));
+    else if (st.kind == ST_DOWN) {
+      size_t b = 0;
+      for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += xvec_bytes_q(st.quant, n); }
+      xreg = std::max(xreg, b);
+    }
+  }
+  const size_t attn_need = (size_t)(512 + ((hd + 3) & ~3) + ((c.max_seq_len + 3) & ~3) + kConsumers + 16) * 4;
+  if (attn_need <= 64 * 1024) xreg = std::max(xreg, attn_need);
+  xreg = align_up(std::max(xreg, (size_t)(512 + ((hd + 3) & ~3) + 64) * 4), 128);
+  const size_t budget = (size_t)kSmemMax - 256;
+  if (kMegaHdr + xreg + 2 * (size_t)kSlotBytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
+  int n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / kSlotBytes);
+  s->mega_smem = kMegaHdr + xreg + (size_t)n_slots * kSlotBytes;
+  s->n_stages = (int)S.size();
+
+  std::vector<unsigned char> buf(sizeof(Program) + (S.size() - 1) * sizeof(Stage));
+  Program* P = reinterpret_cast<Program*>(buf.data());
+  memset(P, 0, sizeof(Program));
+  P->dim = c.dim; P->n_heads = c.n_heads; P->hd = hd; P->nope = nope; P->rope = c.qk_rope_head_dim; P->vh = c.v_head_dim;
+  P->kv_lora = c.kv_lora_rank; P->is_v3 = c.is_v3; P->bs0 = c.bs0 > 0 ? c.bs0 : 1; P->bs1 = c.bs1 > 0 ? c.bs1 : 1;
+  P->act_silu = c.act_silu; P->max_seq = c.max_seq_len; P->E = c.n_routed_experts; P->K = c.n_active_routed;
+  P->norm_topk_prob = c.norm_topk_prob; P->sigmoid = c.scoring_sigmoid; P->topk_method = c.topk_method;
+  P->n_group = std::max(1, c.n_group); P->topk_group = c.topk_group; P->original_max = c.original_max_position;
+  P->eps = c.norm_eps; P->routed_scale = c.routed_scaling_factor; P->expert_first = m->expert_first; P->expert_count = m->expert_count;
+  P->embed_quant = q; P->n_stages = (int)S.size();
+  P->embed_w = m->embed.w; P->embed_scale = m->embed.scale; P->rope_freq = m->rope_freq;
+  P->x = s->x; P->q = s->q; P->q_a = s->q_a; P->kv_a = s->kv_a; P->kv_b = s->kv_b; P->xb2 = s->xb2; P->hbk = s->hbk; P->hbs = s->hbs;
+  P->moe_logits = s->moe_logits; P->moe_scores = s->moe_scores; P->act_w = s->act_w; P->logits = s->logits; P->partial = m->n_ranks > 1 ? s->partial : nullptr;
+  P->act = s->act; P->ctrl = s->ctrl; P->token_log = s->token_log; P->step = s->step;
+  CK(cudaMalloc((void**)&s->att_scratch, (size_t)c.n_heads * (c.max_seq_len + kConsumers + 8) * 4));
+  CK(cudaMalloc((void**)&s->sync_words, 64));
+  CK(cudaMemset(s->sync_words, 0, 64));
+  P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
+  P->n_slots = n_slots; P->xregion_bytes = (int)xreg;
+  memcpy(P->stage, S.data(), S.size() * sizeof(Stage));
+  CK(cudaMalloc((void**)&s->prog, buf.size()));
+  CK(cudaMemcpy(s->prog, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static cudaError_t launch_decode(dsk_model* m, dsk_state* s, int s_begin, int s_end, int from_argmax, cudaStream_t st) {
+  if (s_end <= s_begin) return cudaSuccess;
+  void (*kern)(const Program*, int, int, int) = nullptr;
+  switch (m->c.quant) {
+    case DSK_F32: kern = decode_kernel<Q_F32>; break;
+    case DSK_F16: kern = decode_kernel<Q_F16>; break;
+    case DSK_F8E5M2: kern = decode_kernel<Q_F8>; break;
+    case DSK_Q2_K: kern = decode_kernel<Q_Q2K>; break;
+    default: kern = decode_kernel<Q_Q3K>; break;
+  }
+  g_launch_count++;
+  kern<<<g_sm_count, kMegaThreads, s->mega_smem, st>>>(s->prog, s_begin, s_end, from_argmax);
+  return cudaGetLastError();
+}
+
+// stages [b, e): one resident grid (ENG_MEGA) or one launch per stage (ENG_STAGE); multi-GPU cuts at the all-reduce points
+static int run_stages(dsk_model* m, dsk_state* s, int b, int e, int from_argmax, cudaStream_t st) {
+  const dsk_config& c = m->c;
+  int cur = b;
+  auto flush = [&](int upto) -> int {
+    if (g_engine == ENG_STAGE) { for (int i = cur; i < upto; i++) CKL(launch_decode(m, s, i, i + 1, from_argmax, st)); }
+    else CKL(launch_decode(m, s, cur, upto, from_argmax, st));
+    cur = upto;
+    return 0;
+  };
+  for (int cut : s->cut_after) {
+    if (cut < b || cut >= e) continue;
+    if (flush(cut + 1)) return -2;
+    if (!m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
+    CKN(g_nccl.AllReduce(s->partial, s->partial, c.dim, ncclFloat, ncclSum, m->comm, st));
+    add_vec_kernel<<<cdiv(c.dim, 256), 256, 0, st>>>(s->x, s->partial, c.dim);
+    g_launch_count += 2;
+    CKL(cudaGetLastError());
+  }
+  return flush(e);
+}
+
 static int enqueue_embed(dsk_model* m, dsk_state* s, int from_argmax, cudaStream_t st) {
   const dsk_config& c = m->c;
   EmbedArgs e{};
@@ -867,6 +1148,8 @@ static int enqueue_embed(dsk_model* m, dsk_state* s, int from_argmax, cudaStream
 // Model::_forward_cpu (src/infer.cpp:1265-1317) as one launch sequence
 static int enqueue_forward(dsk_model* m, dsk_state* s, int mode, int from_argmax, cudaStream_t st) {
   const dsk_config& c = m->c;
+  if (g_engine != ENG_V2 && !g_prof)
+    return run_stages(m, s, 0, mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - 1 : s->n_stages, from_argmax, st);
   if (enqueue_embed(m, s, from_argmax, st)) return -2;
   for (int l = 0; l < c.n_layers; l++)
     if (enqueue_layer(m, s, l, st)) return -2;
@@ -935,7 +1218,8 @@ extern "C" int dsk_copy_embedding(dsk_model* m, dsk_state* s, int token) {
   if (!m || !s) return fail(-1, "null model/state");
   fill_ctrl(s->h_ctrl, m->c, token, 0);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  if (enqueue_embed(m, s, 0, s->stream)) return -2;
+  if (g_engine != ENG_V2) { if (run_stages(m, s, 0, 1, 0, s->stream)) return -2; }
+  else if (enqueue_embed(m, s, 0, s->stream)) return -2;
   CK(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -947,7 +1231,8 @@ extern "C" int dsk_block_forward(dsk_model* m, dsk_state* s, int layer, int pos,
   Ctrl* h = s->h_ctrl;
   h->token = 0; h->pos = pos; h->kv_sink = kv_sink; h->kv_pos = kv_pos; h->kv_len = kv_len; h->argmax_key = 0;
   CK(cudaMemcpyAsync(s->ctrl, h, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  if (enqueue_layer(m, s, layer, s->stream)) return -2;
+  if (g_engine != ENG_V2) { if (run_stages(m, s, s->layer_begin[layer], s->layer_end[layer], 0, s->stream)) return -2; }
+  else if (enqueue_layer(m, s, layer, s->stream)) return -2;
   CK(cudaStreamSynchronize(s->stream));
   return 0;
 }
@@ -978,6 +1263,11 @@ extern "C" int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int 
 extern "C" int dsk_launches_per_forward(const dsk_model* m, int mode) {
   if (!m) return 0;
   const dsk_config& c = m->c;
+  if (g_engine == ENG_MEGA) {
+    int cuts = 0;
+    if (m->n_ranks > 1) for (int l = 0; l < c.n_layers; l++) cuts += m->layers[l].is_moe ? 1 : 0;
+    return 1 + cuts * 3;
+  }
   int n = 1;  // embed
   for (int l = 0; l < c.n_layers; l++) {
     n += 4 + (c.q_lora_rank > 0 ? 1 : 0);

@@ -1,0 +1,970 @@
+// dsk_mega.cuh — the persistent decode interpreter ("one resident grid runs the whole token").
+//
+// A token is a PROGRAM: an array of Stage descriptors in device memory (built once per dsk_state).  Stages are the
+// dependent phases of Model::_forward_cpu / Block::_block_cpu / BlockMHA::_attention_impl
+// (/root/reference/src/infer.cpp:810-1049, 1265-1317):
+//     EMBED | per layer: S1 q(+q_a)+kv_a | [S1b wq_b] | S2 kv_b->KV cache | S3 rope+attention | S4 wo+residual |
+//     S5 gate logits | S56 routing + shared/routed w1,w3 with act(h1)*h3 | S7 w2 + weighted accumulate | LM head+argmax
+// decode_kernel<Q> executes stages [s_begin, s_end) with ONE CTA per SM:
+//   * warp 8 is the TMA producer: it walks this CTA's tiles of the current stage — and runs ahead into the NEXT
+//     stage's static weights — issuing cp.async.bulk copies (weight rows + their f8 scale row) into a ring of
+//     shared-memory slots guarded by full/empty mbarriers.  Only routed-expert tiles wait for the routing.
+//   * warps 0-7 are consumers: at stage start they pass the grid barrier, stage the activation vector (RMSNorm /
+//     bit-exact Q8_K fused), compute the routing if the stage needs it, then reduce tiles straight out of shared
+//     memory (warp task = R rows x one column piece), combine pieces in a fixed order and run the epilogue.
+//   * stages are separated by a grid barrier (one release-add + acquire-spin on a monotonically increasing
+//     counter); launched one stage at a time (s_end = s_begin+1) the same code needs no barrier — the fallback mode.
+// HBM traffic is the algorithmic weight bytes only; every byte crosses global->shared exactly once via TMA.
+#pragma once
+
+#include "dsk_kernels.cuh"
+
+namespace dsk {
+
+enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3 };
+
+constexpr int kConsumers = 256;            // warps 0..7
+constexpr int kMegaThreads = 288;          // + producer warp 8
+constexpr int kSlotScale = 2048;           // bytes reserved per ring slot for f8 scale rows
+constexpr int kSlotData = 32 * 1024;       // weight bytes per ring slot
+constexpr int kSlotBytes = kSlotScale + kSlotData;
+constexpr int kMaxSlots = 6;
+constexpr int kMaxPieces = 24;
+constexpr int kMegaHdr = 4096;             // barriers, scratch, piece table, partial results
+
+struct MJob {                              // one weight matrix of a GEMV stage
+  const uint8_t* w; const float* scale;
+  const uint8_t* w_b; const float* scale_b;  // EPI_GLU: the `up` matrix
+  float* out;
+  long long w_stride, s_stride;            // per-expert strides (bytes / floats)
+  int rows, expert_slot, tile_begin, pad;
+};
+
+struct Piece { int seg, g0, g1, pad; };    // column piece: granules [g0,g1) of segment `seg` (granule = 16 B or a 256-block)
+
+struct Stage {
+  int kind, quant, epi, njobs;
+  int n, rows_per_tile, rpass, ntiles;
+  int need_topk, npieces, layer, has_dyn;
+  const float* in; const float* norm_w;
+  MJob job[kMaxJobs];
+  Piece piece[kMaxPieces];
+  // ST_GEMV extras
+  __half* kcache; __half* vcache;          // EPI_KVB / ST_ATTN
+  float* gate_logits; const float* gate_bias;
+  // ST_DOWN
+  const uint8_t* w2; const float* s2; long long w2_stride, s2_stride;
+  const uint8_t* sw2; const float* ss2;
+  int K, mi, sh, add_shared;
+  int seg_stride;                          // bytes between segments inside a ring slot (ST_DOWN)
+  int pad2[3];
+};
+
+struct Program {
+  // model constants
+  int dim, n_heads, hd, nope, rope, vh, kv_lora, is_v3;
+  int bs0, bs1, act_silu, max_seq;
+  int E, K, norm_topk_prob, sigmoid, topk_method, n_group, topk_group, original_max;
+  float eps, routed_scale;
+  int expert_first, expert_count;
+  int embed_quant, n_stages;
+  // buffers
+  const uint8_t* embed_w; const float* embed_scale;
+  const float* rope_freq;
+  float *x, *q, *q_a, *kv_a, *kv_b, *xb2, *hbk, *hbs, *moe_logits, *moe_scores, *act_w, *logits, *partial, *att_scratch;
+  int* act;
+  Ctrl* ctrl;
+  unsigned int* sync_counter;              // grid barrier arrivals (monotonic)
+  unsigned int* sync_base;                 // value of the counter when this launch started
+  int* token_log; int* step;
+  int n_slots, xregion_bytes;
+  Stage stage[1];                          // n_stages entries follow
+};
+
+// ---- consumer-only synchronisation (the producer warp never joins) ---------------------------------------------
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float csum(float v, float* red) {
+  v = warp_sum(v);
+  csync();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  csync();
+  float t = red[0] + red[1] + red[2] + red[3] + red[4] + red[5] + red[6] + red[7];
+  return t;
+}
+__device__ __forceinline__ float cmax(float v, float* red) {
+  v = warp_max(v);
+  csync();
+  if ((threadIdx.x & 31) == 0) red[8 + (threadIdx.x >> 5)] = v;
+  csync();
+  float t = fmaxf(fmaxf(fmaxf(red[8], red[9]), fmaxf(red[10], red[11])), fmaxf(fmaxf(red[12], red[13]), fmaxf(red[14], red[15])));
+  return t;
+}
+// bounded spin: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned long long spins = 0; !ok; spins++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1ull << 24)) __trap();
+  }
+}
+// producer <- consumers: "inputs (and routing) of stage k are ready" as a MONOTONIC stage count in shared memory
+// (an mbarrier phase bit could alias if the consumers ever got two signals ahead of the producer's wait)
+__device__ __forceinline__ void dep_signal(uint32_t addr, int stage_count) {
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(addr), "r"(stage_count) : "memory");
+}
+__device__ __forceinline__ void dep_wait(uint32_t addr, int stage_count) {
+  int v = 0;
+  for (unsigned long long spins = 0;; spins++) {
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    if (v >= stage_count) break;
+    if (spins > (1ull << 27)) __trap();
+  }
+}
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- activation staging with consumer-only barriers -------------------------------------------------------------
+__device__ __forceinline__ float c_rms_scale(const float* __restrict__ in, int n, float eps, float* red) {
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += kConsumers) { const float v = in[i]; ss = fmaf(v, v, ss); }
+  ss = csum(ss, red);
+  return 1.0f / sqrtf(ss / (float)n + eps);
+}
+// one 256-block of quantize_row_q8_K_ref (src/quant.cpp:616-653) by one warp; v[] already scaled/normalised
+__device__ __forceinline__ void q8_block(const float (&v)[8], int b, int lane, const Q8Smem& q) {
+  float amax = 0.f, mx = 0.f;
+  int idx = 0x7fffffff;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float ax = fabsf(v[j]);
+    if (ax > amax) { amax = ax; mx = v[j]; idx = lane * 8 + j; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (oa > amax || (oa == amax && oi < idx)) { amax = oa; mx = om; idx = oi; }
+  }
+  int qv[8];
+  if (amax == 0.f) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) qv[j] = 0;
+    if (lane == 0) q.d[b] = 0.f;
+  } else {
+    const float iscale = __fdiv_rn(-127.f, mx);
+#pragma unroll
+    for (int j = 0; j < 8; j++) qv[j] = min(127, __float2int_rn(__fmul_rn(iscale, v[j])));
+    if (lane == 0) q.d[b] = __fmul_rn(mx, -1.0f / 127.0f);
+  }
+  int s = qv[0] + qv[1] + qv[2] + qv[3] + qv[4] + qv[5] + qv[6] + qv[7];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if ((lane & 1) == 0) q.bsums[b * 16 + (lane >> 1)] = (short)s;
+  const uint32_t p0 = (qv[0] & 0xff) | ((qv[1] & 0xff) << 8) | ((qv[2] & 0xff) << 16) | ((uint32_t)(qv[3] & 0xff) << 24);
+  const uint32_t p1 = (qv[4] & 0xff) | ((qv[5] & 0xff) << 8) | ((qv[6] & 0xff) << 16) | ((uint32_t)(qv[7] & 0xff) << 24);
+  *reinterpret_cast<uint2*>(q.qs + (b << 8) + lane * 8) = make_uint2(p0, p1);
+}
+template <bool KQ>
+__device__ __forceinline__ void c_stage_vec(const float* __restrict__ in, int n, const float* __restrict__ norm_w, float sc,
+                                            float* xs, const Q8Smem& q8) {
+  if constexpr (KQ) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = warp; b < (n >> 8); b += 8) {
+      const int base = (b << 8) + lane * 8;
+      const float4 a0 = *reinterpret_cast<const float4*>(in + base);
+      const float4 a1 = *reinterpret_cast<const float4*>(in + base + 4);
+      float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      if (norm_w) {
+        const float4 w0 = *reinterpret_cast<const float4*>(norm_w + base);
+        const float4 w1 = *reinterpret_cast<const float4*>(norm_w + base + 4);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __fmul_rn(__fmul_rn(v[j], sc), ww[j]);
+      }
+      q8_block(v, b, lane, q8);
+    }
+  } else {
+    if (norm_w) { for (int i = threadIdx.x; i < n; i += kConsumers) xs[i] = __fmul_rn(__fmul_rn(in[i], sc), norm_w[i]); }
+    else { for (int i = threadIdx.x * 4; i < n; i += kConsumers * 4) *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(in + i); }
+  }
+}
+
+// ---- dots over a column piece, weights and f8 scale row both in shared memory -----------------------------------
+template <int Q, int NACC>
+__device__ __forceinline__ void piece_dot_dense(const uint32_t (&wa)[NACC], const uint32_t (&ssm)[NACC], int bs1, int g0, int g1,
+                                                uint32_t xs, int lane, float (&acc)[NACC]) {
+  constexpr int EPC = QTraits<Q>::epc;
+#pragma unroll 2
+  for (int c = g0 + lane; c < g1; c += 32) {
+    float xv[EPC];
+#pragma unroll
+    for (int q = 0; q < EPC / 4; q++) {
+      const uint4 t = lds128(xs + (uint32_t)(c * EPC + q * 4) * 4u);
+      xv[4 * q] = __uint_as_float(t.x); xv[4 * q + 1] = __uint_as_float(t.y);
+      xv[4 * q + 2] = __uint_as_float(t.z); xv[4 * q + 3] = __uint_as_float(t.w);
+    }
+    const uint32_t sidx = (uint32_t)((c * EPC) / bs1) * 4u;
+#pragma unroll
+    for (int r = 0; r < NACC; r++) {
+      const uint4 wv = lds128(wa[r] + (uint32_t)c * 16u);
+      const float p = chunk_dot<Q>(wv, xv);
+      const float s = ssm[r] ? __uint_as_float(lds32(ssm[r] + sidx)) : 1.0f;
+      acc[r] = fmaf(p, s, acc[r]);
+    }
+  }
+}
+// K-quant rows over blocks [b0,b1): same arithmetic as dot_q2k/dot_q3k, block range instead of whole row
+template <int Q>
+__device__ __forceinline__ float piece_dot_kq(uint32_t wrow, int b0, int b1, const Q8Smem& q8, int lane) {
+  float acc = 0.f;
+  const int q0 = b0 * 4, q1 = b1 * 4;
+  for (int base = q0; base < q1; base += 32) {
+    const int qb = base + lane;
+    const bool act = qb < q1;
+    const int b = qb >> 2, h = (qb >> 1) & 1, c = qb & 1;
+    int isum = 0, summs = 0;
+    if constexpr (Q == Q_Q2K) {
+      const uint32_t blk = wrow + (uint32_t)b * kQ2Bytes;
+      if (act) {
+        const uint32_t qp = blk + 16 + 32 * h + 16 * c;
+        const uint32_t w0 = lds32(qp), w1 = lds32(qp + 4), w2 = lds32(qp + 8), w3 = lds32(qp + 12);
+        const uint32_t sA = lds32(blk + 8 * h), sB = lds32(blk + 8 * h + 4);
+        const int8_t* y = q8.qs + b * 256 + 128 * h + 16 * c;
+        const short* bs = q8.bsums + b * 16 + 8 * h + c;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int4 yv = *reinterpret_cast<const int4*>(y + 32 * s);
+          int dp = __dp4a((int)((w0 >> (2 * s)) & 0x03030303u), yv.x, 0);
+          dp = __dp4a((int)((w1 >> (2 * s)) & 0x03030303u), yv.y, dp);
+          dp = __dp4a((int)((w2 >> (2 * s)) & 0x03030303u), yv.z, dp);
+          dp = __dp4a((int)((w3 >> (2 * s)) & 0x03030303u), yv.w, dp);
+          const uint32_t sw = (s < 2) ? sA : sB;
+          const int sc = (sw >> (8 * ((2 * s + c) & 3))) & 0xff;
+          isum += (sc & 0xF) * dp;
+          summs += (sc >> 4) * (int)bs[2 * s];
+        }
+      }
+      isum += __shfl_xor_sync(0xffffffffu, isum, 1);
+      isum += __shfl_xor_sync(0xffffffffu, isum, 2);
+      summs += __shfl_xor_sync(0xffffffffu, summs, 1);
+      summs += __shfl_xor_sync(0xffffffffu, summs, 2);
+      if (act && (lane & 3) == 0) {
+        const uint32_t dm = lds32(blk + 80);
+        const float yd = q8.d[b];
+        acc += (yd * h2f((uint16_t)(dm & 0xffff))) * (float)isum - (yd * h2f((uint16_t)(dm >> 16))) * (float)summs;
+      }
+    } else {
+      const uint32_t blk = wrow + (uint32_t)b * kQ3Bytes;
+      if (act) {
+        const uint4 hm = lds128(blk + 16 * c);
+        const uint4 qq = lds128(blk + 32 + 32 * h + 16 * c);
+        const uint32_t s0 = lds32(blk + 96), s1 = lds32(blk + 100), s2 = lds32(blk + 104);
+        const int8_t* y = q8.qs + b * 256 + 128 * h + 16 * c;
+        const short* bs = q8.bsums + b * 16 + 8 * h + c;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          const int bit = 4 * h + s;
+          const int4 yv = *reinterpret_cast<const int4*>(y + 32 * s);
+          int dp = __dp4a((int)(((qq.x >> (2 * s)) & 0x03030303u) | (((hm.x >> bit) & 0x01010101u) << 2)), yv.x, 0);
+          dp = __dp4a((int)(((qq.y >> (2 * s)) & 0x03030303u) | (((hm.y >> bit) & 0x01010101u) << 2)), yv.y, dp);
+          dp = __dp4a((int)(((qq.z >> (2 * s)) & 0x03030303u) | (((hm.z >> bit) & 0x01010101u) << 2)), yv.z, dp);
+          dp = __dp4a((int)(((qq.w >> (2 * s)) & 0x03030303u) | (((hm.w >> bit) & 0x01010101u) << 2)), yv.w, dp);
+          dp -= 4 * (int)bs[2 * s];
+          const int t = 2 * s + c;
+          const uint32_t lw = (t < 4) ? s0 : s1;
+          const int lob = (lw >> (8 * (t & 3))) & 0xff;
+          const int lo4 = h ? (lob >> 4) : (lob & 0xF);
+          const int hib = (s2 >> (8 * (t & 3))) & 0xff;
+          const int hi2 = (hib >> (2 * (2 * h + (t >> 2)))) & 3;
+          isum += ((lo4 | (hi2 << 4)) - 32) * dp;
+        }
+      }
+      isum += __shfl_xor_sync(0xffffffffu, isum, 1);
+      isum += __shfl_xor_sync(0xffffffffu, isum, 2);
+      if (act && (lane & 3) == 0) {
+        const uint32_t dw = lds32(blk + 108);
+        acc += (h2f((uint16_t)(dw & 0xffff)) * q8.d[b]) * (float)isum;
+      }
+    }
+  }
+  return acc;
+}
+
+// NACC rows x one piece -> NACC warp-reduced partial dots
+template <int Q, int NACC>
+__device__ __forceinline__ void piece_rows(const uint32_t (&wa)[NACC], const uint32_t (&ssm)[NACC], int bs1, int g0, int g1,
+                                           uint32_t xs, const Q8Smem& q8, int lane, float (&out)[NACC]) {
+#pragma unroll
+  for (int r = 0; r < NACC; r++) out[r] = 0.f;
+  if constexpr (QTraits<Q>::kq) {
+#pragma unroll
+    for (int r = 0; r < NACC; r++) out[r] = piece_dot_kq<Q>(wa[r], g0, g1, q8, lane);
+  } else {
+    piece_dot_dense<Q, NACC>(wa, ssm, bs1, g0, g1, xs, lane, out);
+  }
+#pragma unroll
+  for (int r = 0; r < NACC; r++) out[r] = warp_sum(out[r]);
+}
+
+// ---- shared-memory map of the interpreter -----------------------------------------------------------------------
+struct MegaSmem {
+  uint32_t full[kMaxSlots], empty[kMaxSlots], dep;   // shared addresses of the mbarriers
+  float* red;          // 32 floats
+  int* act; float* actw;   // routing (K <= 16)
+  float* res;          // 2 x 512 partial results
+  float* sx;           // 256 gate scores
+  unsigned char* mask; // 256
+  int* sel;            // 16
+  unsigned char* xregion;
+  uint32_t ring;       // shared address of slot 0
+};
+__device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_bytes) {
+  MegaSmem m;
+  const uint32_t b = smem_u32(smem);
+  for (int i = 0; i < kMaxSlots; i++) { m.full[i] = b + 8 * i; m.empty[i] = b + 64 + 8 * i; }
+  m.dep = b + 128;
+  m.red = reinterpret_cast<float*>(smem + 192);            // 32 floats -> 320
+  m.act = reinterpret_cast<int*>(smem + 320);              // 16 ints -> 384
+  m.actw = reinterpret_cast<float*>(smem + 384);           // 16 floats -> 448
+  m.sel = reinterpret_cast<int*>(smem + 448);              // 16 ints -> 512
+  m.mask = smem + 512;                                     // 256 B -> 768
+  m.sx = reinterpret_cast<float*>(smem + 768);             // 256 floats -> 1792
+  m.res = reinterpret_cast<float*>(smem + 1792);           // 2 x 256 floats -> 3840
+  m.xregion = smem + kMegaHdr;
+  m.ring = b + kMegaHdr + (uint32_t)xregion_bytes;
+  return m;
+}
+
+// routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599) by the 256 consumers.
+// Every CTA computes it redundantly from the gate logits; `publish` (CTA 0) also writes the state buffers.
+__device__ __forceinline__ void c_route(const Program& P, const Stage& st, const MegaSmem& sm, bool publish) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int E = P.E;
+  float v = tid < E ? st.gate_logits[tid] : -3.402823466e38f;
+  if (P.sigmoid) {
+    v = 1.0f / (1.0f + expf(-v));
+  } else {
+    const float m = cmax(v, sm.red);
+    const float e = tid < E ? expf(v - m) : 0.f;
+    const float s = csum(e, sm.red);
+    v = e / s;
+  }
+  if (st.gate_bias && tid < E) v += st.gate_bias[tid];
+  if (tid < E) sm.sx[tid] = v;
+  sm.mask[tid] = tid < E ? 0 : 1;
+  csync();
+  if (publish && tid < E) P.moe_scores[tid] = v;   // s.moe_weights() after moe_gate; NOT in place: other CTAs still read the logits
+  if (P.topk_method == 1) {
+    const int gs = E / P.n_group;
+    for (int g = warp; g < P.n_group; g += 8) {
+      for (int k = 0; k < P.topk_group; k++) {
+        float bv = 0.f; int bi = -1;
+        for (int j = g * gs + lane; j < (g + 1) * gs; j += 32)
+          if (!sm.mask[j] && sm.sx[j] > 0.0f && (bi < 0 || sm.sx[j] > bv)) { bv = sm.sx[j]; bi = j; }
+        argmax_pair(bv, bi);
+        if (lane == 0 && bi >= 0) sm.mask[bi] = 2;
+        __syncwarp();
+      }
+    }
+    csync();
+    if (tid < E) sm.mask[tid] = (sm.mask[tid] == 2) ? 0 : 1;
+    csync();
+  }
+  if (warp == 0) {
+    for (int k = 0; k < P.K; k++) {
+      float bv = 0.f; int bi = -1;
+      for (int j = lane; j < E; j += 32)
+        if (!sm.mask[j] && (bi < 0 || sm.sx[j] > bv)) { bv = sm.sx[j]; bi = j; }
+      argmax_pair(bv, bi);
+      if (lane == 0) { sm.sel[k] = bi; if (bi >= 0) sm.mask[bi] = 1; }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      float wsum = 0.f;
+      for (int k = 0; k < P.K; k++) wsum += sm.sel[k] >= 0 ? sm.sx[sm.sel[k]] : 0.f;
+      if (!P.norm_topk_prob) wsum = 1.0f;
+      for (int k = 0; k < P.K; k++) {
+        const int e = sm.sel[k];
+        const float w = e >= 0 ? sm.sx[e] / wsum * P.routed_scale : 0.f;
+        sm.act[k] = e; sm.actw[k] = w;
+        if (publish) { P.act[k] = e; P.act_w[k] = w; }
+      }
+    }
+  }
+  csync();
+}
+
+// ---- producer: one tile -> ring slot --------------------------------------------------------------------------
+// f8 scale row by TMA: source aligned down to 16 B (allocations are padded), returns the byte shift inside the slot
+__device__ __forceinline__ uint32_t scale_copy_bytes(const float* src, int nfloats, const float*& aligned_src, uint32_t& shift) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+  const uintptr_t a0 = a & ~(uintptr_t)15;
+  shift = (uint32_t)(a - a0);
+  aligned_src = reinterpret_cast<const float*>(a0);
+  return (uint32_t)align_up((size_t)shift + (size_t)nfloats * 4, 16);
+}
+
+template <int Q>
+__device__ __forceinline__ void produce_tile(const Program& P, const Stage& st, int t, uint32_t slot, uint32_t full,
+                                             const int* act_smem) {
+  if (st.kind == ST_GEMV) {
+    int j = 0;
+    while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
+    const MJob& jb = st.job[j];
+    const int r0 = (t - jb.tile_begin) * st.rows_per_tile;
+    const int nrows = min(st.rows_per_tile, jb.rows - r0);
+    const size_t rb = QTraits<Q>::row_bytes(st.n);
+    const uint32_t bytes = (uint32_t)align_up((size_t)nrows * rb, 16);
+    const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
+    const int parts = st.epi == EPI_GLU ? 2 : 1;
+    size_t woff = (size_t)r0 * rb, soff = 0;
+    if (jb.expert_slot >= 0) {
+      const int e = act_smem[jb.expert_slot] - P.expert_first;
+      if (e < 0 || e >= P.expert_count) { mbar_expect_tx(full, 0); return; }   // not on this rank: empty tile
+      woff += (size_t)e * jb.w_stride;
+      soff = (size_t)e * jb.s_stride;
+    }
+    const int ncb = (st.n + P.bs1 - 1) / P.bs1;
+    uint32_t total = bytes * parts, sbytes[2] = {0, 0}, shift;
+    const float* ssrc[2] = {nullptr, nullptr};
+    if (jb.scale) {
+      sbytes[0] = scale_copy_bytes(jb.scale + soff + (size_t)(r0 / P.bs0) * ncb, ncb, ssrc[0], shift);
+      if (parts == 2) sbytes[1] = scale_copy_bytes(jb.scale_b + soff + (size_t)(r0 / P.bs0) * ncb, ncb, ssrc[1], shift);
+      total += sbytes[0] + sbytes[1];
+    }
+    mbar_expect_tx(full, total);
+    bulk_g2s(slot + kSlotScale, jb.w + woff, bytes, full);
+    if (parts == 2) bulk_g2s(slot + kSlotScale + part_stride, jb.w_b + woff, bytes, full);
+    if (jb.scale) {
+      bulk_g2s(slot, ssrc[0], sbytes[0], full);
+      if (parts == 2) bulk_g2s(slot + kSlotScale / 2, ssrc[1], sbytes[1], full);
+    }
+  } else {  // ST_DOWN: K routed segments + the shared/dense segment of rows [i0, i0+nrows)
+    const int i0 = t * st.rows_per_tile;
+    const int nrows = min(st.rows_per_tile, P.dim - i0);
+    const size_t rb_mi = QTraits<Q>::row_bytes(st.mi), rb_sh = QTraits<Q>::row_bytes(st.sh);
+    const uint32_t b_mi = (uint32_t)align_up((size_t)nrows * rb_mi, 16), b_sh = (uint32_t)align_up((size_t)nrows * rb_sh, 16);
+    const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
+    const bool use_shared = st.sw2 != nullptr && st.add_shared;
+    uint32_t total = 0, shift;
+    const float* ssrc[kMaxJobs];
+    uint32_t sbytes[kMaxJobs];
+    int eidx[kMaxJobs];
+    for (int k = 0; k < st.K; k++) {
+      const int e = act_smem[k] - P.expert_first;
+      eidx[k] = (e >= 0 && e < P.expert_count) ? e : -1;
+      sbytes[k] = 0;
+      if (eidx[k] < 0) continue;
+      total += b_mi;
+      if (st.s2) { sbytes[k] = scale_copy_bytes(st.s2 + (size_t)e * st.s2_stride + (size_t)(i0 / P.bs0) * ncb_mi, ncb_mi, ssrc[k], shift); total += sbytes[k]; }
+    }
+    sbytes[st.K] = 0;
+    if (use_shared) {
+      total += b_sh;
+      if (st.ss2) { sbytes[st.K] = scale_copy_bytes(st.ss2 + (size_t)(i0 / P.bs0) * ncb_sh, ncb_sh, ssrc[st.K], shift); total += sbytes[st.K]; }
+    }
+    mbar_expect_tx(full, total);
+    const uint32_t sstride = kSlotScale / (uint32_t)(st.K + 1) & ~15u;
+    for (int k = 0; k < st.K; k++) {
+      if (eidx[k] < 0) continue;
+      bulk_g2s(slot + kSlotScale + (uint32_t)k * st.seg_stride, st.w2 + (size_t)eidx[k] * st.w2_stride + (size_t)i0 * rb_mi, b_mi, full);
+      if (sbytes[k]) bulk_g2s(slot + (uint32_t)k * sstride, ssrc[k], sbytes[k], full);
+    }
+    if (use_shared) {
+      bulk_g2s(slot + kSlotScale + (uint32_t)st.K * st.seg_stride, st.sw2 + (size_t)i0 * rb_sh, b_sh, full);
+      if (sbytes[st.K]) bulk_g2s(slot + (uint32_t)st.K * sstride, ssrc[st.K], sbytes[st.K], full);
+    }
+  }
+}
+
+// ---- consumers: one GEMV tile ---------------------------------------------------------------------------------
+template <int Q, int R, bool GLU>
+__device__ __forceinline__ void gemv_tile_tasks(const Program& P, const Stage& st, const MJob& jb, int r0, int nrows, uint32_t slot,
+                                                uint32_t xs, const Q8Smem& q8, float* res, int soff_floats) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t rb = (uint32_t)QTraits<Q>::row_bytes(st.n);
+  const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
+  const int csplit = st.npieces;                        // pieces of ST_GEMV are column splits of the single input
+  const int ngroups = (nrows + R - 1) / R;
+  constexpr int NACC = R * (GLU ? 2 : 1);
+  // scale rows: slot+0 (part 0) and slot+kSlotScale/2 (part 1), shifted by the source misalignment
+  uint32_t s0 = 0, s1 = 0;
+  if (jb.scale) {
+    s0 = slot + (uint32_t)soff_floats;
+    s1 = slot + kSlotScale / 2 + (uint32_t)soff_floats;
+  }
+  for (int task = warp; task < ngroups * csplit; task += 8) {
+    const int g = task / csplit, pc = task - g * csplit;
+    const Piece pcd = st.piece[pc];
+    uint32_t wa[NACC], ssm[NACC];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const int lr = min(g * R + i, nrows - 1);
+      wa[i] = slot + kSlotScale + (uint32_t)lr * rb;
+      ssm[i] = s0;
+      if constexpr (GLU) { wa[R + i] = wa[i] + part_stride; ssm[R + i] = s1; }
+    }
+    float v[NACC];
+    piece_rows<Q, NACC>(wa, ssm, P.bs1, pcd.g0, pcd.g1, xs, q8, lane, v);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < R; i++) {
+        const int lr = g * R + i;
+        if (lr < nrows) {
+          res[(lr * 2 + 0) * csplit + pc] = v[i];
+          if constexpr (GLU) res[(lr * 2 + 1) * csplit + pc] = v[R + i];
+        }
+      }
+    }
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void consume_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, uint32_t xs,
+                                                  const Q8Smem& q8, float* res, const int* act_smem, unsigned long long& best,
+                                                  bool& skip) {
+  int j = 0;
+  while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
+  const MJob& jb = st.job[j];
+  const int r0 = (t - jb.tile_begin) * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, jb.rows - r0);
+  skip = false;
+  size_t soff = 0;
+  if (jb.expert_slot >= 0) {
+    const int e = act_smem[jb.expert_slot] - P.expert_first;
+    if (e < 0 || e >= P.expert_count) { skip = true; return; }
+    soff = (size_t)e * jb.s_stride;
+  }
+  int shift_bytes = 0;
+  if (jb.scale) {
+    const int ncb = (st.n + P.bs1 - 1) / P.bs1;
+    shift_bytes = (int)(reinterpret_cast<uintptr_t>(jb.scale + soff + (size_t)(r0 / P.bs0) * ncb) & 15);
+  }
+  const bool glu = st.epi == EPI_GLU;
+  if (glu) {
+    if (st.rpass >= 2) gemv_tile_tasks<Q, 2, true>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
+    else gemv_tile_tasks<Q, 1, true>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
+  } else {
+    if (st.rpass >= 4) gemv_tile_tasks<Q, 4, false>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
+    else if (st.rpass >= 2) gemv_tile_tasks<Q, 2, false>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
+    else gemv_tile_tasks<Q, 1, false>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
+  }
+  (void)best;
+}
+
+// combine column pieces in a fixed order + epilogue, one thread per row of the tile
+__device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, unsigned long long& best) {
+  int j = 0;
+  while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
+  const MJob& jb = st.job[j];
+  const int r0 = (t - jb.tile_begin) * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, jb.rows - r0);
+  const int lr = threadIdx.x;
+  if (lr >= nrows) return;
+  const int csplit = st.npieces;
+  float v = 0.f, u = 0.f;
+  for (int pc = 0; pc < csplit; pc++) v += res[(lr * 2 + 0) * csplit + pc];
+  const int r = r0 + lr;
+  float val = v;
+  if (st.epi == EPI_GLU) {
+    for (int pc = 0; pc < csplit; pc++) u += res[(lr * 2 + 1) * csplit + pc];
+    val = (P.act_silu ? silu_f(v) : gelu_f(v)) * u;
+  }
+  switch (st.epi) {
+    case EPI_RESID: jb.out[r] = jb.out[r] + val; break;
+    case EPI_KVB: {
+      jb.out[r] = val;
+      const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
+      const int kv_pos = P.ctrl->kv_pos;
+      if (ii < P.nope) st.kcache[(size_t)kv_pos * P.n_heads * P.hd + hh * P.hd + ii] = __float2half_rn(val);
+      else st.vcache[(size_t)kv_pos * P.n_heads * P.vh + hh * P.vh + (ii - P.nope)] = __float2half_rn(val);
+      break;
+    }
+    case EPI_LOGITS: {
+      jb.out[r] = val;
+      const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+      if (key > best) best = key;
+      break;
+    }
+    default: jb.out[r] = val; break;
+  }
+}
+
+// ---- consumers: one DOWN tile (pieces = column pieces of the K routed segments + the shared segment) -----------------
+template <int Q>
+__device__ __forceinline__ void consume_down_tile(const Program& P, const Stage& st, int t, uint32_t slot, const uint32_t* xs_seg,
+                                                  const Q8Smem* q8_seg, float* res, const int* act_smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i0 = t * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, P.dim - i0);
+  const uint32_t rb_mi = (uint32_t)QTraits<Q>::row_bytes(st.mi), rb_sh = (uint32_t)QTraits<Q>::row_bytes(st.sh);
+  const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
+  const uint32_t sstride = kSlotScale / (uint32_t)(st.K + 1) & ~15u;
+  const int np = st.npieces;
+  for (int task = warp; task < nrows * np; task += 8) {
+    const int lr = task / np, pc = task - lr * np;
+    const Piece pcd = st.piece[pc];
+    const int k = pcd.seg;
+    float v[1] = {0.f};
+    bool live = true;
+    uint32_t ssm[1] = {0};
+    if (k < st.K) {
+      const int e = act_smem[k] - P.expert_first;
+      live = e >= 0 && e < P.expert_count;
+      if (live && st.s2)
+        ssm[0] = slot + (uint32_t)k * sstride + (uint32_t)(reinterpret_cast<uintptr_t>(st.s2 + (size_t)e * st.s2_stride + (size_t)(i0 / P.bs0) * ncb_mi) & 15);
+    } else {
+      live = st.sw2 != nullptr && st.add_shared;
+      if (live && st.ss2)
+        ssm[0] = slot + (uint32_t)k * sstride + (uint32_t)(reinterpret_cast<uintptr_t>(st.ss2 + (size_t)(i0 / P.bs0) * ncb_sh) & 15);
+    }
+    if (live) {
+      const uint32_t wa[1] = {slot + kSlotScale + (uint32_t)k * st.seg_stride + (uint32_t)lr * (k < st.K ? rb_mi : rb_sh)};
+      piece_rows<Q, 1>(wa, ssm, P.bs1, pcd.g0, pcd.g1, xs_seg[k], q8_seg[k], lane, v);
+    }
+    if (lane == 0) res[lr * np + pc] = v[0];
+  }
+}
+// x[i] += sum_k w_k * dot_k + dot_shared in the reference's order (src/infer.cpp:873-877, 899-903, 926-930)
+__device__ __forceinline__ void down_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, const float* actw_smem,
+                                                   const int* act_smem) {
+  const int i0 = t * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, P.dim - i0);
+  const int lr = threadIdx.x;
+  if (lr >= nrows) return;
+  const int i = i0 + lr, np = st.npieces;
+  const bool to_partial = P.partial != nullptr && st.K > 0;
+  float acc = to_partial ? 0.f : P.x[i];
+  int pc = 0;
+  for (int k = 0; k <= st.K; k++) {
+    float v = 0.f;
+    for (; pc < np && st.piece[pc].seg == k; pc++) v += res[lr * np + pc];
+    if (k < st.K) {
+      const int e = act_smem[k] - P.expert_first;
+      if (e >= 0 && e < P.expert_count) acc = fmaf(v, actw_smem[k], acc);
+    } else if (st.sw2 != nullptr && st.add_shared) {
+      acc += v;
+    }
+  }
+  if (to_partial) P.partial[i] = acc; else P.x[i] = acc;
+}
+
+// ---- attention stage (one head per CTA; body of attn_kernel with consumer-only barriers) ---------------------------
+__device__ __forceinline__ void c_attention(const Program& P, const Stage& st, const MegaSmem& sm, int h) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* stage = reinterpret_cast<float*>(sm.xregion);            // 512 floats
+  float* qs = stage + 512;
+  const Ctrl* c = P.ctrl;
+  const int pos = c->pos, kv_pos = c->kv_pos, kv_len = c->kv_len, kv_sink = c->kv_sink;
+  float* att = qs + ((P.hd + 3) & ~3);
+  const size_t need = (size_t)(512 + ((P.hd + 3) & ~3) + ((kv_len + 3) & ~3) + kConsumers) * 4;
+  if (need > (size_t)P.xregion_bytes) att = P.att_scratch + (size_t)h * (P.max_seq + kConsumers + 8);
+  float* qh = P.q + (size_t)h * P.hd;
+  const size_t kstride = (size_t)P.n_heads * P.hd, vstride = (size_t)P.n_heads * P.vh;
+  const int half_r = P.rope >> 1;
+  for (int i = tid; i < P.nope; i += kConsumers) qs[i] = qh[i];
+  if (tid < half_r) {
+    float cs, sn; rope_cs(P.rope_freq, tid, pos, cs, sn);
+    const float v0 = qh[P.nope + 2 * tid], v1 = qh[P.nope + 2 * tid + 1];
+    const float r0 = v0 * cs - v1 * sn, r1 = v0 * sn + v1 * cs;
+    if (P.is_v3) { qs[P.nope + 2 * tid] = r0; qs[P.nope + 2 * tid + 1] = r1; }
+    else { qs[P.nope + tid] = r0; qs[P.nope + tid + half_r] = r1; }
+  } else if (tid >= 64 && tid < 64 + half_r) {
+    const int t = tid - 64;
+    float cs, sn; rope_cs(P.rope_freq, t, pos, cs, sn);
+    const float v0 = P.kv_a[P.kv_lora + 2 * t], v1 = P.kv_a[P.kv_lora + 2 * t + 1];
+    const float r0 = v0 * cs - v1 * sn, r1 = v0 * sn + v1 * cs;
+    __half* kr = st.kcache + (size_t)kv_pos * kstride + (size_t)h * P.hd + P.nope;
+    if (P.is_v3) { kr[2 * t] = __float2half_rn(r0); kr[2 * t + 1] = __float2half_rn(r1); }
+    else { kr[t] = __float2half_rn(r0); kr[t + half_r] = __float2half_rn(r1); }
+  } else if (tid >= 128 && tid < 128 + half_r * kv_sink && kv_sink > 0) {
+    const int t = (tid - 128) % half_r, r = (tid - 128) / half_r;
+    float cs, sn; rope_cs(P.rope_freq, t, 1, cs, sn);
+    __half* kr = st.kcache + (size_t)r * kstride + (size_t)h * P.hd + P.nope;
+    const float v0 = __half2float(kr[2 * t]), v1 = __half2float(kr[2 * t + 1]);
+    stage[2 * (r * half_r + t)] = v0 * cs - v1 * sn;
+    stage[2 * (r * half_r + t) + 1] = v0 * sn + v1 * cs;
+  }
+  csync();
+  if (tid >= 128 && tid < 128 + half_r * kv_sink && kv_sink > 0) {
+    const int t = (tid - 128) % half_r, r = (tid - 128) / half_r;
+    __half* kr = st.kcache + (size_t)r * kstride + (size_t)h * P.hd + P.nope;
+    const float r0 = stage[2 * (r * half_r + t)], r1 = stage[2 * (r * half_r + t) + 1];
+    if (P.is_v3) { kr[2 * t] = __float2half_rn(r0); kr[2 * t + 1] = __float2half_rn(r1); }
+    else { kr[t] = __float2half_rn(r0); kr[t + half_r] = __float2half_rn(r1); }
+  }
+  if (tid < P.rope) qh[P.nope + tid] = qs[P.nope + tid];
+  csync();
+  const float inv = sqrtf((float)P.hd);
+  for (int t = warp; t < kv_len; t += 8) {
+    const __half* kr = st.kcache + (size_t)t * kstride + (size_t)h * P.hd;
+    float s = 0.f;
+    for (int i = lane * 2; i < P.hd; i += 64) {
+      const float2 kk = __half22float2(*reinterpret_cast<const __half2*>(kr + i));
+      s = fmaf(qs[i], kk.x, s);
+      s = fmaf(qs[i + 1], kk.y, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) att[t] = s / inv;
+  }
+  csync();
+  float m = -3.402823466e38f;
+  for (int t = tid; t < kv_len; t += kConsumers) m = fmaxf(m, att[t]);
+  m = cmax(m, sm.red);
+  float sum = 0.f;
+  for (int t = tid; t < kv_len; t += kConsumers) { const float e = expf(att[t] - m); att[t] = e; sum += e; }
+  sum = csum(sum, sm.red);
+  for (int t = tid; t < kv_len; t += kConsumers) att[t] = att[t] / sum;
+  csync();
+  float* part = att + ((kv_len + 3) & ~3);
+  if (P.vh <= kConsumers) {
+    const int groups = kConsumers / P.vh;
+    const int i = tid % P.vh, g = tid / P.vh;
+    float acc = 0.f;
+    if (g < groups) {
+      const __half* vb = st.vcache + (size_t)h * P.vh + i;
+      for (int t = g; t < kv_len; t += groups) acc = fmaf(att[t], __half2float(vb[(size_t)t * vstride]), acc);
+      part[g * P.vh + i] = acc;
+    }
+    csync();
+    if (tid < P.vh) {
+      float o = 0.f;
+      for (int g2 = 0; g2 < groups; g2++) o += part[g2 * P.vh + tid];
+      P.xb2[(size_t)h * P.vh + tid] = o;
+    }
+  } else {
+    for (int i = tid; i < P.vh; i += kConsumers) {
+      const __half* vb = st.vcache + (size_t)h * P.vh + i;
+      float acc = 0.f;
+      for (int t = 0; t < kv_len; t++) acc = fmaf(att[t], __half2float(vb[(size_t)t * vstride]), acc);
+      P.xb2[(size_t)h * P.vh + i] = acc;
+    }
+  }
+  csync();
+}
+
+// ---- embedding stage (CTA 0): token feed + step counters + dequantised row (body of embed_kernel) ------------------
+__device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* s_token) {
+  if (threadIdx.x == 0) {
+    Ctrl* c = P.ctrl;
+    int token = c->token;
+    if (from_argmax) {
+      token = (int)(0xFFFFFFFFu - (unsigned)(c->argmax_key & 0xFFFFFFFFull));
+      const int pos = c->pos + 1;
+      const int sink = pos >= P.original_max ? 2 : 0;
+      c->token = token; c->pos = pos; c->kv_sink = sink;
+      c->kv_pos = sink + (pos - sink) % (P.original_max - sink);
+      c->kv_len = pos >= P.original_max ? P.original_max : pos + 1;
+      if (P.token_log && P.step) { P.token_log[*P.step] = token; *P.step = *P.step + 1; }
+    }
+    c->argmax_key = 0ull;
+    *s_token = token;
+  }
+  csync();
+  const int token = *s_token, dim = P.dim;
+  const uint8_t* table = P.embed_w;
+  for (int i = threadIdx.x; i < dim; i += kConsumers) {
+    float val;
+    switch (P.embed_quant) {
+      case Q_F32: val = reinterpret_cast<const float*>(table)[(size_t)token * dim + i]; break;
+      case Q_F16: val = __half2float(reinterpret_cast<const __half*>(table)[(size_t)token * dim + i]); break;
+      case Q_F8: {
+        const int ncb = (dim + P.bs1 - 1) / P.bs1;
+        val = h2f((uint16_t)((uint16_t)table[(size_t)token * dim + i] << 8)) * P.embed_scale[(size_t)(token / P.bs0) * ncb + i / P.bs1];
+        break;
+      }
+      case Q_Q2K: {
+        const int nb = dim >> 8, b = i >> 8, w = i & 255, hh = w >> 7, s = (w >> 5) & 3, l = w & 31;
+        const uint8_t* blk = table + ((size_t)token * nb + b) * kQ2Bytes;
+        const int sc = blk[8 * hh + 2 * s + (l >> 4)];
+        const int qv = (blk[16 + 32 * hh + l] >> (2 * s)) & 3;
+        val = (h2f(*reinterpret_cast<const uint16_t*>(blk + 80)) * (float)(sc & 0xF)) * (float)qv -
+              h2f(*reinterpret_cast<const uint16_t*>(blk + 82)) * (float)(sc >> 4);
+        break;
+      }
+      default: {
+        const int nb = dim >> 8, b = i >> 8, w = i & 255, hh = w >> 7, s = (w >> 5) & 3, l = w & 31;
+        const uint8_t* blk = table + ((size_t)token * nb + b) * kQ3Bytes;
+        const int j = 8 * hh + 2 * s + (l >> 4);
+        const int lob = blk[96 + (j & 7)];
+        const int lo4 = j < 8 ? (lob & 0xF) : (lob >> 4);
+        const int hi2 = (blk[96 + 8 + (j & 3)] >> (2 * (j >> 2))) & 3;
+        const int hb = (blk[l] >> (4 * hh + s)) & 1;
+        const int qv = ((blk[32 + 32 * hh + l] >> (2 * s)) & 3) - (hb ? 0 : 4);
+        val = (h2f(*reinterpret_cast<const uint16_t*>(blk + 108)) * (float)((lo4 | (hi2 << 4)) - 32)) * (float)qv;
+        break;
+      }
+    }
+    P.x[i] = val;
+  }
+}
+
+// ---- per-stage bodies ------------------------------------------------------------------------------------------
+template <int Q>
+__device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
+                                               unsigned long long& best_key, int dep_count) {
+  constexpr bool KQ = QTraits<Q>::kq;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= st.ntiles) {   // no tile of this stage lands on this CTA: nothing to stage
+    if (tid == 0) dep_signal(sm.dep, dep_count);
+    return;
+  }
+  if (st.need_topk) c_route(P, st, sm, blockIdx.x == 0);
+  else if (st.kind == ST_DOWN && st.K > 0) {          // routing published by CTA 0 of the experts stage
+    if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
+    csync();
+  }
+  // activation vector(s) -> shared memory
+  float* xs0 = nullptr;
+  Q8Smem q80{};
+  uint32_t xs_seg[kMaxJobs];
+  Q8Smem q8_seg[kMaxJobs];
+  if (st.kind == ST_GEMV) {
+    carve_x<Q>(sm.xregion, st.n, xs0, q80);
+    float sc = 1.0f;
+    if (st.norm_w) sc = c_rms_scale(st.in, st.n, P.eps, sm.red);
+    c_stage_vec<KQ>(st.in, st.n, st.norm_w, sc, xs0, q80);
+  } else {
+    unsigned char* p = sm.xregion;
+    const bool use_shared = st.sw2 != nullptr && st.add_shared;
+    for (int k = 0; k <= st.K; k++) {
+      const int n = k < st.K ? st.mi : st.sh;
+      float* xk = nullptr;
+      carve_x<Q>(p, n, xk, q8_seg[k]);
+      xs_seg[k] = KQ ? 0u : smem_u32(xk);
+      p += n ? xvec_bytes<Q>(n) : 0;
+      bool live = n > 0;
+      if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
+      else live = live && use_shared;
+      if (live) c_stage_vec<KQ>(k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs, n, nullptr, 1.0f, xk, q8_seg[k]);
+    }
+  }
+  csync();
+  if (tid == 0) dep_signal(sm.dep, dep_count);   // routing + inputs ready
+  const uint32_t xs = KQ ? 0u : smem_u32(xs0);
+  int parity_res = 0;
+  for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
+    const int sl = it % n_slots;
+    const uint32_t slot = sm.ring + (uint32_t)sl * kSlotBytes;
+    mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+    float* res = sm.res + parity_res * 256;
+    bool skip = false;
+    if (st.kind == ST_GEMV) consume_gemv_tile<Q>(P, st, t, slot, xs, q80, res, sm.act, best_key, skip);
+    else consume_down_tile<Q>(P, st, t, slot, xs_seg, q8_seg, res, sm.act);
+    __syncwarp();
+    if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+    csync();
+    if (!skip) {
+      if (st.kind == ST_GEMV) gemv_tile_epilogue(P, st, t, res, best_key);
+      else down_tile_epilogue(P, st, t, res, sm.actw, sm.act);
+    }
+    parity_res ^= 1;
+  }
+}
+
+template <int Q>
+__device__ __forceinline__ void producer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
+                                               int dep_count) {
+  bool dep_waited = false;
+  const bool dyn_all = st.kind == ST_DOWN && st.K > 0;
+  for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
+    bool dyn = dyn_all;
+    if (st.kind == ST_GEMV && st.has_dyn) {
+      int j = 0;
+      while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
+      dyn = st.job[j].expert_slot >= 0;
+    }
+    if (dyn && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
+    const int sl = it % n_slots;
+    if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+    produce_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * kSlotBytes, sm.full[sl], sm.act);
+  }
+  if (!dep_waited) dep_wait(sm.dep, dep_count);   // bounds the run-ahead to one stage
+}
+
+// ---- the interpreter ------------------------------------------------------------------------------------------------
+template <int Q>
+__global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* __restrict__ prog, int s_begin, int s_end,
+                                                                 int from_argmax) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const Program& P = *prog;
+  const MegaSmem sm = carve_mega(smem, P.xregion_bytes);
+  const int n_slots = P.n_slots;
+  const int tid = threadIdx.x;
+  const bool producer = tid >= kConsumers;
+  __shared__ int s_token;
+  if (tid == 0) {
+    for (int i = 0; i < n_slots; i++) { mbar_init(sm.full[i], 1); mbar_init(sm.empty[i], 8); }
+    dep_signal(sm.dep, 0);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  const unsigned int base = *P.sync_base;
+  const unsigned int G = gridDim.x;
+  int it = 0;                      // tiles this CTA has pushed through the ring (same sequence on both sides)
+  unsigned long long best_key = 0ull;
+  int nstage_seen = 0;
+  for (int s = s_begin; s < s_end; s++, nstage_seen++) {
+    const Stage& st = P.stage[s];
+    const bool streams = st.kind == ST_GEMV || st.kind == ST_DOWN;
+    if (producer) {
+      if (tid == kConsumers && streams) {
+        if (st.quant == Q_F32 && Q != Q_F32) producer_stage<Q_F32>(P, st, sm, it, n_slots, nstage_seen + 1);
+        else producer_stage<Q>(P, st, sm, it, n_slots, nstage_seen + 1);
+      } else if (tid == kConsumers) {
+        dep_wait(sm.dep, nstage_seen + 1);
+      }
+      continue;
+    }
+    // ---- consumers ----
+    if (s > s_begin) {             // grid barrier: every CTA has finished (and flushed) stage s-1
+      if (tid == 0) {
+        const unsigned int target = base + (unsigned int)(s - s_begin) * G;
+        for (unsigned long long spins = 0; (int)(ld_acquire(P.sync_counter) - target) < 0; spins++) {
+          if (spins > (1ull << 23)) __trap();
+        }
+      }
+      csync();
+    }
+    if (st.kind == ST_EMBED) {
+      if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
+      if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
+    } else if (st.kind == ST_ATTN) {
+      for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
+      if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
+    } else {
+      if (st.quant == Q_F32 && Q != Q_F32) consumer_stage<Q_F32>(P, st, sm, it, n_slots, best_key, nstage_seen + 1);
+      else consumer_stage<Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1);
+      if (st.epi == EPI_LOGITS) {
+        unsigned long long b = best_key;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const unsigned long long ob = __shfl_xor_sync(0xffffffffu, b, o); if (ob > b) b = ob; }
+        if ((tid & 31) == 0 && b) atomicMax(&P.ctrl->argmax_key, b);
+        best_key = 0ull;
+      }
+    }
+    // stage done: make this CTA's writes visible, then arrive on the grid barrier
+    if (s + 1 < s_end) {
+      __threadfence();
+      csync();
+      if (tid == 0) red_release_add(P.sync_counter, 1u);
+    }
+  }
+  // last stage of the launch: publish the new barrier base for the next launch (single writer, after all arrivals)
+  if (!producer && blockIdx.x == 0 && tid == 0 && s_end - s_begin > 1) {
+    const unsigned int target = base + (unsigned int)(s_end - s_begin - 1) * G;
+    for (unsigned long long spins = 0; (int)(ld_acquire(P.sync_counter) - target) < 0; spins++) {
+      if (spins > (1ull << 23)) __trap();
+    }
+    *P.sync_base = target;
+  }
+}
+
+}  // namespace dsk
