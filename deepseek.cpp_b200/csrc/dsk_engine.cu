@@ -207,11 +207,11 @@ extern "C" int dsk_init(int device) {
       else if (!strcmp(en, "v2")) g_engine = ENG_V2;
       else g_engine = ENG_MEGA;
     }
-    CK(cudaFuncSetAttribute(decode_kernel<Q_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_Q2K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_Q3K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 64));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_Q2K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
+    CK(cudaFuncSetAttribute(decode_kernel<Q_Q3K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
     g_attrs_set = true;
   }
   return 0;
@@ -1065,7 +1065,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   const size_t attn_need = (size_t)(512 + ((hd + 3) & ~3) + ((c.max_seq_len + 3) & ~3) + kConsumers + 16) * 4;
   if (attn_need <= 64 * 1024) xreg = std::max(xreg, attn_need);
   xreg = align_up(std::max(xreg, (size_t)(512 + ((hd + 3) & ~3) + 64) * 4), 128);
-  const size_t budget = (size_t)kSmemMax - 256;
+  const size_t budget = (size_t)kSmemMax - 2048;
   if (kMegaHdr + xreg + 2 * (size_t)kSlotBytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
   int n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / kSlotBytes);
   s->mega_smem = kMegaHdr + xreg + (size_t)n_slots * kSlotBytes;
