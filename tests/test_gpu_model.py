@@ -49,7 +49,7 @@ def test_forward_teacher_forced(dsk, ckpt, preset, quant):
 
 @pytest.mark.parametrize("preset", PRESETS)
 # fp32: the reference's scalar F32 GEMV is re-associated by -ffast-math vectorisation, so its own noise is ~4e-5
-@pytest.mark.parametrize("quant,tol", [("fp32", 2e-4), ("f8e5m2", 2e-5), ("q2_k", 2e-5), ("q3_k", 2e-5)])
+@pytest.mark.parametrize("quant,tol", [("fp32", 2e-4), ("f8e5m2", 5e-5), ("q2_k", 5e-5), ("q3_k", 5e-5)])
 def test_layers_resynchronised(dsk, ckpt, preset, quant, tol):
     """T2: each layer is fed the checker's layer input AND the checker's KV cache, so a rounding flip upstream
     cannot leak in; K-quant outputs then agree to fp32 re-association unless a Q8_K rounding flips inside the
