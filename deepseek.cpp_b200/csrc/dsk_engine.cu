@@ -141,6 +141,8 @@ struct dsk_state {
   Program* prog = nullptr;              // device
   float* att_scratch = nullptr;
   unsigned int* sync_words = nullptr;   // [0] arrivals counter, [1] base
+  unsigned long long* tstamp = nullptr;
+  std::vector<std::string> stage_names;
   int n_stages = 0;
   size_t mega_smem = 0;
   std::vector<int> layer_begin, layer_end;  // stage ranges per layer
@@ -545,7 +547,7 @@ extern "C" void dsk_state_destroy(dsk_state* s) {
   for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (s->graph[a][b]) cudaGraphExecDestroy(s->graph[a][b]);
   float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->kv_a, s->kv_b, s->moe_logits, s->moe_scores, s->act_w, s->logits, s->partial};
   for (float* b : bufs) cudaFree(b);
-  cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words);
+  cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words); cudaFree(s->tstamp);
   cudaFree(s->act); cudaFree(s->ctrl); cudaFreeHost(s->h_ctrl); cudaFree(s->token_log); cudaFree(s->step);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   cudaStreamDestroy(s->stream);
@@ -1090,6 +1092,15 @@ static int build_program(dsk_model* m, dsk_state* s) {
   CK(cudaMemset(s->sync_words, 0, 64));
   P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
   P->n_slots = n_slots; P->xregion_bytes = (int)xreg;
+  CK(cudaMalloc((void**)&s->tstamp, S.size() * 4 * sizeof(unsigned long long)));
+  CK(cudaMemset(s->tstamp, 0, S.size() * 4 * sizeof(unsigned long long)));
+  P->tstamp = s->tstamp;
+  for (const Stage& st : S) {
+    char nm[96];
+    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
+    snprintf(nm, sizeof(nm), "%-8s n=%5d tiles=%5d rt=%2d r=%d pieces=%2d", kind, st.kind == ST_DOWN ? st.K * st.mi + st.sh : st.n, st.ntiles, st.rows_per_tile, st.rpass, st.npieces);
+    s->stage_names.push_back(nm);
+  }
   memcpy(P->stage, S.data(), S.size() * sizeof(Stage));
   CK(cudaMalloc((void**)&s->prog, buf.size()));
   CK(cudaMemcpy(s->prog, buf.data(), buf.size(), cudaMemcpyHostToDevice));
@@ -1514,6 +1525,37 @@ extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, i
 extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos, char* out, size_t cap) {
   if (need_device()) return -1;
   if (!m || !s || !out) return fail(-1, "bad arguments");
+  if (g_engine != ENG_V2) {
+    // stage-level timeline of the last token from the interpreter's own globaltimer stamps (CTA 0)
+    float* lg = nullptr; (void)lg;
+    if (dsk_forward(m, s, token, pos, 1, nullptr, nullptr)) return -2;
+    std::vector<unsigned long long> ts((size_t)s->n_stages * 4);
+    CK(cudaMemcpy(ts.data(), s->tstamp, ts.size() * 8, cudaMemcpyDeviceToHost));
+    struct Agg { int n = 0; double wait = 0, stage = 0, tiles = 0, arrive = 0; };
+    std::map<std::string, Agg> agg;
+    double total = 0;
+    for (int i = 0; i < s->n_stages; i++) {
+      const double t0 = (double)ts[i * 4], t1 = (double)ts[i * 4 + 1], t2 = (double)ts[i * 4 + 2], t3 = (double)ts[i * 4 + 3];
+      const double prev_end = i > 0 ? (double)ts[(i - 1) * 4 + 3] : t0;
+      Agg& a = agg[s->stage_names[i]];
+      a.n++;
+      a.wait += (t0 - prev_end) / 1e3;                      // grid barrier wait
+      a.stage += (t1 > 0 ? (t1 - t0) : 0) / 1e3;           // routing + activation staging
+      a.tiles += (t2 - (t1 > 0 ? t1 : t0)) / 1e3;          // tile loop (or attention / embed body)
+      a.arrive += (t3 - t2) / 1e3;                         // fence + arrive
+      if (i + 1 == s->n_stages) total = ((double)ts[i * 4 + 3] - (double)ts[0]) / 1e3;
+    }
+    size_t off = 0;
+    for (auto& kv : agg) {
+      const Agg& a = kv.second;
+      int n = snprintf(out + off, cap - off, "%s x%3d  barrier %6.2f  stage-in %6.2f  tiles %6.2f  fence+arrive %6.2f  (us avg)  sum %8.1f us\n",
+                       kv.first.c_str(), a.n, a.wait / a.n, a.stage / a.n, a.tiles / a.n, a.arrive / a.n, a.wait + a.stage + a.tiles + a.arrive);
+      if (n < 0 || (size_t)n >= cap - off) break;
+      off += n;
+    }
+    snprintf(out + off, cap - off, "token total %.1f us over %d stages (CTA 0 timeline)\n", total, s->n_stages);
+    return 0;
+  }
   std::vector<ProfRec> recs;
   fill_ctrl(s->h_ctrl, m->c, token, pos);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));

@@ -78,6 +78,7 @@ struct Program {
   unsigned int* sync_base;                 // value of the counter when this launch started
   int* token_log; int* step;
   int n_slots, xregion_bytes;
+  unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
   Stage stage[1];                          // n_stages entries follow
 };
 
@@ -120,6 +121,11 @@ __device__ __forceinline__ void dep_wait(uint32_t addr, int stage_count) {
     if (v >= stage_count) break;
     if (spins > (1ull << 27)) __trap();
   }
+}
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   unsigned int v;
@@ -848,6 +854,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   }
   csync();
   if (tid == 0) dep_signal(sm.dep, dep_count);   // routing + inputs ready
+  if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[(&st - P.stage) * 4 + 1] = gtime();
   const uint32_t xs = KQ ? 0u : smem_u32(xs0);
   int parity_res = 0;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
@@ -924,6 +931,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       continue;
     }
     // ---- consumers ----
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 3] = 0;
     if (s > s_begin) {             // grid barrier: every CTA has finished (and flushed) stage s-1
       if (tid == 0) {
         const unsigned int target = base + (unsigned int)(s - s_begin) * G;
@@ -933,6 +941,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       }
       csync();
     }
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 0] = gtime();
     if (st.kind == ST_EMBED) {
       if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
@@ -951,11 +960,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       }
     }
     // stage done: make this CTA's writes visible, then arrive on the grid barrier
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 2] = gtime();
     if (s + 1 < s_end) {
       __threadfence();
       csync();
       if (tid == 0) red_release_add(P.sync_counter, 1u);
     }
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 3] = gtime();
   }
   // last stage of the launch: publish the new barrier base for the next launch (single writer, after all arrivals)
   if (!producer && blockIdx.x == 0 && tid == 0 && s_end - s_begin > 1) {
