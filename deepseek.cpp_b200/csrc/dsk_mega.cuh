@@ -17,6 +17,8 @@
 // HBM traffic is the algorithmic weight bytes only; every byte crosses global->shared exactly once via TMA.
 #pragma once
 
+#include <cstddef>
+
 #include "dsk_kernels.cuh"
 
 namespace dsk {
@@ -30,7 +32,8 @@ constexpr int kSlotData = 32 * 1024;       // weight bytes per ring slot
 constexpr int kSlotBytes = kSlotScale + kSlotData;
 constexpr int kMaxSlots = 6;
 constexpr int kMaxPieces = 24;
-constexpr int kMegaHdr = 4096;             // barriers, scratch, piece table, partial results
+constexpr int kMegaHdr = 8192;             // barriers, scratch, partial results, smem copies of Program + 2 Stage descriptors
+constexpr int kStageSlot = 1536;           // bytes reserved per cached Stage descriptor
 
 struct MJob {                              // one weight matrix of a GEMV stage
   const uint8_t* w; const float* scale;
@@ -60,6 +63,9 @@ struct Stage {
   int pad2[3];
 };
 
+static_assert(sizeof(Stage) <= kStageSlot, "Stage descriptor must fit its shared-memory cache slot");
+static_assert(sizeof(Stage) % 16 == 0, "Stage is copied in 16-byte words");
+
 struct Program {
   // model constants
   int dim, n_heads, hd, nope, rope, vh, kv_lora, is_v3;
@@ -79,8 +85,11 @@ struct Program {
   int* token_log; int* step;
   int n_slots, xregion_bytes;
   unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
+  long long pad_to16;
   Stage stage[1];                          // n_stages entries follow
 };
+constexpr int kProgHdrBytes = (int)offsetof(Program, stage);
+static_assert(kProgHdrBytes <= 1024 && kProgHdrBytes % 16 == 0, "Program header is cached in 1 KB of shared memory");
 
 // ---- consumer-only synchronisation (the producer warp never joins) ---------------------------------------------
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -330,6 +339,9 @@ struct MegaSmem {
   int* sel;            // 16
   unsigned char* xregion;
   uint32_t ring;       // shared address of slot 0
+  Stage* st_c;         // consumers' copy of the current stage descriptor
+  Stage* st_p;         // producer's copy (it may be one stage ahead)
+  Program* prog;       // header copy (no stage array)
 };
 __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_bytes) {
   MegaSmem m;
@@ -343,68 +355,89 @@ __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_
   m.mask = smem + 512;                                     // 256 B -> 768
   m.sx = reinterpret_cast<float*>(smem + 768);             // 256 floats -> 1792
   m.res = reinterpret_cast<float*>(smem + 1792);           // 2 x 256 floats -> 3840
+  m.st_c = reinterpret_cast<Stage*>(smem + 4096);
+  m.st_p = reinterpret_cast<Stage*>(smem + 4096 + kStageSlot);
+  m.prog = reinterpret_cast<Program*>(smem + 4096 + 2 * kStageSlot);
   m.xregion = smem + kMegaHdr;
   m.ring = b + kMegaHdr + (uint32_t)xregion_bytes;
   return m;
 }
 
-// routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599) by the 256 consumers.
-// Every CTA computes it redundantly from the gate logits; `publish` (CTA 0) also writes the state buffers.
-__device__ __forceinline__ void c_route(const Program& P, const Stage& st, const MegaSmem& sm, bool publish) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599) by ONE warp with the
+// E <= 256 scores in registers (lane holds experts lane, lane+32, ...).  Every CTA computes it redundantly from the gate
+// logits; `publish` (CTA 0) also writes the state buffers.  Ties: lowest index (the reference's strict `>` scans).
+__device__ __forceinline__ void warp_route(const Program& P, const Stage& st, const MegaSmem& sm, bool publish) {
+  const int lane = threadIdx.x & 31;
   const int E = P.E;
-  float v = tid < E ? st.gate_logits[tid] : -3.402823466e38f;
-  if (P.sigmoid) {
-    v = 1.0f / (1.0f + expf(-v));
-  } else {
-    const float m = cmax(v, sm.red);
-    const float e = tid < E ? expf(v - m) : 0.f;
-    const float s = csum(e, sm.red);
-    v = e / s;
+  float v[8];
+  unsigned mask = 0;   // bit i set = expert lane+32*i not selectable
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int j = lane + 32 * i;
+    v[i] = j < E ? st.gate_logits[j] : -3.402823466e38f;
+    if (j >= E) mask |= 1u << i;
   }
-  if (st.gate_bias && tid < E) v += st.gate_bias[tid];
-  if (tid < E) sm.sx[tid] = v;
-  sm.mask[tid] = tid < E ? 0 : 1;
-  csync();
-  if (publish && tid < E) P.moe_scores[tid] = v;   // s.moe_weights() after moe_gate; NOT in place: other CTAs still read the logits
-  if (P.topk_method == 1) {
+  if (P.sigmoid) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = 1.0f / (1.0f + expf(-v[i]));
+  } else {
+    float mx = v[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) mx = fmaxf(mx, v[i]);
+    mx = warp_max(mx);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { v[i] = (lane + 32 * i) < E ? expf(v[i] - mx) : 0.f; s += v[i]; }
+    s = warp_sum(s);
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = v[i] / s;
+  }
+  if (st.gate_bias) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) if ((lane + 32 * i) < E) v[i] += st.gate_bias[lane + 32 * i];
+  }
+  if (publish) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) if ((lane + 32 * i) < E) P.moe_scores[lane + 32 * i] = v[i];
+  }
+  if (P.topk_method == 1) {   // keep only the topk_group best (positive) experts of every group
     const int gs = E / P.n_group;
-    for (int g = warp; g < P.n_group; g += 8) {
+    unsigned cand = 0;
+    for (int g = 0; g < P.n_group; g++) {
       for (int k = 0; k < P.topk_group; k++) {
         float bv = 0.f; int bi = -1;
-        for (int j = g * gs + lane; j < (g + 1) * gs; j += 32)
-          if (!sm.mask[j] && sm.sx[j] > 0.0f && (bi < 0 || sm.sx[j] > bv)) { bv = sm.sx[j]; bi = j; }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int j = lane + 32 * i;
+          if (j >= g * gs && j < (g + 1) * gs && !((mask | cand) >> i & 1u) && v[i] > 0.0f && (bi < 0 || v[i] > bv)) { bv = v[i]; bi = j; }
+        }
         argmax_pair(bv, bi);
-        if (lane == 0 && bi >= 0) sm.mask[bi] = 2;
-        __syncwarp();
+        if (bi >= 0 && (bi & 31) == lane) cand |= 1u << (bi >> 5);
       }
     }
-    csync();
-    if (tid < E) sm.mask[tid] = (sm.mask[tid] == 2) ? 0 : 1;
-    csync();
+    mask |= ~cand & 0xffu;
   }
-  if (warp == 0) {
-    for (int k = 0; k < P.K; k++) {
-      float bv = 0.f; int bi = -1;
-      for (int j = lane; j < E; j += 32)
-        if (!sm.mask[j] && (bi < 0 || sm.sx[j] > bv)) { bv = sm.sx[j]; bi = j; }
-      argmax_pair(bv, bi);
-      if (lane == 0) { sm.sel[k] = bi; if (bi >= 0) sm.mask[bi] = 1; }
-      __syncwarp();
+  float wsum = 0.f;
+  float myw = 0.f; int mye = -1;   // lane k keeps selection k
+  for (int k = 0; k < P.K; k++) {
+    float bv = 0.f; int bi = -1;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int j = lane + 32 * i;
+      if (!((mask >> i) & 1u) && (bi < 0 || v[i] > bv)) { bv = v[i]; bi = j; }
     }
-    if (lane == 0) {
-      float wsum = 0.f;
-      for (int k = 0; k < P.K; k++) wsum += sm.sel[k] >= 0 ? sm.sx[sm.sel[k]] : 0.f;
-      if (!P.norm_topk_prob) wsum = 1.0f;
-      for (int k = 0; k < P.K; k++) {
-        const int e = sm.sel[k];
-        const float w = e >= 0 ? sm.sx[e] / wsum * P.routed_scale : 0.f;
-        sm.act[k] = e; sm.actw[k] = w;
-        if (publish) { P.act[k] = e; P.act_w[k] = w; }
-      }
-    }
+    argmax_pair(bv, bi);
+    if (bi >= 0 && (bi & 31) == lane) mask |= 1u << (bi >> 5);
+    if (bi >= 0) wsum += bv;
+    if (lane == k) { mye = bi; myw = bv; }
   }
-  csync();
+  if (!P.norm_topk_prob) wsum = 1.0f;
+  if (lane < P.K) {
+    const float w = mye >= 0 ? myw / wsum * P.routed_scale : 0.f;
+    sm.act[lane] = mye; sm.actw[lane] = w;
+    if (publish) { P.act[lane] = mye; P.act_w[lane] = w; }
+  }
+  __syncwarp();
 }
 
 // ---- producer: one tile -> ring slot --------------------------------------------------------------------------
@@ -813,19 +846,94 @@ __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* 
 }
 
 // ---- per-stage bodies ------------------------------------------------------------------------------------------
+// GEMV activation staging: one pass over the input with the values kept in registers (n <= 8192), RMSNorm and Q8_K fused
+template <int Q>
+__device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage& st, const MegaSmem& sm, float* xs0, const Q8Smem& q80) {
+  constexpr bool KQ = QTraits<Q>::kq;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = st.n;
+  if (n > 8192) {   // long vectors: two passes through L1/L2
+    float sc = 1.0f;
+    if (st.norm_w) sc = c_rms_scale(st.in, n, P.eps, sm.red);
+    c_stage_vec<KQ>(st.in, n, st.norm_w, sc, xs0, q80);
+    return;
+  }
+  if constexpr (KQ) {
+    float v[4][8];
+    const int nb = n >> 8;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int b = warp + 8 * k;
+      if (b < nb) {
+        const float4 a0 = *reinterpret_cast<const float4*>(st.in + (b << 8) + lane * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(st.in + (b << 8) + lane * 8 + 4);
+        v[k][0] = a0.x; v[k][1] = a0.y; v[k][2] = a0.z; v[k][3] = a0.w; v[k][4] = a1.x; v[k][5] = a1.y; v[k][6] = a1.z; v[k][7] = a1.w;
+#pragma unroll
+        for (int j = 0; j < 8; j++) ss = fmaf(v[k][j], v[k][j], ss);
+      }
+    }
+    float sc = 1.0f;
+    if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int b = warp + 8 * k;
+      if (b < nb) {
+        if (st.norm_w) {
+          const float4 w0 = *reinterpret_cast<const float4*>(st.norm_w + (b << 8) + lane * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(st.norm_w + (b << 8) + lane * 8 + 4);
+          const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; j++) v[k][j] = __fmul_rn(__fmul_rn(v[k][j], sc), ww[j]);
+        }
+        q8_block(v[k], b, lane, q80);
+      }
+    }
+  } else {
+    float4 v[8];
+    const int nf = n >> 2;
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int f = tid + k * kConsumers;
+      if (f < nf) {
+        v[k] = reinterpret_cast<const float4*>(st.in)[f];
+        ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+      }
+    }
+    float sc = 1.0f;
+    if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int f = tid + k * kConsumers;
+      if (f < nf) {
+        float4 o = v[k];
+        if (st.norm_w) {
+          const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
+          o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
+          o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
+        }
+        reinterpret_cast<float4*>(xs0)[f] = o;
+      }
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
-                                               unsigned long long& best_key, int dep_count) {
+                                               unsigned long long& best_key, int dep_count, int stage_index) {
   constexpr bool KQ = QTraits<Q>::kq;
   const int tid = threadIdx.x;
   if ((int)blockIdx.x >= st.ntiles) {   // no tile of this stage lands on this CTA: nothing to stage
     if (tid == 0) dep_signal(sm.dep, dep_count);
     return;
   }
-  if (st.need_topk) c_route(P, st, sm, blockIdx.x == 0);
-  else if (st.kind == ST_DOWN && st.K > 0) {          // routing published by CTA 0 of the experts stage
-    if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
+  // routing first (one warp, registers): it unblocks the producer's routed-expert tiles
+  if (st.need_topk) { if (tid < 32) warp_route(P, st, sm, blockIdx.x == 0); }
+  else if (st.kind == ST_DOWN && st.K > 0) { if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; } }
+  if (st.need_topk || (st.kind == ST_DOWN && st.K > 0)) {
     csync();
+    if (tid == 0) dep_signal(sm.dep, dep_count);
   }
   // activation vector(s) -> shared memory
   float* xs0 = nullptr;
@@ -834,9 +942,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   Q8Smem q8_seg[kMaxJobs];
   if (st.kind == ST_GEMV) {
     carve_x<Q>(sm.xregion, st.n, xs0, q80);
-    float sc = 1.0f;
-    if (st.norm_w) sc = c_rms_scale(st.in, st.n, P.eps, sm.red);
-    c_stage_vec<KQ>(st.in, st.n, st.norm_w, sc, xs0, q80);
+    c_stage_gemv_input<Q>(P, st, sm, xs0, q80);
   } else {
     unsigned char* p = sm.xregion;
     const bool use_shared = st.sw2 != nullptr && st.add_shared;
@@ -853,8 +959,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     }
   }
   csync();
-  if (tid == 0) dep_signal(sm.dep, dep_count);   // routing + inputs ready
-  if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[(&st - P.stage) * 4 + 1] = gtime();
+  if (!(st.need_topk || (st.kind == ST_DOWN && st.K > 0)) && tid == 0) dep_signal(sm.dep, dep_count);
+  if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 4 + 1] = gtime();
   const uint32_t xs = KQ ? 0u : smem_u32(xs0);
   int parity_res = 0;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
@@ -897,16 +1003,23 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
 }
 
 // ---- the interpreter ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_desc(void* dst, const void* src, int bytes, int t, int nthreads) {
+  for (int i = t; i < bytes / 16; i += nthreads) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+
 template <int Q>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* __restrict__ prog, int s_begin, int s_end,
                                                                  int from_argmax) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const Program& P = *prog;
-  const MegaSmem sm = carve_mega(smem, P.xregion_bytes);
-  const int n_slots = P.n_slots;
   const int tid = threadIdx.x;
   const bool producer = tid >= kConsumers;
   __shared__ int s_token;
+  // header copy first: everything below reads the Program / Stage descriptors out of shared memory
+  copy_desc(smem + 4096 + 2 * kStageSlot, prog, kProgHdrBytes, tid, kMegaThreads);
+  __syncthreads();
+  const Program& P = *reinterpret_cast<const Program*>(smem + 4096 + 2 * kStageSlot);
+  const MegaSmem sm = carve_mega(smem, P.xregion_bytes);
+  const int n_slots = P.n_slots;
   if (tid == 0) {
     for (int i = 0; i < n_slots; i++) { mbar_init(sm.full[i], 1); mbar_init(sm.empty[i], 8); }
     dep_signal(sm.dep, 0);
@@ -919,20 +1032,30 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
   unsigned long long best_key = 0ull;
   int nstage_seen = 0;
   for (int s = s_begin; s < s_end; s++, nstage_seen++) {
-    const Stage& st = P.stage[s];
-    const bool streams = st.kind == ST_GEMV || st.kind == ST_DOWN;
     if (producer) {
+      // the producer keeps its own descriptor copy: it may already be one stage ahead of the consumers
+      copy_desc(sm.st_p, &prog->stage[s], (int)sizeof(Stage), tid - kConsumers, 32);
+      __syncwarp();
+      const Stage& st = *sm.st_p;
+      const bool streams = st.kind == ST_GEMV || st.kind == ST_DOWN;
       if (tid == kConsumers && streams) {
         if (st.quant == Q_F32 && Q != Q_F32) producer_stage<Q_F32>(P, st, sm, it, n_slots, nstage_seen + 1);
         else producer_stage<Q>(P, st, sm, it, n_slots, nstage_seen + 1);
       } else if (tid == kConsumers) {
         dep_wait(sm.dep, nstage_seen + 1);
       }
+      __syncwarp();
       continue;
     }
     // ---- consumers ----
-    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 3] = 0;
-    if (s > s_begin) {             // grid barrier: every CTA has finished (and flushed) stage s-1
+    // descriptor copy + norm-weight prefetch happen BEFORE the grid barrier: they do not depend on the previous stage
+    copy_desc(sm.st_c, &prog->stage[s], (int)sizeof(Stage), tid, kConsumers);
+    csync();
+    const Stage& st = *sm.st_c;
+    if (st.kind == ST_GEMV && st.norm_w && (int)blockIdx.x < st.ntiles) {
+      for (int i = tid * 32; i < st.n; i += kConsumers * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(st.norm_w + i));
+    }
+    if (s > s_begin) {             // grid barrier: every CTA has finished (and released) stage s-1
       if (tid == 0) {
         const unsigned int target = base + (unsigned int)(s - s_begin) * G;
         for (unsigned long long spins = 0; (int)(ld_acquire(P.sync_counter) - target) < 0; spins++) {
@@ -941,7 +1064,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       }
       csync();
     }
-    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 0] = gtime();
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 4 + 0] = gtime(); P.tstamp[s * 4 + 1] = 0; }
     if (st.kind == ST_EMBED) {
       if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
@@ -949,8 +1072,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else {
-      if (st.quant == Q_F32 && Q != Q_F32) consumer_stage<Q_F32>(P, st, sm, it, n_slots, best_key, nstage_seen + 1);
-      else consumer_stage<Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1);
+      if (st.quant == Q_F32 && Q != Q_F32) consumer_stage<Q_F32>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
+      else consumer_stage<Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
       if (st.epi == EPI_LOGITS) {
         unsigned long long b = best_key;
 #pragma unroll
@@ -959,13 +1082,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
         best_key = 0ull;
       }
     }
-    // stage done: make this CTA's writes visible, then arrive on the grid barrier
+    // stage done: the CTA barrier orders every consumer's writes before thread 0's release-add (cumulative)
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 2] = gtime();
-    if (s + 1 < s_end) {
-      __threadfence();
-      csync();
-      if (tid == 0) red_release_add(P.sync_counter, 1u);
-    }
+    csync();
+    if (s + 1 < s_end && tid == 0) red_release_add(P.sync_counter, 1u);
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 3] = gtime();
   }
   // last stage of the launch: publish the new barrier base for the next launch (single writer, after all arrivals)
