@@ -1092,8 +1092,8 @@ static int build_program(dsk_model* m, dsk_state* s) {
   CK(cudaMemset(s->sync_words, 0, 64));
   P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
   P->n_slots = n_slots; P->xregion_bytes = (int)xreg;
-  CK(cudaMalloc((void**)&s->tstamp, S.size() * 4 * sizeof(unsigned long long)));
-  CK(cudaMemset(s->tstamp, 0, S.size() * 4 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&s->tstamp, S.size() * 8 * sizeof(unsigned long long)));
+  CK(cudaMemset(s->tstamp, 0, S.size() * 8 * sizeof(unsigned long long)));
   P->tstamp = s->tstamp;
   for (const Stage& st : S) {
     char nm[96];
@@ -1529,27 +1529,28 @@ extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos,
     // stage-level timeline of the last token from the interpreter's own globaltimer stamps (CTA 0)
     float* lg = nullptr; (void)lg;
     if (dsk_forward(m, s, token, pos, 1, nullptr, nullptr)) return -2;
-    std::vector<unsigned long long> ts((size_t)s->n_stages * 4);
+    std::vector<unsigned long long> ts((size_t)s->n_stages * 8);
     CK(cudaMemcpy(ts.data(), s->tstamp, ts.size() * 8, cudaMemcpyDeviceToHost));
-    struct Agg { int n = 0; double wait = 0, stage = 0, tiles = 0, arrive = 0; };
+    struct Agg { int n = 0; double wait = 0, stage = 0, tiles = 0, arrive = 0, cw = 0, ct = 0, cs = 0, ce = 0; };
     std::map<std::string, Agg> agg;
     double total = 0;
     for (int i = 0; i < s->n_stages; i++) {
-      const double t0 = (double)ts[i * 4], t1 = (double)ts[i * 4 + 1], t2 = (double)ts[i * 4 + 2], t3 = (double)ts[i * 4 + 3];
-      const double prev_end = i > 0 ? (double)ts[(i - 1) * 4 + 3] : t0;
+      const double t0 = (double)ts[i * 8], t1 = (double)ts[i * 8 + 1], t2 = (double)ts[i * 8 + 2], t3 = (double)ts[i * 8 + 3];
+      const double prev_end = i > 0 ? (double)ts[(i - 1) * 8 + 3] : t0;
       Agg& a = agg[s->stage_names[i]];
       a.n++;
       a.wait += (t0 - prev_end) / 1e3;                      // grid barrier wait
       a.stage += (t1 > 0 ? (t1 - t0) : 0) / 1e3;           // routing + activation staging
       a.tiles += (t2 - (t1 > 0 ? t1 : t0)) / 1e3;          // tile loop (or attention / embed body)
       a.arrive += (t3 - t2) / 1e3;                         // fence + arrive
-      if (i + 1 == s->n_stages) total = ((double)ts[i * 4 + 3] - (double)ts[0]) / 1e3;
+      a.cw += (double)ts[i * 8 + 4]; a.ct += (double)ts[i * 8 + 5]; a.cs += (double)ts[i * 8 + 6]; a.ce += (double)ts[i * 8 + 7];
+      if (i + 1 == s->n_stages) total = ((double)ts[i * 8 + 3] - (double)ts[0]) / 1e3;
     }
     size_t off = 0;
     for (auto& kv : agg) {
       const Agg& a = kv.second;
-      int n = snprintf(out + off, cap - off, "%s x%3d  barrier %6.2f  stage-in %6.2f  tiles %6.2f  fence+arrive %6.2f  (us avg)  sum %8.1f us\n",
-                       kv.first.c_str(), a.n, a.wait / a.n, a.stage / a.n, a.tiles / a.n, a.arrive / a.n, a.wait + a.stage + a.tiles + a.arrive);
+      int n = snprintf(out + off, cap - off, "%s x%3d  barrier %6.2f  stage-in %6.2f  tiles %6.2f  arrive %5.2f us | kcyc/stage: wait %6.1f task %6.1f sync %6.1f epi %6.1f | sum %8.1f us\n",
+                       kv.first.c_str(), a.n, a.wait / a.n, a.stage / a.n, a.tiles / a.n, a.arrive / a.n, a.cw / a.n / 1e3, a.ct / a.n / 1e3, a.cs / a.n / 1e3, a.ce / a.n / 1e3, a.wait + a.stage + a.tiles + a.arrive);
       if (n < 0 || (size_t)n >= cap - off) break;
       off += n;
     }

@@ -61,7 +61,7 @@ struct Stage {
   int K, mi, sh, add_shared;
   int seg_stride;                          // bytes between segments inside a ring slot (ST_DOWN)
   int pad2[3];
-};
+} __attribute__((aligned(16)));
 
 static_assert(sizeof(Stage) <= kStageSlot, "Stage descriptor must fit its shared-memory cache slot");
 static_assert(sizeof(Stage) % 16 == 0, "Stage is copied in 16-byte words");
@@ -85,7 +85,6 @@ struct Program {
   int* token_log; int* step;
   int n_slots, xregion_bytes;
   unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
-  long long pad_to16;
   Stage stage[1];                          // n_stages entries follow
 };
 constexpr int kProgHdrBytes = (int)offsetof(Program, stage);
@@ -960,25 +959,36 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   }
   csync();
   if (!(st.need_topk || (st.kind == ST_DOWN && st.K > 0)) && tid == 0) dep_signal(sm.dep, dep_count);
-  if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 4 + 1] = gtime();
+  if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
   const uint32_t xs = KQ ? 0u : smem_u32(xs0);
   int parity_res = 0;
+  long long c_wait = 0, c_task = 0, c_sync = 0, c_epi = 0;
+  const bool timing = tid == 0 && blockIdx.x == 0 && P.tstamp;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     const int sl = it % n_slots;
     const uint32_t slot = sm.ring + (uint32_t)sl * kSlotBytes;
+    const long long k0 = clock64();
     mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+    const long long k1 = clock64();
     float* res = sm.res + parity_res * 256;
     bool skip = false;
     if (st.kind == ST_GEMV) consume_gemv_tile<Q>(P, st, t, slot, xs, q80, res, sm.act, best_key, skip);
     else consume_down_tile<Q>(P, st, t, slot, xs_seg, q8_seg, res, sm.act);
     __syncwarp();
     if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+    const long long k2 = clock64();
     csync();
+    const long long k3 = clock64();
     if (!skip) {
       if (st.kind == ST_GEMV) gemv_tile_epilogue(P, st, t, res, best_key);
       else down_tile_epilogue(P, st, t, res, sm.actw, sm.act);
     }
     parity_res ^= 1;
+    c_wait += k1 - k0; c_task += k2 - k1; c_sync += k3 - k2; c_epi += clock64() - k3;
+  }
+  if (timing) {
+    P.tstamp[stage_index * 8 + 4] = (unsigned long long)c_wait; P.tstamp[stage_index * 8 + 5] = (unsigned long long)c_task;
+    P.tstamp[stage_index * 8 + 6] = (unsigned long long)c_sync; P.tstamp[stage_index * 8 + 7] = (unsigned long long)c_epi;
   }
 }
 
@@ -1064,7 +1074,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       }
       csync();
     }
-    if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 4 + 0] = gtime(); P.tstamp[s * 4 + 1] = 0; }
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 8 + 0] = gtime(); P.tstamp[s * 8 + 1] = 0; P.tstamp[s * 8 + 4] = 0; P.tstamp[s * 8 + 5] = 0; P.tstamp[s * 8 + 6] = 0; P.tstamp[s * 8 + 7] = 0; }
     if (st.kind == ST_EMBED) {
       if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
@@ -1083,10 +1093,10 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       }
     }
     // stage done: the CTA barrier orders every consumer's writes before thread 0's release-add (cumulative)
-    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 2] = gtime();
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 2] = gtime();
     csync();
     if (s + 1 < s_end && tid == 0) red_release_add(P.sync_counter, 1u);
-    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 4 + 3] = gtime();
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 3] = gtime();
   }
   // last stage of the launch: publish the new barrier base for the next launch (single writer, after all arrivals)
   if (!producer && blockIdx.x == 0 && tid == 0 && s_end - s_begin > 1) {
