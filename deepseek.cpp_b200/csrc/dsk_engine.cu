@@ -1078,7 +1078,8 @@ static int build_program(dsk_model* m, dsk_state* s) {
   memset(P, 0, sizeof(Program));
   P->dim = c.dim; P->n_heads = c.n_heads; P->hd = hd; P->nope = nope; P->rope = c.qk_rope_head_dim; P->vh = c.v_head_dim;
   P->kv_lora = c.kv_lora_rank; P->is_v3 = c.is_v3; P->bs0 = c.bs0 > 0 ? c.bs0 : 1; P->bs1 = c.bs1 > 0 ? c.bs1 : 1;
-  P->act_silu = c.act_silu; P->max_seq = c.max_seq_len; P->E = c.n_routed_experts; P->K = c.n_active_routed;
+  P->act_silu = c.act_silu; P->max_seq = c.max_seq_len;
+  { int b1 = P->bs1, sh = 0; while ((1 << sh) < b1) sh++; P->bs1_shift = ((1 << sh) == b1) ? sh : -1; } P->E = c.n_routed_experts; P->K = c.n_active_routed;
   P->norm_topk_prob = c.norm_topk_prob; P->sigmoid = c.scoring_sigmoid; P->topk_method = c.topk_method;
   P->n_group = std::max(1, c.n_group); P->topk_group = c.topk_group; P->original_max = c.original_max_position;
   P->eps = c.norm_eps; P->routed_scale = c.routed_scaling_factor; P->expert_first = m->expert_first; P->expert_count = m->expert_count;

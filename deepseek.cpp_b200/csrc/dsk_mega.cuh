@@ -70,6 +70,7 @@ struct Program {
   // model constants
   int dim, n_heads, hd, nope, rope, vh, kv_lora, is_v3;
   int bs0, bs1, act_silu, max_seq;
+  int bs1_shift, pad_i[3];
   int E, K, norm_topk_prob, sigmoid, topk_method, n_group, topk_group, original_max;
   float eps, routed_scale;
   int expert_first, expert_count;
@@ -144,6 +145,15 @@ __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v)
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Shared-memory layout of the fp32 activations.  An F8 lane-chunk needs 16 consecutive floats (4 float4), so lanes
+// stride 64 B and a straight layout is 4-way bank conflicted; float4 (chunk c, quarter q) is stored at
+// 4c + (q ^ ((c >> 1) & 3)) instead, which spreads 8 consecutive lanes over all 8 sixteen-byte bank groups.
+template <int Q>
+__device__ __forceinline__ int xswz(int f) {   // f = logical float4 index
+  if constexpr (Q == Q_F8) return (f & ~3) | ((f & 3) ^ ((f >> 3) & 3));
+  else return f;
+}
+
 // ---- activation staging with consumer-only barriers -------------------------------------------------------------
 __device__ __forceinline__ float c_rms_scale(const float* __restrict__ in, int n, float eps, float* red) {
   float ss = 0.f;
@@ -185,9 +195,10 @@ __device__ __forceinline__ void q8_block(const float (&v)[8], int b, int lane, c
   const uint32_t p1 = (qv[4] & 0xff) | ((qv[5] & 0xff) << 8) | ((qv[6] & 0xff) << 16) | ((uint32_t)(qv[7] & 0xff) << 24);
   *reinterpret_cast<uint2*>(q.qs + (b << 8) + lane * 8) = make_uint2(p0, p1);
 }
-template <bool KQ>
+template <int Q>
 __device__ __forceinline__ void c_stage_vec(const float* __restrict__ in, int n, const float* __restrict__ norm_w, float sc,
                                             float* xs, const Q8Smem& q8) {
+  constexpr bool KQ = QTraits<Q>::kq;
   if constexpr (KQ) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int b = warp; b < (n >> 8); b += 8) {
@@ -205,14 +216,38 @@ __device__ __forceinline__ void c_stage_vec(const float* __restrict__ in, int n,
       q8_block(v, b, lane, q8);
     }
   } else {
-    if (norm_w) { for (int i = threadIdx.x; i < n; i += kConsumers) xs[i] = __fmul_rn(__fmul_rn(in[i], sc), norm_w[i]); }
-    else { for (int i = threadIdx.x * 4; i < n; i += kConsumers * 4) *reinterpret_cast<float4*>(xs + i) = *reinterpret_cast<const float4*>(in + i); }
+    for (int f = threadIdx.x; f < (n >> 2); f += kConsumers) {
+      float4 o = reinterpret_cast<const float4*>(in)[f];
+      if (norm_w) {
+        const float4 w = reinterpret_cast<const float4*>(norm_w)[f];
+        o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
+        o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
+      }
+      reinterpret_cast<float4*>(xs)[xswz<Q>(f)] = o;
+    }
   }
 }
 
 // ---- dots over a column piece, weights and f8 scale row both in shared memory -----------------------------------
+// 16 weight bytes x EPC activations with TWO interleaved partial sums (halves the dependent FMA chain)
+template <int Q>
+__device__ __forceinline__ float chunk_dot2(const uint4& wv, const float* xv) {
+  float p0 = 0.f, p1 = 0.f;
+  if constexpr (Q == Q_F8) {
+    float2 a, b;
+    a = f8x2_lo(wv.x); b = f8x2_hi(wv.x); p0 = fmaf(a.x, xv[0], p0); p1 = fmaf(a.y, xv[1], p1); p0 = fmaf(b.x, xv[2], p0); p1 = fmaf(b.y, xv[3], p1);
+    a = f8x2_lo(wv.y); b = f8x2_hi(wv.y); p0 = fmaf(a.x, xv[4], p0); p1 = fmaf(a.y, xv[5], p1); p0 = fmaf(b.x, xv[6], p0); p1 = fmaf(b.y, xv[7], p1);
+    a = f8x2_lo(wv.z); b = f8x2_hi(wv.z); p0 = fmaf(a.x, xv[8], p0); p1 = fmaf(a.y, xv[9], p1); p0 = fmaf(b.x, xv[10], p0); p1 = fmaf(b.y, xv[11], p1);
+    a = f8x2_lo(wv.w); b = f8x2_hi(wv.w); p0 = fmaf(a.x, xv[12], p0); p1 = fmaf(a.y, xv[13], p1); p0 = fmaf(b.x, xv[14], p0); p1 = fmaf(b.y, xv[15], p1);
+    return p0 + p1;
+  } else {
+    return chunk_dot<Q>(wv, xv);
+  }
+}
+
+// sshift >= 0: scale block index = (c * EPC) >> sshift (power-of-two block width); < 0: generic division by bs1
 template <int Q, int NACC>
-__device__ __forceinline__ void piece_dot_dense(const uint32_t (&wa)[NACC], const uint32_t (&ssm)[NACC], int bs1, int g0, int g1,
+__device__ __forceinline__ void piece_dot_dense(const uint32_t (&wa)[NACC], const uint32_t (&ssm)[NACC], int bs1, int sshift, int g0, int g1,
                                                 uint32_t xs, int lane, float (&acc)[NACC]) {
   constexpr int EPC = QTraits<Q>::epc;
 #pragma unroll 2
@@ -220,15 +255,15 @@ __device__ __forceinline__ void piece_dot_dense(const uint32_t (&wa)[NACC], cons
     float xv[EPC];
 #pragma unroll
     for (int q = 0; q < EPC / 4; q++) {
-      const uint4 t = lds128(xs + (uint32_t)(c * EPC + q * 4) * 4u);
+      const uint4 t = lds128(xs + (uint32_t)xswz<Q>(c * (EPC / 4) + q) * 16u);
       xv[4 * q] = __uint_as_float(t.x); xv[4 * q + 1] = __uint_as_float(t.y);
       xv[4 * q + 2] = __uint_as_float(t.z); xv[4 * q + 3] = __uint_as_float(t.w);
     }
-    const uint32_t sidx = (uint32_t)((c * EPC) / bs1) * 4u;
+    const uint32_t sidx = (sshift >= 0 ? (uint32_t)(c * EPC) >> sshift : (uint32_t)((c * EPC) / bs1)) * 4u;
 #pragma unroll
     for (int r = 0; r < NACC; r++) {
       const uint4 wv = lds128(wa[r] + (uint32_t)c * 16u);
-      const float p = chunk_dot<Q>(wv, xv);
+      const float p = chunk_dot2<Q>(wv, xv);
       const float s = ssm[r] ? __uint_as_float(lds32(ssm[r] + sidx)) : 1.0f;
       acc[r] = fmaf(p, s, acc[r]);
     }
@@ -313,7 +348,7 @@ __device__ __forceinline__ float piece_dot_kq(uint32_t wrow, int b0, int b1, con
 
 // NACC rows x one piece -> NACC warp-reduced partial dots
 template <int Q, int NACC>
-__device__ __forceinline__ void piece_rows(const uint32_t (&wa)[NACC], const uint32_t (&ssm)[NACC], int bs1, int g0, int g1,
+__device__ __forceinline__ void piece_rows(const uint32_t (&wa)[NACC], const uint32_t (&ssm)[NACC], int bs1, int sshift, int g0, int g1,
                                            uint32_t xs, const Q8Smem& q8, int lane, float (&out)[NACC]) {
 #pragma unroll
   for (int r = 0; r < NACC; r++) out[r] = 0.f;
@@ -321,7 +356,7 @@ __device__ __forceinline__ void piece_rows(const uint32_t (&wa)[NACC], const uin
 #pragma unroll
     for (int r = 0; r < NACC; r++) out[r] = piece_dot_kq<Q>(wa[r], g0, g1, q8, lane);
   } else {
-    piece_dot_dense<Q, NACC>(wa, ssm, bs1, g0, g1, xs, lane, out);
+    piece_dot_dense<Q, NACC>(wa, ssm, bs1, sshift, g0, g1, xs, lane, out);
   }
 #pragma unroll
   for (int r = 0; r < NACC; r++) out[r] = warp_sum(out[r]);
@@ -550,7 +585,7 @@ __device__ __forceinline__ void gemv_tile_tasks(const Program& P, const Stage& s
       if constexpr (GLU) { wa[R + i] = wa[i] + part_stride; ssm[R + i] = s1; }
     }
     float v[NACC];
-    piece_rows<Q, NACC>(wa, ssm, P.bs1, pcd.g0, pcd.g1, xs, q8, lane, v);
+    piece_rows<Q, NACC>(wa, ssm, P.bs1, P.bs1_shift, pcd.g0, pcd.g1, xs, q8, lane, v);
     if (lane == 0) {
 #pragma unroll
       for (int i = 0; i < R; i++) {
@@ -598,7 +633,8 @@ __device__ __forceinline__ void consume_gemv_tile(const Program& P, const Stage&
 }
 
 // combine column pieces in a fixed order + epilogue, one thread per row of the tile
-__device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, unsigned long long& best) {
+__device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, unsigned long long& best,
+                                                   float xres) {
   int j = 0;
   while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
   const MJob& jb = st.job[j];
@@ -616,7 +652,7 @@ __device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage
     val = (P.act_silu ? silu_f(v) : gelu_f(v)) * u;
   }
   switch (st.epi) {
-    case EPI_RESID: jb.out[r] = jb.out[r] + val; break;
+    case EPI_RESID: jb.out[r] = xres + val; break;
     case EPI_KVB: {
       jb.out[r] = val;
       const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
@@ -665,21 +701,21 @@ __device__ __forceinline__ void consume_down_tile(const Program& P, const Stage&
     }
     if (live) {
       const uint32_t wa[1] = {slot + kSlotScale + (uint32_t)k * st.seg_stride + (uint32_t)lr * (k < st.K ? rb_mi : rb_sh)};
-      piece_rows<Q, 1>(wa, ssm, P.bs1, pcd.g0, pcd.g1, xs_seg[k], q8_seg[k], lane, v);
+      piece_rows<Q, 1>(wa, ssm, P.bs1, P.bs1_shift, pcd.g0, pcd.g1, xs_seg[k], q8_seg[k], lane, v);
     }
     if (lane == 0) res[lr * np + pc] = v[0];
   }
 }
 // x[i] += sum_k w_k * dot_k + dot_shared in the reference's order (src/infer.cpp:873-877, 899-903, 926-930)
 __device__ __forceinline__ void down_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, const float* actw_smem,
-                                                   const int* act_smem) {
+                                                   const int* act_smem, float xres) {
   const int i0 = t * st.rows_per_tile;
   const int nrows = min(st.rows_per_tile, P.dim - i0);
   const int lr = threadIdx.x;
   if (lr >= nrows) return;
   const int i = i0 + lr, np = st.npieces;
   const bool to_partial = P.partial != nullptr && st.K > 0;
-  float acc = to_partial ? 0.f : P.x[i];
+  float acc = to_partial ? 0.f : xres;
   int pc = 0;
   for (int k = 0; k <= st.K; k++) {
     float v = 0.f;
@@ -854,7 +890,7 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
   if (n > 8192) {   // long vectors: two passes through L1/L2
     float sc = 1.0f;
     if (st.norm_w) sc = c_rms_scale(st.in, n, P.eps, sm.red);
-    c_stage_vec<KQ>(st.in, n, st.norm_w, sc, xs0, q80);
+    c_stage_vec<Q>(st.in, n, st.norm_w, sc, xs0, q80);
     return;
   }
   if constexpr (KQ) {
@@ -912,7 +948,7 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
           o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
           o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
         }
-        reinterpret_cast<float4*>(xs0)[f] = o;
+        reinterpret_cast<float4*>(xs0)[xswz<Q>(f)] = o;
       }
     }
   }
@@ -954,7 +990,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       bool live = n > 0;
       if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
       else live = live && use_shared;
-      if (live) c_stage_vec<KQ>(k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs, n, nullptr, 1.0f, xk, q8_seg[k]);
+      if (live) c_stage_vec<Q>(k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs, n, nullptr, 1.0f, xk, q8_seg[k]);
     }
   }
   csync();
@@ -972,6 +1008,15 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     const long long k1 = clock64();
     float* res = sm.res + parity_res * 256;
     bool skip = false;
+    // residual operand of the epilogue fetched now, so its L2 latency hides behind the tile's dot products
+    float xres = 0.f;
+    if (st.kind == ST_DOWN) {
+      const int i = t * st.rows_per_tile + tid;
+      if (tid < st.rows_per_tile && i < P.dim && !(P.partial != nullptr && st.K > 0)) xres = P.x[i];
+    } else if (st.epi == EPI_RESID) {
+      const int r = (t - st.job[0].tile_begin) * st.rows_per_tile + tid;
+      if (tid < st.rows_per_tile && r < st.job[0].rows) xres = st.job[0].out[r];
+    }
     if (st.kind == ST_GEMV) consume_gemv_tile<Q>(P, st, t, slot, xs, q80, res, sm.act, best_key, skip);
     else consume_down_tile<Q>(P, st, t, slot, xs_seg, q8_seg, res, sm.act);
     __syncwarp();
@@ -980,8 +1025,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     csync();
     const long long k3 = clock64();
     if (!skip) {
-      if (st.kind == ST_GEMV) gemv_tile_epilogue(P, st, t, res, best_key);
-      else down_tile_epilogue(P, st, t, res, sm.actw, sm.act);
+      if (st.kind == ST_GEMV) gemv_tile_epilogue(P, st, t, res, best_key, xres);
+      else down_tile_epilogue(P, st, t, res, sm.actw, sm.act, xres);
     }
     parity_res ^= 1;
     c_wait += k1 - k0; c_task += k2 - k1; c_sync += k3 - k2; c_epi += clock64() - k3;
