@@ -171,6 +171,7 @@ static int cdiv(int a, int b) { return (a + b - 1) / b; }
 static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 static constexpr size_t kSmemBudget = 200 * 1024;
 static bool g_use_pdl = true;
+static bool g_use_mma = true;   // F8E5M2 tiles through mma.sync (DSK_NO_MMA=1: CUDA-core dequant path)
 enum { ENG_MEGA = 0, ENG_STAGE = 1, ENG_V2 = 2 };
 static int g_engine = ENG_MEGA;
 
@@ -204,6 +205,7 @@ extern "C" int dsk_init(int device) {
     CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     g_use_pdl = getenv("DSK_NO_PDL") == nullptr;
+    g_use_mma = getenv("DSK_NO_MMA") == nullptr;
     if (const char* en = getenv("DSK_ENGINE")) {
       if (!strcmp(en, "stage")) g_engine = ENG_STAGE;
       else if (!strcmp(en, "v2")) g_engine = ENG_V2;
@@ -891,6 +893,26 @@ static bool kq_quant(int q) { return q == DSK_Q2_K || q == DSK_Q3_K; }
 static void plan_gemv_stage(Stage& st, int quant, int G) {
   const size_t rb = dev_row_bytes(quant, st.n);
   const int parts = st.epi == EPI_GLU ? 2 : 1;
+  if (quant == DSK_F8E5M2 && st.n % 64 == 0 && g_use_mma) {
+    // tensor-core tiles: 16 weight rows per mma row group (8 + 8 for the gate/up pair), K split into 64-column pieces
+    st.use_mma = 1;
+    int total_rows = 0;
+    for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
+    int RT = parts == 2 ? 8 : 16;
+    while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)kSlotData) RT >>= 1;
+    while (RT * 2 <= 32 && align_up((size_t)RT * 2 * rb, 128) * parts <= (size_t)kSlotData && cdiv(total_rows, RT * 2) >= 2 * G) RT *= 2;
+    st.rows_per_tile = RT;
+    st.rpass = 1;
+    const int rpg = parts == 2 ? 8 : 16, groups = cdiv(RT, rpg), gran = st.n / 64;
+    int csplit = std::max(1, std::min(std::min(8 / std::max(1, groups), gran), 8));
+    st.npieces = csplit;
+    for (int cs = 0; cs < csplit; cs++) st.piece[cs] = Piece{0, (int)((long long)cs * gran / csplit), (int)((long long)(cs + 1) * gran / csplit), 0};
+    int t = 0;
+    st.has_dyn = 0;
+    for (int j = 0; j < st.njobs; j++) { st.job[j].tile_begin = t; t += cdiv(st.job[j].rows, RT); if (st.job[j].expert_slot >= 0) st.has_dyn = 1; }
+    st.ntiles = t;
+    return;
+  }
   int total_rows = 0;
   for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
   int RT = 32;
@@ -929,9 +951,10 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
   st.rows_per_tile = RT;
   st.seg_stride = (int)align_up((size_t)RT * rb_mi, 128);
   st.ntiles = cdiv(dim, RT);
-  const int g_mi = st.mi ? granules(quant, st.mi) : 0, g_sh = st.sh ? granules(quant, st.sh) : 0;
+  st.use_mma = (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma) ? 1 : 0;
+  const int g_mi = st.mi ? (st.use_mma ? st.mi / 64 : granules(quant, st.mi)) : 0, g_sh = st.sh ? (st.use_mma ? st.sh / 64 : granules(quant, st.sh)) : 0;
   const long long total = (long long)g_mi * st.K + g_sh;
-  const int want = std::max(1, cdiv(16, RT));
+  const int want = st.use_mma ? 8 : std::max(1, cdiv(16, RT));
   const long long L = std::max<long long>(1, cdiv((int)total, want));
   int np = 0;
   for (int k = 0; k <= st.K; k++) {
@@ -1057,10 +1080,10 @@ static int build_program(dsk_model* m, dsk_state* s) {
   // shared-memory budget: activation region = max over stages, the rest is ring slots
   size_t xreg = 8192;
   for (const Stage& st : S) {
-    if (st.kind == ST_GEMV) xreg = std::max(xreg, xvec_bytes_q(st.quant, st.n));
+    if (st.kind == ST_GEMV) xreg = std::max(xreg, st.use_mma ? x16_bytes(st.n) : xvec_bytes_q(st.quant, st.n));
     else if (st.kind == ST_DOWN) {
       size_t b = 0;
-      for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += xvec_bytes_q(st.quant, n); }
+      for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += st.use_mma ? x16_bytes(n) : xvec_bytes_q(st.quant, n); }
       xreg = std::max(xreg, b);
     }
   }

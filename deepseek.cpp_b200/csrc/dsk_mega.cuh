@@ -49,6 +49,7 @@ struct Stage {
   int kind, quant, epi, njobs;
   int n, rows_per_tile, rpass, ntiles;
   int need_topk, npieces, layer, has_dyn;
+  int use_mma, pad3[3];          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
   const float* in; const float* norm_w;
   MJob job[kMaxJobs];
   Piece piece[kMaxPieces];
@@ -226,6 +227,74 @@ __device__ __forceinline__ void c_stage_vec(const float* __restrict__ in, int n,
       reinterpret_cast<float4*>(xs)[xswz<Q>(f)] = o;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tensor-core path for F8E5M2 weights.  Batch-1 GEMV is bandwidth-bound on paper, but dequantising every weight on the
+// CUDA cores costs ~2.7 instructions per byte and one resident CTA per SM cannot issue that fast.  Instead:
+//   * f8e5m2 -> f16 is exact (the byte is the top half of an fp16): one PRMT per two weights builds the A fragment;
+//   * the fp32 activation x is split EXACTLY into two fp16 values (hi = rn(x*2^e), lo = rn(x*2^e - hi)), with a
+//     power-of-two normalisation 2^e per 64-column group so the split keeps ~22 significant bits for any magnitude;
+//   * mma.sync.m16n8k16 (f16 x f16 -> f32): A = 16 weight rows x 16 columns, B columns 0/1 = hi/lo -> every product is
+//     exact in fp32 and the accumulation is fp32; the 128x128 block scale and 2^-e are applied per 64-column group.
+// The K index inside one mma is permuted (thread-in-group t owns 4 consecutive columns) identically for A and B.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+struct X16 { uint32_t hi, lo, gs; };   // shared addresses: hi halves [n], lo halves [n], per-64-column 2^-e floats [n/64]
+__host__ __device__ inline size_t x16_bytes(int n) { return align_up((size_t)n * 4 + (size_t)(n / 64) * 4, 128); }
+__device__ __forceinline__ X16 carve_x16(unsigned char* p, int n) {
+  X16 x; x.hi = smem_u32(p); x.lo = x.hi + (uint32_t)n * 2u; x.gs = x.hi + (uint32_t)n * 4u; return x;
+}
+// one float4 (4 consecutive columns) -> hi/lo halves; 16 lanes (= 64 columns) share the normalisation
+__device__ __forceinline__ void x16_store(const X16& x, int f, float4 v) {
+  float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+  const unsigned active = __activemask();   // 16-lane groups are always fully in or out (n % 64 == 0)
+#pragma unroll
+  for (int o = 8; o; o >>= 1) am = fmaxf(am, __shfl_xor_sync(active, am, o));
+  const unsigned eb = (__float_as_uint(am) >> 23) & 0xffu;                 // biased exponent of the group maximum
+  const unsigned sb = am > 0.f ? min(max(267u - eb, 1u), 254u) : 127u;     // 2^(13 - floor(log2 amax))
+  const float sc = __uint_as_float(sb << 23), inv = __uint_as_float((254u - sb) << 23);
+  const float a0 = v.x * sc, a1 = v.y * sc, a2 = v.z * sc, a3 = v.w * sc;  // exact (power of two)
+  const __half h0 = __float2half_rn(a0), h1 = __float2half_rn(a1), h2 = __float2half_rn(a2), h3 = __float2half_rn(a3);
+  const __half l0 = __float2half_rn(a0 - __half2float(h0)), l1 = __float2half_rn(a1 - __half2float(h1));
+  const __half l2 = __float2half_rn(a2 - __half2float(h2)), l3 = __float2half_rn(a3 - __half2float(h3));
+  const uint32_t hw0 = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+  const uint32_t hw1 = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+  const uint32_t lw0 = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+  const uint32_t lw1 = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(x.hi + (uint32_t)f * 8u), "r"(hw0), "r"(hw1) : "memory");
+  asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(x.lo + (uint32_t)f * 8u), "r"(lw0), "r"(lw1) : "memory");
+  if ((f & 15) == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(x.gs + (uint32_t)(f >> 4) * 4u), "f"(inv) : "memory");
+}
+// rows (gid) and (gid+8) of a 16-row group over columns [col0, col1) (multiples of 64).  a_lo/a_hi: shared addresses of the
+// two weight rows; s_lo/s_hi: their f8 scale rows (0 = none).  Results valid in lanes with (lane & 3) == 0.
+__device__ __forceinline__ void mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32_t s_lo, uint32_t s_hi, int sshift, int bs1, int col0, int col1,
+                                            const X16& x, int lane, float& out_lo, float& out_hi) {
+  const int gid = lane >> 2, tig = lane & 3;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  const uint32_t xsrc = gid == 0 ? x.hi : x.lo;
+#pragma unroll 2
+  for (int cb = col0; cb < col1; cb += 64) {
+    const uint4 w0 = lds128(a_lo + (uint32_t)(cb + 16 * tig));
+    const uint4 w1 = lds128(a_hi + (uint32_t)(cb + 16 * tig));
+    uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
+    if (gid < 2) { b0 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u); b1 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u + 16u); }
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_f16(c, __byte_perm(w0.x, 0, 0x1404), __byte_perm(w1.x, 0, 0x1404), __byte_perm(w0.x, 0, 0x3424), __byte_perm(w1.x, 0, 0x3424), b0.x, b0.y);
+    mma_f16(c, __byte_perm(w0.y, 0, 0x1404), __byte_perm(w1.y, 0, 0x1404), __byte_perm(w0.y, 0, 0x3424), __byte_perm(w1.y, 0, 0x3424), b0.z, b0.w);
+    mma_f16(c, __byte_perm(w0.z, 0, 0x1404), __byte_perm(w1.z, 0, 0x1404), __byte_perm(w0.z, 0, 0x3424), __byte_perm(w1.z, 0, 0x3424), b1.x, b1.y);
+    mma_f16(c, __byte_perm(w0.w, 0, 0x1404), __byte_perm(w1.w, 0, 0x1404), __byte_perm(w0.w, 0, 0x3424), __byte_perm(w1.w, 0, 0x3424), b1.z, b1.w);
+    const float g = __uint_as_float(lds32(x.gs + (uint32_t)(cb >> 6) * 4u));
+    const uint32_t sidx = (sshift >= 0 ? (uint32_t)cb >> sshift : (uint32_t)(cb / bs1)) * 4u;
+    const float f_lo = s_lo ? g * __uint_as_float(lds32(s_lo + sidx)) : g;
+    const float f_hi = s_hi ? g * __uint_as_float(lds32(s_hi + sidx)) : g;
+    t0 = fmaf(c[0], f_lo, t0); t1 = fmaf(c[1], f_lo, t1); t2 = fmaf(c[2], f_hi, t2); t3 = fmaf(c[3], f_hi, t3);
+  }
+  out_lo = t0 + t1;   // hi-part + lo-part contributions
+  out_hi = t2 + t3;
 }
 
 // ---- dots over a column piece, weights and f8 scale row both in shared memory -----------------------------------
@@ -599,10 +668,50 @@ __device__ __forceinline__ void gemv_tile_tasks(const Program& P, const Stage& s
   }
 }
 
+// F8 tile through the tensor cores: one 16-row group (8 rows x {gate, up} for GLU) per task, K split over the pieces
+template <bool GLU>
+__device__ __forceinline__ void gemv_tile_tasks_mma(const Program& P, const Stage& st, const MJob& jb, int nrows, uint32_t slot,
+                                                    const X16& x16, float* res, int shift_bytes) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2;
+  const uint32_t rb = (uint32_t)st.n;   // f8: one byte per weight
+  const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
+  const int csplit = st.npieces;
+  constexpr int RPG = GLU ? 8 : 16;     // tile rows per mma row group
+  const int ngroups = (nrows + RPG - 1) / RPG;
+  uint32_t s0 = 0, s1 = 0;
+  if (jb.scale) { s0 = slot + (uint32_t)shift_bytes; s1 = slot + kSlotScale / 2 + (uint32_t)shift_bytes; }
+  for (int task = warp; task < ngroups * csplit; task += 8) {
+    const int g = task / csplit, pc = task - g * csplit;
+    const Piece pcd = st.piece[pc];
+    int r_lo, r_hi;
+    uint32_t a_lo, a_hi;
+    if constexpr (GLU) {
+      r_lo = g * 8 + gid; r_hi = r_lo;
+      const int lr = min(r_lo, nrows - 1);
+      a_lo = slot + kSlotScale + (uint32_t)lr * rb;
+      a_hi = a_lo + part_stride;
+    } else {
+      r_lo = g * 16 + gid; r_hi = r_lo + 8;
+      a_lo = slot + kSlotScale + (uint32_t)min(r_lo, nrows - 1) * rb;
+      a_hi = slot + kSlotScale + (uint32_t)min(r_hi, nrows - 1) * rb;
+    }
+    float v_lo, v_hi;
+    mma_rows_f8(a_lo, a_hi, s0, GLU ? s1 : s0, P.bs1_shift, P.bs1, pcd.g0 * 64, pcd.g1 * 64, x16, lane, v_lo, v_hi);
+    if ((lane & 3) == 0) {
+      if constexpr (GLU) {
+        if (r_lo < nrows) { res[(r_lo * 2 + 0) * csplit + pc] = v_lo; res[(r_lo * 2 + 1) * csplit + pc] = v_hi; }
+      } else {
+        if (r_lo < nrows) res[(r_lo * 2 + 0) * csplit + pc] = v_lo;
+        if (r_hi < nrows) res[(r_hi * 2 + 0) * csplit + pc] = v_hi;
+      }
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void consume_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, uint32_t xs,
-                                                  const Q8Smem& q8, float* res, const int* act_smem, unsigned long long& best,
-                                                  bool& skip) {
+                                                  const Q8Smem& q8, const X16& x16, float* res, const int* act_smem,
+                                                  unsigned long long& best, bool& skip) {
   int j = 0;
   while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
   const MJob& jb = st.job[j];
@@ -621,6 +730,12 @@ __device__ __forceinline__ void consume_gemv_tile(const Program& P, const Stage&
     shift_bytes = (int)(reinterpret_cast<uintptr_t>(jb.scale + soff + (size_t)(r0 / P.bs0) * ncb) & 15);
   }
   const bool glu = st.epi == EPI_GLU;
+  if (Q == Q_F8 && st.use_mma) {
+    if (glu) gemv_tile_tasks_mma<true>(P, st, jb, nrows, slot, x16, res, shift_bytes);
+    else gemv_tile_tasks_mma<false>(P, st, jb, nrows, slot, x16, res, shift_bytes);
+    (void)best;
+    return;
+  }
   if (glu) {
     if (st.rpass >= 2) gemv_tile_tasks<Q, 2, true>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
     else gemv_tile_tasks<Q, 1, true>(P, st, jb, r0, nrows, slot, xs, q8, res, shift_bytes);
@@ -672,6 +787,45 @@ __device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage
 }
 
 // ---- consumers: one DOWN tile (pieces = column pieces of the K routed segments + the shared segment) -----------------
+// ST_DOWN tile through the tensor cores: task = one column piece of one segment, all (<= 8) rows of the tile at once
+__device__ __forceinline__ void consume_down_tile_mma(const Program& P, const Stage& st, int t, uint32_t slot, const X16* x16_seg,
+                                                      float* res, const int* act_smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2;
+  const int i0 = t * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, P.dim - i0);
+  const uint32_t rb_mi = (uint32_t)st.mi, rb_sh = (uint32_t)st.sh;
+  const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
+  const uint32_t sstride = kSlotScale / (uint32_t)(st.K + 1) & ~15u;
+  const int np = st.npieces;
+  for (int pc = warp; pc < np; pc += 8) {
+    const Piece pcd = st.piece[pc];
+    const int k = pcd.seg;
+    bool live = true;
+    uint32_t ssm = 0;
+    if (k < st.K) {
+      const int e = act_smem[k] - P.expert_first;
+      live = e >= 0 && e < P.expert_count;
+      if (live && st.s2)
+        ssm = slot + (uint32_t)k * sstride + (uint32_t)(reinterpret_cast<uintptr_t>(st.s2 + (size_t)e * st.s2_stride + (size_t)(i0 / P.bs0) * ncb_mi) & 15);
+    } else {
+      live = st.sw2 != nullptr && st.add_shared;
+      if (live && st.ss2)
+        ssm = slot + (uint32_t)k * sstride + (uint32_t)(reinterpret_cast<uintptr_t>(st.ss2 + (size_t)(i0 / P.bs0) * ncb_sh) & 15);
+    }
+    float v_lo = 0.f, v_hi = 0.f;
+    if (live) {
+      const uint32_t rb = k < st.K ? rb_mi : rb_sh;
+      const uint32_t base = slot + kSlotScale + (uint32_t)k * st.seg_stride;
+      const uint32_t a_lo = base + (uint32_t)min(gid, nrows - 1) * rb, a_hi = base + (uint32_t)min(gid + 8, nrows - 1) * rb;
+      mma_rows_f8(a_lo, a_hi, ssm, ssm, P.bs1_shift, P.bs1, pcd.g0 * 64, pcd.g1 * 64, x16_seg[k], lane, v_lo, v_hi);
+    }
+    if ((lane & 3) == 0) {
+      if (gid < nrows) res[gid * np + pc] = v_lo;
+      if (gid + 8 < nrows) res[(gid + 8) * np + pc] = v_hi;
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void consume_down_tile(const Program& P, const Stage& st, int t, uint32_t slot, const uint32_t* xs_seg,
                                                   const Q8Smem* q8_seg, float* res, const int* act_smem) {
@@ -954,6 +1108,51 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
   }
 }
 
+// GEMV activation staging for the tensor-core path: RMSNorm fused, values split into fp16 hi/lo (n <= 8192 in registers)
+__device__ __forceinline__ void c_stage_gemv_input_x16(const Program& P, const Stage& st, const MegaSmem& sm, const X16& x16) {
+  const int tid = threadIdx.x;
+  const int n = st.n, nf = n >> 2;
+  if (n <= 8192) {
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int f = tid + k * kConsumers;
+      if (f < nf) {
+        v[k] = reinterpret_cast<const float4*>(st.in)[f];
+        ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+      }
+    }
+    float sc = 1.0f;
+    if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int f = tid + k * kConsumers;
+      if (f < nf) {   // nf is a multiple of 16, so the 16 lanes of a 64-column group are in or out together
+        float4 o = v[k];
+        if (st.norm_w) {
+          const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
+          o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
+          o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
+        }
+        x16_store(x16, f, o);
+      }
+    }
+  } else {
+    float sc = 1.0f;
+    if (st.norm_w) sc = c_rms_scale(st.in, n, P.eps, sm.red);
+    for (int f = tid; f < nf; f += kConsumers) {
+      float4 o = reinterpret_cast<const float4*>(st.in)[f];
+      if (st.norm_w) {
+        const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
+        o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
+        o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
+      }
+      x16_store(x16, f, o);
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
                                                unsigned long long& best_key, int dep_count, int stage_index) {
@@ -975,7 +1174,37 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   Q8Smem q80{};
   uint32_t xs_seg[kMaxJobs];
   Q8Smem q8_seg[kMaxJobs];
-  if (st.kind == ST_GEMV) {
+  X16 x16_0{};
+  X16 x16_seg[kMaxJobs];
+  const bool mma = Q == Q_F8 && st.use_mma;
+  if (st.kind == ST_GEMV && mma) {
+    x16_0 = carve_x16(sm.xregion, st.n);
+    c_stage_gemv_input_x16(P, st, sm, x16_0);
+  } else if (st.kind == ST_DOWN && mma) {
+    unsigned char* p = sm.xregion;
+    const bool use_shared = st.sw2 != nullptr && st.add_shared;
+    // all K+1 vectors in ONE flattened loop: every thread's loads are in flight together
+    int off[kMaxJobs + 1];
+    off[0] = 0;
+    for (int k = 0; k <= st.K; k++) {
+      const int n = k < st.K ? st.mi : st.sh;
+      x16_seg[k] = carve_x16(p, n);
+      p += n ? x16_bytes(n) : 0;
+      off[k + 1] = off[k] + (n >> 2);
+    }
+    for (int f = tid; f < off[st.K + 1]; f += kConsumers) {
+      int k = 0;
+      while (f >= off[k + 1]) k++;
+      bool live = true;
+      if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = e >= 0 && e < P.expert_count; }
+      else live = use_shared;
+      const int fl = f - off[k];
+      const float* src = k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) v = reinterpret_cast<const float4*>(src)[fl];
+      x16_store(x16_seg[k], fl, v);
+    }
+  } else if (st.kind == ST_GEMV) {
     carve_x<Q>(sm.xregion, st.n, xs0, q80);
     c_stage_gemv_input<Q>(P, st, sm, xs0, q80);
   } else {
@@ -1017,7 +1246,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       const int r = (t - st.job[0].tile_begin) * st.rows_per_tile + tid;
       if (tid < st.rows_per_tile && r < st.job[0].rows) xres = st.job[0].out[r];
     }
-    if (st.kind == ST_GEMV) consume_gemv_tile<Q>(P, st, t, slot, xs, q80, res, sm.act, best_key, skip);
+    if (st.kind == ST_GEMV) consume_gemv_tile<Q>(P, st, t, slot, xs, q80, x16_0, res, sm.act, best_key, skip);
+    else if (mma) consume_down_tile_mma(P, st, t, slot, x16_seg, res, sm.act);
     else consume_down_tile<Q>(P, st, t, slot, xs_seg, q8_seg, res, sm.act);
     __syncwarp();
     if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
