@@ -890,6 +890,8 @@ static int granules(int quant, int n) {
 }
 static bool kq_quant(int q) { return q == DSK_Q2_K || q == DSK_Q3_K; }
 
+static int g_slot_data = kSlotData, g_slot_scale = kSlotScale;   // set per program: 16 KB tiles for the warp-per-tile tensor-core path
+
 static void plan_gemv_stage(Stage& st, int quant, int G) {
   const size_t rb = dev_row_bytes(quant, st.n);
   const int parts = st.epi == EPI_GLU ? 2 : 1;
@@ -899,10 +901,10 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     int total_rows = 0;
     for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
     int RT = parts == 2 ? 8 : 16;
-    while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)kSlotData) RT >>= 1;
-    while (RT * 2 <= 32 && align_up((size_t)RT * 2 * rb, 128) * parts <= (size_t)kSlotData && cdiv(total_rows, RT * 2) >= 2 * G) RT *= 2;
+    while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
     st.rows_per_tile = RT;
     st.rpass = 1;
+    st.wp = 1;   // one warp reduces the whole tile
     const int rpg = parts == 2 ? 8 : 16, groups = cdiv(RT, rpg), gran = st.n / 64;
     int csplit = std::max(1, std::min(std::min(8 / std::max(1, groups), gran), 8));
     st.npieces = csplit;
@@ -916,7 +918,7 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
   int total_rows = 0;
   for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
   int RT = 32;
-  while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)kSlotData) RT >>= 1;
+  while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
   int min_rt = 1;
   if (quant == DSK_Q2_K) { const int nb = st.n / 256; min_rt = (nb % 4 == 0) ? 1 : (nb % 2 == 0 ? 2 : 4); }  // 16-byte TMA source alignment
   while (RT > std::max(min_rt, 4) && cdiv(total_rows, RT) < G) RT >>= 1;   // at least one tile per CTA when possible
@@ -940,10 +942,29 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
 
 static int plan_down_stage(Stage& st, int quant, int dim) {
   const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
+  if (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma) {
+    // warp-per-tile pieces: (segment, rows [g0, g0+g1) of an 8-row output group), whole rows, <= one slot each
+    st.use_mma = 1; st.wp = 1; st.down_rows = 8; st.rows_per_tile = 8; st.seg_stride = 0;
+    int np = 0;
+    for (int k = 0; k <= st.K; k++) {
+      const int n = k < st.K ? st.mi : st.sh;
+      if (n == 0) continue;
+      int pr = 8;
+      while (pr > 1 && (size_t)pr * n > (size_t)g_slot_data) pr >>= 1;
+      if ((size_t)pr * n > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
+      for (int r0 = 0; r0 < 8; r0 += pr) {
+        if (np >= 16) return fail(-4, "too many down-projection pieces");
+        st.piece[np++] = Piece{k, r0, pr, 0};
+      }
+    }
+    st.npieces = np;
+    st.ntiles = cdiv(dim, 8) * np;
+    return 0;
+  }
   int RT = 8;
   auto bytes = [&](int r) { return align_up((size_t)r * rb_mi, 128) * st.K + align_up((size_t)r * rb_sh, 128); };
-  while (RT > 1 && bytes(RT) > (size_t)kSlotData) RT >>= 1;
-  if (bytes(RT) > (size_t)kSlotData) return fail(-4, "down-projection row (%zu bytes) does not fit a ring slot", bytes(1));
+  while (RT > 1 && bytes(RT) > (size_t)g_slot_data) RT >>= 1;
+  if (bytes(RT) > (size_t)g_slot_data) return fail(-4, "down-projection row (%zu bytes) does not fit a ring slot", bytes(1));
   if (quant == DSK_Q2_K) {
     auto ok = [&](int n) { const int nb = n / 256; return n == 0 || (RT * nb) % 4 == 0; };
     if (!ok(st.mi) || !ok(st.sh)) return fail(-4, "Q2_K down projection: tile rows x blocks not 16-byte aligned");
@@ -951,7 +972,7 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
   st.rows_per_tile = RT;
   st.seg_stride = (int)align_up((size_t)RT * rb_mi, 128);
   st.ntiles = cdiv(dim, RT);
-  st.use_mma = (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma) ? 1 : 0;
+  st.use_mma = 0;
   const int g_mi = st.mi ? (st.use_mma ? st.mi / 64 : granules(quant, st.mi)) : 0, g_sh = st.sh ? (st.use_mma ? st.sh / 64 : granules(quant, st.sh)) : 0;
   const long long total = (long long)g_mi * st.K + g_sh;
   const int want = st.use_mma ? 8 : std::max(1, cdiv(16, RT));
@@ -978,6 +999,9 @@ static MJob mjob(const DTensor& t, float* out) {
 static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
+  const bool wp_model = q == DSK_F8E5M2 && g_use_mma;
+  g_slot_data = wp_model ? 16 * 1024 : kSlotData;
+  g_slot_scale = kSlotScale;
   std::vector<Stage> S;
   auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {
     Stage st{};
@@ -1091,9 +1115,10 @@ static int build_program(dsk_model* m, dsk_state* s) {
   if (attn_need <= 64 * 1024) xreg = std::max(xreg, attn_need);
   xreg = align_up(std::max(xreg, (size_t)(512 + ((hd + 3) & ~3) + 64) * 4), 128);
   const size_t budget = (size_t)kSmemMax - 2048;
-  if (kMegaHdr + xreg + 2 * (size_t)kSlotBytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
-  int n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / kSlotBytes);
-  s->mega_smem = kMegaHdr + xreg + (size_t)n_slots * kSlotBytes;
+  const size_t slot_bytes = (size_t)g_slot_data + g_slot_scale;
+  if (kMegaHdr + xreg + 2 * slot_bytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
+  int n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / slot_bytes);
+  s->mega_smem = kMegaHdr + xreg + (size_t)n_slots * slot_bytes;
   s->n_stages = (int)S.size();
 
   std::vector<unsigned char> buf(sizeof(Program) + (S.size() - 1) * sizeof(Stage));
@@ -1116,6 +1141,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   CK(cudaMemset(s->sync_words, 0, 64));
   P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
   P->n_slots = n_slots; P->xregion_bytes = (int)xreg;
+  P->slot_data = g_slot_data; P->slot_scale = g_slot_scale; P->slot_bytes = (int)slot_bytes;
   CK(cudaMalloc((void**)&s->tstamp, S.size() * 8 * sizeof(unsigned long long)));
   CK(cudaMemset(s->tstamp, 0, S.size() * 8 * sizeof(unsigned long long)));
   P->tstamp = s->tstamp;

@@ -30,7 +30,7 @@ constexpr int kMegaThreads = 288;          // + producer warp 8
 constexpr int kSlotScale = 2048;           // bytes reserved per ring slot for f8 scale rows
 constexpr int kSlotData = 32 * 1024;       // weight bytes per ring slot
 constexpr int kSlotBytes = kSlotScale + kSlotData;
-constexpr int kMaxSlots = 6;
+constexpr int kMaxSlots = 12;
 constexpr int kMaxPieces = 24;
 constexpr int kMegaHdr = 8192;             // barriers, scratch, partial results, smem copies of Program + 2 Stage descriptors
 constexpr int kStageSlot = 1536;           // bytes reserved per cached Stage descriptor
@@ -49,7 +49,7 @@ struct Stage {
   int kind, quant, epi, njobs;
   int n, rows_per_tile, rpass, ntiles;
   int need_topk, npieces, layer, has_dyn;
-  int use_mma, pad3[3];          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
+  int use_mma, wp, down_rows, pad3;   // wp: warp-per-tile stage (tensor-core tiles owned by single warps)          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
   const float* in; const float* norm_w;
   MJob job[kMaxJobs];
   Piece piece[kMaxPieces];
@@ -86,6 +86,7 @@ struct Program {
   unsigned int* sync_base;                 // value of the counter when this launch started
   int* token_log; int* step;
   int n_slots, xregion_bytes;
+  int slot_data, slot_scale, slot_bytes, pad_s;   // ring slot geometry (bytes): [scale rows | weight tile]
   unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
   Stage stage[1];                          // n_stages entries follow
 };
@@ -449,14 +450,14 @@ struct MegaSmem {
 __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_bytes) {
   MegaSmem m;
   const uint32_t b = smem_u32(smem);
-  for (int i = 0; i < kMaxSlots; i++) { m.full[i] = b + 8 * i; m.empty[i] = b + 64 + 8 * i; }
-  m.dep = b + 128;
-  m.red = reinterpret_cast<float*>(smem + 192);            // 32 floats -> 320
-  m.act = reinterpret_cast<int*>(smem + 320);              // 16 ints -> 384
-  m.actw = reinterpret_cast<float*>(smem + 384);           // 16 floats -> 448
-  m.sel = reinterpret_cast<int*>(smem + 448);              // 16 ints -> 512
-  m.mask = smem + 512;                                     // 256 B -> 768
-  m.sx = reinterpret_cast<float*>(smem + 768);             // 256 floats -> 1792
+  for (int i = 0; i < kMaxSlots; i++) { m.full[i] = b + 8 * i; m.empty[i] = b + 96 + 8 * i; }
+  m.dep = b + 192;
+  m.red = reinterpret_cast<float*>(smem + 256);            // 32 floats -> 384
+  m.act = reinterpret_cast<int*>(smem + 384);              // 16 ints -> 448
+  m.actw = reinterpret_cast<float*>(smem + 448);           // 16 floats -> 512
+  m.sel = reinterpret_cast<int*>(smem + 512);              // 16 ints: warp-per-tile DOWN completion counters -> 576
+  m.mask = smem + 576;                                     // 192 B spare -> 768
+  m.sx = reinterpret_cast<float*>(smem + 768);             // 256 floats: warp-per-tile DOWN partial sums [8][pieces<=4..] -> 1792
   m.res = reinterpret_cast<float*>(smem + 1792);           // 2 x 256 floats -> 3840
   m.st_c = reinterpret_cast<Stage*>(smem + 4096);
   m.st_p = reinterpret_cast<Stage*>(smem + 4096 + kStageSlot);
@@ -582,11 +583,11 @@ __device__ __forceinline__ void produce_tile(const Program& P, const Stage& st, 
       total += sbytes[0] + sbytes[1];
     }
     mbar_expect_tx(full, total);
-    bulk_g2s(slot + kSlotScale, jb.w + woff, bytes, full);
-    if (parts == 2) bulk_g2s(slot + kSlotScale + part_stride, jb.w_b + woff, bytes, full);
+    bulk_g2s(slot + (uint32_t)P.slot_scale, jb.w + woff, bytes, full);
+    if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale + part_stride, jb.w_b + woff, bytes, full);
     if (jb.scale) {
       bulk_g2s(slot, ssrc[0], sbytes[0], full);
-      if (parts == 2) bulk_g2s(slot + kSlotScale / 2, ssrc[1], sbytes[1], full);
+      if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale / 2, ssrc[1], sbytes[1], full);
     }
   } else {  // ST_DOWN: K routed segments + the shared/dense segment of rows [i0, i0+nrows)
     const int i0 = t * st.rows_per_tile;
@@ -613,14 +614,14 @@ __device__ __forceinline__ void produce_tile(const Program& P, const Stage& st, 
       if (st.ss2) { sbytes[st.K] = scale_copy_bytes(st.ss2 + (size_t)(i0 / P.bs0) * ncb_sh, ncb_sh, ssrc[st.K], shift); total += sbytes[st.K]; }
     }
     mbar_expect_tx(full, total);
-    const uint32_t sstride = kSlotScale / (uint32_t)(st.K + 1) & ~15u;
+    const uint32_t sstride = (uint32_t)P.slot_scale / (uint32_t)(st.K + 1) & ~15u;
     for (int k = 0; k < st.K; k++) {
       if (eidx[k] < 0) continue;
-      bulk_g2s(slot + kSlotScale + (uint32_t)k * st.seg_stride, st.w2 + (size_t)eidx[k] * st.w2_stride + (size_t)i0 * rb_mi, b_mi, full);
+      bulk_g2s(slot + (uint32_t)P.slot_scale + (uint32_t)k * st.seg_stride, st.w2 + (size_t)eidx[k] * st.w2_stride + (size_t)i0 * rb_mi, b_mi, full);
       if (sbytes[k]) bulk_g2s(slot + (uint32_t)k * sstride, ssrc[k], sbytes[k], full);
     }
     if (use_shared) {
-      bulk_g2s(slot + kSlotScale + (uint32_t)st.K * st.seg_stride, st.sw2 + (size_t)i0 * rb_sh, b_sh, full);
+      bulk_g2s(slot + (uint32_t)P.slot_scale + (uint32_t)st.K * st.seg_stride, st.sw2 + (size_t)i0 * rb_sh, b_sh, full);
       if (sbytes[st.K]) bulk_g2s(slot + (uint32_t)st.K * sstride, ssrc[st.K], sbytes[st.K], full);
     }
   }
@@ -640,7 +641,7 @@ __device__ __forceinline__ void gemv_tile_tasks(const Program& P, const Stage& s
   uint32_t s0 = 0, s1 = 0;
   if (jb.scale) {
     s0 = slot + (uint32_t)soff_floats;
-    s1 = slot + kSlotScale / 2 + (uint32_t)soff_floats;
+    s1 = slot + (uint32_t)P.slot_scale / 2 + (uint32_t)soff_floats;
   }
   for (int task = warp; task < ngroups * csplit; task += 8) {
     const int g = task / csplit, pc = task - g * csplit;
@@ -649,7 +650,7 @@ __device__ __forceinline__ void gemv_tile_tasks(const Program& P, const Stage& s
 #pragma unroll
     for (int i = 0; i < R; i++) {
       const int lr = min(g * R + i, nrows - 1);
-      wa[i] = slot + kSlotScale + (uint32_t)lr * rb;
+      wa[i] = slot + (uint32_t)P.slot_scale + (uint32_t)lr * rb;
       ssm[i] = s0;
       if constexpr (GLU) { wa[R + i] = wa[i] + part_stride; ssm[R + i] = s1; }
     }
@@ -679,7 +680,7 @@ __device__ __forceinline__ void gemv_tile_tasks_mma(const Program& P, const Stag
   constexpr int RPG = GLU ? 8 : 16;     // tile rows per mma row group
   const int ngroups = (nrows + RPG - 1) / RPG;
   uint32_t s0 = 0, s1 = 0;
-  if (jb.scale) { s0 = slot + (uint32_t)shift_bytes; s1 = slot + kSlotScale / 2 + (uint32_t)shift_bytes; }
+  if (jb.scale) { s0 = slot + (uint32_t)shift_bytes; s1 = slot + (uint32_t)P.slot_scale / 2 + (uint32_t)shift_bytes; }
   for (int task = warp; task < ngroups * csplit; task += 8) {
     const int g = task / csplit, pc = task - g * csplit;
     const Piece pcd = st.piece[pc];
@@ -688,12 +689,12 @@ __device__ __forceinline__ void gemv_tile_tasks_mma(const Program& P, const Stag
     if constexpr (GLU) {
       r_lo = g * 8 + gid; r_hi = r_lo;
       const int lr = min(r_lo, nrows - 1);
-      a_lo = slot + kSlotScale + (uint32_t)lr * rb;
+      a_lo = slot + (uint32_t)P.slot_scale + (uint32_t)lr * rb;
       a_hi = a_lo + part_stride;
     } else {
       r_lo = g * 16 + gid; r_hi = r_lo + 8;
-      a_lo = slot + kSlotScale + (uint32_t)min(r_lo, nrows - 1) * rb;
-      a_hi = slot + kSlotScale + (uint32_t)min(r_hi, nrows - 1) * rb;
+      a_lo = slot + (uint32_t)P.slot_scale + (uint32_t)min(r_lo, nrows - 1) * rb;
+      a_hi = slot + (uint32_t)P.slot_scale + (uint32_t)min(r_hi, nrows - 1) * rb;
     }
     float v_lo, v_hi;
     mma_rows_f8(a_lo, a_hi, s0, GLU ? s1 : s0, P.bs1_shift, P.bs1, pcd.g0 * 64, pcd.g1 * 64, x16, lane, v_lo, v_hi);
@@ -795,7 +796,7 @@ __device__ __forceinline__ void consume_down_tile_mma(const Program& P, const St
   const int nrows = min(st.rows_per_tile, P.dim - i0);
   const uint32_t rb_mi = (uint32_t)st.mi, rb_sh = (uint32_t)st.sh;
   const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
-  const uint32_t sstride = kSlotScale / (uint32_t)(st.K + 1) & ~15u;
+  const uint32_t sstride = (uint32_t)P.slot_scale / (uint32_t)(st.K + 1) & ~15u;
   const int np = st.npieces;
   for (int pc = warp; pc < np; pc += 8) {
     const Piece pcd = st.piece[pc];
@@ -815,7 +816,7 @@ __device__ __forceinline__ void consume_down_tile_mma(const Program& P, const St
     float v_lo = 0.f, v_hi = 0.f;
     if (live) {
       const uint32_t rb = k < st.K ? rb_mi : rb_sh;
-      const uint32_t base = slot + kSlotScale + (uint32_t)k * st.seg_stride;
+      const uint32_t base = slot + (uint32_t)P.slot_scale + (uint32_t)k * st.seg_stride;
       const uint32_t a_lo = base + (uint32_t)min(gid, nrows - 1) * rb, a_hi = base + (uint32_t)min(gid + 8, nrows - 1) * rb;
       mma_rows_f8(a_lo, a_hi, ssm, ssm, P.bs1_shift, P.bs1, pcd.g0 * 64, pcd.g1 * 64, x16_seg[k], lane, v_lo, v_hi);
     }
@@ -834,7 +835,7 @@ __device__ __forceinline__ void consume_down_tile(const Program& P, const Stage&
   const int nrows = min(st.rows_per_tile, P.dim - i0);
   const uint32_t rb_mi = (uint32_t)QTraits<Q>::row_bytes(st.mi), rb_sh = (uint32_t)QTraits<Q>::row_bytes(st.sh);
   const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
-  const uint32_t sstride = kSlotScale / (uint32_t)(st.K + 1) & ~15u;
+  const uint32_t sstride = (uint32_t)P.slot_scale / (uint32_t)(st.K + 1) & ~15u;
   const int np = st.npieces;
   for (int task = warp; task < nrows * np; task += 8) {
     const int lr = task / np, pc = task - lr * np;
@@ -854,7 +855,7 @@ __device__ __forceinline__ void consume_down_tile(const Program& P, const Stage&
         ssm[0] = slot + (uint32_t)k * sstride + (uint32_t)(reinterpret_cast<uintptr_t>(st.ss2 + (size_t)(i0 / P.bs0) * ncb_sh) & 15);
     }
     if (live) {
-      const uint32_t wa[1] = {slot + kSlotScale + (uint32_t)k * st.seg_stride + (uint32_t)lr * (k < st.K ? rb_mi : rb_sh)};
+      const uint32_t wa[1] = {slot + (uint32_t)P.slot_scale + (uint32_t)k * st.seg_stride + (uint32_t)lr * (k < st.K ? rb_mi : rb_sh)};
       piece_rows<Q, 1>(wa, ssm, P.bs1, P.bs1_shift, pcd.g0, pcd.g1, xs_seg[k], q8_seg[k], lane, v);
     }
     if (lane == 0) res[lr * np + pc] = v[0];
@@ -1108,6 +1109,173 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-per-tile stages (F8E5M2 through the tensor cores).  A tile is small enough (<= slot_data bytes) that ONE warp
+// reduces it over the full K range with the accumulators in registers: no per-tile CTA barrier, no partial-sum
+// exchange, and with 8 consumer warps up to 8 tiles are being reduced while the producer keeps the other slots filling.
+//   ST_GEMV: tile = rows [r0, r0+RT) of one job (RT <= 16; EPI_GLU: RT <= 8 gate rows + the same RT up rows)
+//   ST_DOWN: tile = one PIECE (segment k, rows [pr0, pr0+pnr) of an 8-row output group); the warp that completes the
+//            group's last piece combines the partial sums in the reference's order and applies the residual update.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, const X16& x16,
+                                             const int* act_smem, unsigned long long& best) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  int j = 0;
+  while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
+  const MJob& jb = st.job[j];
+  const int r0 = (t - jb.tile_begin) * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, jb.rows - r0);
+  size_t soff = 0;
+  if (jb.expert_slot >= 0) {
+    const int e = act_smem[jb.expert_slot] - P.expert_first;
+    if (e < 0 || e >= P.expert_count) return;
+    soff = (size_t)e * jb.s_stride;
+  }
+  const bool glu = st.epi == EPI_GLU;
+  const uint32_t rb = (uint32_t)st.n;
+  const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
+  uint32_t s0 = 0, s1 = 0;
+  if (jb.scale) {
+    const int ncb = (st.n + P.bs1 - 1) / P.bs1;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(jb.scale + soff + (size_t)(r0 / P.bs0) * ncb) & 15);
+    s0 = slot + sh;
+    s1 = glu ? slot + (uint32_t)P.slot_scale / 2 + sh : s0;
+  }
+  const uint32_t data = slot + (uint32_t)P.slot_scale;
+  const int r_lo = gid, r_hi = glu ? gid : gid + 8;
+  const uint32_t a_lo = data + (uint32_t)min(r_lo, nrows - 1) * rb;
+  const uint32_t a_hi = (glu ? data + part_stride : data) + (uint32_t)min(r_hi, nrows - 1) * rb;
+  // residual operand first: its L2 latency hides behind the K loop
+  float xres_lo = 0.f, xres_hi = 0.f;
+  if (st.epi == EPI_RESID && tig == 0) {
+    if (r_lo < nrows) xres_lo = jb.out[r0 + r_lo];
+    if (r_hi < nrows) xres_hi = jb.out[r0 + r_hi];
+  }
+  float v_lo, v_hi;
+  mma_rows_f8(a_lo, a_hi, s0, s1, P.bs1_shift, P.bs1, 0, st.n, x16, lane, v_lo, v_hi);
+  if (tig != 0) return;
+  if (glu) {
+    if (r_lo < nrows) jb.out[r0 + r_lo] = (P.act_silu ? silu_f(v_lo) : gelu_f(v_lo)) * v_hi;
+    return;
+  }
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    const int lr = half ? r_hi : r_lo;
+    if (lr >= nrows) continue;
+    const int r = r0 + lr;
+    const float val = half ? v_hi : v_lo;
+    switch (st.epi) {
+      case EPI_RESID: jb.out[r] = (half ? xres_hi : xres_lo) + val; break;
+      case EPI_KVB: {
+        jb.out[r] = val;
+        const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
+        const int kv_pos = P.ctrl->kv_pos;
+        if (ii < P.nope) st.kcache[(size_t)kv_pos * P.n_heads * P.hd + hh * P.hd + ii] = __float2half_rn(val);
+        else st.vcache[(size_t)kv_pos * P.n_heads * P.vh + hh * P.vh + (ii - P.nope)] = __float2half_rn(val);
+        break;
+      }
+      case EPI_LOGITS: {
+        jb.out[r] = val;
+        const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+        if (key > best) best = key;
+        break;
+      }
+      default: jb.out[r] = val; break;
+    }
+  }
+}
+
+// producer side of a warp-per-tile DOWN piece: rows [i0+pr0, +pnr) of segment k, whole rows (contiguous bytes)
+__device__ __forceinline__ void wp_produce_down_piece(const Program& P, const Stage& st, int rg, int pc, uint32_t slot, uint32_t full,
+                                                      const int* act_smem) {
+  const Piece pcd = st.piece[pc];
+  const int k = pcd.seg, i0 = rg * st.down_rows + pcd.g0;
+  const int nrows = min(pcd.g1, P.dim - i0);
+  const bool routed = k < st.K;
+  int e = 0;
+  if (routed) {
+    e = act_smem[k] - P.expert_first;
+    if (e < 0 || e >= P.expert_count) { mbar_expect_tx(full, 0); return; }
+  } else if (!(st.sw2 != nullptr && st.add_shared)) { mbar_expect_tx(full, 0); return; }
+  if (nrows <= 0) { mbar_expect_tx(full, 0); return; }
+  const int n = routed ? st.mi : st.sh;
+  const uint32_t bytes = (uint32_t)align_up((size_t)nrows * n, 16);
+  const uint8_t* src = routed ? st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * n : st.sw2 + (size_t)i0 * n;
+  const float* sc = routed ? st.s2 : st.ss2;
+  uint32_t total = bytes, sbytes = 0, shift = 0;
+  const float* ssrc = nullptr;
+  if (sc) {
+    const int ncb = (n + P.bs1 - 1) / P.bs1;
+    sbytes = scale_copy_bytes(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb, ncb, ssrc, shift);
+    total += sbytes;
+  }
+  mbar_expect_tx(full, total);
+  bulk_g2s(slot + (uint32_t)P.slot_scale, src, bytes, full);
+  if (sbytes) bulk_g2s(slot, ssrc, sbytes, full);
+}
+
+// consumer side: one warp reduces the piece; the last piece of a row group triggers the ordered combine
+__device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st, const MegaSmem& sm, int rg, int rg_local, int pc,
+                                              uint32_t slot, const X16* x16_seg) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const Piece pcd = st.piece[pc];
+  const int k = pcd.seg, i0 = rg * st.down_rows + pcd.g0;
+  const int nrows = min(pcd.g1, P.dim - i0);
+  const bool routed = k < st.K;
+  bool live = nrows > 0;
+  int e = 0;
+  if (routed) { e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
+  else live = live && st.sw2 != nullptr && st.add_shared;
+  const int np = st.npieces;
+  float* part = sm.res + (size_t)(rg_local & 3) * 128;    // [4 row groups in flight][np <= 16][8 rows]
+  int* cnt = sm.sel + (rg_local & 3);
+  if (live) {
+    const int n = routed ? st.mi : st.sh;
+    const float* sc = routed ? st.s2 : st.ss2;
+    uint32_t ssm = 0;
+    if (sc) {
+      const int ncb = (n + P.bs1 - 1) / P.bs1;
+      ssm = slot + (uint32_t)(reinterpret_cast<uintptr_t>(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb) & 15);
+    }
+    const uint32_t data = slot + (uint32_t)P.slot_scale;
+    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)n;
+    float v_lo, v_hi;
+    mma_rows_f8(a_lo, a_lo, ssm, ssm, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
+    if (tig == 0 && gid < nrows) part[pc * 8 + pcd.g0 + gid] = v_lo;
+  }
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) { __threadfence_block(); last = atomicAdd(cnt, 1) == np - 1; }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence_block();
+  // combine: lane r < rows of the group; segments in the reference's order (src/infer.cpp:873-877, 899-903, 926-930)
+  const int gi0 = rg * st.down_rows;
+  const int grows = min(st.down_rows, P.dim - gi0);
+  if (lane < grows) {
+    const int i = gi0 + lane;
+    const bool to_partial = P.partial != nullptr && st.K > 0;
+    float acc = to_partial ? 0.f : P.x[i];
+    int p2 = 0;
+    for (int kk = 0; kk <= st.K; kk++) {
+      float v = 0.f;
+      bool any = false;
+      for (; p2 < np && st.piece[p2].seg == kk; p2++) {
+        const Piece q = st.piece[p2];
+        if (lane >= q.g0 && lane < q.g0 + q.g1) { v += part[p2 * 8 + lane]; any = true; }
+      }
+      if (!any) continue;
+      if (kk < st.K) {
+        const int ee = sm.act[kk] - P.expert_first;
+        if (ee >= 0 && ee < P.expert_count) acc = fmaf(v, sm.actw[kk], acc);
+      } else if (st.sw2 != nullptr && st.add_shared) acc += v;
+    }
+    if (to_partial) P.partial[i] = acc; else P.x[i] = acc;
+  }
+  __syncwarp();
+  if (lane == 0) *cnt = 0;
+}
+
 // GEMV activation staging for the tensor-core path: RMSNorm fused, values split into fp16 hi/lo (n <= 8192 in registers)
 __device__ __forceinline__ void c_stage_gemv_input_x16(const Program& P, const Stage& st, const MegaSmem& sm, const X16& x16) {
   const int tid = threadIdx.x;
@@ -1158,7 +1326,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
                                                unsigned long long& best_key, int dep_count, int stage_index) {
   constexpr bool KQ = QTraits<Q>::kq;
   const int tid = threadIdx.x;
-  if ((int)blockIdx.x >= st.ntiles) {   // no tile of this stage lands on this CTA: nothing to stage
+  const int my_units = (st.kind == ST_DOWN && st.wp) ? (P.dim + st.down_rows - 1) / st.down_rows : st.ntiles;
+  if ((int)blockIdx.x >= my_units) {    // no tile of this stage lands on this CTA: nothing to stage
     if (tid == 0) dep_signal(sm.dep, dep_count);
     return;
   }
@@ -1225,13 +1394,43 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   csync();
   if (!(st.need_topk || (st.kind == ST_DOWN && st.K > 0)) && tid == 0) dep_signal(sm.dep, dep_count);
   if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
+  if (mma && st.wp) {   // warp-per-tile: every consumer warp owns the tiles whose local index is congruent to its id
+    const int warp = tid >> 5, lane = tid & 31;
+    if (st.kind == ST_GEMV) {
+      int li = 0;
+      for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++, li++) {
+        if ((li & 7) != warp) continue;
+        const int sl = it % n_slots;
+        mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+        wp_gemv_tile(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_0, sm.act, best_key);
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+      }
+    } else {
+      if (tid < 4) sm.sel[tid] = 0;
+      csync();
+      const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
+      int li = 0, rgl = 0;
+      for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
+        for (int pc = 0; pc < st.npieces; pc++, it++, li++) {
+          if ((li & 7) != warp) continue;
+          const int sl = it % n_slots;
+          mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+          wp_down_piece(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_seg);
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+        }
+      }
+    }
+    return;
+  }
   const uint32_t xs = KQ ? 0u : smem_u32(xs0);
   int parity_res = 0;
   long long c_wait = 0, c_task = 0, c_sync = 0, c_epi = 0;
   const bool timing = tid == 0 && blockIdx.x == 0 && P.tstamp;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     const int sl = it % n_slots;
-    const uint32_t slot = sm.ring + (uint32_t)sl * kSlotBytes;
+    const uint32_t slot = sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes;
     const long long k0 = clock64();
     mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
     const long long k1 = clock64();
@@ -1249,10 +1448,9 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     if (st.kind == ST_GEMV) consume_gemv_tile<Q>(P, st, t, slot, xs, q80, x16_0, res, sm.act, best_key, skip);
     else if (mma) consume_down_tile_mma(P, st, t, slot, x16_seg, res, sm.act);
     else consume_down_tile<Q>(P, st, t, slot, xs_seg, q8_seg, res, sm.act);
-    __syncwarp();
-    if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
     const long long k2 = clock64();
-    csync();
+    csync();                       // every warp is done with the slot -> one arrival frees it
+    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
     const long long k3 = clock64();
     if (!skip) {
       if (st.kind == ST_GEMV) gemv_tile_epilogue(P, st, t, res, best_key, xres);
@@ -1272,6 +1470,19 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
                                                int dep_count) {
   bool dep_waited = false;
   const bool dyn_all = st.kind == ST_DOWN && st.K > 0;
+  if (st.kind == ST_DOWN && st.wp) {
+    const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
+    for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x) {
+      for (int pc = 0; pc < st.npieces; pc++, it++) {
+        if (st.piece[pc].seg < st.K && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
+        const int sl = it % n_slots;
+        if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+        wp_produce_down_piece(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
+      }
+    }
+    if (!dep_waited) dep_wait(sm.dep, dep_count);
+    return;
+  }
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     bool dyn = dyn_all;
     if (st.kind == ST_GEMV && st.has_dyn) {
@@ -1282,7 +1493,7 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
     if (dyn && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
     const int sl = it % n_slots;
     if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
-    produce_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * kSlotBytes, sm.full[sl], sm.act);
+    produce_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
   }
   if (!dep_waited) dep_wait(sm.dep, dep_count);   // bounds the run-ahead to one stage
 }
@@ -1306,7 +1517,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
   const MegaSmem sm = carve_mega(smem, P.xregion_bytes);
   const int n_slots = P.n_slots;
   if (tid == 0) {
-    for (int i = 0; i < n_slots; i++) { mbar_init(sm.full[i], 1); mbar_init(sm.empty[i], 8); }
+    for (int i = 0; i < n_slots; i++) { mbar_init(sm.full[i], 1); mbar_init(sm.empty[i], 1); }
     dep_signal(sm.dep, 0);
     fence_proxy_async();
   }
