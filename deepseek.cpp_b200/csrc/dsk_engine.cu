@@ -901,10 +901,10 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     int total_rows = 0;
     for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
     int RT = parts == 2 ? 8 : 16;
-    while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
+    while (RT > 1 && align_up((size_t)RT * (rb + kRowPad), 128) * parts > (size_t)g_slot_data) RT >>= 1;
     st.rows_per_tile = RT;
     st.rpass = 1;
-    st.wp = 1;   // one warp reduces the whole tile
+    st.wp = 1;   // one warp reduces the whole tile (rows at a padded pitch)
     const int rpg = parts == 2 ? 8 : 16, groups = cdiv(RT, rpg), gran = st.n / 64;
     int csplit = std::max(1, std::min(std::min(8 / std::max(1, groups), gran), 8));
     st.npieces = csplit;
@@ -950,8 +950,8 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
       const int n = k < st.K ? st.mi : st.sh;
       if (n == 0) continue;
       int pr = 8;
-      while (pr > 1 && (size_t)pr * n > (size_t)g_slot_data) pr >>= 1;
-      if ((size_t)pr * n > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
+      while (pr > 1 && (size_t)pr * (n + kRowPad) > (size_t)g_slot_data) pr >>= 1;
+      if ((size_t)pr * (n + kRowPad) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
       for (int r0 = 0; r0 < 8; r0 += pr) {
         if (np >= 16) return fail(-4, "too many down-projection pieces");
         st.piece[np++] = Piece{k, r0, pr, 0};
@@ -1000,7 +1000,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
   const bool wp_model = q == DSK_F8E5M2 && g_use_mma;
-  g_slot_data = wp_model ? 16 * 1024 : kSlotData;
+  g_slot_data = wp_model ? 16 * 1024 + 512 : kSlotData;   // 8 rows x (2048 + 16) B fit one slot
   g_slot_scale = kSlotScale;
   std::vector<Stage> S;
   auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {

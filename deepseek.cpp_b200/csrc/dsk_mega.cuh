@@ -24,6 +24,7 @@
 namespace dsk {
 
 enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3 };
+constexpr int kRowPad = 16;   // warp-per-tile tiles: row pitch = n + 16 B so that 8 rows x 4 chunks of an A-fragment load are bank-conflict free
 
 constexpr int kConsumers = 256;            // warps 0..7
 constexpr int kMegaThreads = 288;          // + producer warp 8
@@ -271,7 +272,9 @@ __device__ __forceinline__ void x16_store(const X16& x, int f, float4 v) {
   if ((f & 15) == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(x.gs + (uint32_t)(f >> 4) * 4u), "f"(inv) : "memory");
 }
 // rows (gid) and (gid+8) of a 16-row group over columns [col0, col1) (multiples of 64).  a_lo/a_hi: shared addresses of the
-// two weight rows; s_lo/s_hi: their f8 scale rows (0 = none).  Results valid in lanes with (lane & 3) == 0.
+// two weight rows (a_hi == 0: no upper rows, their fragment registers are zero); s_lo/s_hi: f8 scale rows (0 = none).
+// The four mma of a 64-column group use independent accumulators (legacy HMMA latency is long).  Results valid in lanes
+// with (lane & 3) == 0.
 __device__ __forceinline__ void mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32_t s_lo, uint32_t s_hi, int sshift, int bs1, int col0, int col1,
                                             const X16& x, int lane, float& out_lo, float& out_hi) {
   const int gid = lane >> 2, tig = lane & 3;
@@ -280,19 +283,23 @@ __device__ __forceinline__ void mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32
 #pragma unroll 2
   for (int cb = col0; cb < col1; cb += 64) {
     const uint4 w0 = lds128(a_lo + (uint32_t)(cb + 16 * tig));
-    const uint4 w1 = lds128(a_hi + (uint32_t)(cb + 16 * tig));
+    uint4 w1 = make_uint4(0, 0, 0, 0);
+    if (a_hi) w1 = lds128(a_hi + (uint32_t)(cb + 16 * tig));
     uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
     if (gid < 2) { b0 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u); b1 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u + 16u); }
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_f16(c, __byte_perm(w0.x, 0, 0x1404), __byte_perm(w1.x, 0, 0x1404), __byte_perm(w0.x, 0, 0x3424), __byte_perm(w1.x, 0, 0x3424), b0.x, b0.y);
-    mma_f16(c, __byte_perm(w0.y, 0, 0x1404), __byte_perm(w1.y, 0, 0x1404), __byte_perm(w0.y, 0, 0x3424), __byte_perm(w1.y, 0, 0x3424), b0.z, b0.w);
-    mma_f16(c, __byte_perm(w0.z, 0, 0x1404), __byte_perm(w1.z, 0, 0x1404), __byte_perm(w0.z, 0, 0x3424), __byte_perm(w1.z, 0, 0x3424), b1.x, b1.y);
-    mma_f16(c, __byte_perm(w0.w, 0, 0x1404), __byte_perm(w1.w, 0, 0x1404), __byte_perm(w0.w, 0, 0x3424), __byte_perm(w1.w, 0, 0x3424), b1.z, b1.w);
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_f16(c0, __byte_perm(w0.x, 0, 0x1404), __byte_perm(w1.x, 0, 0x1404), __byte_perm(w0.x, 0, 0x3424), __byte_perm(w1.x, 0, 0x3424), b0.x, b0.y);
+    mma_f16(c1, __byte_perm(w0.y, 0, 0x1404), __byte_perm(w1.y, 0, 0x1404), __byte_perm(w0.y, 0, 0x3424), __byte_perm(w1.y, 0, 0x3424), b0.z, b0.w);
+    mma_f16(c2, __byte_perm(w0.z, 0, 0x1404), __byte_perm(w1.z, 0, 0x1404), __byte_perm(w0.z, 0, 0x3424), __byte_perm(w1.z, 0, 0x3424), b1.x, b1.y);
+    mma_f16(c3, __byte_perm(w0.w, 0, 0x1404), __byte_perm(w1.w, 0, 0x1404), __byte_perm(w0.w, 0, 0x3424), __byte_perm(w1.w, 0, 0x3424), b1.z, b1.w);
     const float g = __uint_as_float(lds32(x.gs + (uint32_t)(cb >> 6) * 4u));
     const uint32_t sidx = (sshift >= 0 ? (uint32_t)cb >> sshift : (uint32_t)(cb / bs1)) * 4u;
     const float f_lo = s_lo ? g * __uint_as_float(lds32(s_lo + sidx)) : g;
     const float f_hi = s_hi ? g * __uint_as_float(lds32(s_hi + sidx)) : g;
-    t0 = fmaf(c[0], f_lo, t0); t1 = fmaf(c[1], f_lo, t1); t2 = fmaf(c[2], f_hi, t2); t3 = fmaf(c[3], f_hi, t3);
+    t0 = fmaf((c0[0] + c1[0]) + (c2[0] + c3[0]), f_lo, t0);
+    t1 = fmaf((c0[1] + c1[1]) + (c2[1] + c3[1]), f_lo, t1);
+    t2 = fmaf((c0[2] + c1[2]) + (c2[2] + c3[2]), f_hi, t2);
+    t3 = fmaf((c0[3] + c1[3]) + (c2[3] + c3[3]), f_hi, t3);
   }
   out_lo = t0 + t1;   // hi-part + lo-part contributions
   out_hi = t2 + t3;
@@ -581,6 +588,21 @@ __device__ __forceinline__ void produce_tile(const Program& P, const Stage& st, 
       sbytes[0] = scale_copy_bytes(jb.scale + soff + (size_t)(r0 / P.bs0) * ncb, ncb, ssrc[0], shift);
       if (parts == 2) sbytes[1] = scale_copy_bytes(jb.scale_b + soff + (size_t)(r0 / P.bs0) * ncb, ncb, ssrc[1], shift);
       total += sbytes[0] + sbytes[1];
+    }
+    if (st.wp) {   // one copy per row into the padded pitch (f8: rb = n bytes, a multiple of 64)
+      const uint32_t pitch = (uint32_t)rb + kRowPad;
+      const uint32_t pstride = (uint32_t)align_up((size_t)st.rows_per_tile * pitch, 128);
+      total = (uint32_t)(nrows * rb) * parts + sbytes[0] + sbytes[1];
+      mbar_expect_tx(full, total);
+      for (int r = 0; r < nrows; r++) {
+        bulk_g2s(slot + (uint32_t)P.slot_scale + (uint32_t)r * pitch, jb.w + woff + (size_t)r * rb, (uint32_t)rb, full);
+        if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale + pstride + (uint32_t)r * pitch, jb.w_b + woff + (size_t)r * rb, (uint32_t)rb, full);
+      }
+      if (jb.scale) {
+        bulk_g2s(slot, ssrc[0], sbytes[0], full);
+        if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale / 2, ssrc[1], sbytes[1], full);
+      }
+      return;
     }
     mbar_expect_tx(full, total);
     bulk_g2s(slot + (uint32_t)P.slot_scale, jb.w + woff, bytes, full);
@@ -1132,7 +1154,7 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
     soff = (size_t)e * jb.s_stride;
   }
   const bool glu = st.epi == EPI_GLU;
-  const uint32_t rb = (uint32_t)st.n;
+  const uint32_t rb = (uint32_t)st.n + kRowPad;   // padded pitch
   const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
   uint32_t s0 = 0, s1 = 0;
   if (jb.scale) {
@@ -1144,7 +1166,8 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
   const uint32_t data = slot + (uint32_t)P.slot_scale;
   const int r_lo = gid, r_hi = glu ? gid : gid + 8;
   const uint32_t a_lo = data + (uint32_t)min(r_lo, nrows - 1) * rb;
-  const uint32_t a_hi = (glu ? data + part_stride : data) + (uint32_t)min(r_hi, nrows - 1) * rb;
+  uint32_t a_hi = (glu ? data + part_stride : data) + (uint32_t)min(r_hi, nrows - 1) * rb;
+  if (!glu && nrows <= 8) a_hi = 0;   // no upper rows in this tile: skip their loads
   // residual operand first: its L2 latency hides behind the K loop
   float xres_lo = 0.f, xres_hi = 0.f;
   if (st.epi == EPI_RESID && tig == 0) {
@@ -1209,8 +1232,10 @@ __device__ __forceinline__ void wp_produce_down_piece(const Program& P, const St
     sbytes = scale_copy_bytes(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb, ncb, ssrc, shift);
     total += sbytes;
   }
+  total = (uint32_t)(nrows * n) + sbytes;
+  (void)bytes;
   mbar_expect_tx(full, total);
-  bulk_g2s(slot + (uint32_t)P.slot_scale, src, bytes, full);
+  for (int r = 0; r < nrows; r++) bulk_g2s(slot + (uint32_t)P.slot_scale + (uint32_t)r * (uint32_t)(n + kRowPad), src + (size_t)r * n, (uint32_t)n, full);
   if (sbytes) bulk_g2s(slot, ssrc, sbytes, full);
 }
 
@@ -1238,9 +1263,9 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
       ssm = slot + (uint32_t)(reinterpret_cast<uintptr_t>(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb) & 15);
     }
     const uint32_t data = slot + (uint32_t)P.slot_scale;
-    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)n;
+    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)(n + kRowPad);
     float v_lo, v_hi;
-    mma_rows_f8(a_lo, a_lo, ssm, ssm, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
+    mma_rows_f8(a_lo, 0u, ssm, 0u, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
     if (tig == 0 && gid < nrows) part[pc * 8 + pcd.g0 + gid] = v_lo;
   }
   __syncwarp();
