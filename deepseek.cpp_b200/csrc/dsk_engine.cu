@@ -161,7 +161,16 @@ static size_t disk_row_bytes(int quant, int cols) {
 }
 static size_t dev_row_bytes(int quant, int cols) {
   if (quant == DSK_Q3_K) return (size_t)(cols / 256) * kQ3Bytes;
+  if (quant == DSK_F8E5M2) return (size_t)cols + kF8RowPad;   // re-pitched rows (see kF8RowPad)
   return disk_row_bytes(quant, cols);
+}
+// rows of `drb` disk bytes -> device rows of `vrb` bytes (no-op layouts use a flat copy)
+static cudaError_t copy_rows(void* dst, size_t vrb, const void* src, size_t drb, size_t nrows, int on_dev) {
+  const cudaMemcpyKind kind = on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (vrb == drb) return cudaMemcpy(dst, src, drb * nrows, kind);
+  cudaError_t e = cudaMemset(dst, 0, vrb * nrows);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy2D(dst, vrb, src, drb, drb, nrows, kind);
 }
 static int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -378,7 +387,7 @@ static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expe
     CK(cudaDeviceSynchronize());
     if (staging) cudaFree(staging);
   } else {
-    CK(cudaMemcpy(t.w, src, local_disk, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    CK(copy_rows(t.w, vrb, src, drb, (size_t)rows * count, on_dev));
   }
   return 0;
 }
@@ -901,7 +910,7 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     int total_rows = 0;
     for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
     int RT = parts == 2 ? 8 : 16;
-    while (RT > 1 && align_up((size_t)RT * (rb + kRowPad), 128) * parts > (size_t)g_slot_data) RT >>= 1;
+    while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
     st.rows_per_tile = RT;
     st.rpass = 1;
     st.wp = 1;   // one warp reduces the whole tile (rows at a padded pitch)
@@ -950,8 +959,8 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
       const int n = k < st.K ? st.mi : st.sh;
       if (n == 0) continue;
       int pr = 8;
-      while (pr > 1 && (size_t)pr * (n + kRowPad) > (size_t)g_slot_data) pr >>= 1;
-      if ((size_t)pr * (n + kRowPad) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
+      while (pr > 1 && (size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) pr >>= 1;
+      if ((size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
       for (int r0 = 0; r0 < 8; r0 += pr) {
         if (np >= 16) return fail(-4, "too many down-projection pieces");
         st.piece[np++] = Piece{k, r0, pr, 0};
@@ -1389,7 +1398,7 @@ extern "C" int dsk_gemv(int quant, int d, int n, const void* w, const float* sca
     const size_t nblocks = drb * d / kQ3Disk;
     q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256>>>(st, dw, nblocks);
   } else {
-    CK(cudaMemcpy(dw, w, drb * d, cudaMemcpyHostToDevice));
+    CK(copy_rows(dw, vrb, w, drb, (size_t)d, 0));
   }
   float* ds = scale ? t.up<float>(scale, (size_t)cdiv(d, bs0) * cdiv(n, bs1)) : nullptr;
   float* dx = t.up<float>(x, n);

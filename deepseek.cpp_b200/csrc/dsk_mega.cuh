@@ -24,7 +24,6 @@
 namespace dsk {
 
 enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3 };
-constexpr int kRowPad = 16;   // warp-per-tile tiles: row pitch = n + 16 B so that 8 rows x 4 chunks of an A-fragment load are bank-conflict free
 
 constexpr int kConsumers = 256;            // warps 0..7
 constexpr int kMegaThreads = 288;          // + producer warp 8
@@ -589,21 +588,6 @@ __device__ __forceinline__ void produce_tile(const Program& P, const Stage& st, 
       if (parts == 2) sbytes[1] = scale_copy_bytes(jb.scale_b + soff + (size_t)(r0 / P.bs0) * ncb, ncb, ssrc[1], shift);
       total += sbytes[0] + sbytes[1];
     }
-    if (st.wp) {   // one copy per row into the padded pitch (f8: rb = n bytes, a multiple of 64)
-      const uint32_t pitch = (uint32_t)rb + kRowPad;
-      const uint32_t pstride = (uint32_t)align_up((size_t)st.rows_per_tile * pitch, 128);
-      total = (uint32_t)(nrows * rb) * parts + sbytes[0] + sbytes[1];
-      mbar_expect_tx(full, total);
-      for (int r = 0; r < nrows; r++) {
-        bulk_g2s(slot + (uint32_t)P.slot_scale + (uint32_t)r * pitch, jb.w + woff + (size_t)r * rb, (uint32_t)rb, full);
-        if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale + pstride + (uint32_t)r * pitch, jb.w_b + woff + (size_t)r * rb, (uint32_t)rb, full);
-      }
-      if (jb.scale) {
-        bulk_g2s(slot, ssrc[0], sbytes[0], full);
-        if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale / 2, ssrc[1], sbytes[1], full);
-      }
-      return;
-    }
     mbar_expect_tx(full, total);
     bulk_g2s(slot + (uint32_t)P.slot_scale, jb.w + woff, bytes, full);
     if (parts == 2) bulk_g2s(slot + (uint32_t)P.slot_scale + part_stride, jb.w_b + woff, bytes, full);
@@ -696,7 +680,7 @@ template <bool GLU>
 __device__ __forceinline__ void gemv_tile_tasks_mma(const Program& P, const Stage& st, const MJob& jb, int nrows, uint32_t slot,
                                                     const X16& x16, float* res, int shift_bytes) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2;
-  const uint32_t rb = (uint32_t)st.n;   // f8: one byte per weight
+  const uint32_t rb = (uint32_t)st.n + kF8RowPad;   // f8 device row pitch
   const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
   const int csplit = st.npieces;
   constexpr int RPG = GLU ? 8 : 16;     // tile rows per mma row group
@@ -816,7 +800,7 @@ __device__ __forceinline__ void consume_down_tile_mma(const Program& P, const St
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2;
   const int i0 = t * st.rows_per_tile;
   const int nrows = min(st.rows_per_tile, P.dim - i0);
-  const uint32_t rb_mi = (uint32_t)st.mi, rb_sh = (uint32_t)st.sh;
+  const uint32_t rb_mi = (uint32_t)st.mi + kF8RowPad, rb_sh = (uint32_t)st.sh + kF8RowPad;
   const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
   const uint32_t sstride = (uint32_t)P.slot_scale / (uint32_t)(st.K + 1) & ~15u;
   const int np = st.npieces;
@@ -1028,7 +1012,7 @@ __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* 
       case Q_F16: val = __half2float(reinterpret_cast<const __half*>(table)[(size_t)token * dim + i]); break;
       case Q_F8: {
         const int ncb = (dim + P.bs1 - 1) / P.bs1;
-        val = h2f((uint16_t)((uint16_t)table[(size_t)token * dim + i] << 8)) * P.embed_scale[(size_t)(token / P.bs0) * ncb + i / P.bs1];
+        val = h2f((uint16_t)((uint16_t)table[(size_t)token * (dim + kF8RowPad) + i] << 8)) * P.embed_scale[(size_t)(token / P.bs0) * ncb + i / P.bs1];
         break;
       }
       case Q_Q2K: {
@@ -1154,7 +1138,7 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
     soff = (size_t)e * jb.s_stride;
   }
   const bool glu = st.epi == EPI_GLU;
-  const uint32_t rb = (uint32_t)st.n + kRowPad;   // padded pitch
+  const uint32_t rb = (uint32_t)st.n + kF8RowPad;   // device row pitch of f8 weights
   const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
   uint32_t s0 = 0, s1 = 0;
   if (jb.scale) {
@@ -1222,8 +1206,9 @@ __device__ __forceinline__ void wp_produce_down_piece(const Program& P, const St
   } else if (!(st.sw2 != nullptr && st.add_shared)) { mbar_expect_tx(full, 0); return; }
   if (nrows <= 0) { mbar_expect_tx(full, 0); return; }
   const int n = routed ? st.mi : st.sh;
-  const uint32_t bytes = (uint32_t)align_up((size_t)nrows * n, 16);
-  const uint8_t* src = routed ? st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * n : st.sw2 + (size_t)i0 * n;
+  const size_t pitch = (size_t)n + kF8RowPad;
+  const uint32_t bytes = (uint32_t)(nrows * pitch);
+  const uint8_t* src = routed ? st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * pitch : st.sw2 + (size_t)i0 * pitch;
   const float* sc = routed ? st.s2 : st.ss2;
   uint32_t total = bytes, sbytes = 0, shift = 0;
   const float* ssrc = nullptr;
@@ -1232,10 +1217,8 @@ __device__ __forceinline__ void wp_produce_down_piece(const Program& P, const St
     sbytes = scale_copy_bytes(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb, ncb, ssrc, shift);
     total += sbytes;
   }
-  total = (uint32_t)(nrows * n) + sbytes;
-  (void)bytes;
   mbar_expect_tx(full, total);
-  for (int r = 0; r < nrows; r++) bulk_g2s(slot + (uint32_t)P.slot_scale + (uint32_t)r * (uint32_t)(n + kRowPad), src + (size_t)r * n, (uint32_t)n, full);
+  bulk_g2s(slot + (uint32_t)P.slot_scale, src, bytes, full);
   if (sbytes) bulk_g2s(slot, ssrc, sbytes, full);
 }
 
@@ -1263,7 +1246,7 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
       ssm = slot + (uint32_t)(reinterpret_cast<uintptr_t>(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb) & 15);
     }
     const uint32_t data = slot + (uint32_t)P.slot_scale;
-    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)(n + kRowPad);
+    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)(n + kF8RowPad);
     float v_lo, v_hi;
     mma_rows_f8(a_lo, 0u, ssm, 0u, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
     if (tig == 0 && gid < nrows) part[pc * 8 + pcd.g0 + gid] = v_lo;
