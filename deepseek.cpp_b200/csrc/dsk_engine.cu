@@ -953,21 +953,21 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
   const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
   if (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma) {
     // warp-per-tile pieces: (segment, rows [g0, g0+g1) of an 8-row output group), whole rows, <= one slot each
-    st.use_mma = 1; st.wp = 1; st.down_rows = 8; st.rows_per_tile = 8; st.seg_stride = 0;
+    st.use_mma = 1; st.wp = 1; st.down_rows = 16; st.rows_per_tile = 16; st.seg_stride = 0;
     int np = 0;
     for (int k = 0; k <= st.K; k++) {
       const int n = k < st.K ? st.mi : st.sh;
       if (n == 0) continue;
-      int pr = 8;
+      int pr = 16;
       while (pr > 1 && (size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) pr >>= 1;
       if ((size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
-      for (int r0 = 0; r0 < 8; r0 += pr) {
+      for (int r0 = 0; r0 < 16; r0 += pr) {
         if (np >= 16) return fail(-4, "too many down-projection pieces");
         st.piece[np++] = Piece{k, r0, pr, 0};
       }
     }
     st.npieces = np;
-    st.ntiles = cdiv(dim, 8) * np;
+    st.ntiles = cdiv(dim, 16) * np;
     return 0;
   }
   int RT = 8;
@@ -1009,7 +1009,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
   const bool wp_model = q == DSK_F8E5M2 && g_use_mma;
-  g_slot_data = wp_model ? 16 * 1024 + 512 : kSlotData;   // 8 rows x (2048 + 16) B fit one slot
+  g_slot_data = wp_model ? 33 * 1024 + 256 : kSlotData;   // 16 rows x (2048 + 16) B: every HMMA row is a real weight row
   g_slot_scale = kSlotScale;
   std::vector<Stage> S;
   auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {

@@ -1235,8 +1235,8 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
   if (routed) { e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
   else live = live && st.sw2 != nullptr && st.add_shared;
   const int np = st.npieces;
-  float* part = sm.res + (size_t)(rg_local & 3) * 128;    // [4 row groups in flight][np <= 16][8 rows]
-  int* cnt = sm.sel + (rg_local & 3);
+  float* part = sm.res + (size_t)(rg_local & 1) * 256;    // [2 row groups in flight][np <= 16][16 rows]
+  int* cnt = sm.sel + (rg_local & 1);
   if (live) {
     const int n = routed ? st.mi : st.sh;
     const float* sc = routed ? st.s2 : st.ss2;
@@ -1247,9 +1247,11 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
     }
     const uint32_t data = slot + (uint32_t)P.slot_scale;
     const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)(n + kF8RowPad);
+    const uint32_t a_hi = nrows > 8 ? data + (uint32_t)min(gid + 8, nrows - 1) * (uint32_t)(n + kF8RowPad) : 0u;
     float v_lo, v_hi;
-    mma_rows_f8(a_lo, 0u, ssm, 0u, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
-    if (tig == 0 && gid < nrows) part[pc * 8 + pcd.g0 + gid] = v_lo;
+    mma_rows_f8(a_lo, a_hi, ssm, a_hi ? ssm : 0u, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
+    if (tig == 0 && gid < nrows) part[pc * 16 + pcd.g0 + gid] = v_lo;
+    if (tig == 0 && gid + 8 < nrows) part[pc * 16 + pcd.g0 + gid + 8] = v_hi;
   }
   __syncwarp();
   int last = 0;
@@ -1270,7 +1272,7 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
       bool any = false;
       for (; p2 < np && st.piece[p2].seg == kk; p2++) {
         const Piece q = st.piece[p2];
-        if (lane >= q.g0 && lane < q.g0 + q.g1) { v += part[p2 * 8 + lane]; any = true; }
+        if (lane >= q.g0 && lane < q.g0 + q.g1) { v += part[p2 * 16 + lane]; any = true; }
       }
       if (!any) continue;
       if (kk < st.K) {
