@@ -899,6 +899,7 @@ static int granules(int quant, int n) {
 }
 static bool kq_quant(int q) { return q == DSK_Q2_K || q == DSK_Q3_K; }
 
+static int g_wp_rows = 16;
 static int g_slot_data = kSlotData, g_slot_scale = kSlotScale;   // set per program: 16 KB tiles for the warp-per-tile tensor-core path
 
 static void plan_gemv_stage(Stage& st, int quant, int G) {
@@ -909,7 +910,7 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     st.use_mma = 1;
     int total_rows = 0;
     for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
-    int RT = parts == 2 ? 8 : 16;
+    int RT = parts == 2 ? g_wp_rows / 2 : g_wp_rows;
     while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
     st.rows_per_tile = RT;
     st.rpass = 1;
@@ -953,21 +954,21 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
   const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
   if (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma) {
     // warp-per-tile pieces: (segment, rows [g0, g0+g1) of an 8-row output group), whole rows, <= one slot each
-    st.use_mma = 1; st.wp = 1; st.down_rows = 16; st.rows_per_tile = 16; st.seg_stride = 0;
+    st.use_mma = 1; st.wp = 1; st.down_rows = g_wp_rows; st.rows_per_tile = g_wp_rows; st.seg_stride = 0;
     int np = 0;
     for (int k = 0; k <= st.K; k++) {
       const int n = k < st.K ? st.mi : st.sh;
       if (n == 0) continue;
-      int pr = 16;
+      int pr = g_wp_rows;
       while (pr > 1 && (size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) pr >>= 1;
       if ((size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
-      for (int r0 = 0; r0 < 16; r0 += pr) {
+      for (int r0 = 0; r0 < g_wp_rows; r0 += pr) {
         if (np >= 16) return fail(-4, "too many down-projection pieces");
         st.piece[np++] = Piece{k, r0, pr, 0};
       }
     }
     st.npieces = np;
-    st.ntiles = cdiv(dim, 16) * np;
+    st.ntiles = cdiv(dim, g_wp_rows) * np;
     return 0;
   }
   int RT = 8;
@@ -1009,7 +1010,9 @@ static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
   const bool wp_model = q == DSK_F8E5M2 && g_use_mma;
-  g_slot_data = wp_model ? 33 * 1024 + 256 : kSlotData;   // 16 rows x (2048 + 16) B: every HMMA row is a real weight row
+  g_wp_rows = getenv("DSK_WP_ROWS") ? atoi(getenv("DSK_WP_ROWS")) : 16;
+  if (g_wp_rows != 8) g_wp_rows = 16;
+  g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : kSlotData;   // 16 (or 8) rows x (2048 + 16) B
   g_slot_scale = kSlotScale;
   std::vector<Stage> S;
   auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {

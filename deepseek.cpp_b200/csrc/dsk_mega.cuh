@@ -1407,10 +1407,11 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   if (mma && st.wp) {   // warp-per-tile: every consumer warp owns the tiles whose local index is congruent to its id
     const int warp = tid >> 5, lane = tid & 31;
     if (st.kind == ST_GEMV) {
-      int li = 0;
-      for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++, li++) {
-        if ((li & 7) != warp) continue;
+      // ring slot s is always consumed by warp (s mod 8): every slot's uses are awaited in order by ONE warp, so an
+      // mbarrier parity can never be mistaken for an earlier use of the same slot
+      for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
         const int sl = it % n_slots;
+        if ((sl & 7) != warp) continue;
         mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
         wp_gemv_tile(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_0, sm.act, best_key);
         __syncwarp();
@@ -1420,11 +1421,11 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       if (tid < 4) sm.sel[tid] = 0;
       csync();
       const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
-      int li = 0, rgl = 0;
+      int rgl = 0;
       for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
-        for (int pc = 0; pc < st.npieces; pc++, it++, li++) {
-          if ((li & 7) != warp) continue;
+        for (int pc = 0; pc < st.npieces; pc++, it++) {
           const int sl = it % n_slots;
+          if ((sl & 7) != warp) continue;
           mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
           wp_down_piece(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_seg);
           __syncwarp();
