@@ -112,15 +112,20 @@ def make_config(dsk, w):
 
 def mint_on_gpu(dsk, w, rank, n_ranks, device):
     """Random-init weights of the named architecture, generated on the GPU."""
+    import zlib
+
     import torch
-    torch.manual_seed(1234)
     dev = torch.device("cuda", device)
     m = dsk.Model(make_config(dsk, w), rank, n_ranks, device)
+
+    def seed(name):   # per-tensor seed: every rank mints identical tensors no matter which expert chunks it skips
+        torch.manual_seed(1234 + zlib.crc32(name.encode()))
     quant = w["quant"]
     plan, f32 = tensor_plan(w)
     E = w["n_routed_experts"]
     per = -(-E // n_ranks) if E else 0
     for name, n in f32:
+        seed(name)
         if name.endswith("moegate.weight"):
             t = torch.randn(n, device=dev) * (w["dim"] ** -0.5) * 4.0
         elif name.endswith("moegate.bias"):
@@ -131,10 +136,12 @@ def mint_on_gpu(dsk, w, rank, n_ranks, device):
         m.upload_device(name, "F32", (n,), t.data_ptr(), t.numel() * 4)
     for name, rows, cols, ne in plan:
         lead = max(1, ne)
+        seed(name)
         if quant == "f8e5m2":
             chunks_q, chunks_s = [], []
             for e0 in range(0, lead, 16):
                 e1 = min(lead, e0 + 16)
+                seed(f"{name}#{e0}")
                 if ne and n_ranks > 1 and (e1 <= rank * per or e0 >= (rank + 1) * per):
                     # another rank's experts: the library drops them anyway; skip the randn, keep shapes
                     chunks_q.append(torch.zeros(e1 - e0, rows, cols, dtype=torch.uint8, device=dev))
@@ -415,6 +422,21 @@ def main():
 
     vocab = w["vocab_size"]
     pr = prompt_ids(vocab)
+    sharded_check = None
+    if world > 1 and os.environ.get("DSK_CHECK_SHARDED", "1") == "1" and m.resident_bytes() * world < 60e9:
+        # consistency of the expert-sharded path: same synthetic weights unsharded on rank 0, teacher-forced logits compared
+        errs = []
+        ref_m = mint_on_gpu(dsk, w, 0, 1, local_rank) if rank == 0 else None
+        for p, t in enumerate(pr[:4]):
+            lg, _ = m.forward(t, p)
+            if rank == 0:
+                lg = lg.copy()
+                lr, _ = ref_m.forward(t, p)
+                errs.append(float(np.linalg.norm(lg - lr) / np.linalg.norm(lr)))
+        if rank == 0:
+            sharded_check = {"rel_l2_vs_single_gpu": max(errs), "positions": len(errs)}
+            ref_m.close()
+            log(f"sharded vs single-GPU logits rel-L2 (max over {len(errs)} positions): {max(errs):.2e}")
 
     def hydrate():
         for p, t in enumerate(pr):
@@ -513,7 +535,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": GEN_TOKENS * 48, "d2h_bytes_per_step": GEN_TOKENS * vocab * 4},
                 "gpu_launches": m.launches_per_forward(dsk.OUTPUT_LOGITS) * GEN_TOKENS * a.steps,
                 "launches_per_token": m.launches_per_forward(dsk.OUTPUT_LOGITS),
-                "roofline": roof, "clocks": clk, "resident_gb": m.resident_bytes() / 1e9, "sample_tokens": toks[:8].tolist()})
+                "roofline": roof, "clocks": clk, "sharded_check": sharded_check, "resident_gb": m.resident_bytes() / 1e9, "sample_tokens": toks[:8].tolist()})
     if a.gpus == 1 and not a.no_cpu_baseline:
         try:
             tps, desc = cpu_reference_leg(w, 2, 1)
