@@ -361,6 +361,13 @@ def cpu_reference_leg(w, steps, warmup, tokens_per_step=8):
 
 # ----------------------------------------------------------------------------------------------------
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL banner, the reference's loader chatter) go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -392,14 +399,14 @@ def main():
         try:
             tps, desc = cpu_reference_leg(w, max(1, a.steps), max(1, a.warmup))
         except Exception as e:  # the oracle always exists in this tier; this only trips if _ref did not travel
-            print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+            emit({"impl": "reference", "unavailable": str(e)[:200]})
             return 0
         out = dict(base)
         out.update({"impl": "reference", "value": tps, "ms_per_step": GEN_TOKENS / tps * 1e3, "n_gpus": a.gpus,
                     "cpu_baseline": dict(desc, value=tps, unit="tok/s"),
                     "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                     "gpu_launches": 0, "dtype": "reference CPU path (AVX2/F16C, OpenMP)"})
-        print(json.dumps(out))
+        emit(out)
         return 0
 
     import torch
@@ -542,7 +549,7 @@ def main():
             out["cpu_baseline"] = dict(desc, value=tps, unit="tok/s")
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "reference", "sample": f"failed: {str(e)[:150]}"}
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
