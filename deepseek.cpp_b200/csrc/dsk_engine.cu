@@ -927,6 +927,22 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
   }
   int total_rows = 0;
   for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
+  if (kq_quant(quant) && (st.n / 256) * 4 <= 32 * kKqMaxPass && g_use_mma) {
+    // warp-per-tile K-quant tiles: up to 32 rows (lane r keeps row r), as many as fit one slot, TMA-aligned
+    const int nb = st.n / 256;
+    const int step = quant == DSK_Q2_K ? ((nb % 4 == 0) ? 1 : (nb % 2 == 0 ? 2 : 4)) : 1;
+    int RT = (int)std::min<size_t>(32, ((size_t)g_slot_data / parts) / rb);
+    RT = RT / std::max(step, 4) * std::max(step, 4);
+    if (RT >= 4) {
+      st.wp = 1; st.rows_per_tile = RT; st.rpass = 1; st.npieces = 1;
+      st.piece[0] = Piece{0, 0, nb, 0};
+      int t = 0;
+      st.has_dyn = 0;
+      for (int j = 0; j < st.njobs; j++) { st.job[j].tile_begin = t; t += cdiv(st.job[j].rows, RT); if (st.job[j].expert_slot >= 0) st.has_dyn = 1; }
+      st.ntiles = t;
+      return;
+    }
+  }
   int RT = 32;
   while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
   int min_rt = 1;
@@ -971,6 +987,23 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
     st.ntiles = cdiv(dim, g_wp_rows) * np;
     return 0;
   }
+  if (kq_quant(quant) && (std::max(st.mi, st.sh) / 256) * 4 <= 32 * kKqMaxPass && g_use_mma) {
+    // warp-per-tile K-quant pieces: (segment, rows of a 16-row output group)
+    st.wp = 1; st.down_rows = 16; st.rows_per_tile = 16; st.seg_stride = 0;
+    int np = 0;
+    for (int k = 0; k <= st.K; k++) {
+      const int n = k < st.K ? st.mi : st.sh;
+      if (n == 0) continue;
+      const size_t rb = dev_row_bytes(quant, n);
+      int pr = 16;
+      while (pr > 4 && (size_t)pr * rb > (size_t)g_slot_data) pr >>= 1;
+      if ((size_t)pr * rb > (size_t)g_slot_data) { np = -1; break; }
+      for (int r0 = 0; r0 < 16; r0 += pr) { if (np >= 16) { np = -1; break; } st.piece[np++] = Piece{k, r0, pr, 0}; }
+      if (np < 0) break;
+    }
+    if (np > 0) { st.npieces = np; st.ntiles = cdiv(dim, 16) * np; return 0; }
+    st.wp = 0; st.down_rows = 0;
+  }
   int RT = 8;
   auto bytes = [&](int r) { return align_up((size_t)r * rb_mi, 128) * st.K + align_up((size_t)r * rb_sh, 128); };
   while (RT > 1 && bytes(RT) > (size_t)g_slot_data) RT >>= 1;
@@ -1010,9 +1043,10 @@ static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
   const bool wp_model = q == DSK_F8E5M2 && g_use_mma;
+  const bool kq_model = kq_quant(q) && g_use_mma;
   g_wp_rows = getenv("DSK_WP_ROWS") ? atoi(getenv("DSK_WP_ROWS")) : 16;
   if (g_wp_rows != 8) g_wp_rows = 16;
-  g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : kSlotData;   // 16 (or 8) rows x (2048 + 16) B
+  g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : (kq_model ? 16 * 1024 + 512 : kSlotData);   // 16 (or 8) rows x (2048 + 16) B
   g_slot_scale = kSlotScale;
   std::vector<Stage> S;
   auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {

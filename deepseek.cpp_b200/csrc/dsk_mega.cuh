@@ -938,16 +938,23 @@ __device__ __forceinline__ void c_attention(const Program& P, const Stage& st, c
   if (tid < P.rope) qh[P.nope + tid] = qs[P.nope + tid];
   csync();
   const float inv = sqrtf((float)P.hd);
-  for (int t = warp; t < kv_len; t += 8) {
-    const __half* kr = st.kcache + (size_t)t * kstride + (size_t)h * P.hd;
-    float s = 0.f;
+  for (int t0 = warp * 4; t0 < kv_len; t0 += 32) {   // 4 cache rows per warp pass: their loads overlap
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = lane * 2; i < P.hd; i += 64) {
-      const float2 kk = __half22float2(*reinterpret_cast<const __half2*>(kr + i));
-      s = fmaf(qs[i], kk.x, s);
-      s = fmaf(qs[i + 1], kk.y, s);
+      float2 kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int t = min(t0 + u, kv_len - 1);
+        kk[u] = __half22float2(*reinterpret_cast<const __half2*>(st.kcache + (size_t)t * kstride + (size_t)h * P.hd + i));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) { s[u] = fmaf(qs[i], kk[u].x, s[u]); s[u] = fmaf(qs[i + 1], kk[u].y, s[u]); }
     }
-    s = warp_sum(s);
-    if (lane == 0) att[t] = s / inv;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const float r = warp_sum(s[u]);
+      if (lane == 0 && t0 + u < kv_len) att[t0 + u] = r / inv;
+    }
   }
   csync();
   float m = -3.402823466e38f;
@@ -965,7 +972,13 @@ __device__ __forceinline__ void c_attention(const Program& P, const Stage& st, c
     float acc = 0.f;
     if (g < groups) {
       const __half* vb = st.vcache + (size_t)h * P.vh + i;
-      for (int t = g; t < kv_len; t += groups) acc = fmaf(att[t], __half2float(vb[(size_t)t * vstride]), acc);
+      int t = g;
+      for (; t + 3 * groups < kv_len; t += 4 * groups) {   // 4 independent loads in flight, accumulation order unchanged
+        const float v0 = __half2float(vb[(size_t)t * vstride]), v1 = __half2float(vb[(size_t)(t + groups) * vstride]);
+        const float v2 = __half2float(vb[(size_t)(t + 2 * groups) * vstride]), v3 = __half2float(vb[(size_t)(t + 3 * groups) * vstride]);
+        acc = fmaf(att[t], v0, acc); acc = fmaf(att[t + groups], v1, acc); acc = fmaf(att[t + 2 * groups], v2, acc); acc = fmaf(att[t + 3 * groups], v3, acc);
+      }
+      for (; t < kv_len; t += groups) acc = fmaf(att[t], __half2float(vb[(size_t)t * vstride]), acc);
       part[g * P.vh + i] = acc;
     }
     csync();
@@ -1286,6 +1299,257 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
   if (lane == 0) *cnt = 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-per-tile K-quant stages (Q2_K / Q3_K x Q8_K, w2a8 / w3a8 integer dots — src/quant.cpp:434-783).
+// Lane l owns quarter-blocks l, l+32, ... of every row (block b = qb/4, 128-half h, 16-byte half c), so its slice of the
+// Q8_K activation vector — 64 int8, 4 block sums, the block scale — is loaded into REGISTERS once per stage (per piece
+// for ST_DOWN) and reused for every weight row: the shared-memory pipe only carries the weight tile itself.
+// Rows are reduced one after another (integer dp4a per quarter block, exact int32 block sums via 2 shuffles, fp32 across
+// blocks, one warp_sum per row); lane r keeps the result of tile row r, so the epilogue runs 32 rows wide.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kKqMaxPass = 4;   // up to 128 quarter-blocks (n <= 8192) register-resident
+struct YRegs { int4 y[4]; int bs[4]; float d; };
+
+template <int NP>
+__device__ __forceinline__ void kq_load_y(const Q8Smem& q8, int nb, int lane, YRegs (&yr)[NP]) {
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    const int qb = lane + 32 * p;
+    const int b = min(qb >> 2, nb - 1), h = (qb >> 1) & 1, c = qb & 1;
+    const int8_t* y = q8.qs + b * 256 + 128 * h + 16 * c;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+      yr[p].y[s] = *reinterpret_cast<const int4*>(y + 32 * s);
+      yr[p].bs[s] = (int)q8.bsums[b * 16 + 8 * h + c + 2 * s];
+    }
+    yr[p].d = q8.d[b];
+  }
+}
+
+// one row x one pass: this lane's quarter block; returns the block's fp32 contribution in lanes with (lane & 3) == 0
+template <int Q>
+__device__ __forceinline__ float kq_quarter(uint32_t row, int qb, int nqb, const YRegs& yr) {
+  const bool act = qb < nqb;
+  const int b = qb >> 2, h = (qb >> 1) & 1, c = qb & 1;
+  int isum = 0, summs = 0;
+  float out = 0.f;
+  if constexpr (Q == Q_Q2K) {
+    const uint32_t blk = row + (uint32_t)b * kQ2Bytes;
+    if (act) {
+      const uint32_t qp = blk + 16 + 32 * h + 16 * c;
+      const uint32_t w0 = lds32(qp), w1 = lds32(qp + 4), w2 = lds32(qp + 8), w3 = lds32(qp + 12);
+      const uint32_t sA = lds32(blk + 8 * h), sB = lds32(blk + 8 * h + 4);
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        int dp = __dp4a((int)((w0 >> (2 * s)) & 0x03030303u), yr.y[s].x, 0);
+        dp = __dp4a((int)((w1 >> (2 * s)) & 0x03030303u), yr.y[s].y, dp);
+        dp = __dp4a((int)((w2 >> (2 * s)) & 0x03030303u), yr.y[s].z, dp);
+        dp = __dp4a((int)((w3 >> (2 * s)) & 0x03030303u), yr.y[s].w, dp);
+        const uint32_t sw = (s < 2) ? sA : sB;
+        const int sc = (sw >> (8 * ((2 * s + c) & 3))) & 0xff;
+        isum += (sc & 0xF) * dp;
+        summs += (sc >> 4) * yr.bs[s];
+      }
+    }
+    isum += __shfl_xor_sync(0xffffffffu, isum, 1);
+    isum += __shfl_xor_sync(0xffffffffu, isum, 2);
+    summs += __shfl_xor_sync(0xffffffffu, summs, 1);
+    summs += __shfl_xor_sync(0xffffffffu, summs, 2);
+    if (act && (qb & 3) == 0) {
+      const uint32_t dm = lds32(blk + 80);
+      out = (yr.d * h2f((uint16_t)(dm & 0xffff))) * (float)isum - (yr.d * h2f((uint16_t)(dm >> 16))) * (float)summs;
+    }
+  } else {
+    const uint32_t blk = row + (uint32_t)b * kQ3Bytes;
+    if (act) {
+      const uint4 hm = lds128(blk + 16 * c);
+      const uint4 qq = lds128(blk + 32 + 32 * h + 16 * c);
+      const uint32_t s0 = lds32(blk + 96), s1 = lds32(blk + 100), s2 = lds32(blk + 104);
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        const int bit = 4 * h + s;
+        int dp = __dp4a((int)(((qq.x >> (2 * s)) & 0x03030303u) | (((hm.x >> bit) & 0x01010101u) << 2)), yr.y[s].x, 0);
+        dp = __dp4a((int)(((qq.y >> (2 * s)) & 0x03030303u) | (((hm.y >> bit) & 0x01010101u) << 2)), yr.y[s].y, dp);
+        dp = __dp4a((int)(((qq.z >> (2 * s)) & 0x03030303u) | (((hm.z >> bit) & 0x01010101u) << 2)), yr.y[s].z, dp);
+        dp = __dp4a((int)(((qq.w >> (2 * s)) & 0x03030303u) | (((hm.w >> bit) & 0x01010101u) << 2)), yr.y[s].w, dp);
+        dp -= 4 * yr.bs[s];
+        const int t = 2 * s + c;
+        const uint32_t lw = (t < 4) ? s0 : s1;
+        const int lob = (lw >> (8 * (t & 3))) & 0xff;
+        const int lo4 = h ? (lob >> 4) : (lob & 0xF);
+        const int hib = (s2 >> (8 * (t & 3))) & 0xff;
+        const int hi2 = (hib >> (2 * (2 * h + (t >> 2)))) & 3;
+        isum += ((lo4 | (hi2 << 4)) - 32) * dp;
+      }
+    }
+    isum += __shfl_xor_sync(0xffffffffu, isum, 1);
+    isum += __shfl_xor_sync(0xffffffffu, isum, 2);
+    if (act && (qb & 3) == 0) {
+      const uint32_t dw = lds32(blk + 108);
+      out = (h2f((uint16_t)(dw & 0xffff)) * yr.d) * (float)isum;
+    }
+  }
+  return out;
+}
+
+// all rows of a tile: returns in lane r the dot product of tile row r (r < nrows <= 32)
+template <int Q, int NP>
+__device__ __forceinline__ float kq_tile_rows(uint32_t base, uint32_t rb, int nrows, int nb, const YRegs (&yr)[NP], int lane) {
+  const int nqb = nb * 4;
+  float mine = 0.f;
+#pragma unroll 2
+  for (int r = 0; r < nrows; r++) {
+    const uint32_t row = base + (uint32_t)r * rb;
+    float acc = 0.f;
+#pragma unroll
+    for (int p = 0; p < NP; p++) acc += kq_quarter<Q>(row, lane + 32 * p, nqb, yr[p]);
+    acc = warp_sum(acc);
+    if (lane == r) mine = acc;
+  }
+  return mine;
+}
+
+template <int Q, int NP>
+__device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, const YRegs (&yr)[NP],
+                                                const int* act_smem, unsigned long long& best) {
+  const int lane = threadIdx.x & 31;
+  int j = 0;
+  while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
+  const MJob& jb = st.job[j];
+  const int r0 = (t - jb.tile_begin) * st.rows_per_tile;
+  const int nrows = min(st.rows_per_tile, jb.rows - r0);
+  if (jb.expert_slot >= 0) {
+    const int e = act_smem[jb.expert_slot] - P.expert_first;
+    if (e < 0 || e >= P.expert_count) return;
+  }
+  const bool glu = st.epi == EPI_GLU;
+  const uint32_t rb = (uint32_t)QTraits<Q>::row_bytes(st.n);
+  const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
+  const uint32_t data = slot + (uint32_t)P.slot_scale;
+  const int nb = st.n >> 8;
+  float xres = 0.f;
+  if (st.epi == EPI_RESID && lane < nrows) xres = jb.out[r0 + lane];
+  const float v = kq_tile_rows<Q, NP>(data, rb, nrows, nb, yr, lane);
+  float u = 0.f;
+  if (glu) u = kq_tile_rows<Q, NP>(data + part_stride, rb, nrows, nb, yr, lane);
+  if (lane >= nrows) return;
+  const int r = r0 + lane;
+  float val = v;
+  if (glu) val = (P.act_silu ? silu_f(v) : gelu_f(v)) * u;
+  switch (st.epi) {
+    case EPI_RESID: jb.out[r] = xres + val; break;
+    case EPI_KVB: {
+      jb.out[r] = val;
+      const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
+      const int kv_pos = P.ctrl->kv_pos;
+      if (ii < P.nope) st.kcache[(size_t)kv_pos * P.n_heads * P.hd + hh * P.hd + ii] = __float2half_rn(val);
+      else st.vcache[(size_t)kv_pos * P.n_heads * P.vh + hh * P.vh + (ii - P.nope)] = __float2half_rn(val);
+      break;
+    }
+    case EPI_LOGITS: {
+      jb.out[r] = val;
+      const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+      if (key > best) best = key;
+      break;
+    }
+    default: jb.out[r] = val; break;
+  }
+}
+
+// ST_DOWN piece (segment k, rows [g0, g0+g1) of a row group) for K-quants; producer side = wp_produce_down_piece_q
+template <int Q>
+__device__ __forceinline__ void wp_produce_down_piece_q(const Program& P, const Stage& st, int rg, int pc, uint32_t slot, uint32_t full,
+                                                        const int* act_smem) {
+  const Piece pcd = st.piece[pc];
+  const int k = pcd.seg, i0 = rg * st.down_rows + pcd.g0;
+  const int nrows = min(pcd.g1, P.dim - i0);
+  const bool routed = k < st.K;
+  int e = 0;
+  if (routed) {
+    e = act_smem[k] - P.expert_first;
+    if (e < 0 || e >= P.expert_count) { mbar_expect_tx(full, 0); return; }
+  } else if (!(st.sw2 != nullptr && st.add_shared)) { mbar_expect_tx(full, 0); return; }
+  if (nrows <= 0) { mbar_expect_tx(full, 0); return; }
+  const size_t rb = QTraits<Q>::row_bytes(routed ? st.mi : st.sh);
+  const uint32_t bytes = (uint32_t)align_up((size_t)nrows * rb, 16);
+  const uint8_t* src = routed ? st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * rb : st.sw2 + (size_t)i0 * rb;
+  mbar_expect_tx(full, bytes);
+  bulk_g2s(slot + (uint32_t)P.slot_scale, src, bytes, full);
+}
+
+template <int Q>
+__device__ __forceinline__ void wp_kq_down_piece(const Program& P, const Stage& st, const MegaSmem& sm, int rg, int rg_local, int pc,
+                                                 uint32_t slot, const Q8Smem* q8_seg) {
+  const int lane = threadIdx.x & 31;
+  const Piece pcd = st.piece[pc];
+  const int k = pcd.seg, i0 = rg * st.down_rows + pcd.g0;
+  const int nrows = min(pcd.g1, P.dim - i0);
+  const bool routed = k < st.K;
+  bool live = nrows > 0;
+  if (routed) { const int e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
+  else live = live && st.sw2 != nullptr && st.add_shared;
+  const int np = st.npieces;
+  float* part = sm.res + (size_t)(rg_local & 1) * 256;
+  int* cnt = sm.sel + (rg_local & 1);
+  if (live) {
+    const int n = routed ? st.mi : st.sh, nb = n >> 8;
+    const int npass = (nb * 4 + 31) / 32;
+    const uint32_t base = slot + (uint32_t)P.slot_scale, rb = (uint32_t)QTraits<Q>::row_bytes(n);
+    float v;
+    if (npass <= 1) { YRegs yr[1]; kq_load_y<1>(q8_seg[k], nb, lane, yr); v = kq_tile_rows<Q, 1>(base, rb, nrows, nb, yr, lane); }
+    else if (npass <= 2) { YRegs yr[2]; kq_load_y<2>(q8_seg[k], nb, lane, yr); v = kq_tile_rows<Q, 2>(base, rb, nrows, nb, yr, lane); }
+    else { YRegs yr[4]; kq_load_y<4>(q8_seg[k], nb, lane, yr); v = kq_tile_rows<Q, 4>(base, rb, nrows, nb, yr, lane); }
+    if (lane < nrows) part[pc * 16 + pcd.g0 + lane] = v;
+  }
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) { __threadfence_block(); last = atomicAdd(cnt, 1) == np - 1; }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence_block();
+  const int gi0 = rg * st.down_rows;
+  const int grows = min(st.down_rows, P.dim - gi0);
+  if (lane < grows) {
+    const int i = gi0 + lane;
+    const bool to_partial = P.partial != nullptr && st.K > 0;
+    float acc = to_partial ? 0.f : P.x[i];
+    int p2 = 0;
+    for (int kk = 0; kk <= st.K; kk++) {
+      float v = 0.f;
+      bool any = false;
+      for (; p2 < np && st.piece[p2].seg == kk; p2++) {
+        const Piece q = st.piece[p2];
+        if (lane >= q.g0 && lane < q.g0 + q.g1) { v += part[p2 * 16 + lane]; any = true; }
+      }
+      if (!any) continue;
+      if (kk < st.K) {
+        const int ee = sm.act[kk] - P.expert_first;
+        if (ee >= 0 && ee < P.expert_count) acc = fmaf(v, sm.actw[kk], acc);
+      } else if (st.sw2 != nullptr && st.add_shared) acc += v;
+    }
+    if (to_partial) P.partial[i] = acc; else P.x[i] = acc;
+  }
+  __syncwarp();
+  if (lane == 0) *cnt = 0;
+}
+
+// the tile loop of a warp-per-tile K-quant GEMV stage; this lane's activation slice lives in NP register sets
+template <int Q, int NP>
+__device__ __forceinline__ void kq_gemv_loop(const Program& P, const Stage& st, const MegaSmem& sm, const Q8Smem& q80, int& it, int n_slots,
+                                             unsigned long long& best_key) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  YRegs yr[NP];
+  kq_load_y<NP>(q80, st.n >> 8, lane, yr);
+  for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
+    const int sl = it % n_slots;
+    if ((sl & 7) != warp) continue;
+    mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+    wp_kq_gemv_tile<Q, NP>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, yr, sm.act, best_key);
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+  }
+}
+
 // GEMV activation staging for the tensor-core path: RMSNorm fused, values split into fp16 hi/lo (n <= 8192 in registers)
 __device__ __forceinline__ void c_stage_gemv_input_x16(const Program& P, const Stage& st, const MegaSmem& sm, const X16& x16) {
   const int tid = threadIdx.x;
@@ -1371,17 +1635,27 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       p += n ? x16_bytes(n) : 0;
       off[k + 1] = off[k] + (n >> 2);
     }
-    for (int f = tid; f < off[st.K + 1]; f += kConsumers) {
-      int k = 0;
-      while (f >= off[k + 1]) k++;
-      bool live = true;
-      if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = e >= 0 && e < P.expert_count; }
-      else live = use_shared;
-      const int fl = f - off[k];
-      const float* src = k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) v = reinterpret_cast<const float4*>(src)[fl];
-      x16_store(x16_seg[k], fl, v);
+    const int nf_all = off[st.K + 1];
+    for (int f0 = tid; f0 < nf_all; f0 += kConsumers * 4) {   // 4 independent L2 loads in flight per thread
+      float4 v[4];
+      int kk[4], fl[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int f = f0 + u * kConsumers;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        kk[u] = -1; fl[u] = 0;
+        if (f < nf_all) {
+          int k = 0;
+          while (f >= off[k + 1]) k++;
+          bool live = true;
+          if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = e >= 0 && e < P.expert_count; }
+          else live = use_shared;
+          kk[u] = k; fl[u] = f - off[k];
+          if (live) v[u] = reinterpret_cast<const float4*>(k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs)[fl[u]];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) if (kk[u] >= 0) x16_store(x16_seg[kk[u]], fl[u], v[u]);
     }
   } else if (st.kind == ST_GEMV) {
     carve_x<Q>(sm.xregion, st.n, xs0, q80);
@@ -1404,6 +1678,31 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   csync();
   if (!(st.need_topk || (st.kind == ST_DOWN && st.K > 0)) && tid == 0) dep_signal(sm.dep, dep_count);
   if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
+  if (KQ && st.wp) {   // warp-per-tile K-quant stage
+    const int warp = tid >> 5, lane = tid & 31;
+    if (st.kind == ST_GEMV) {
+      const int nb = st.n >> 8, npass = (nb * 4 + 31) / 32;
+      if (npass <= 1) kq_gemv_loop<Q, 1>(P, st, sm, q80, it, n_slots, best_key);
+      else if (npass <= 2) kq_gemv_loop<Q, 2>(P, st, sm, q80, it, n_slots, best_key);
+      else kq_gemv_loop<Q, 4>(P, st, sm, q80, it, n_slots, best_key);
+    } else {
+      if (tid < 4) sm.sel[tid] = 0;
+      csync();
+      const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
+      int rgl = 0;
+      for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
+        for (int pc = 0; pc < st.npieces; pc++, it++) {
+          const int sl = it % n_slots;
+          if ((sl & 7) != warp) continue;
+          mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+          wp_kq_down_piece<Q>(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, q8_seg);
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+        }
+      }
+    }
+    return;
+  }
   if (mma && st.wp) {   // warp-per-tile: every consumer warp owns the tiles whose local index is congruent to its id
     const int warp = tid >> 5, lane = tid & 31;
     if (st.kind == ST_GEMV) {
@@ -1488,7 +1787,8 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
         if (st.piece[pc].seg < st.K && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
         const int sl = it % n_slots;
         if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
-        wp_produce_down_piece(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
+        if constexpr (QTraits<Q>::kq) wp_produce_down_piece_q<Q>(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
+        else wp_produce_down_piece(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
       }
     }
     if (!dep_waited) dep_wait(sm.dep, dep_count);
