@@ -279,41 +279,28 @@ __device__ __forceinline__ void mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32
   const int gid = lane >> 2, tig = lane & 3;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
   const uint32_t xsrc = gid == 0 ? x.hi : x.lo;
-  // Legacy HMMA has a long latency on this part: issue FOUR 64-column groups (16 independent mma) back to back, then
-  // reduce them — the tensor pipe, not the dependency chain, sets the pace.
-  for (int cb0 = col0; cb0 < col1; cb0 += 256) {
-    float c[4][4][4];
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-#pragma unroll
-      for (int j = 0; j < 4; j++) { c[g][j][0] = 0.f; c[g][j][1] = 0.f; c[g][j][2] = 0.f; c[g][j][3] = 0.f; }
-      const int cb = cb0 + 64 * g;
-      if (cb < col1) {
-        const uint4 w0 = lds128(a_lo + (uint32_t)(cb + 16 * tig));
-        uint4 w1 = make_uint4(0, 0, 0, 0);
-        if (a_hi) w1 = lds128(a_hi + (uint32_t)(cb + 16 * tig));
-        uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-        if (gid < 2) { b0 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u); b1 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u + 16u); }
-        mma_f16(c[g][0], __byte_perm(w0.x, 0, 0x1404), __byte_perm(w1.x, 0, 0x1404), __byte_perm(w0.x, 0, 0x3424), __byte_perm(w1.x, 0, 0x3424), b0.x, b0.y);
-        mma_f16(c[g][1], __byte_perm(w0.y, 0, 0x1404), __byte_perm(w1.y, 0, 0x1404), __byte_perm(w0.y, 0, 0x3424), __byte_perm(w1.y, 0, 0x3424), b0.z, b0.w);
-        mma_f16(c[g][2], __byte_perm(w0.z, 0, 0x1404), __byte_perm(w1.z, 0, 0x1404), __byte_perm(w0.z, 0, 0x3424), __byte_perm(w1.z, 0, 0x3424), b1.x, b1.y);
-        mma_f16(c[g][3], __byte_perm(w0.w, 0, 0x1404), __byte_perm(w1.w, 0, 0x1404), __byte_perm(w0.w, 0, 0x3424), __byte_perm(w1.w, 0, 0x3424), b1.z, b1.w);
-      }
-    }
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      const int cb = cb0 + 64 * g;
-      if (cb < col1) {
-        const float gs = __uint_as_float(lds32(x.gs + (uint32_t)(cb >> 6) * 4u));
-        const uint32_t sidx = (sshift >= 0 ? (uint32_t)cb >> sshift : (uint32_t)(cb / bs1)) * 4u;
-        const float f_lo = s_lo ? gs * __uint_as_float(lds32(s_lo + sidx)) : gs;
-        const float f_hi = s_hi ? gs * __uint_as_float(lds32(s_hi + sidx)) : gs;
-        t0 = fmaf((c[g][0][0] + c[g][1][0]) + (c[g][2][0] + c[g][3][0]), f_lo, t0);
-        t1 = fmaf((c[g][0][1] + c[g][1][1]) + (c[g][2][1] + c[g][3][1]), f_lo, t1);
-        t2 = fmaf((c[g][0][2] + c[g][1][2]) + (c[g][2][2] + c[g][3][2]), f_hi, t2);
-        t3 = fmaf((c[g][0][3] + c[g][1][3]) + (c[g][2][3] + c[g][3][3]), f_hi, t3);
-      }
-    }
+  // the four mma of a 64-column group use independent accumulators; two groups are unrolled so ~8 mma are in flight
+  // (deeper unrolling spills at the interpreter's 168-register cap and is slower — measured)
+#pragma unroll 2
+  for (int cb = col0; cb < col1; cb += 64) {
+    const uint4 w0 = lds128(a_lo + (uint32_t)(cb + 16 * tig));
+    uint4 w1 = make_uint4(0, 0, 0, 0);
+    if (a_hi) w1 = lds128(a_hi + (uint32_t)(cb + 16 * tig));
+    uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
+    if (gid < 2) { b0 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u); b1 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u + 16u); }
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_f16(c0, __byte_perm(w0.x, 0, 0x1404), __byte_perm(w1.x, 0, 0x1404), __byte_perm(w0.x, 0, 0x3424), __byte_perm(w1.x, 0, 0x3424), b0.x, b0.y);
+    mma_f16(c1, __byte_perm(w0.y, 0, 0x1404), __byte_perm(w1.y, 0, 0x1404), __byte_perm(w0.y, 0, 0x3424), __byte_perm(w1.y, 0, 0x3424), b0.z, b0.w);
+    mma_f16(c2, __byte_perm(w0.z, 0, 0x1404), __byte_perm(w1.z, 0, 0x1404), __byte_perm(w0.z, 0, 0x3424), __byte_perm(w1.z, 0, 0x3424), b1.x, b1.y);
+    mma_f16(c3, __byte_perm(w0.w, 0, 0x1404), __byte_perm(w1.w, 0, 0x1404), __byte_perm(w0.w, 0, 0x3424), __byte_perm(w1.w, 0, 0x3424), b1.z, b1.w);
+    const float g = __uint_as_float(lds32(x.gs + (uint32_t)(cb >> 6) * 4u));
+    const uint32_t sidx = (sshift >= 0 ? (uint32_t)cb >> sshift : (uint32_t)(cb / bs1)) * 4u;
+    const float f_lo = s_lo ? g * __uint_as_float(lds32(s_lo + sidx)) : g;
+    const float f_hi = s_hi ? g * __uint_as_float(lds32(s_hi + sidx)) : g;
+    t0 = fmaf((c0[0] + c1[0]) + (c2[0] + c3[0]), f_lo, t0);
+    t1 = fmaf((c0[1] + c1[1]) + (c2[1] + c3[1]), f_lo, t1);
+    t2 = fmaf((c0[2] + c1[2]) + (c2[2] + c3[2]), f_hi, t2);
+    t3 = fmaf((c0[3] + c1[3]) + (c2[3] + c3[3]), f_hi, t3);
   }
   out_lo = t0 + t1;   // hi-part + lo-part contributions
   out_hi = t2 + t3;
