@@ -1785,6 +1785,72 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   }
 }
 
+// Producer loop of a GEMV stage with everything tile-invariant hoisted into registers: per tile it only advances the
+// source pointers, waits for the slot, posts the byte count and issues the bulk copies.
+template <int Q>
+__device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
+                                                   int dep_count, bool& dep_waited) {
+  const size_t rb = QTraits<Q>::row_bytes(st.n);
+  const int RT = st.rows_per_tile, parts = st.epi == EPI_GLU ? 2 : 1;
+  const uint32_t part_stride = (uint32_t)align_up((size_t)RT * rb, 128);
+  const uint32_t full_bytes = (uint32_t)align_up((size_t)RT * rb, 16);
+  const uint32_t slot_scale = (uint32_t)P.slot_scale, slot_bytes = (uint32_t)P.slot_bytes;
+  const int ncb = (st.n + P.bs1 - 1) / P.bs1, bs0 = P.bs0;
+  const uint32_t ring = sm.ring;
+  // current job, cached
+  int j = -1, j_begin = 0, j_end = 0, j_rows = 0;
+  const uint8_t *w = nullptr, *wb = nullptr;
+  const float *sc = nullptr, *scb = nullptr;
+  bool j_dyn = false, j_live = true;
+  for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
+    if (t >= j_end) {   // (re)load the job this tile belongs to
+      do {
+        j++;
+        j_begin = st.job[j].tile_begin;
+        j_end = (j + 1 < st.njobs) ? st.job[j + 1].tile_begin : st.ntiles;
+      } while (t >= j_end);
+      const MJob& jb = st.job[j];
+      j_rows = jb.rows; w = jb.w; wb = jb.w_b; sc = jb.scale; scb = jb.scale_b;
+      j_dyn = jb.expert_slot >= 0;
+      j_live = true;
+      if (j_dyn) {
+        if (!dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
+        const int e = sm.act[jb.expert_slot] - P.expert_first;
+        j_live = e >= 0 && e < P.expert_count;
+        if (j_live) {
+          w += (size_t)e * jb.w_stride;
+          if (wb) wb += (size_t)e * jb.w_stride;
+          if (sc) sc += (size_t)e * jb.s_stride;
+          if (scb) scb += (size_t)e * jb.s_stride;
+        }
+      }
+    }
+    const int sl = it % n_slots;
+    const uint32_t slot = ring + (uint32_t)sl * slot_bytes, full = sm.full[sl];
+    if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+    if (!j_live) { mbar_expect_tx(full, 0); continue; }
+    const int r0 = (t - j_begin) * RT;
+    const int nrows = min(RT, j_rows - r0);
+    const uint32_t bytes = nrows == RT ? full_bytes : (uint32_t)align_up((size_t)nrows * rb, 16);
+    const size_t woff = (size_t)r0 * rb;
+    uint32_t total = bytes * (uint32_t)parts, sb0 = 0, sb1 = 0, shift;
+    const float *ss0 = nullptr, *ss1 = nullptr;
+    if (sc) {
+      const size_t so = (size_t)(r0 / bs0) * ncb;
+      sb0 = scale_copy_bytes(sc + so, ncb, ss0, shift);
+      if (parts == 2) sb1 = scale_copy_bytes(scb + so, ncb, ss1, shift);
+      total += sb0 + sb1;
+    }
+    mbar_expect_tx(full, total);
+    bulk_g2s(slot + slot_scale, w + woff, bytes, full);
+    if (parts == 2) bulk_g2s(slot + slot_scale + part_stride, wb + woff, bytes, full);
+    if (sc) {
+      bulk_g2s(slot, ss0, sb0, full);
+      if (parts == 2) bulk_g2s(slot + slot_scale / 2, ss1, sb1, full);
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
                                                int dep_count) {
@@ -1801,6 +1867,11 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
         else wp_produce_down_piece(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
       }
     }
+    if (!dep_waited) dep_wait(sm.dep, dep_count);
+    return;
+  }
+  if (st.kind == ST_GEMV) {
+    producer_gemv_fast<Q>(P, st, sm, it, n_slots, dep_count, dep_waited);
     if (!dep_waited) dep_wait(sm.dep, dep_count);
     return;
   }
