@@ -49,7 +49,7 @@ struct Stage {
   int kind, quant, epi, njobs;
   int n, rows_per_tile, rpass, ntiles;
   int need_topk, npieces, layer, has_dyn;
-  int use_mma, wp, down_rows, prestage;   // prestage: 1 = also stage the NEXT stage's (same) input in the model's format, 2 = input already staged by the previous stage; wp: warp-per-tile stage (tensor-core tiles owned by single warps)          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
+  int use_mma, wp, down_rows, pad3;   // wp: warp-per-tile stage (tensor-core tiles owned by single warps)          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
   const float* in; const float* norm_w;
   MJob job[kMaxJobs];
   Piece piece[kMaxPieces];
@@ -1605,102 +1605,16 @@ __device__ __forceinline__ void c_stage_gemv_input_x16(const Program& P, const S
   }
 }
 
-// Gate stage (F32 weights) of a MoE layer: every CTA also prepares the NEXT stage's activation (same vector, model
-// format QM: fp16 hi/lo split or Q8_K) at the start of the activation region while most CTAs would only wait for the
-// few gate tiles.  own_xs (nullable): this CTA's fp32 copy for its own gate tiles.
-template <int QM>
-__device__ __forceinline__ void c_prestage_dual(const Program& P, const Stage& st, const MegaSmem& sm, float* own_xs) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = st.n;
-  if constexpr (QTraits<QM>::kq) {
-    float* dummy = nullptr;
-    Q8Smem q80{};
-    carve_x<QM>(sm.xregion, n, dummy, q80);
-    float v[4][8];
-    const int nb = n >> 8;
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int b = warp + 8 * k;
-      if (b < nb) {
-        const float4 a0 = *reinterpret_cast<const float4*>(st.in + (b << 8) + lane * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(st.in + (b << 8) + lane * 8 + 4);
-        v[k][0] = a0.x; v[k][1] = a0.y; v[k][2] = a0.z; v[k][3] = a0.w; v[k][4] = a1.x; v[k][5] = a1.y; v[k][6] = a1.z; v[k][7] = a1.w;
-#pragma unroll
-        for (int j = 0; j < 8; j++) ss = fmaf(v[k][j], v[k][j], ss);
-      }
-    }
-    ss = csum(ss, sm.red);
-    const float sc = 1.0f / sqrtf(ss / (float)n + P.eps);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const int b = warp + 8 * k;
-      if (b < nb) {
-        const float4 w0 = *reinterpret_cast<const float4*>(st.norm_w + (b << 8) + lane * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(st.norm_w + (b << 8) + lane * 8 + 4);
-        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[k][j] = __fmul_rn(__fmul_rn(v[k][j], sc), ww[j]);
-        if (own_xs) {
-          *reinterpret_cast<float4*>(own_xs + (b << 8) + lane * 8) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
-          *reinterpret_cast<float4*>(own_xs + (b << 8) + lane * 8 + 4) = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
-        }
-        q8_block(v[k], b, lane, q80);
-      }
-    }
-  } else {
-    const X16 x16 = carve_x16(sm.xregion, n);
-    const int nf = n >> 2;
-    float4 v[8];
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int f = tid + k * kConsumers;
-      if (f < nf) {
-        v[k] = reinterpret_cast<const float4*>(st.in)[f];
-        ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
-      }
-    }
-    ss = csum(ss, sm.red);
-    const float sc = 1.0f / sqrtf(ss / (float)n + P.eps);
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      const int f = tid + k * kConsumers;
-      if (f < nf) {
-        const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
-        float4 o = v[k];
-        o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
-        o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
-        if (own_xs) reinterpret_cast<float4*>(own_xs)[f] = o;
-        x16_store(x16, f, o);
-      }
-    }
-  }
-}
-__host__ __device__ inline size_t prestage_bytes(int qm, int n) {
-  return qm == Q_F8 ? x16_bytes(n) : align_up((size_t)n + (size_t)(n / 256) * 4 + (size_t)(n / 16) * 2, 128);
-}
-
-template <int Q, int QM>
+template <int Q>
 __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
-                                               unsigned long long& best_key, int dep_count, int stage_index, bool first_in_launch) {
+                                               unsigned long long& best_key, int dep_count, int stage_index) {
   constexpr bool KQ = QTraits<Q>::kq;
   const int tid = threadIdx.x;
   const int my_units = (st.kind == ST_DOWN && st.wp) ? (P.dim + st.down_rows - 1) / st.down_rows : st.ntiles;
-  const bool has_tiles = (int)blockIdx.x < my_units;
-  float* pre_xs = nullptr;
-  if constexpr (Q == Q_F32 && QM != Q_F32) {
-    if (st.prestage == 1) {
-      pre_xs = reinterpret_cast<float*>(sm.xregion + prestage_bytes(QM, st.n));
-      c_prestage_dual<QM>(P, st, sm, has_tiles ? pre_xs : nullptr);
-    }
-  }
-  if (!has_tiles) {    // no tile of this stage lands on this CTA: nothing (else) to stage
-    if (st.prestage == 1) csync();
+  if ((int)blockIdx.x >= my_units) {    // no tile of this stage lands on this CTA: nothing to stage
     if (tid == 0) dep_signal(sm.dep, dep_count);
     return;
   }
-  const bool prestaged = st.prestage == 2 && !first_in_launch;
   // routing first (one warp, registers): it unblocks the producer's routed-expert tiles
   if (st.need_topk) { if (tid < 32) warp_route(P, st, sm, blockIdx.x == 0); }
   else if (st.kind == ST_DOWN && st.K > 0) { if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; } }
@@ -1718,7 +1632,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   const bool mma = Q == Q_F8 && st.use_mma;
   if (st.kind == ST_GEMV && mma) {
     x16_0 = carve_x16(sm.xregion, st.n);
-    if (!prestaged) c_stage_gemv_input_x16(P, st, sm, x16_0);
+    c_stage_gemv_input_x16(P, st, sm, x16_0);
   } else if (st.kind == ST_DOWN && mma) {
     unsigned char* p = sm.xregion;
     const bool use_shared = st.sw2 != nullptr && st.add_shared;
@@ -1755,8 +1669,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     }
   } else if (st.kind == ST_GEMV) {
     carve_x<Q>(sm.xregion, st.n, xs0, q80);
-    if (pre_xs) xs0 = pre_xs;
-    else if (!prestaged) c_stage_gemv_input<Q>(P, st, sm, xs0, q80);
+    c_stage_gemv_input<Q>(P, st, sm, xs0, q80);
   } else {
     unsigned char* p = sm.xregion;
     const bool use_shared = st.sw2 != nullptr && st.add_shared;
@@ -2047,8 +1960,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else {
-      if (st.quant == Q_F32 && Q != Q_F32) consumer_stage<Q_F32, Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s, s == s_begin);
-      else consumer_stage<Q, Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s, s == s_begin);
+      if (st.quant == Q_F32 && Q != Q_F32) consumer_stage<Q_F32>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
+      else consumer_stage<Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
       if (st.epi == EPI_LOGITS) {
         unsigned long long b = best_key;
 #pragma unroll

@@ -87,6 +87,10 @@ _lib = None
 
 def build(force: bool = False) -> str:
     """Compiles libdsk.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    if os.environ.get("DSK_LIB"):       # explicit library (A/B runs of two builds); never rebuilt
+        if not os.path.exists(os.environ["DSK_LIB"]):
+            raise DskError(f"DSK_LIB={os.environ['DSK_LIB']} does not exist")
+        return os.environ["DSK_LIB"]
     srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh"))]
     srcs.append(os.path.join(REPO, "include", "dsk.h"))
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
