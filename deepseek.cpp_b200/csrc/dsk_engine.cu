@@ -161,7 +161,7 @@ static size_t disk_row_bytes(int quant, int cols) {
 }
 static size_t dev_row_bytes(int quant, int cols) {
   if (quant == DSK_Q3_K) return (size_t)(cols / 256) * kQ3Bytes;
-  if (quant == DSK_F8E5M2) return (size_t)cols + kF8RowPad;   // re-pitched rows (see kF8RowPad)
+  if (quant == DSK_F8E5M2) return f8_pitch((size_t)cols);   // re-pitched rows (see f8_pitch)
   return disk_row_bytes(quant, cols);
 }
 // rows of `drb` disk bytes -> device rows of `vrb` bytes (no-op layouts use a flat copy)
@@ -180,6 +180,8 @@ static int cdiv(int a, int b) { return (a + b - 1) / b; }
 static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 static constexpr size_t kSmemBudget = 200 * 1024;
 static bool g_use_pdl = true;
+static bool g_f8_mma_ok = true;   // f8 scale-block width is a power of two (the tensor-core loop shifts instead of dividing)
+static bool g_coop_small = true, g_kq_small = true;   // DSK_COOP_SMALL=0 / DSK_KQ_SMALL=0: A/B switches of the tile planner
 static bool g_use_mma = true;   // F8E5M2 tiles through mma.sync (DSK_NO_MMA=1: CUDA-core dequant path)
 enum { ENG_MEGA = 0, ENG_STAGE = 1, ENG_V2 = 2 };
 static int g_engine = ENG_MEGA;
@@ -215,6 +217,8 @@ extern "C" int dsk_init(int device) {
     CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     g_use_pdl = getenv("DSK_NO_PDL") == nullptr;
     g_use_mma = getenv("DSK_NO_MMA") == nullptr;
+    if (const char* e = getenv("DSK_COOP_SMALL")) g_coop_small = atoi(e) != 0;
+    if (const char* e = getenv("DSK_KQ_SMALL")) g_kq_small = atoi(e) != 0;
     if (const char* en = getenv("DSK_ENGINE")) {
       if (!strcmp(en, "stage")) g_engine = ENG_STAGE;
       else if (!strcmp(en, "v2")) g_engine = ENG_V2;
@@ -905,7 +909,7 @@ static int g_slot_data = kSlotData, g_slot_scale = kSlotScale;   // set per prog
 static void plan_gemv_stage(Stage& st, int quant, int G) {
   const size_t rb = dev_row_bytes(quant, st.n);
   const int parts = st.epi == EPI_GLU ? 2 : 1;
-  if (quant == DSK_F8E5M2 && st.n % 64 == 0 && g_use_mma) {
+  if (quant == DSK_F8E5M2 && st.n % 64 == 0 && g_use_mma && g_f8_mma_ok) {
     // tensor-core tiles: 16 weight rows per mma row group (8 + 8 for the gate/up pair), K split into 64-column pieces
     st.use_mma = 1;
     int total_rows = 0;
@@ -923,6 +927,9 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     st.has_dyn = 0;
     for (int j = 0; j < st.njobs; j++) { st.job[j].tile_begin = t; t += cdiv(st.job[j].rows, RT); if (st.job[j].expert_slot >= 0) st.has_dyn = 1; }
     st.ntiles = t;
+    // short stages (at most ~2 tiles per CTA of long rows): one warp per tile would leave 6-7 warps idle behind a single
+    // 5 us tile, so all eight warps share each tile instead (column pieces, combined in a fixed order)
+    if (g_coop_small && st.ntiles <= 2 * G && st.n >= 1024 && csplit > 1) st.wp = 0;
     return;
   }
   int total_rows = 0;
@@ -933,6 +940,12 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     const int step = quant == DSK_Q2_K ? ((nb % 4 == 0) ? 1 : (nb % 2 == 0 ? 2 : 4)) : 1;
     int RT = (int)std::min<size_t>(32, ((size_t)g_slot_data / parts) / rb);
     RT = RT / std::max(step, 4) * std::max(step, 4);
+    if (g_kq_small && RT >= 4) {   // short stages: enough tiles for every consumer warp of every CTA (tile >= 2 KB)
+      const int unit = std::max(step, 4);
+      int want = cdiv(cdiv(total_rows, G * 8), unit) * unit;
+      while ((size_t)want * rb * parts < 2048) want += unit;
+      RT = std::max(unit, std::min(RT, want));
+    }
     if (RT >= 4) {
       st.wp = 1; st.rows_per_tile = RT; st.rpass = 1; st.npieces = 1;
       st.piece[0] = Piece{0, 0, nb, 0};
@@ -968,7 +981,7 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
 
 static int plan_down_stage(Stage& st, int quant, int dim) {
   const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
-  if (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma) {
+  if (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma && g_f8_mma_ok) {
     // warp-per-tile pieces: (segment, rows [g0, g0+g1) of an 8-row output group), whole rows, <= one slot each
     st.use_mma = 1; st.wp = 1; st.down_rows = g_wp_rows; st.rows_per_tile = g_wp_rows; st.seg_stride = 0;
     int np = 0;
@@ -976,8 +989,8 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
       const int n = k < st.K ? st.mi : st.sh;
       if (n == 0) continue;
       int pr = g_wp_rows;
-      while (pr > 1 && (size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) pr >>= 1;
-      if ((size_t)pr * (n + kF8RowPad) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
+      while (pr > 1 && (size_t)pr * f8_pitch((size_t)n) > (size_t)g_slot_data) pr >>= 1;
+      if ((size_t)pr * f8_pitch((size_t)n) > (size_t)g_slot_data) return fail(-4, "down-projection row (%d bytes) does not fit a ring slot", n);
       for (int r0 = 0; r0 < g_wp_rows; r0 += pr) {
         if (np >= 16) return fail(-4, "too many down-projection pieces");
         st.piece[np++] = Piece{k, r0, pr, 0};
@@ -1042,7 +1055,8 @@ static MJob mjob(const DTensor& t, float* out) {
 static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
-  const bool wp_model = q == DSK_F8E5M2 && g_use_mma;
+  g_f8_mma_ok = c.bs1 > 0 && (c.bs1 & (c.bs1 - 1)) == 0;
+  const bool wp_model = q == DSK_F8E5M2 && g_use_mma && g_f8_mma_ok;
   const bool kq_model = kq_quant(q) && g_use_mma;
   g_wp_rows = getenv("DSK_WP_ROWS") ? atoi(getenv("DSK_WP_ROWS")) : 16;
   if (g_wp_rows != 8) g_wp_rows = 16;
@@ -1153,7 +1167,9 @@ static int build_program(dsk_model* m, dsk_state* s) {
     if (st.kind == ST_GEMV) xreg = std::max(xreg, st.use_mma ? x16_bytes(st.n) : xvec_bytes_q(st.quant, st.n));
     else if (st.kind == ST_DOWN) {
       size_t b = 0;
-      for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += st.use_mma ? x16_bytes(n) : xvec_bytes_q(st.quant, n); }
+      if (st.use_mma) b = down_x16_bytes(st.K, st.mi, st.sh);
+      else if (kq_quant(st.quant)) b = down_q8_bytes<Q_Q2K>(st.K, st.mi, st.sh);
+      else for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += xvec_bytes_q(st.quant, n); }
       xreg = std::max(xreg, b);
     }
   }

@@ -31,10 +31,11 @@ constexpr int kQ2Bytes = 84;    // block_q2_K on disk and on device (src/quant.h
 constexpr int kQ3Disk = 110;    // block_q3_K on disk (src/quant.h:70-76)
 constexpr int kQ3Bytes = 112;   // device repack: 110 B + 2 B pad -> 16-byte aligned blocks
 constexpr int kMaxJobs = 9;
-// F8E5M2 rows are stored on the device with a pitch of n + 16 bytes (re-pitched at upload; disk format untouched): a tile
-// of consecutive rows copied by ONE TMA bulk copy then has a shared-memory row pitch that is not a multiple of 128 B,
-// which makes the 8-rows x 4-chunks access pattern of the tensor-core A fragments bank-conflict free.
-constexpr int kF8RowPad = 16;
+// F8E5M2 rows are stored on the device with a pitch of roundup(n, 128) + 64 bytes (re-pitched at upload; disk format
+// untouched): a tile of consecutive rows copied by ONE TMA bulk copy then has a shared-memory row pitch of 64 mod 128, so
+// the 16-byte A-fragment loads of a quarter warp (2 rows x 4 chunks) cover all 32 banks exactly once (measured with
+// tools/mmarows_bench.cu: 8 warps, 174 vs 235 cycles per 64-column group against a pitch of n + 16).
+__host__ __device__ constexpr inline size_t f8_pitch(size_t n) { return ((n + 127) & ~(size_t)127) + 64; }
 
 // control words living in device memory so one CUDA graph serves every token
 struct Ctrl {
@@ -120,6 +121,14 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
   uint4 r;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+// 16-byte shared load executed only by lanes with p set (the others get zeros and generate no shared-memory wavefronts)
+__device__ __forceinline__ uint4 lds128_pred(uint32_t a, uint32_t p) {
+  uint4 r;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
+               "@q ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a), "r"(p));
   return r;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a) {
@@ -240,7 +249,7 @@ __device__ __forceinline__ void stage_input_q8(const float* __restrict__ in, int
 template <int Q> struct QTraits;
 template <> struct QTraits<Q_F32> { static constexpr bool kq = false; static constexpr int epc = 4;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)n * 4; } };
 template <> struct QTraits<Q_F16> { static constexpr bool kq = false; static constexpr int epc = 8;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)n * 2; } };
-template <> struct QTraits<Q_F8>  { static constexpr bool kq = false; static constexpr int epc = 16; static __host__ __device__ size_t row_bytes(int n) { return (size_t)n + kF8RowPad; } };
+template <> struct QTraits<Q_F8>  { static constexpr bool kq = false; static constexpr int epc = 16; static __host__ __device__ size_t row_bytes(int n) { return f8_pitch((size_t)n); } };
 template <> struct QTraits<Q_Q2K> { static constexpr bool kq = true;  static constexpr int epc = 0;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)(n >> 8) * kQ2Bytes; } };
 template <> struct QTraits<Q_Q3K> { static constexpr bool kq = true;  static constexpr int epc = 0;  static __host__ __device__ size_t row_bytes(int n) { return (size_t)(n >> 8) * kQ3Bytes; } };
 
@@ -973,7 +982,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const __grid_constant__ Embe
       break;
     }
     case Q_F8: {
-      const uint8_t* t = a.table + (size_t)token * (dim + kF8RowPad);
+      const uint8_t* t = a.table + (size_t)token * f8_pitch((size_t)dim);
       const int ncb = (dim + a.bs1 - 1) / a.bs1;
       for (int i = threadIdx.x; i < dim; i += blockDim.x) {
         const float sc = a.scale[(size_t)(token / a.bs0) * ncb + i / a.bs1];

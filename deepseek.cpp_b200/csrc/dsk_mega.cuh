@@ -120,6 +120,16 @@ __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
     if (spins > (1ull << 24)) __trap();
   }
 }
+// producer side (waiting for a ring slot to be released): same, with a back-off between polls
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned long long spins = 0; !ok; spins++) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok) __nanosleep(40);
+    if (spins > (1ull << 24)) __trap();
+  }
+}
 // producer <- consumers: "inputs (and routing) of stage k are ready" as a MONOTONIC stage count in shared memory
 // (an mbarrier phase bit could alias if the consumers ever got two signals ahead of the producer's wait)
 __device__ __forceinline__ void dep_signal(uint32_t addr, int stage_count) {
@@ -130,7 +140,8 @@ __device__ __forceinline__ void dep_wait(uint32_t addr, int stage_count) {
   for (unsigned long long spins = 0;; spins++) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     if (v >= stage_count) break;
-    if (spins > (1ull << 27)) __trap();
+    __nanosleep(40);   // the producer shares a sub-partition with two consumer warps: do not spin in their issue slots
+    if (spins > (1ull << 24)) __trap();
   }
 }
 __device__ __forceinline__ unsigned long long gtime() {
@@ -164,7 +175,10 @@ __device__ __forceinline__ float c_rms_scale(const float* __restrict__ in, int n
   return 1.0f / sqrtf(ss / (float)n + eps);
 }
 // one 256-block of quantize_row_q8_K_ref (src/quant.cpp:616-653) by one warp; v[] already scaled/normalised
-__device__ __forceinline__ void q8_block(const float (&v)[8], int b, int lane, const Q8Smem& q) {
+__device__ __noinline__ void q8_block_nf(float4 va, float4 vb, int b, int8_t* q_qs, float* q_d, short* q_bsums) {
+  const int lane = threadIdx.x & 31;
+  const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+  Q8Smem q; q.qs = q_qs; q.d = q_d; q.bsums = q_bsums;
   float amax = 0.f, mx = 0.f;
   int idx = 0x7fffffff;
 #pragma unroll
@@ -196,6 +210,11 @@ __device__ __forceinline__ void q8_block(const float (&v)[8], int b, int lane, c
   const uint32_t p0 = (qv[0] & 0xff) | ((qv[1] & 0xff) << 8) | ((qv[2] & 0xff) << 16) | ((uint32_t)(qv[3] & 0xff) << 24);
   const uint32_t p1 = (qv[4] & 0xff) | ((qv[5] & 0xff) << 8) | ((qv[6] & 0xff) << 16) | ((uint32_t)(qv[7] & 0xff) << 24);
   *reinterpret_cast<uint2*>(q.qs + (b << 8) + lane * 8) = make_uint2(p0, p1);
+}
+// out-of-line on purpose: one copy for every staging site (instruction-cache footprint)
+__device__ __forceinline__ void q8_block(const float (&v)[8], int b, int lane, const Q8Smem& q) {
+  (void)lane;
+  q8_block_nf(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), b, q.qs, q.d, q.bsums);
 }
 template <int Q>
 __device__ __forceinline__ void c_stage_vec(const float* __restrict__ in, int n, const float* __restrict__ norm_w, float sc,
@@ -250,7 +269,9 @@ __device__ __forceinline__ X16 carve_x16(unsigned char* p, int n) {
   X16 x; x.hi = smem_u32(p); x.lo = x.hi + (uint32_t)n * 2u; x.gs = x.hi + (uint32_t)n * 4u; return x;
 }
 // one float4 (4 consecutive columns) -> hi/lo halves; 16 lanes (= 64 columns) share the normalisation
-__device__ __forceinline__ void x16_store(const X16& x, int f, float4 v) {
+__device__ __forceinline__ void x16_store(const X16& x, int f, float4 v);
+__device__ __noinline__ void x16_store_nf(uint32_t xhi, uint32_t xlo, uint32_t xgs, int f, float4 v) {
+  X16 x; x.hi = xhi; x.lo = xlo; x.gs = xgs;
   float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
   const unsigned active = __activemask();   // 16-lane groups are always fully in or out (n % 64 == 0)
 #pragma unroll
@@ -270,40 +291,83 @@ __device__ __forceinline__ void x16_store(const X16& x, int f, float4 v) {
   asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(x.lo + (uint32_t)f * 8u), "r"(lw0), "r"(lw1) : "memory");
   if ((f & 15) == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(x.gs + (uint32_t)(f >> 4) * 4u), "f"(inv) : "memory");
 }
+__device__ __forceinline__ void x16_store(const X16& x, int f, float4 v) { x16_store_nf(x.hi, x.lo, x.gs, f, v); }
 // rows (gid) and (gid+8) of a 16-row group over columns [col0, col1) (multiples of 64).  a_lo/a_hi: shared addresses of the
-// two weight rows (a_hi == 0: no upper rows, their fragment registers are zero); s_lo/s_hi: f8 scale rows (0 = none).
-// The four mma of a 64-column group use independent accumulators (legacy HMMA latency is long).  Results valid in lanes
-// with (lane & 3) == 0.
-__device__ __forceinline__ void mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32_t s_lo, uint32_t s_hi, int sshift, int bs1, int col0, int col1,
-                                            const X16& x, int lane, float& out_lo, float& out_hi) {
-  const int gid = lane >> 2, tig = lane & 3;
+// two weight rows (a_hi == 0: no upper rows); s_lo/s_hi: f8 scale rows (0 = none; block width 2^sshift columns).
+// ONE out-of-line copy shared by every stage kind (instruction-cache footprint), written as a single basic block per
+// 64-column group so ptxas can overlap the shared-memory loads, PRMTs and HMMAs of four unrolled groups: no predicated
+// loads (idle B lanes read a zero block with stride 0, missing rows/scales alias valid memory), no division.
+// Returns {rows gid, rows gid+8}, valid in lanes with (lane & 3) == 0.
+constexpr uint32_t kHdrZero = 576;   // 32 zero bytes in the CTA header
+constexpr uint32_t kHdrOne = 608;    // 1.0f
+__device__ __forceinline__ void mma_f16_zero(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+// A fragments of one mma from word k of the two 16-byte row chunks: bytes (0,1) -> k-pair 0, bytes (2,3) -> k-pair 1
+#define DSK_A4(wl, wh) __byte_perm(wl, 0, 0x1404), __byte_perm(wh, 0, 0x1404), __byte_perm(wl, 0, 0x3424), __byte_perm(wh, 0, 0x3424)
+__device__ __noinline__ float2 mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32_t s_lo, uint32_t s_hi, int sshift, int col0, int col1,
+                                           uint32_t xhi, uint32_t xlo, uint32_t xgs) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  const uint32_t hdr = smem_u32(dsk_dyn_smem);
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  uint32_t pa_lo = a_lo + (uint32_t)(col0 + 16 * tig);
+  uint32_t pa_hi = (a_hi ? a_hi : a_lo) + (uint32_t)(col0 + 16 * tig);
+  // B columns 0/1 = hi/lo halves of x: only lanes gid 0 and 1 load (predicated, no divergence), columns 2..7 are zero
+  const uint32_t bp = gid < 2 ? 1u : 0u;
+  uint32_t pb = (gid == 1 ? xlo : xhi) + (uint32_t)(col0 + 16 * tig) * 2u;
+  const uint32_t pb_step = 128u;
+  uint32_t pg = xgs + (uint32_t)(col0 >> 6) * 4u;
+  const uint32_t smask = s_lo ? 0xffffffffu : 0u;
+  const uint32_t ps_lo = s_lo ? s_lo : hdr + kHdrOne, ps_hi = s_hi ? s_hi : hdr + kHdrOne;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  const uint32_t xsrc = gid == 0 ? x.hi : x.lo;
-  // the four mma of a 64-column group use independent accumulators; two groups are unrolled so ~8 mma are in flight
-  // (deeper unrolling spills at the interpreter's 168-register cap and is slower — measured)
-#pragma unroll 2
-  for (int cb = col0; cb < col1; cb += 64) {
-    const uint4 w0 = lds128(a_lo + (uint32_t)(cb + 16 * tig));
-    uint4 w1 = make_uint4(0, 0, 0, 0);
-    if (a_hi) w1 = lds128(a_hi + (uint32_t)(cb + 16 * tig));
-    uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-    if (gid < 2) { b0 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u); b1 = lds128(xsrc + (uint32_t)(cb + 16 * tig) * 2u + 16u); }
-    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
-    mma_f16(c0, __byte_perm(w0.x, 0, 0x1404), __byte_perm(w1.x, 0, 0x1404), __byte_perm(w0.x, 0, 0x3424), __byte_perm(w1.x, 0, 0x3424), b0.x, b0.y);
-    mma_f16(c1, __byte_perm(w0.y, 0, 0x1404), __byte_perm(w1.y, 0, 0x1404), __byte_perm(w0.y, 0, 0x3424), __byte_perm(w1.y, 0, 0x3424), b0.z, b0.w);
-    mma_f16(c2, __byte_perm(w0.z, 0, 0x1404), __byte_perm(w1.z, 0, 0x1404), __byte_perm(w0.z, 0, 0x3424), __byte_perm(w1.z, 0, 0x3424), b1.x, b1.y);
-    mma_f16(c3, __byte_perm(w0.w, 0, 0x1404), __byte_perm(w1.w, 0, 0x1404), __byte_perm(w0.w, 0, 0x3424), __byte_perm(w1.w, 0, 0x3424), b1.z, b1.w);
-    const float g = __uint_as_float(lds32(x.gs + (uint32_t)(cb >> 6) * 4u));
-    const uint32_t sidx = (sshift >= 0 ? (uint32_t)cb >> sshift : (uint32_t)(cb / bs1)) * 4u;
-    const float f_lo = s_lo ? g * __uint_as_float(lds32(s_lo + sidx)) : g;
-    const float f_hi = s_hi ? g * __uint_as_float(lds32(s_hi + sidx)) : g;
-    t0 = fmaf((c0[0] + c1[0]) + (c2[0] + c3[0]), f_lo, t0);
-    t1 = fmaf((c0[1] + c1[1]) + (c2[1] + c3[1]), f_lo, t1);
-    t2 = fmaf((c0[2] + c1[2]) + (c2[2] + c3[2]), f_hi, t2);
-    t3 = fmaf((c0[3] + c1[3]) + (c2[3] + c3[3]), f_hi, t3);
+  int cb = col0;
+  // two 64-column groups per iteration, issued interleaved: the eight mma form four 2-deep chains (A.xy, A.zw, B.xy, B.zw),
+  // so consecutive HMMAs are independent and the tensor pipe is fed back to back (inline asm keeps this source order)
+  for (; cb + 128 <= col1; cb += 128) {
+    const uint4 wa0 = lds128(pa_lo), wa1 = lds128(pa_hi), ba0 = lds128_pred(pb, bp), ba1 = lds128_pred(pb + 16u, bp);
+    const uint4 wb0 = lds128(pa_lo + 64u), wb1 = lds128(pa_hi + 64u), bb0 = lds128_pred(pb + pb_step, bp), bb1 = lds128_pred(pb + pb_step + 16u, bp);
+    const float ga = __uint_as_float(lds32(pg)), gb = __uint_as_float(lds32(pg + 4u));
+    const uint32_t sia = (((uint32_t)cb >> sshift) << 2) & smask, sib = (((uint32_t)(cb + 64) >> sshift) << 2) & smask;
+    const float sla = __uint_as_float(lds32(ps_lo + sia)), sha = __uint_as_float(lds32(ps_hi + sia));
+    const float slb = __uint_as_float(lds32(ps_lo + sib)), shb = __uint_as_float(lds32(ps_hi + sib));
+    float ca0[4], ca1[4], cb0[4], cb1[4];
+    mma_f16_zero(ca0, DSK_A4(wa0.x, wa1.x), ba0.x, ba0.y);
+    mma_f16_zero(ca1, DSK_A4(wa0.z, wa1.z), ba1.x, ba1.y);
+    mma_f16_zero(cb0, DSK_A4(wb0.x, wb1.x), bb0.x, bb0.y);
+    mma_f16_zero(cb1, DSK_A4(wb0.z, wb1.z), bb1.x, bb1.y);
+    mma_f16(ca0, DSK_A4(wa0.y, wa1.y), ba0.z, ba0.w);
+    mma_f16(ca1, DSK_A4(wa0.w, wa1.w), ba1.z, ba1.w);
+    mma_f16(cb0, DSK_A4(wb0.y, wb1.y), bb0.z, bb0.w);
+    mma_f16(cb1, DSK_A4(wb0.w, wb1.w), bb1.z, bb1.w);
+    const float fla = ga * sla, fha = ga * sha, flb = gb * slb, fhb = gb * shb;
+    t0 = fmaf(ca0[0] + ca1[0], fla, t0);
+    t1 = fmaf(ca0[1] + ca1[1], fla, t1);
+    t2 = fmaf(ca0[2] + ca1[2], fha, t2);
+    t3 = fmaf(ca0[3] + ca1[3], fha, t3);
+    t0 = fmaf(cb0[0] + cb1[0], flb, t0);
+    t1 = fmaf(cb0[1] + cb1[1], flb, t1);
+    t2 = fmaf(cb0[2] + cb1[2], fhb, t2);
+    t3 = fmaf(cb0[3] + cb1[3], fhb, t3);
+    pa_lo += 128u; pa_hi += 128u; pb += 2u * pb_step; pg += 8u;
   }
-  out_lo = t0 + t1;   // hi-part + lo-part contributions
-  out_hi = t2 + t3;
+  if (cb < col1) {   // odd group count: one more 64-column group
+    const uint4 wa0 = lds128(pa_lo), wa1 = lds128(pa_hi), ba0 = lds128_pred(pb, bp), ba1 = lds128_pred(pb + 16u, bp);
+    const float ga = __uint_as_float(lds32(pg));
+    const uint32_t sia = (((uint32_t)cb >> sshift) << 2) & smask;
+    const float sla = __uint_as_float(lds32(ps_lo + sia)), sha = __uint_as_float(lds32(ps_hi + sia));
+    float ca0[4], ca1[4];
+    mma_f16_zero(ca0, DSK_A4(wa0.x, wa1.x), ba0.x, ba0.y);
+    mma_f16_zero(ca1, DSK_A4(wa0.z, wa1.z), ba1.x, ba1.y);
+    mma_f16(ca0, DSK_A4(wa0.y, wa1.y), ba0.z, ba0.w);
+    mma_f16(ca1, DSK_A4(wa0.w, wa1.w), ba1.z, ba1.w);
+    const float fla = ga * sla, fha = ga * sha;
+    t0 = fmaf(ca0[0] + ca1[0], fla, t0);
+    t1 = fmaf(ca0[1] + ca1[1], fla, t1);
+    t2 = fmaf(ca0[2] + ca1[2], fha, t2);
+    t3 = fmaf(ca0[3] + ca1[3], fha, t3);
+  }
+  return make_float2(t0 + t1, t2 + t3);   // hi-part + lo-part contributions
 }
 
 // ---- dots over a column piece, weights and f8 scale row both in shared memory -----------------------------------
@@ -478,65 +542,66 @@ __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_
 // routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599) by ONE warp with the
 // E <= 256 scores in registers (lane holds experts lane, lane+32, ...).  Every CTA computes it redundantly from the gate
 // logits; `publish` (CTA 0) also writes the state buffers.  Ties: lowest index (the reference's strict `>` scans).
-__device__ __forceinline__ void warp_route(const Program& P, const Stage& st, const MegaSmem& sm, bool publish) {
+__device__ __noinline__ void warp_route(const Program* Pp, const Stage* stp, int* act_smem, float* actw_smem, bool publish) {
+  // Compact on purpose (rolled loops over the scores kept in shared memory): this runs once per MoE layer on ONE warp
+  // with a cold instruction cache, so its cost is its code size, not its arithmetic.
+  const Program& P = *Pp; const Stage& st = *stp;
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  float* sx = reinterpret_cast<float*>(dsk_dyn_smem + 768);   // 256 scores (MegaSmem::sx)
   const int lane = threadIdx.x & 31;
   const int E = P.E;
-  float v[8];
-  unsigned mask = 0;   // bit i set = expert lane+32*i not selectable
-#pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int j = lane + 32 * i;
-    v[i] = j < E ? st.gate_logits[j] : -3.402823466e38f;
-    if (j >= E) mask |= 1u << i;
-  }
+  float mx = -3.402823466e38f;
+#pragma unroll 1
+  for (int j = lane; j < E; j += 32) { const float v = st.gate_logits[j]; sx[j] = v; mx = fmaxf(mx, v); }
   if (P.sigmoid) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = 1.0f / (1.0f + expf(-v[i]));
+#pragma unroll 1
+    for (int j = lane; j < E; j += 32) sx[j] = 1.0f / (1.0f + expf(-sx[j]));
   } else {
-    float mx = v[0];
-#pragma unroll
-    for (int i = 1; i < 8; i++) mx = fmaxf(mx, v[i]);
     mx = warp_max(mx);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) { v[i] = (lane + 32 * i) < E ? expf(v[i] - mx) : 0.f; s += v[i]; }
-    s = warp_sum(s);
-#pragma unroll
-    for (int i = 0; i < 8; i++) v[i] = v[i] / s;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int j = lane; j < E; j += 32) { const float e = expf(sx[j] - mx); sx[j] = e; sum += e; }
+    sum = warp_sum(sum);
+#pragma unroll 1
+    for (int j = lane; j < E; j += 32) sx[j] = sx[j] / sum;
   }
   if (st.gate_bias) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) if ((lane + 32 * i) < E) v[i] += st.gate_bias[lane + 32 * i];
+#pragma unroll 1
+    for (int j = lane; j < E; j += 32) sx[j] += st.gate_bias[j];
   }
   if (publish) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) if ((lane + 32 * i) < E) P.moe_scores[lane + 32 * i] = v[i];
+#pragma unroll 1
+    for (int j = lane; j < E; j += 32) P.moe_scores[j] = sx[j];
   }
+  unsigned mask = 0;   // bit i set = expert lane+32*i not selectable (this lane's experts only)
   if (P.topk_method == 1) {   // keep only the topk_group best (positive) experts of every group
     const int gs = E / P.n_group;
     unsigned cand = 0;
+#pragma unroll 1
     for (int g = 0; g < P.n_group; g++) {
+#pragma unroll 1
       for (int k = 0; k < P.topk_group; k++) {
         float bv = 0.f; int bi = -1;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int j = lane + 32 * i;
-          if (j >= g * gs && j < (g + 1) * gs && !((mask | cand) >> i & 1u) && v[i] > 0.0f && (bi < 0 || v[i] > bv)) { bv = v[i]; bi = j; }
+#pragma unroll 1
+        for (int j = lane, i = 0; j < E; j += 32, i++) {
+          const float v = sx[j];
+          if (j >= g * gs && j < (g + 1) * gs && !((cand >> i) & 1u) && v > 0.0f && (bi < 0 || v > bv)) { bv = v; bi = j; }
         }
         argmax_pair(bv, bi);
         if (bi >= 0 && (bi & 31) == lane) cand |= 1u << (bi >> 5);
       }
     }
-    mask |= ~cand & 0xffu;
+    mask = ~cand;
   }
   float wsum = 0.f;
   float myw = 0.f; int mye = -1;   // lane k keeps selection k
+#pragma unroll 1
   for (int k = 0; k < P.K; k++) {
     float bv = 0.f; int bi = -1;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const int j = lane + 32 * i;
-      if (!((mask >> i) & 1u) && (bi < 0 || v[i] > bv)) { bv = v[i]; bi = j; }
+#pragma unroll 1
+    for (int j = lane, i = 0; j < E; j += 32, i++) {
+      const float v = sx[j];
+      if (!((mask >> i) & 1u) && (bi < 0 || v > bv)) { bv = v; bi = j; }
     }
     argmax_pair(bv, bi);
     if (bi >= 0 && (bi & 31) == lane) mask |= 1u << (bi >> 5);
@@ -546,7 +611,7 @@ __device__ __forceinline__ void warp_route(const Program& P, const Stage& st, co
   if (!P.norm_topk_prob) wsum = 1.0f;
   if (lane < P.K) {
     const float w = mye >= 0 ? myw / wsum * P.routed_scale : 0.f;
-    sm.act[lane] = mye; sm.actw[lane] = w;
+    act_smem[lane] = mye; actw_smem[lane] = w;
     if (publish) { P.act[lane] = mye; P.act_w[lane] = w; }
   }
   __syncwarp();
@@ -682,7 +747,7 @@ template <bool GLU>
 __device__ __forceinline__ void gemv_tile_tasks_mma(const Program& P, const Stage& st, const MJob& jb, int nrows, uint32_t slot,
                                                     const X16& x16, float* res, int shift_bytes) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2;
-  const uint32_t rb = (uint32_t)st.n + kF8RowPad;   // f8 device row pitch
+  const uint32_t rb = (uint32_t)f8_pitch((size_t)st.n);   // f8 device row pitch
   const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
   const int csplit = st.npieces;
   constexpr int RPG = GLU ? 8 : 16;     // tile rows per mma row group
@@ -705,7 +770,7 @@ __device__ __forceinline__ void gemv_tile_tasks_mma(const Program& P, const Stag
       a_hi = slot + (uint32_t)P.slot_scale + (uint32_t)min(r_hi, nrows - 1) * rb;
     }
     float v_lo, v_hi;
-    mma_rows_f8(a_lo, a_hi, s0, GLU ? s1 : s0, P.bs1_shift, P.bs1, pcd.g0 * 64, pcd.g1 * 64, x16, lane, v_lo, v_hi);
+    { const float2 vv = mma_rows_f8(a_lo, a_hi, s0, GLU ? s1 : s0, P.bs1_shift, pcd.g0 * 64, pcd.g1 * 64, x16.hi, x16.lo, x16.gs); v_lo = vv.x; v_hi = vv.y; }
     if ((lane & 3) == 0) {
       if constexpr (GLU) {
         if (r_lo < nrows) { res[(r_lo * 2 + 0) * csplit + pc] = v_lo; res[(r_lo * 2 + 1) * csplit + pc] = v_hi; }
@@ -802,7 +867,7 @@ __device__ __forceinline__ void consume_down_tile_mma(const Program& P, const St
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2;
   const int i0 = t * st.rows_per_tile;
   const int nrows = min(st.rows_per_tile, P.dim - i0);
-  const uint32_t rb_mi = (uint32_t)st.mi + kF8RowPad, rb_sh = (uint32_t)st.sh + kF8RowPad;
+  const uint32_t rb_mi = (uint32_t)f8_pitch((size_t)st.mi), rb_sh = (uint32_t)f8_pitch((size_t)st.sh);
   const int ncb_mi = (st.mi + P.bs1 - 1) / P.bs1, ncb_sh = (st.sh + P.bs1 - 1) / P.bs1;
   const uint32_t sstride = (uint32_t)P.slot_scale / (uint32_t)(st.K + 1) & ~15u;
   const int np = st.npieces;
@@ -826,7 +891,7 @@ __device__ __forceinline__ void consume_down_tile_mma(const Program& P, const St
       const uint32_t rb = k < st.K ? rb_mi : rb_sh;
       const uint32_t base = slot + (uint32_t)P.slot_scale + (uint32_t)k * st.seg_stride;
       const uint32_t a_lo = base + (uint32_t)min(gid, nrows - 1) * rb, a_hi = base + (uint32_t)min(gid + 8, nrows - 1) * rb;
-      mma_rows_f8(a_lo, a_hi, ssm, ssm, P.bs1_shift, P.bs1, pcd.g0 * 64, pcd.g1 * 64, x16_seg[k], lane, v_lo, v_hi);
+      { const X16 xk = x16_seg[k]; const float2 vv = mma_rows_f8(a_lo, a_hi, ssm, ssm, P.bs1_shift, pcd.g0 * 64, pcd.g1 * 64, xk.hi, xk.lo, xk.gs); v_lo = vv.x; v_hi = vv.y; }
     }
     if ((lane & 3) == 0) {
       if (gid < nrows) res[gid * np + pc] = v_lo;
@@ -1027,7 +1092,7 @@ __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* 
       case Q_F16: val = __half2float(reinterpret_cast<const __half*>(table)[(size_t)token * dim + i]); break;
       case Q_F8: {
         const int ncb = (dim + P.bs1 - 1) / P.bs1;
-        val = h2f((uint16_t)((uint16_t)table[(size_t)token * (dim + kF8RowPad) + i] << 8)) * P.embed_scale[(size_t)(token / P.bs0) * ncb + i / P.bs1];
+        val = h2f((uint16_t)((uint16_t)table[(size_t)token * f8_pitch((size_t)dim) + i] << 8)) * P.embed_scale[(size_t)(token / P.bs0) * ncb + i / P.bs1];
         break;
       }
       case Q_Q2K: {
@@ -1059,13 +1124,19 @@ __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* 
 // ---- per-stage bodies ------------------------------------------------------------------------------------------
 // GEMV activation staging: one pass over the input with the values kept in registers (n <= 8192), RMSNorm and Q8_K fused
 template <int Q>
-__device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage& st, const MegaSmem& sm, float* xs0, const Q8Smem& q80) {
+__device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage& st, const MegaSmem& sm, float* xs0, const Q8Smem& q80, int dep_count, int stage_index) {
   constexpr bool KQ = QTraits<Q>::kq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = st.n;
   if (n > 8192) {   // long vectors: two passes through L1/L2
     float sc = 1.0f;
     if (st.norm_w) sc = c_rms_scale(st.in, n, P.eps, sm.red);
+    if (st.need_topk && threadIdx.x < 32) {   // routing by warp 0 while the other warps convert: it releases the producer itself
+      const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
+      warp_route(&P, &st, sm.act, sm.actw, blockIdx.x == 0);
+      if (threadIdx.x == 0) dep_signal(sm.dep, dep_count);
+      if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
+    }
     c_stage_vec<Q>(st.in, n, st.norm_w, sc, xs0, q80);
     return;
   }
@@ -1086,6 +1157,12 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
     }
     float sc = 1.0f;
     if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+    if (st.need_topk && threadIdx.x < 32) {   // routing by warp 0 while the other warps convert: it releases the producer itself
+      const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
+      warp_route(&P, &st, sm.act, sm.actw, blockIdx.x == 0);
+      if (threadIdx.x == 0) dep_signal(sm.dep, dep_count);
+      if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int b = warp + 8 * k;
@@ -1114,6 +1191,12 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
     }
     float sc = 1.0f;
     if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+    if (st.need_topk && threadIdx.x < 32) {   // routing by warp 0 while the other warps convert: it releases the producer itself
+      const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
+      warp_route(&P, &st, sm.act, sm.actw, blockIdx.x == 0);
+      if (threadIdx.x == 0) dep_signal(sm.dep, dep_count);
+      if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int f = tid + k * kConsumers;
@@ -1153,7 +1236,7 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
     soff = (size_t)e * jb.s_stride;
   }
   const bool glu = st.epi == EPI_GLU;
-  const uint32_t rb = (uint32_t)st.n + kF8RowPad;   // device row pitch of f8 weights
+  const uint32_t rb = (uint32_t)f8_pitch((size_t)st.n);   // device row pitch of f8 weights
   const uint32_t part_stride = (uint32_t)align_up((size_t)st.rows_per_tile * rb, 128);
   uint32_t s0 = 0, s1 = 0;
   if (jb.scale) {
@@ -1174,7 +1257,7 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
     if (r_hi < nrows) xres_hi = jb.out[r0 + r_hi];
   }
   float v_lo, v_hi;
-  mma_rows_f8(a_lo, a_hi, s0, s1, P.bs1_shift, P.bs1, 0, st.n, x16, lane, v_lo, v_hi);
+  { const float2 vv = mma_rows_f8(a_lo, a_hi, s0, s1, P.bs1_shift, 0, st.n, x16.hi, x16.lo, x16.gs); v_lo = vv.x; v_hi = vv.y; }
   if (tig != 0) return;
   if (glu) {
     if (r_lo < nrows) jb.out[r0 + r_lo] = (P.act_silu ? silu_f(v_lo) : gelu_f(v_lo)) * v_hi;
@@ -1221,7 +1304,7 @@ __device__ __forceinline__ void wp_produce_down_piece(const Program& P, const St
   } else if (!(st.sw2 != nullptr && st.add_shared)) { mbar_expect_tx(full, 0); return; }
   if (nrows <= 0) { mbar_expect_tx(full, 0); return; }
   const int n = routed ? st.mi : st.sh;
-  const size_t pitch = (size_t)n + kF8RowPad;
+  const size_t pitch = f8_pitch((size_t)n);
   const uint32_t bytes = (uint32_t)(nrows * pitch);
   const uint8_t* src = routed ? st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * pitch : st.sw2 + (size_t)i0 * pitch;
   const float* sc = routed ? st.s2 : st.ss2;
@@ -1261,10 +1344,10 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
       ssm = slot + (uint32_t)(reinterpret_cast<uintptr_t>(sc + (routed ? (size_t)e * st.s2_stride : 0) + (size_t)(i0 / P.bs0) * ncb) & 15);
     }
     const uint32_t data = slot + (uint32_t)P.slot_scale;
-    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)(n + kF8RowPad);
-    const uint32_t a_hi = nrows > 8 ? data + (uint32_t)min(gid + 8, nrows - 1) * (uint32_t)(n + kF8RowPad) : 0u;
+    const uint32_t a_lo = data + (uint32_t)min(gid, nrows - 1) * (uint32_t)f8_pitch((size_t)n);
+    const uint32_t a_hi = nrows > 8 ? data + (uint32_t)min(gid + 8, nrows - 1) * (uint32_t)f8_pitch((size_t)n) : 0u;
     float v_lo, v_hi;
-    mma_rows_f8(a_lo, a_hi, ssm, a_hi ? ssm : 0u, P.bs1_shift, P.bs1, 0, n, x16_seg[k], lane, v_lo, v_hi);
+    { const X16 xk = x16_seg[k]; const float2 vv = mma_rows_f8(a_lo, a_hi, ssm, ssm, P.bs1_shift, 0, n, xk.hi, xk.lo, xk.gs); v_lo = vv.x; v_hi = vv.y; }
     if (tig == 0 && gid < nrows) part[pc * 16 + pcd.g0 + gid] = v_lo;
     if (tig == 0 && gid + 8 < nrows) part[pc * 16 + pcd.g0 + gid + 8] = v_hi;
   }
@@ -1312,101 +1395,98 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
 constexpr int kKqMaxPass = 4;   // up to 128 quarter-blocks (n <= 8192) register-resident
 struct YRegs { int4 y[4]; int bs[4]; float d; };
 
-template <int NP>
-__device__ __forceinline__ void kq_load_y(const Q8Smem& q8, int nb, int lane, YRegs (&yr)[NP]) {
+// this lane's slice of the Q8_K activations for pass p (quarter block lane + 32 p): 64 int8, 4 sub-block sums, scale
+__device__ __forceinline__ void kq_load_y(uint32_t a_qs, uint32_t a_d, uint32_t a_bsums, int nb, int qb, YRegs& yr) {
+  const int b = min(qb >> 2, nb - 1), h = (qb >> 1) & 1, c = qb & 1;
+  const uint32_t y = a_qs + (uint32_t)(b * 256 + 128 * h + 16 * c);
 #pragma unroll
-  for (int p = 0; p < NP; p++) {
-    const int qb = lane + 32 * p;
-    const int b = min(qb >> 2, nb - 1), h = (qb >> 1) & 1, c = qb & 1;
-    const int8_t* y = q8.qs + b * 256 + 128 * h + 16 * c;
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-      yr[p].y[s] = *reinterpret_cast<const int4*>(y + 32 * s);
-      yr[p].bs[s] = (int)q8.bsums[b * 16 + 8 * h + c + 2 * s];
-    }
-    yr[p].d = q8.d[b];
+  for (int s = 0; s < 4; s++) {
+    const uint4 t = lds128(y + 32u * s);
+    yr.y[s] = make_int4((int)t.x, (int)t.y, (int)t.z, (int)t.w);
+    short bsv;
+    asm volatile("ld.shared.s16 %0, [%1];" : "=h"(bsv) : "r"(a_bsums + (uint32_t)(b * 16 + 8 * h + c + 2 * s) * 2u));
+    yr.bs[s] = (int)bsv;
   }
+  yr.d = __uint_as_float(lds32(a_d + (uint32_t)b * 4u));
 }
 
 // one row x one pass: this lane's quarter block; returns the block's fp32 contribution in lanes with (lane & 3) == 0
 template <int Q>
 __device__ __forceinline__ float kq_quarter(uint32_t row, int qb, int nqb, const YRegs& yr) {
+  // branch-free: lanes past the end of the row (qb >= nqb) read the last block and contribute zero, so the four rows a
+  // caller interleaves form one basic block
   const bool act = qb < nqb;
-  const int b = qb >> 2, h = (qb >> 1) & 1, c = qb & 1;
+  const int qc = act ? qb : nqb - 1;
+  const int b = qc >> 2, h = (qc >> 1) & 1, c = qc & 1;
   int isum = 0, summs = 0;
   float out = 0.f;
   if constexpr (Q == Q_Q2K) {
     const uint32_t blk = row + (uint32_t)b * kQ2Bytes;
-    if (act) {
-      const uint32_t qp = blk + 16 + 32 * h + 16 * c;
-      const uint32_t w0 = lds32(qp), w1 = lds32(qp + 4), w2 = lds32(qp + 8), w3 = lds32(qp + 12);
-      const uint32_t sA = lds32(blk + 8 * h), sB = lds32(blk + 8 * h + 4);
+    const uint32_t qp = blk + 16 + 32 * h + 16 * c;
+    const uint32_t w0 = lds32(qp), w1 = lds32(qp + 4), w2 = lds32(qp + 8), w3 = lds32(qp + 12);
+    const uint32_t sA = lds32(blk + 8 * h), sB = lds32(blk + 8 * h + 4);
+    const uint32_t dm = lds32(blk + 80);
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
-        int dp = __dp4a((int)((w0 >> (2 * s)) & 0x03030303u), yr.y[s].x, 0);
-        dp = __dp4a((int)((w1 >> (2 * s)) & 0x03030303u), yr.y[s].y, dp);
-        dp = __dp4a((int)((w2 >> (2 * s)) & 0x03030303u), yr.y[s].z, dp);
-        dp = __dp4a((int)((w3 >> (2 * s)) & 0x03030303u), yr.y[s].w, dp);
-        const uint32_t sw = (s < 2) ? sA : sB;
-        const int sc = (sw >> (8 * ((2 * s + c) & 3))) & 0xff;
-        isum += (sc & 0xF) * dp;
-        summs += (sc >> 4) * yr.bs[s];
-      }
+    for (int s = 0; s < 4; s++) {
+      int dp = __dp4a((int)((w0 >> (2 * s)) & 0x03030303u), yr.y[s].x, 0);
+      dp = __dp4a((int)((w1 >> (2 * s)) & 0x03030303u), yr.y[s].y, dp);
+      dp = __dp4a((int)((w2 >> (2 * s)) & 0x03030303u), yr.y[s].z, dp);
+      dp = __dp4a((int)((w3 >> (2 * s)) & 0x03030303u), yr.y[s].w, dp);
+      const uint32_t sw = (s < 2) ? sA : sB;
+      const int sc = (sw >> (8 * ((2 * s + c) & 3))) & 0xff;
+      isum += (sc & 0xF) * dp;
+      summs += (sc >> 4) * yr.bs[s];
     }
-    isum += __shfl_xor_sync(0xffffffffu, isum, 1);
-    isum += __shfl_xor_sync(0xffffffffu, isum, 2);
-    summs += __shfl_xor_sync(0xffffffffu, summs, 1);
-    summs += __shfl_xor_sync(0xffffffffu, summs, 2);
-    if (act && (qb & 3) == 0) {
-      const uint32_t dm = lds32(blk + 80);
-      out = (yr.d * h2f((uint16_t)(dm & 0xffff))) * (float)isum - (yr.d * h2f((uint16_t)(dm >> 16))) * (float)summs;
-    }
+    // per-quarter fp32 contribution (the integer sums are exact in fp32; the four quarters of a block are added in fp32 by the
+    // row reduction instead of in int32 first: same value up to fp32 re-association, two dependent shuffle pairs fewer)
+    const float o = (yr.d * h2f((uint16_t)(dm & 0xffff))) * (float)isum - (yr.d * h2f((uint16_t)(dm >> 16))) * (float)summs;
+    out = act ? o : 0.f;
   } else {
     const uint32_t blk = row + (uint32_t)b * kQ3Bytes;
-    if (act) {
-      const uint4 hm = lds128(blk + 16 * c);
-      const uint4 qq = lds128(blk + 32 + 32 * h + 16 * c);
-      const uint32_t s0 = lds32(blk + 96), s1 = lds32(blk + 100), s2 = lds32(blk + 104);
+    const uint4 hm = lds128(blk + 16 * c);
+    const uint4 qq = lds128(blk + 32 + 32 * h + 16 * c);
+    const uint32_t s0 = lds32(blk + 96), s1 = lds32(blk + 100), s2 = lds32(blk + 104);
+    const uint32_t dw = lds32(blk + 108);
 #pragma unroll
-      for (int s = 0; s < 4; s++) {
-        const int bit = 4 * h + s;
-        int dp = __dp4a((int)(((qq.x >> (2 * s)) & 0x03030303u) | (((hm.x >> bit) & 0x01010101u) << 2)), yr.y[s].x, 0);
-        dp = __dp4a((int)(((qq.y >> (2 * s)) & 0x03030303u) | (((hm.y >> bit) & 0x01010101u) << 2)), yr.y[s].y, dp);
-        dp = __dp4a((int)(((qq.z >> (2 * s)) & 0x03030303u) | (((hm.z >> bit) & 0x01010101u) << 2)), yr.y[s].z, dp);
-        dp = __dp4a((int)(((qq.w >> (2 * s)) & 0x03030303u) | (((hm.w >> bit) & 0x01010101u) << 2)), yr.y[s].w, dp);
-        dp -= 4 * yr.bs[s];
-        const int t = 2 * s + c;
-        const uint32_t lw = (t < 4) ? s0 : s1;
-        const int lob = (lw >> (8 * (t & 3))) & 0xff;
-        const int lo4 = h ? (lob >> 4) : (lob & 0xF);
-        const int hib = (s2 >> (8 * (t & 3))) & 0xff;
-        const int hi2 = (hib >> (2 * (2 * h + (t >> 2)))) & 3;
-        isum += ((lo4 | (hi2 << 4)) - 32) * dp;
-      }
+    for (int s = 0; s < 4; s++) {
+      const int bit = 4 * h + s;
+      int dp = __dp4a((int)(((qq.x >> (2 * s)) & 0x03030303u) | (((hm.x >> bit) & 0x01010101u) << 2)), yr.y[s].x, 0);
+      dp = __dp4a((int)(((qq.y >> (2 * s)) & 0x03030303u) | (((hm.y >> bit) & 0x01010101u) << 2)), yr.y[s].y, dp);
+      dp = __dp4a((int)(((qq.z >> (2 * s)) & 0x03030303u) | (((hm.z >> bit) & 0x01010101u) << 2)), yr.y[s].z, dp);
+      dp = __dp4a((int)(((qq.w >> (2 * s)) & 0x03030303u) | (((hm.w >> bit) & 0x01010101u) << 2)), yr.y[s].w, dp);
+      dp -= 4 * yr.bs[s];
+      const int t = 2 * s + c;
+      const uint32_t lw = (t < 4) ? s0 : s1;
+      const int lob = (lw >> (8 * (t & 3))) & 0xff;
+      const int lo4 = h ? (lob >> 4) : (lob & 0xF);
+      const int hib = (s2 >> (8 * (t & 3))) & 0xff;
+      const int hi2 = (hib >> (2 * (2 * h + (t >> 2)))) & 3;
+      isum += ((lo4 | (hi2 << 4)) - 32) * dp;
     }
-    isum += __shfl_xor_sync(0xffffffffu, isum, 1);
-    isum += __shfl_xor_sync(0xffffffffu, isum, 2);
-    if (act && (qb & 3) == 0) {
-      const uint32_t dw = lds32(blk + 108);
-      out = (h2f((uint16_t)(dw & 0xffff)) * yr.d) * (float)isum;
-    }
+    const float o = (h2f((uint16_t)(dw & 0xffff)) * yr.d) * (float)isum;
+    out = act ? o : 0.f;
   }
   return out;
 }
 
-// all rows of a tile: returns in lane r the dot product of tile row r (r < nrows <= 32)
-template <int Q, int NP>
-__device__ __forceinline__ float kq_tile_rows(uint32_t base, uint32_t rb, int nrows, int nb, const YRegs (&yr)[NP], int lane) {
-  const int nqb = nb * 4;
+// all rows of a tile: returns in lane r the dot product of tile row r (r < nrows <= 32).  ONE out-of-line copy per
+// quant for every GEMV / DOWN stage (instruction-cache footprint): four rows are interleaved (four independent dp4a /
+// shuffle chains), passes over long rows are a rolled loop that re-reads this lane's activation slice from shared memory.
+template <int Q>
+__device__ __noinline__ float kq_tile_rows(uint32_t base, uint32_t rb, int nrows, int nb, uint32_t q_qs, uint32_t q_d, uint32_t q_bsums) {
+  const int lane = threadIdx.x & 31;
+  const int nqb = nb * 4, npass = (nqb + 31) >> 5;
   float mine = 0.f;
-  for (int r0 = 0; r0 < nrows; r0 += 4) {   // four rows at a time: four independent dp4a / shuffle chains in flight
-    float acc[4];
+  YRegs yr;
+  if (npass == 1) kq_load_y(q_qs, q_d, q_bsums, nb, lane, yr);
+#pragma unroll 1
+  for (int r0 = 0; r0 < nrows; r0 += 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int p = 0; p < npass; p++) {
+      if (npass > 1) kq_load_y(q_qs, q_d, q_bsums, nb, lane + 32 * p, yr);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const uint32_t row = base + (uint32_t)min(r0 + i, nrows - 1) * rb;
-      acc[i] = 0.f;
-#pragma unroll
-      for (int p = 0; p < NP; p++) acc[i] += kq_quarter<Q>(row, lane + 32 * p, nqb, yr[p]);
+      for (int i = 0; i < 4; i++) acc[i] += kq_quarter<Q>(base + (uint32_t)min(r0 + i, nrows - 1) * rb, lane + 32 * p, nqb, yr);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
@@ -1419,8 +1499,8 @@ __device__ __forceinline__ float kq_tile_rows(uint32_t base, uint32_t rb, int nr
   return mine;
 }
 
-template <int Q, int NP>
-__device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, const YRegs (&yr)[NP],
+template <int Q>
+__device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, const Q8Smem& q8,
                                                 const int* act_smem, unsigned long long& best) {
   const int lane = threadIdx.x & 31;
   int j = 0;
@@ -1439,9 +1519,9 @@ __device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& s
   const int nb = st.n >> 8;
   float xres = 0.f;
   if (st.epi == EPI_RESID && lane < nrows) xres = jb.out[r0 + lane];
-  const float v = kq_tile_rows<Q, NP>(data, rb, nrows, nb, yr, lane);
+  const float v = kq_tile_rows<Q>(data, rb, nrows, nb, smem_u32(q8.qs), smem_u32(q8.d), smem_u32(q8.bsums));
   float u = 0.f;
-  if (glu) u = kq_tile_rows<Q, NP>(data + part_stride, rb, nrows, nb, yr, lane);
+  if (glu) u = kq_tile_rows<Q>(data + part_stride, rb, nrows, nb, smem_u32(q8.qs), smem_u32(q8.d), smem_u32(q8.bsums));
   if (lane >= nrows) return;
   const int r = r0 + lane;
   float val = v;
@@ -1503,12 +1583,9 @@ __device__ __forceinline__ void wp_kq_down_piece(const Program& P, const Stage& 
   int* cnt = sm.sel + (rg_local & 1);
   if (live) {
     const int n = routed ? st.mi : st.sh, nb = n >> 8;
-    const int npass = (nb * 4 + 31) / 32;
     const uint32_t base = slot + (uint32_t)P.slot_scale, rb = (uint32_t)QTraits<Q>::row_bytes(n);
-    float v;
-    if (npass <= 1) { YRegs yr[1]; kq_load_y<1>(q8_seg[k], nb, lane, yr); v = kq_tile_rows<Q, 1>(base, rb, nrows, nb, yr, lane); }
-    else if (npass <= 2) { YRegs yr[2]; kq_load_y<2>(q8_seg[k], nb, lane, yr); v = kq_tile_rows<Q, 2>(base, rb, nrows, nb, yr, lane); }
-    else { YRegs yr[4]; kq_load_y<4>(q8_seg[k], nb, lane, yr); v = kq_tile_rows<Q, 4>(base, rb, nrows, nb, yr, lane); }
+    const Q8Smem qk = q8_seg[k];
+    const float v = kq_tile_rows<Q>(base, rb, nrows, nb, smem_u32(qk.qs), smem_u32(qk.d), smem_u32(qk.bsums));
     if (lane < nrows) part[pc * 16 + pcd.g0 + lane] = v;
   }
   __syncwarp();
@@ -1544,65 +1621,148 @@ __device__ __forceinline__ void wp_kq_down_piece(const Program& P, const Stage& 
 }
 
 // the tile loop of a warp-per-tile K-quant GEMV stage; this lane's activation slice lives in NP register sets
-template <int Q, int NP>
+template <int Q>
 __device__ __forceinline__ void kq_gemv_loop(const Program& P, const Stage& st, const MegaSmem& sm, const Q8Smem& q80, int& it, int n_slots,
-                                             unsigned long long& best_key) {
+                                             unsigned long long& best_key, int stage_index) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  YRegs yr[NP];
-  kq_load_y<NP>(q80, st.n >> 8, lane, yr);
+  long long c_wait = 0, c_task = 0;
+  int n_mine = 0;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     const int sl = it % n_slots;
     if ((sl & 7) != warp) continue;
+    const long long k0 = clock64();
     mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
-    wp_kq_gemv_tile<Q, NP>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, yr, sm.act, best_key);
+    const long long k1 = clock64();
+    wp_kq_gemv_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, q80, sm.act, best_key);
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+    c_wait += k1 - k0; c_task += clock64() - k1; n_mine++;
+  }
+  if (lane == 0 && blockIdx.x == 0 && P.tstamp && n_mine && !st.need_topk) {   // profiling: cycles per tile waiting / reducing
+    if (warp == 0) { P.tstamp[stage_index * 8 + 4] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 5] = (unsigned long long)(c_task / n_mine); }
+    if (warp == 1) { P.tstamp[stage_index * 8 + 6] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 7] = (unsigned long long)(c_task / n_mine); }
   }
 }
 
-// GEMV activation staging for the tensor-core path: RMSNorm fused, values split into fp16 hi/lo (n <= 8192 in registers)
-__device__ __forceinline__ void c_stage_gemv_input_x16(const Program& P, const Stage& st, const MegaSmem& sm, const X16& x16) {
-  const int tid = threadIdx.x;
-  const int n = st.n, nf = n >> 2;
-  if (n <= 8192) {
+// ---- shared activation staging (ONE out-of-line copy each, used by every GEMV stage and by the DOWN stage) -------------
+// The code of a stage phase runs once per stage with a cold instruction cache, so its cost is its size (tools/
+// icache_bench.cu: ~0.2 us per KB fetched from L2): both routines are deliberately small, and the DOWN stage reuses them
+// on a flat layout (routed hidden vectors concatenated: K*mi values, then the shared/dense vector).
+//   n floats at `in` -> RMSNorm (optional) -> fp16 hi/lo split (stage_x16) or Q8_K blocks (stage_q8); `route` >= 0: warp 0
+//   runs the MoE routing between the norm reduction and its share of the conversion and releases the producer (dep count).
+__device__ __forceinline__ void stage_route_hook(const Program& P, const Stage& st, int route, int stage_index) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  if (route >= 0 && threadIdx.x < 32) {
+    const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
+    warp_route(&P, &st, reinterpret_cast<int*>(dsk_dyn_smem + 384), reinterpret_cast<float*>(dsk_dyn_smem + 448), blockIdx.x == 0);
+    if (threadIdx.x == 0) dep_signal(smem_u32(dsk_dyn_smem) + 192u, route);
+    if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
+  }
+}
+__device__ __noinline__ void stage_x16(const Program* Pp, const Stage* stp, const float* __restrict__ in, int n, const float* __restrict__ norm_w,
+                                       uint32_t xhi, uint32_t xlo, uint32_t xgs, int route, int stage_index) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  const Program& P = *Pp; const Stage& st = *stp;
+  float* red = reinterpret_cast<float*>(dsk_dyn_smem + 256);
+  const int tid = threadIdx.x, nf = n >> 2;
+  float sc = 1.0f;
+  bool sc_known = norm_w == nullptr;
+  if (norm_w && nf > 8 * kConsumers) { sc = c_rms_scale(in, n, P.eps, red); sc_known = true; }   // long vectors: extra pass
+  bool routed = route < 0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < nf; c0 += 8 * kConsumers) {   // eight float4 per thread in flight
     float4 v[8];
     float ss = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const int f = tid + k * kConsumers;
+      const int f = c0 + tid + k * kConsumers;
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (f < nf) {
-        v[k] = reinterpret_cast<const float4*>(st.in)[f];
+        v[k] = reinterpret_cast<const float4*>(in)[f];
         ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
       }
     }
-    float sc = 1.0f;
-    if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+    if (!sc_known) { ss = csum(ss, red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); sc_known = true; }
+    if (!routed) { stage_route_hook(P, st, route, stage_index); routed = true; }
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const int f = tid + k * kConsumers;
+      const int f = c0 + tid + k * kConsumers;
       if (f < nf) {   // nf is a multiple of 16, so the 16 lanes of a 64-column group are in or out together
         float4 o = v[k];
-        if (st.norm_w) {
-          const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
+        if (norm_w) {
+          const float4 w = reinterpret_cast<const float4*>(norm_w)[f];
           o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
           o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
         }
-        x16_store(x16, f, o);
+        x16_store_nf(xhi, xlo, xgs, f, o);
       }
-    }
-  } else {
-    float sc = 1.0f;
-    if (st.norm_w) sc = c_rms_scale(st.in, n, P.eps, sm.red);
-    for (int f = tid; f < nf; f += kConsumers) {
-      float4 o = reinterpret_cast<const float4*>(st.in)[f];
-      if (st.norm_w) {
-        const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
-        o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
-        o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
-      }
-      x16_store(x16, f, o);
     }
   }
+  if (!routed) stage_route_hook(P, st, route, stage_index);
+}
+__device__ __noinline__ void stage_q8(const Program* Pp, const Stage* stp, const float* __restrict__ in, int n, const float* __restrict__ norm_w,
+                                      int8_t* q_qs, float* q_d, short* q_bsums, int route, int stage_index) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  const Program& P = *Pp; const Stage& st = *stp;
+  float* red = reinterpret_cast<float*>(dsk_dyn_smem + 256);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = n >> 8;
+  float sc = 1.0f;
+  bool sc_known = norm_w == nullptr;
+  if (norm_w && nb > 32) { sc = c_rms_scale(in, n, P.eps, red); sc_known = true; }
+  bool routed = route < 0;
+#pragma unroll 1
+  for (int b0 = 0; b0 < nb; b0 += 32) {   // a warp per 256-block, four blocks per warp in flight
+    float4 va[4], vb[4];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int b = b0 + warp + 8 * k;
+      va[k] = make_float4(0.f, 0.f, 0.f, 0.f); vb[k] = va[k];
+      if (b < nb) {
+        va[k] = *reinterpret_cast<const float4*>(in + (b << 8) + lane * 8);
+        vb[k] = *reinterpret_cast<const float4*>(in + (b << 8) + lane * 8 + 4);
+        ss = fmaf(va[k].x, va[k].x, ss); ss = fmaf(va[k].y, va[k].y, ss); ss = fmaf(va[k].z, va[k].z, ss); ss = fmaf(va[k].w, va[k].w, ss);
+        ss = fmaf(vb[k].x, vb[k].x, ss); ss = fmaf(vb[k].y, vb[k].y, ss); ss = fmaf(vb[k].z, vb[k].z, ss); ss = fmaf(vb[k].w, vb[k].w, ss);
+      }
+    }
+    if (!sc_known) { ss = csum(ss, red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); sc_known = true; }
+    if (!routed) { stage_route_hook(P, st, route, stage_index); routed = true; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int b = b0 + warp + 8 * k;
+      if (b < nb) {
+        float4 a = va[k], c = vb[k];
+        if (norm_w) {
+          const float4 w0 = *reinterpret_cast<const float4*>(norm_w + (b << 8) + lane * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(norm_w + (b << 8) + lane * 8 + 4);
+          a.x = __fmul_rn(__fmul_rn(a.x, sc), w0.x); a.y = __fmul_rn(__fmul_rn(a.y, sc), w0.y);
+          a.z = __fmul_rn(__fmul_rn(a.z, sc), w0.z); a.w = __fmul_rn(__fmul_rn(a.w, sc), w0.w);
+          c.x = __fmul_rn(__fmul_rn(c.x, sc), w1.x); c.y = __fmul_rn(__fmul_rn(c.y, sc), w1.y);
+          c.z = __fmul_rn(__fmul_rn(c.z, sc), w1.z); c.w = __fmul_rn(__fmul_rn(c.w, sc), w1.w);
+        }
+        q8_block_nf(a, c, b, q_qs, q_d, q_bsums);
+      }
+    }
+  }
+  if (!routed) stage_route_hook(P, st, route, stage_index);
+}
+// flat activation layout of a DOWN stage: [routed: K*mi values][shared / dense: sh values]; per-segment views by offset
+__host__ __device__ inline size_t down_x16_bytes(int K, int mi, int sh) { return (K * mi ? x16_bytes(K * mi) : 0) + (sh ? x16_bytes(sh) : 0); }
+__device__ __forceinline__ void carve_down_x16(unsigned char* p, int K, int mi, int sh, X16* seg) {
+  const X16 r = carve_x16(p, K * mi);
+  for (int k = 0; k < K; k++) { seg[k].hi = r.hi + (uint32_t)(k * mi) * 2u; seg[k].lo = r.lo + (uint32_t)(k * mi) * 2u; seg[k].gs = r.gs + (uint32_t)(k * (mi >> 6)) * 4u; }
+  seg[K] = carve_x16(p + (K * mi ? x16_bytes(K * mi) : 0), sh);
+}
+template <int Q>
+__host__ __device__ inline size_t down_q8_bytes(int K, int mi, int sh) { return (K * mi ? xvec_bytes<Q>(K * mi) : 0) + (sh ? xvec_bytes<Q>(sh) : 0); }
+template <int Q>
+__device__ __forceinline__ void carve_down_q8(unsigned char* p, int K, int mi, int sh, Q8Smem* seg) {
+  float* dummy = nullptr;
+  Q8Smem r{};
+  carve_x<Q>(p, K * mi, dummy, r);
+  const int nbm = mi >> 8;
+  for (int k = 0; k < K; k++) { seg[k].qs = r.qs + k * mi; seg[k].d = r.d + k * nbm; seg[k].bsums = r.bsums + k * nbm * 16; }
+  carve_x<Q>(p + (K * mi ? xvec_bytes<Q>(K * mi) : 0), sh, dummy, seg[K]);
 }
 
 template <int Q>
@@ -1616,11 +1776,11 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     return;
   }
   // routing first (one warp, registers): it unblocks the producer's routed-expert tiles
-  if (st.need_topk) { if (tid < 32) warp_route(P, st, sm, blockIdx.x == 0); }
-  else if (st.kind == ST_DOWN && st.K > 0) { if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; } }
-  if (st.need_topk || (st.kind == ST_DOWN && st.K > 0)) {
+  if (st.kind == ST_DOWN && st.K > 0) {
+    if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
     csync();
     if (tid == 0) dep_signal(sm.dep, dep_count);
+    if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 4] = (gtime() - P.tstamp[stage_index * 8]) * 1000ull;
   }
   // activation vector(s) -> shared memory
   float* xs0 = nullptr;
@@ -1630,46 +1790,27 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   X16 x16_0{};
   X16 x16_seg[kMaxJobs];
   const bool mma = Q == Q_F8 && st.use_mma;
+  const int route = st.need_topk ? dep_count : -1;
   if (st.kind == ST_GEMV && mma) {
     x16_0 = carve_x16(sm.xregion, st.n);
-    c_stage_gemv_input_x16(P, st, sm, x16_0);
+    stage_x16(&P, &st, st.in, st.n, st.norm_w, x16_0.hi, x16_0.lo, x16_0.gs, route, stage_index);
   } else if (st.kind == ST_DOWN && mma) {
-    unsigned char* p = sm.xregion;
     const bool use_shared = st.sw2 != nullptr && st.add_shared;
-    // all K+1 vectors in ONE flattened loop: every thread's loads are in flight together
-    int off[kMaxJobs + 1];
-    off[0] = 0;
-    for (int k = 0; k <= st.K; k++) {
-      const int n = k < st.K ? st.mi : st.sh;
-      x16_seg[k] = carve_x16(p, n);
-      p += n ? x16_bytes(n) : 0;
-      off[k + 1] = off[k] + (n >> 2);
-    }
-    const int nf_all = off[st.K + 1];
-    for (int f0 = tid; f0 < nf_all; f0 += kConsumers * 4) {   // 4 independent L2 loads in flight per thread
-      float4 v[4];
-      int kk[4], fl[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int f = f0 + u * kConsumers;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        kk[u] = -1; fl[u] = 0;
-        if (f < nf_all) {
-          int k = 0;
-          while (f >= off[k + 1]) k++;
-          bool live = true;
-          if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = e >= 0 && e < P.expert_count; }
-          else live = use_shared;
-          kk[u] = k; fl[u] = f - off[k];
-          if (live) v[u] = reinterpret_cast<const float4*>(k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs)[fl[u]];
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) if (kk[u] >= 0) x16_store(x16_seg[kk[u]], fl[u], v[u]);
-    }
+    carve_down_x16(sm.xregion, st.K, st.mi, st.sh, x16_seg);
+    if (st.K > 0) stage_x16(&P, &st, P.hbk, st.K * st.mi, nullptr, x16_seg[0].hi, x16_seg[0].lo, x16_seg[0].gs, -1, stage_index);
+    if (use_shared && st.sh > 0) stage_x16(&P, &st, P.hbs, st.sh, nullptr, x16_seg[st.K].hi, x16_seg[st.K].lo, x16_seg[st.K].gs, -1, stage_index);
+  } else if (st.kind == ST_GEMV && KQ) {
+    carve_x<Q>(sm.xregion, st.n, xs0, q80);
+    stage_q8(&P, &st, st.in, st.n, st.norm_w, q80.qs, q80.d, q80.bsums, route, stage_index);
+  } else if (st.kind == ST_DOWN && KQ) {
+    const bool use_shared = st.sw2 != nullptr && st.add_shared;
+    carve_down_q8<Q>(sm.xregion, st.K, st.mi, st.sh, q8_seg);
+    for (int k = 0; k <= st.K; k++) xs_seg[k] = 0u;
+    if (st.K > 0) stage_q8(&P, &st, P.hbk, st.K * st.mi, nullptr, q8_seg[0].qs, q8_seg[0].d, q8_seg[0].bsums, -1, stage_index);
+    if (use_shared && st.sh > 0) stage_q8(&P, &st, P.hbs, st.sh, nullptr, q8_seg[st.K].qs, q8_seg[st.K].d, q8_seg[st.K].bsums, -1, stage_index);
   } else if (st.kind == ST_GEMV) {
     carve_x<Q>(sm.xregion, st.n, xs0, q80);
-    c_stage_gemv_input<Q>(P, st, sm, xs0, q80);
+    c_stage_gemv_input<Q>(P, st, sm, xs0, q80, dep_count, stage_index);
   } else {
     unsigned char* p = sm.xregion;
     const bool use_shared = st.sw2 != nullptr && st.add_shared;
@@ -1677,7 +1818,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       const int n = k < st.K ? st.mi : st.sh;
       float* xk = nullptr;
       carve_x<Q>(p, n, xk, q8_seg[k]);
-      xs_seg[k] = KQ ? 0u : smem_u32(xk);
+      xs_seg[k] = smem_u32(xk);
       p += n ? xvec_bytes<Q>(n) : 0;
       bool live = n > 0;
       if (k < st.K) { const int e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
@@ -1685,16 +1826,14 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       if (live) c_stage_vec<Q>(k < st.K ? P.hbk + (size_t)k * st.mi : P.hbs, n, nullptr, 1.0f, xk, q8_seg[k]);
     }
   }
+  if (tid == 0 && blockIdx.x == 0 && P.tstamp && st.kind == ST_DOWN) P.tstamp[stage_index * 8 + 5] = (gtime() - P.tstamp[stage_index * 8]) * 1000ull;
   csync();
   if (!(st.need_topk || (st.kind == ST_DOWN && st.K > 0)) && tid == 0) dep_signal(sm.dep, dep_count);
   if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
   if (KQ && st.wp) {   // warp-per-tile K-quant stage
     const int warp = tid >> 5, lane = tid & 31;
     if (st.kind == ST_GEMV) {
-      const int nb = st.n >> 8, npass = (nb * 4 + 31) / 32;
-      if (npass <= 1) kq_gemv_loop<Q, 1>(P, st, sm, q80, it, n_slots, best_key);
-      else if (npass <= 2) kq_gemv_loop<Q, 2>(P, st, sm, q80, it, n_slots, best_key);
-      else kq_gemv_loop<Q, 4>(P, st, sm, q80, it, n_slots, best_key);
+      kq_gemv_loop<Q>(P, st, sm, q80, it, n_slots, best_key, stage_index);
     } else {
       if (tid < 4) sm.sel[tid] = 0;
       csync();
@@ -1718,13 +1857,26 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     if (st.kind == ST_GEMV) {
       // ring slot s is always consumed by warp (s mod 8): every slot's uses are awaited in order by ONE warp, so an
       // mbarrier parity can never be mistaken for an earlier use of the same slot
+      long long c_wait = 0, c_task = 0;
+      int n_mine = 0;
       for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
         const int sl = it % n_slots;
         if ((sl & 7) != warp) continue;
+        const long long k0 = clock64();
         mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+        const long long k1 = clock64();
         wp_gemv_tile(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_0, sm.act, best_key);
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+        c_wait += k1 - k0; c_task += clock64() - k1; n_mine++;
+      }
+      if (lane == 0 && blockIdx.x == 0 && P.tstamp) {   // CTA 0: cycles per tile waiting for TMA / reducing, warp 0 (shares its
+        if (warp == 0 && n_mine) {                        // sub-partition with the producer warp) and warp 1 (does not)
+          P.tstamp[stage_index * 8 + 4] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 5] = (unsigned long long)(c_task / n_mine);
+        }
+        if (warp == 1 && n_mine) {
+          P.tstamp[stage_index * 8 + 6] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 7] = (unsigned long long)(c_task / n_mine);
+        }
       }
     } else {
       if (tid < 4) sm.sel[tid] = 0;
@@ -1827,7 +1979,7 @@ __device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage
     }
     const int sl = it % n_slots;
     const uint32_t slot = ring + (uint32_t)sl * slot_bytes, full = sm.full[sl];
-    if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+    if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
     if (!j_live) { mbar_expect_tx(full, 0); continue; }
     const int r0 = (t - j_begin) * RT;
     const int nrows = min(RT, j_rows - r0);
@@ -1862,7 +2014,7 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
       for (int pc = 0; pc < st.npieces; pc++, it++) {
         if (st.piece[pc].seg < st.K && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
         const int sl = it % n_slots;
-        if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+        if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
         if constexpr (QTraits<Q>::kq) wp_produce_down_piece_q<Q>(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
         else wp_produce_down_piece(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
       }
@@ -1884,11 +2036,31 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
     }
     if (dyn && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
     const int sl = it % n_slots;
-    if (it >= n_slots) mbar_wait_guard(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+    if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
     produce_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
   }
   if (!dep_waited) dep_wait(sm.dep, dep_count);   // bounds the run-ahead to one stage
 }
+
+#ifdef DSK_JUNK
+// instruction-cache sensitivity experiment: DSK_JUNK=1 -> 2048 straight-line instructions (32 KB of code) per stage,
+// DSK_JUNK=2 -> the same instruction count as a 64-instruction loop (1 KB of code)
+__device__ __noinline__ unsigned junk_code(unsigned a) {
+  unsigned b = a * 3u, c = a ^ 5u, d = a + 7u;
+#define DSK_JUNK_STEP { a = a * 1664525u + 1013904223u; b ^= a >> 7; c += b * 22695477u; d = (d << 1) ^ c; }
+#if DSK_JUNK == 1
+#pragma unroll
+  for (int i = 0; i < 384; i++) DSK_JUNK_STEP
+#else
+#pragma unroll 1
+  for (int j = 0; j < 32; j++) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) DSK_JUNK_STEP
+  }
+#endif
+  return a ^ b ^ c ^ d;
+}
+#endif
 
 // ---- the interpreter ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void copy_desc(void* dst, const void* src, int bytes, int t, int nthreads) {
@@ -1910,6 +2082,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
   const int n_slots = P.n_slots;
   if (tid == 0) {
     for (int i = 0; i < n_slots; i++) { mbar_init(sm.full[i], 1); mbar_init(sm.empty[i], 1); }
+    for (int i = 0; i < 8; i++) reinterpret_cast<uint32_t*>(smem + kHdrZero)[i] = 0u;
+    for (int i = 0; i < 4; i++) reinterpret_cast<float*>(smem + kHdrOne)[i] = 1.0f;
     dep_signal(sm.dep, 0);
     fence_proxy_async();
   }
@@ -1952,6 +2126,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       }
       csync();
     }
+#ifdef DSK_JUNK
+    if (tid >= 224) { const unsigned jv = junk_code((unsigned)s); if (jv == 0x12345u) sm.sel[15] = (int)jv; }   // one warp only
+#endif
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 8 + 0] = gtime(); P.tstamp[s * 8 + 1] = 0; P.tstamp[s * 8 + 4] = 0; P.tstamp[s * 8 + 5] = 0; P.tstamp[s * 8 + 6] = 0; P.tstamp[s * 8 + 7] = 0; }
     if (st.kind == ST_EMBED) {
       if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
