@@ -1177,6 +1177,21 @@ static int build_program(dsk_model* m, dsk_state* s) {
   if (attn_need <= 64 * 1024) xreg = std::max(xreg, attn_need);
   xreg = align_up(std::max(xreg, (size_t)(512 + ((hd + 3) & ~3) + 64) * 4), 128);
   const size_t budget = (size_t)kSmemMax - 2048;
+  {  // scale-row area of a ring slot: as small as this program's f8 scale rows allow (a 5th 34 KB slot fits for V2-Lite)
+    size_t need = 0;
+    bool generic = false;
+    const int bs1 = c.bs1 > 0 ? c.bs1 : 1;
+    for (const Stage& st : S) {
+      if (st.kind == ST_GEMV && st.quant == DSK_F8E5M2) need = std::max(need, (size_t)(cdiv(st.n, bs1) * 4 + 16) * (st.epi == EPI_GLU ? 2 : 1));
+      else if (st.kind == ST_DOWN && st.quant == DSK_F8E5M2) {
+        if (!st.wp) generic = true;
+        need = std::max(need, (size_t)(cdiv(std::max(st.mi, st.sh), bs1) * 4 + 16));
+      }
+    }
+    if (q != DSK_F8E5M2) g_slot_scale = 128;                       // no scale rows at all (F32 / F16 / K-quants)
+    else if (!generic && need <= 512) g_slot_scale = 512;
+    else g_slot_scale = kSlotScale;
+  }
   const size_t slot_bytes = (size_t)g_slot_data + g_slot_scale;
   if (kMegaHdr + xreg + 2 * slot_bytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
   int n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / slot_bytes);
