@@ -322,25 +322,30 @@ __device__ __noinline__ float2 mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32_
   const uint32_t ps_lo = s_lo ? s_lo : hdr + kHdrOne, ps_hi = s_hi ? s_hi : hdr + kHdrOne;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
   int cb = col0;
-  // two 64-column groups per iteration, issued interleaved: the eight mma form four 2-deep chains (A.xy, A.zw, B.xy, B.zw),
-  // so consecutive HMMAs are independent and the tensor pipe is fed back to back (inline asm keeps this source order)
-  for (; cb + 128 <= col1; cb += 128) {
-    const uint4 wa0 = lds128(pa_lo), wa1 = lds128(pa_hi), ba0 = lds128_pred(pb, bp), ba1 = lds128_pred(pb + 16u, bp);
-    const uint4 wb0 = lds128(pa_lo + 64u), wb1 = lds128(pa_hi + 64u), bb0 = lds128_pred(pb + pb_step, bp), bb1 = lds128_pred(pb + pb_step + 16u, bp);
-    const float ga = __uint_as_float(lds32(pg)), gb = __uint_as_float(lds32(pg + 4u));
-    const uint32_t sia = (((uint32_t)cb >> sshift) << 2) & smask, sib = (((uint32_t)(cb + 64) >> sshift) << 2) & smask;
-    const float sla = __uint_as_float(lds32(ps_lo + sia)), sha = __uint_as_float(lds32(ps_hi + sia));
-    const float slb = __uint_as_float(lds32(ps_lo + sib)), shb = __uint_as_float(lds32(ps_hi + sib));
+  // Two 64-column groups (128 columns) per iteration as four 2-deep HMMA chains; the operands of iteration i+1 are loaded
+  // while iteration i computes (register double buffering: ptxas does not move loads across the loop edge by itself, and a
+  // single warp per sub-partition is otherwise exposed to the full shared-memory latency every iteration).
+  struct Frag { uint4 wa0, wa1, ba0, ba1, wb0, wb1, bb0, bb1; float ga, gb, sla, sha, slb, shb; };
+  auto load_frag = [&](Frag& F, int c) {
+    F.wa0 = lds128(pa_lo); F.wa1 = lds128(pa_hi); F.ba0 = lds128_pred(pb, bp); F.ba1 = lds128_pred(pb + 16u, bp);
+    F.wb0 = lds128(pa_lo + 64u); F.wb1 = lds128(pa_hi + 64u); F.bb0 = lds128_pred(pb + pb_step, bp); F.bb1 = lds128_pred(pb + pb_step + 16u, bp);
+    F.ga = __uint_as_float(lds32(pg)); F.gb = __uint_as_float(lds32(pg + 4u));
+    const uint32_t sia = (((uint32_t)c >> sshift) << 2) & smask, sib = (((uint32_t)(c + 64) >> sshift) << 2) & smask;
+    F.sla = __uint_as_float(lds32(ps_lo + sia)); F.sha = __uint_as_float(lds32(ps_hi + sia));
+    F.slb = __uint_as_float(lds32(ps_lo + sib)); F.shb = __uint_as_float(lds32(ps_hi + sib));
+    pa_lo += 128u; pa_hi += 128u; pb += 2u * pb_step; pg += 8u;
+  };
+  auto compute_frag = [&](const Frag& F) {
     float ca0[4], ca1[4], cb0[4], cb1[4];
-    mma_f16_zero(ca0, DSK_A4(wa0.x, wa1.x), ba0.x, ba0.y);
-    mma_f16_zero(ca1, DSK_A4(wa0.z, wa1.z), ba1.x, ba1.y);
-    mma_f16_zero(cb0, DSK_A4(wb0.x, wb1.x), bb0.x, bb0.y);
-    mma_f16_zero(cb1, DSK_A4(wb0.z, wb1.z), bb1.x, bb1.y);
-    mma_f16(ca0, DSK_A4(wa0.y, wa1.y), ba0.z, ba0.w);
-    mma_f16(ca1, DSK_A4(wa0.w, wa1.w), ba1.z, ba1.w);
-    mma_f16(cb0, DSK_A4(wb0.y, wb1.y), bb0.z, bb0.w);
-    mma_f16(cb1, DSK_A4(wb0.w, wb1.w), bb1.z, bb1.w);
-    const float fla = ga * sla, fha = ga * sha, flb = gb * slb, fhb = gb * shb;
+    mma_f16_zero(ca0, DSK_A4(F.wa0.x, F.wa1.x), F.ba0.x, F.ba0.y);
+    mma_f16_zero(ca1, DSK_A4(F.wa0.z, F.wa1.z), F.ba1.x, F.ba1.y);
+    mma_f16_zero(cb0, DSK_A4(F.wb0.x, F.wb1.x), F.bb0.x, F.bb0.y);
+    mma_f16_zero(cb1, DSK_A4(F.wb0.z, F.wb1.z), F.bb1.x, F.bb1.y);
+    mma_f16(ca0, DSK_A4(F.wa0.y, F.wa1.y), F.ba0.z, F.ba0.w);
+    mma_f16(ca1, DSK_A4(F.wa0.w, F.wa1.w), F.ba1.z, F.ba1.w);
+    mma_f16(cb0, DSK_A4(F.wb0.y, F.wb1.y), F.bb0.z, F.bb0.w);
+    mma_f16(cb1, DSK_A4(F.wb0.w, F.wb1.w), F.bb1.z, F.bb1.w);
+    const float fla = F.ga * F.sla, fha = F.ga * F.sha, flb = F.gb * F.slb, fhb = F.gb * F.shb;
     t0 = fmaf(ca0[0] + ca1[0], fla, t0);
     t1 = fmaf(ca0[1] + ca1[1], fla, t1);
     t2 = fmaf(ca0[2] + ca1[2], fha, t2);
@@ -349,7 +354,17 @@ __device__ __noinline__ float2 mma_rows_f8(uint32_t a_lo, uint32_t a_hi, uint32_
     t1 = fmaf(cb0[1] + cb1[1], flb, t1);
     t2 = fmaf(cb0[2] + cb1[2], fhb, t2);
     t3 = fmaf(cb0[3] + cb1[3], fhb, t3);
-    pa_lo += 128u; pa_hi += 128u; pb += 2u * pb_step; pg += 8u;
+  };
+  if (cb + 128 <= col1) {
+    Frag cur, nxt;
+    load_frag(cur, cb);
+    for (; cb + 256 <= col1; cb += 128) {
+      load_frag(nxt, cb + 128);
+      compute_frag(cur);
+      cur = nxt;
+    }
+    compute_frag(cur);
+    cb += 128;
   }
   if (cb < col1) {   // odd group count: one more 64-column group
     const uint4 wa0 = lds128(pa_lo), wa1 = lds128(pa_hi), ba0 = lds128_pred(pb, bp), ba1 = lds128_pred(pb + 16u, bp);
@@ -505,6 +520,10 @@ __device__ __forceinline__ void piece_rows(const uint32_t (&wa)[NACC], const uin
 }
 
 // ---- shared-memory map of the interpreter -----------------------------------------------------------------------
+// Static ring-slot ownership of the warp-per-tile stages: slot s is consumed by warp kWarpOfSlot[s & 7] = {1,2,3,5,6,7,0,4}.
+// With 4-5 slots (34 KB F8 tiles) the busy warps land on sub-partitions 1-3, away from the producer warp (warp 8 lives on
+// sub-partition 0 with warps 0 and 4): measured 7.3 vs 4.9 kcycles per tile for a consumer sharing the producer's scheduler.
+__device__ __forceinline__ int slot_of_warp(int warp) { return (int)((0x54372106u >> (4 * warp)) & 7u); }
 struct MegaSmem {
   uint32_t full[kMaxSlots], empty[kMaxSlots], dep;   // shared addresses of the mbarriers
   float* red;          // 32 floats
@@ -1238,7 +1257,7 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
 //            group's last piece combines the partial sums in the reference's order and applies the residual update.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, int t, uint32_t slot, const X16& x16,
-                                             const int* act_smem, unsigned long long& best) {
+                                             const int* act_smem, unsigned long long& best, long long& c_mma) {
   const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   int j = 0;
   while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
@@ -1273,7 +1292,7 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
     if (r_hi < nrows) xres_hi = jb.out[r0 + r_hi];
   }
   float v_lo, v_hi;
-  { const float2 vv = mma_rows_f8(a_lo, a_hi, s0, s1, P.bs1_shift, 0, st.n, x16.hi, x16.lo, x16.gs); v_lo = vv.x; v_hi = vv.y; }
+  { const long long km = clock64(); const float2 vv = mma_rows_f8(a_lo, a_hi, s0, s1, P.bs1_shift, 0, st.n, x16.hi, x16.lo, x16.gs); v_lo = vv.x; v_hi = vv.y; c_mma += clock64() - km; }
   if (tig != 0) return;
   if (glu) {
     if (r_lo < nrows) jb.out[r0 + r_lo] = (P.act_silu ? silu_f(v_lo) : gelu_f(v_lo)) * v_hi;
@@ -1645,7 +1664,7 @@ __device__ __forceinline__ void kq_gemv_loop(const Program& P, const Stage& st, 
   int n_mine = 0;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     const int sl = it % n_slots;
-    if ((sl & 7) != warp) continue;
+    if ((sl & 7) != slot_of_warp(warp)) continue;
     const long long k0 = clock64();
     mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
     const long long k1 = clock64();
@@ -1858,7 +1877,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
         for (int pc = 0; pc < st.npieces; pc++, it++) {
           const int sl = it % n_slots;
-          if ((sl & 7) != warp) continue;
+          if ((sl & 7) != slot_of_warp(warp)) continue;
           mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
           wp_kq_down_piece<Q>(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, q8_seg);
           __syncwarp();
@@ -1873,15 +1892,15 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     if (st.kind == ST_GEMV) {
       // ring slot s is always consumed by warp (s mod 8): every slot's uses are awaited in order by ONE warp, so an
       // mbarrier parity can never be mistaken for an earlier use of the same slot
-      long long c_wait = 0, c_task = 0;
+      long long c_wait = 0, c_task = 0, c_mma = 0;
       int n_mine = 0;
       for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
         const int sl = it % n_slots;
-        if ((sl & 7) != warp) continue;
+        if ((sl & 7) != slot_of_warp(warp)) continue;
         const long long k0 = clock64();
         mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
         const long long k1 = clock64();
-        wp_gemv_tile(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_0, sm.act, best_key);
+        wp_gemv_tile(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_0, sm.act, best_key, c_mma);
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
         c_wait += k1 - k0; c_task += clock64() - k1; n_mine++;
@@ -1890,8 +1909,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
         if (warp == 0 && n_mine) {                        // sub-partition with the producer warp) and warp 1 (does not)
           P.tstamp[stage_index * 8 + 4] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 5] = (unsigned long long)(c_task / n_mine);
         }
-        if (warp == 1 && n_mine) {
-          P.tstamp[stage_index * 8 + 6] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 7] = (unsigned long long)(c_task / n_mine);
+        if (warp == 1 && n_mine) {   // warp 1: cycles inside mma_rows_f8 / whole tile
+          P.tstamp[stage_index * 8 + 6] = (unsigned long long)(c_mma / n_mine); P.tstamp[stage_index * 8 + 7] = (unsigned long long)(c_task / n_mine);
         }
       }
     } else {
@@ -1902,7 +1921,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
       for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
         for (int pc = 0; pc < st.npieces; pc++, it++) {
           const int sl = it % n_slots;
-          if ((sl & 7) != warp) continue;
+          if ((sl & 7) != slot_of_warp(warp)) continue;
           mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
           wp_down_piece(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_seg);
           __syncwarp();
