@@ -1219,9 +1219,10 @@ static int build_program(dsk_model* m, dsk_state* s) {
   P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
   P->n_slots = n_slots; P->xregion_bytes = (int)xreg;
   P->slot_data = g_slot_data; P->slot_scale = g_slot_scale; P->slot_bytes = (int)slot_bytes;
-  CK(cudaMalloc((void**)&s->tstamp, S.size() * 8 * sizeof(unsigned long long)));
-  CK(cudaMemset(s->tstamp, 0, S.size() * 8 * sizeof(unsigned long long)));
+  CK(cudaMalloc((void**)&s->tstamp, (S.size() * 8 + 8) * sizeof(unsigned long long)));
+  CK(cudaMemset(s->tstamp, 0, (S.size() * 8 + 8) * sizeof(unsigned long long)));
   P->tstamp = s->tstamp;
+  P->route_prof = reinterpret_cast<long long*>(s->tstamp + S.size() * 8);
   for (const Stage& st : S) {
     char nm[96];
     const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
@@ -1656,7 +1657,7 @@ extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos,
     // stage-level timeline of the last token from the interpreter's own globaltimer stamps (CTA 0)
     float* lg = nullptr; (void)lg;
     if (dsk_forward(m, s, token, pos, 1, nullptr, nullptr)) return -2;
-    std::vector<unsigned long long> ts((size_t)s->n_stages * 8);
+    std::vector<unsigned long long> ts((size_t)s->n_stages * 8 + 8);
     CK(cudaMemcpy(ts.data(), s->tstamp, ts.size() * 8, cudaMemcpyDeviceToHost));
     struct Agg { int n = 0; double wait = 0, stage = 0, tiles = 0, arrive = 0, cw = 0, ct = 0, cs = 0, ce = 0; };
     std::map<std::string, Agg> agg;
@@ -1680,6 +1681,11 @@ extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos,
                        kv.first.c_str(), a.n, a.wait / a.n, a.stage / a.n, a.tiles / a.n, a.arrive / a.n, a.cw / a.n / 1e3, a.ct / a.n / 1e3, a.cs / a.n / 1e3, a.ce / a.n / 1e3, a.wait + a.stage + a.tiles + a.arrive);
       if (n < 0 || (size_t)n >= cap - off) break;
       off += n;
+    }
+    {
+      const unsigned long long* rp = ts.data() + (size_t)s->n_stages * 8;
+      int n = snprintf(out + off, cap - off, "routing phases (cycles, last MoE layer, CTA 0): scores %llu  bias/publish/groups %llu  top-k %llu  finish %llu\n", rp[0], rp[1], rp[2], rp[3]);
+      if (n > 0 && (size_t)n < cap - off) off += n;
     }
     snprintf(out + off, cap - off, "token total %.1f us over %d stages (CTA 0 timeline)\n", total, s->n_stages);
     return 0;

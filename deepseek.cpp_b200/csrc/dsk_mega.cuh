@@ -87,6 +87,7 @@ struct Program {
   int* token_log; int* step;
   int n_slots, xregion_bytes;
   int slot_data, slot_scale, slot_bytes, pad_s;   // ring slot geometry (bytes): [scale rows | weight tile]
+  long long* route_prof;                   // profiling: 4 phase durations of the last routing (cycles)
   unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
   Stage stage[1];                          // n_stages entries follow
 };
@@ -561,36 +562,46 @@ __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_
 // routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599) by ONE warp with the
 // E <= 256 scores in registers (lane holds experts lane, lane+32, ...).  Every CTA computes it redundantly from the gate
 // logits; `publish` (CTA 0) also writes the state buffers.  Ties: lowest index (the reference's strict `>` scans).
+// warp-wide arg-max over (value, index) pairs with REDUX (one instruction per reduction instead of a 5-level shuffle tree):
+// largest value wins, ties go to the lowest index (the reference's strict `>` scans); idx < 0 = this lane has no candidate
+__device__ __forceinline__ void argmax_redux(float& v, int& i) {
+  const unsigned key = i >= 0 ? orderable(v) : 0u;
+  const unsigned best = __reduce_max_sync(0xffffffffu, key);
+  const int cand = (i >= 0 && key == best) ? i : 0x7fffffff;
+  const int bi = __reduce_min_sync(0xffffffffu, cand);
+  const unsigned src = __ballot_sync(0xffffffffu, cand == bi && bi != 0x7fffffff);
+  if (bi == 0x7fffffff) { i = -1; return; }
+  v = __shfl_sync(0xffffffffu, v, __ffs(src) - 1);
+  i = bi;
+}
 __device__ __noinline__ void warp_route(const Program* Pp, const Stage* stp, int* act_smem, float* actw_smem, bool publish) {
   // Compact on purpose (rolled loops over the scores kept in shared memory): this runs once per MoE layer on ONE warp
-  // with a cold instruction cache, so its cost is its code size, not its arithmetic.
+  // with a cold instruction cache, so its cost is its code size and its dependent collectives, not its arithmetic.
   const Program& P = *Pp; const Stage& st = *stp;
   extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
   float* sx = reinterpret_cast<float*>(dsk_dyn_smem + 768);   // 256 scores (MegaSmem::sx)
   const int lane = threadIdx.x & 31;
-  const int E = P.E;
+  const int E = P.E, ni = (E + 31) >> 5;                      // every lane runs the same ni iterations (uniform control flow)
+  const long long rk0 = clock64();
   float mx = -3.402823466e38f;
 #pragma unroll 1
-  for (int j = lane; j < E; j += 32) { const float v = st.gate_logits[j]; sx[j] = v; mx = fmaxf(mx, v); }
+  for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) { const float v = __ldcg(st.gate_logits + j); sx[j] = v; mx = fmaxf(mx, v); } }
   if (P.sigmoid) {
 #pragma unroll 1
-    for (int j = lane; j < E; j += 32) sx[j] = 1.0f / (1.0f + expf(-sx[j]));
+    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) sx[j] = 1.0f / (1.0f + expf(-sx[j])); }
   } else {
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll 1
-    for (int j = lane; j < E; j += 32) { const float e = expf(sx[j] - mx); sx[j] = e; sum += e; }
+    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) { const float e = expf(sx[j] - mx); sx[j] = e; sum += e; } }
     sum = warp_sum(sum);
 #pragma unroll 1
-    for (int j = lane; j < E; j += 32) sx[j] = sx[j] / sum;
+    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) sx[j] = sx[j] / sum; }
   }
+  const long long rk1 = clock64();
   if (st.gate_bias) {
 #pragma unroll 1
-    for (int j = lane; j < E; j += 32) sx[j] += st.gate_bias[j];
-  }
-  if (publish) {
-#pragma unroll 1
-    for (int j = lane; j < E; j += 32) P.moe_scores[j] = sx[j];
+    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) sx[j] += st.gate_bias[j]; }
   }
   unsigned mask = 0;   // bit i set = expert lane+32*i not selectable (this lane's experts only)
   if (P.topk_method == 1) {   // keep only the topk_group best (positive) experts of every group
@@ -602,38 +613,51 @@ __device__ __noinline__ void warp_route(const Program* Pp, const Stage* stp, int
       for (int k = 0; k < P.topk_group; k++) {
         float bv = 0.f; int bi = -1;
 #pragma unroll 1
-        for (int j = lane, i = 0; j < E; j += 32, i++) {
-          const float v = sx[j];
-          if (j >= g * gs && j < (g + 1) * gs && !((cand >> i) & 1u) && v > 0.0f && (bi < 0 || v > bv)) { bv = v; bi = j; }
+        for (int i = 0; i < ni; i++) {
+          const int j = lane + 32 * i;
+          if (j < E) {
+            const float v = sx[j];
+            if (j >= g * gs && j < (g + 1) * gs && !((cand >> i) & 1u) && v > 0.0f && (bi < 0 || v > bv)) { bv = v; bi = j; }
+          }
         }
-        argmax_pair(bv, bi);
+        argmax_redux(bv, bi);
         if (bi >= 0 && (bi & 31) == lane) cand |= 1u << (bi >> 5);
       }
     }
     mask = ~cand;
   }
+  const long long rk2 = clock64();
   float wsum = 0.f;
   float myw = 0.f; int mye = -1;   // lane k keeps selection k
 #pragma unroll 1
   for (int k = 0; k < P.K; k++) {
     float bv = 0.f; int bi = -1;
 #pragma unroll 1
-    for (int j = lane, i = 0; j < E; j += 32, i++) {
-      const float v = sx[j];
-      if (!((mask >> i) & 1u) && (bi < 0 || v > bv)) { bv = v; bi = j; }
+    for (int i = 0; i < ni; i++) {
+      const int j = lane + 32 * i;
+      if (j < E) {
+        const float v = sx[j];
+        if (!((mask >> i) & 1u) && (bi < 0 || v > bv)) { bv = v; bi = j; }
+      }
     }
-    argmax_pair(bv, bi);
+    argmax_redux(bv, bi);
     if (bi >= 0 && (bi & 31) == lane) mask |= 1u << (bi >> 5);
     if (bi >= 0) wsum += bv;
-    if (lane == k) { mye = bi; myw = bv; }
+    if (lane == k) { mye = bi; myw = bi >= 0 ? bv : 0.f; }
   }
+  const long long rk3 = clock64();
   if (!P.norm_topk_prob) wsum = 1.0f;
   if (lane < P.K) {
     const float w = mye >= 0 ? myw / wsum * P.routed_scale : 0.f;
     act_smem[lane] = mye; actw_smem[lane] = w;
     if (publish) { P.act[lane] = mye; P.act_w[lane] = w; }
   }
+  if (publish) {   // state buffers for the host (CTA 0 only), after the selection so that it is not on anybody's critical path
+#pragma unroll 1
+    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) P.moe_scores[j] = sx[j]; }
+  }
   __syncwarp();
+  if (P.tstamp && blockIdx.x == 0 && lane == 0 && P.route_prof) { P.route_prof[0] = rk1 - rk0; P.route_prof[1] = rk2 - rk1; P.route_prof[2] = rk3 - rk2; P.route_prof[3] = clock64() - rk3; }
 }
 
 // ---- producer: one tile -> ring slot --------------------------------------------------------------------------
