@@ -60,6 +60,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -72,6 +73,7 @@ static int nccl_load() {
   g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy || !g_nccl.GetErrorString)
@@ -120,6 +122,12 @@ struct dsk_model {
   float* rope_freq = nullptr;  // qk_rope_head_dim/2 floats, tabulated on the host (src/infer.cpp:655)
   size_t resident = 0;
   ncclComm_t comm = nullptr;
+  // peer-memory exchange of the MoE partial sums (n_ranks > 1): one buffer per rank, mapped into every peer through CUDA IPC
+  bool p2p = false;
+  int p2p_epoch = 0;
+  float* xchg = nullptr;                 // [2 parities][n_ranks][dim] floats, then n_ranks arrival flags
+  float* xchg_peer[kMaxRanks] = {};      // the same buffer of every rank, as seen from this process
+  unsigned* xflag_peer[kMaxRanks] = {};
   std::vector<void*> allocs;
 };
 
@@ -147,6 +155,10 @@ struct dsk_state {
   size_t mega_smem = 0;
   std::vector<int> layer_begin, layer_end;  // stage ranges per layer
   std::vector<int> cut_after;           // multi-GPU: stage indices followed by the partial-sum all-reduce
+  int built_epoch = 0;                  // m->p2p_epoch the program was built for
+  int n_xchg = 0;                       // in-kernel exchanges per token (peer-memory mode)
+  std::vector<int> xchg_before;         // exchanges preceding stage i within a token (size n_stages + 1)
+  long long xchg_done = 0;              // exchanges completed so far on this state (host mirror of Ctrl::pad[0] + n_xchg)
 };
 
 static size_t disk_row_bytes(int quant, int cols) {
@@ -311,6 +323,8 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
 extern "C" void dsk_model_destroy(dsk_model* m) {
   if (!m) return;
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+  for (int q = 0; q < kMaxRanks; q++) if (m->xchg_peer[q] && q != m->rank) cudaIpcCloseMemHandle(m->xchg_peer[q]);
+  if (m->xchg) cudaFree(m->xchg);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
 }
@@ -1063,6 +1077,8 @@ static int build_program(dsk_model* m, dsk_state* s) {
   g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : (kq_model ? 16 * 1024 + 512 : kSlotData);   // 16 (or 8) rows x (2048 + 16) B
   g_slot_scale = kSlotScale;
   std::vector<Stage> S;
+  int n_xchg = 0;
+  s->cut_after.clear();
   auto gemv = [&](int quant, const float* in, const float* norm_w, int n, int epi, int layer) {
     Stage st{};
     st.kind = ST_GEMV; st.quant = quant; st.epi = epi; st.in = in; st.norm_w = norm_w; st.n = n; st.layer = layer;
@@ -1134,8 +1150,13 @@ static int build_program(dsk_model* m, dsk_state* s) {
         st.K = c.n_active_routed; st.mi = mi; st.sh = sh;
         st.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
         if (plan_down_stage(st, q, c.dim)) return -4;
+        st.xchg_ord = n_xchg;
         S.push_back(st);
-        if (m->n_ranks > 1) s->cut_after.push_back((int)S.size() - 1);
+        if (m->n_ranks > 1 && m->p2p) {   // in-kernel exchange over peer memory: the token stays ONE kernel
+          Stage xs{};
+          xs.kind = ST_XCHG; xs.quant = q; xs.layer = l; xs.xchg_ord = n_xchg++;
+          S.push_back(xs);
+        } else if (m->n_ranks > 1) s->cut_after.push_back((int)S.size() - 1);
       }
     } else {
       {
@@ -1221,11 +1242,17 @@ static int build_program(dsk_model* m, dsk_state* s) {
   P->slot_data = g_slot_data; P->slot_scale = g_slot_scale; P->slot_bytes = (int)slot_bytes;
   CK(cudaMalloc((void**)&s->tstamp, (S.size() * 8 + 8) * sizeof(unsigned long long)));
   CK(cudaMemset(s->tstamp, 0, (S.size() * 8 + 8) * sizeof(unsigned long long)));
+  P->n_ranks = m->n_ranks; P->rank = m->rank; P->n_xchg = n_xchg;
+  for (int qq = 0; qq < kMaxRanks; qq++) { P->xchg_peer[qq] = m->xchg_peer[qq]; P->xflag_peer[qq] = m->xflag_peer[qq]; }
+  s->n_xchg = n_xchg;
+  s->xchg_before.assign(S.size() + 1, 0);
+  for (size_t i = 0; i < S.size(); i++) s->xchg_before[i + 1] = s->xchg_before[i] + (S[i].kind == ST_XCHG ? 1 : 0);
+  s->built_epoch = m->p2p_epoch;
   P->tstamp = s->tstamp;
   P->route_prof = reinterpret_cast<long long*>(s->tstamp + S.size() * 8);
   for (const Stage& st : S) {
     char nm[96];
-    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
+    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_XCHG ? "xchg" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
     snprintf(nm, sizeof(nm), "%-8s n=%5d tiles=%5d rt=%2d r=%d pieces=%2d", kind, st.kind == ST_DOWN ? st.K * st.mi + st.sh : st.n, st.ntiles, st.rows_per_tile, st.rpass, st.npieces);
     s->stage_names.push_back(nm);
   }
@@ -1251,6 +1278,23 @@ static cudaError_t launch_decode(dsk_model* m, dsk_state* s, int s_begin, int s_
 }
 
 // stages [b, e): one resident grid (ENG_MEGA) or one launch per stage (ENG_STAGE); multi-GPU cuts at the all-reduce points
+// The state (and its program) may have been created before dsk_comm_init() mapped the peers: rebuild it once.
+static int ensure_program(dsk_model* m, dsk_state* s) {
+  if (s->built_epoch == m->p2p_epoch) return 0;
+  CK(cudaStreamSynchronize(s->stream));
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (s->graph[a][b]) { cudaGraphExecDestroy(s->graph[a][b]); s->graph[a][b] = nullptr; }
+  cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words); cudaFree(s->tstamp);
+  s->prog = nullptr; s->att_scratch = nullptr; s->sync_words = nullptr; s->tstamp = nullptr;
+  s->stage_names.clear(); s->layer_begin.clear(); s->layer_end.clear();
+  return build_program(m, s);
+}
+// Ctrl::pad[0] = exchanges completed before the token the launch [b, e) belongs to (peer-memory mode)
+static void set_xchg_base(dsk_state* s, int b, int e) {
+  if (s->n_xchg == 0) return;
+  s->h_ctrl->pad[0] = (int)(s->xchg_done - s->xchg_before[b]);
+  s->xchg_done += s->xchg_before[e] - s->xchg_before[b];
+}
+
 static int run_stages(dsk_model* m, dsk_state* s, int b, int e, int from_argmax, cudaStream_t st) {
   const dsk_config& c = m->c;
   int cur = b;
@@ -1337,11 +1381,13 @@ extern "C" int dsk_forward(dsk_model* m, dsk_state* s, int token, int pos, int m
   if (token < 0 || token >= c.vocab_size) return fail(-4, "token %d out of range", token);
   if (pos < 0) return fail(-4, "negative pos");
   mode = mode ? 1 : 0;
+  if (ensure_program(m, s)) return -2;
   fill_ctrl(s->h_ctrl, c, token, pos);
   if (s->h_ctrl->kv_pos >= c.max_seq_len || s->h_ctrl->kv_len > c.max_seq_len)
     return fail(-4, "pos %d does not fit the KV cache (max_seq_len %d; the reference would overrun it)", pos, c.max_seq_len);
   cudaGraphExec_t g;
   if (get_graph(m, s, mode, 0, &g)) return -2;
+  if (g_engine != ENG_V2) set_xchg_base(s, 0, mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - 1 : s->n_stages);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
   CK(cudaGraphLaunch(g, s->stream));
   if (mode && host_logits) CK(cudaMemcpyAsync(host_logits, s->logits, (size_t)c.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -1355,7 +1401,9 @@ extern "C" int dsk_forward(dsk_model* m, dsk_state* s, int token, int pos, int m
 extern "C" int dsk_copy_embedding(dsk_model* m, dsk_state* s, int token) {
   if (need_device()) return -1;
   if (!m || !s) return fail(-1, "null model/state");
+  if (ensure_program(m, s)) return -2;
   fill_ctrl(s->h_ctrl, m->c, token, 0);
+  if (g_engine != ENG_V2) set_xchg_base(s, 0, 1);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
   if (g_engine != ENG_V2) { if (run_stages(m, s, 0, 1, 0, s->stream)) return -2; }
   else if (enqueue_embed(m, s, 0, s->stream)) return -2;
@@ -1367,8 +1415,10 @@ extern "C" int dsk_block_forward(dsk_model* m, dsk_state* s, int layer, int pos,
   if (need_device()) return -1;
   if (!m || !s) return fail(-1, "null model/state");
   if (layer < 0 || layer >= m->c.n_layers) return fail(-4, "bad layer %d", layer);
+  if (ensure_program(m, s)) return -2;
   Ctrl* h = s->h_ctrl;
   h->token = 0; h->pos = pos; h->kv_sink = kv_sink; h->kv_pos = kv_pos; h->kv_len = kv_len; h->argmax_key = 0;
+  if (g_engine != ENG_V2) set_xchg_base(s, s->layer_begin[layer], s->layer_end[layer]);
   CK(cudaMemcpyAsync(s->ctrl, h, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
   if (g_engine != ENG_V2) { if (run_stages(m, s, s->layer_begin[layer], s->layer_end[layer], 0, s->stream)) return -2; }
   else if (enqueue_layer(m, s, layer, s->stream)) return -2;
@@ -1386,8 +1436,14 @@ extern "C" int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int 
   const dsk_config& c = m->c;
   if (c.original_max_position > c.max_seq_len && start_pos + n_steps > c.max_seq_len)
     return fail(-4, "decode would run past the KV cache (%d)", c.max_seq_len);
+  if (ensure_program(m, s)) return -2;
   cudaGraphExec_t g;
   if (get_graph(m, s, 1, 1, &g)) return -2;
+  if (s->n_xchg > 0) {   // the embedding stage of every replay advances the exchange base by n_xchg
+    s->h_ctrl->pad[0] = (int)(s->xchg_done - s->n_xchg);
+    CK(cudaMemcpyAsync(&s->ctrl->pad[0], &s->h_ctrl->pad[0], sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    s->xchg_done += (long long)n_steps * s->n_xchg;
+  }
   CK(cudaMemsetAsync(s->step, 0, sizeof(int), s->stream));
   CK(cudaEventRecord(s->ev0, s->stream));
   for (int i = 0; i < n_steps; i++) CK(cudaGraphLaunch(g, s->stream));
@@ -1404,7 +1460,7 @@ extern "C" int dsk_launches_per_forward(const dsk_model* m, int mode) {
   const dsk_config& c = m->c;
   if (g_engine == ENG_MEGA) {
     int cuts = 0;
-    if (m->n_ranks > 1) for (int l = 0; l < c.n_layers; l++) cuts += m->layers[l].is_moe ? 1 : 0;
+    if (m->n_ranks > 1 && !m->p2p) for (int l = 0; l < c.n_layers; l++) cuts += m->layers[l].is_moe ? 1 : 0;   // peer-memory mode: one kernel
     return 1 + cuts * 3;
   }
   int n = 1;  // embed
@@ -1435,6 +1491,47 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
   ncclUniqueId id;
   memcpy(&id, nccl_unique_id128, 128);
   CKN(g_nccl.CommInitRank(&m->comm, m->n_ranks, id, m->rank));
+  // Peer-memory exchange (DSK_P2P=0 keeps the NCCL all-reduce between kernel segments): every rank allocates one exchange
+  // buffer and maps every peer's through CUDA IPC; the handles travel through the NCCL communicator just created.
+  const char* p2p_env = getenv("DSK_P2P");
+  if (p2p_env && atoi(p2p_env) == 0) return 0;
+  if (m->n_ranks > kMaxRanks || !g_nccl.AllGather) return 0;
+  const int N = m->n_ranks;
+  const size_t data_bytes = (size_t)2 * N * m->c.dim * sizeof(float), total = data_bytes + 256;
+  cudaIpcMemHandle_t mine;
+  unsigned char* d_handles = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(N);
+  memset(&mine, 0, sizeof(mine));
+  bool ok = cudaMalloc((void**)&m->xchg, total) == cudaSuccess && cudaMemset(m->xchg, 0, total) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine, m->xchg) == cudaSuccess;
+  // every rank takes part in the collectives below whatever happened locally (a failed rank is voted out afterwards)
+  cudaStream_t st = nullptr;
+  CK(cudaMalloc((void**)&d_handles, (size_t)N * sizeof(mine)));
+  CK(cudaMemcpy(d_handles + (size_t)m->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  CKN(g_nccl.AllGather(d_handles + (size_t)m->rank * sizeof(mine), d_handles, sizeof(mine), ncclChar, m->comm, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemcpy(all.data(), d_handles, (size_t)N * sizeof(mine), cudaMemcpyDeviceToHost));
+  for (int q = 0; ok && q < N; q++) {
+    void* ptr = m->xchg;
+    if (q != m->rank && cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+    m->xchg_peer[q] = (float*)ptr;
+    m->xflag_peer[q] = (unsigned*)((unsigned char*)ptr + data_bytes);
+  }
+  if (d_handles) cudaFree(d_handles);
+  cudaGetLastError();
+  // agree on the mode: one rank without peer access sends everybody back to the NCCL path (all-reduce of a flag)
+  float* flag = nullptr;
+  CK(cudaMalloc((void**)&flag, sizeof(float)));
+  const float mine_ok = ok ? 0.f : 1.f;
+  CK(cudaMemcpy(flag, &mine_ok, sizeof(float), cudaMemcpyHostToDevice));
+  CKN(g_nccl.AllReduce(flag, flag, 1, ncclFloat, ncclSum, m->comm, st));
+  CK(cudaStreamSynchronize(st));
+  float bad = 0.f;
+  CK(cudaMemcpy(&bad, flag, sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(flag);
+  m->p2p = bad == 0.f;
+  if (!m->p2p) { fprintf(stderr, "[dsk] rank %d: peer-memory exchange unavailable, using NCCL all-reduce between kernel segments\n", m->rank); return 0; }
+  m->p2p_epoch++;
   return 0;
 }
 

@@ -23,7 +23,8 @@
 
 namespace dsk {
 
-enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3 };
+enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3, ST_XCHG = 4 };
+constexpr int kMaxRanks = 8;
 
 constexpr int kConsumers = 256;            // warps 0..7
 constexpr int kMegaThreads = 288;          // + producer warp 8
@@ -61,7 +62,8 @@ struct Stage {
   const uint8_t* sw2; const float* ss2;
   int K, mi, sh, add_shared;
   int seg_stride;                          // bytes between segments inside a ring slot (ST_DOWN)
-  int pad2[3];
+  int xchg_ord;                            // peer-memory mode: ordinal (within a token) of the exchange this DOWN / XCHG stage belongs to
+  int pad2[2];
 } __attribute__((aligned(16)));
 
 static_assert(sizeof(Stage) <= kStageSlot, "Stage descriptor must fit its shared-memory cache slot");
@@ -87,6 +89,12 @@ struct Program {
   int* token_log; int* step;
   int n_slots, xregion_bytes;
   int slot_data, slot_scale, slot_bytes, pad_s;   // ring slot geometry (bytes): [scale rows | weight tile]
+  // multi-GPU, peer-memory mode: every rank stores its MoE partial sums straight into every peer's exchange buffer over
+  // NVLink (plain stores to IPC-mapped memory), then raises a flag there; an ST_XCHG stage waits for the N flags and adds the
+  // N partials in rank order — no kernel boundary, no NCCL call on the token path
+  int n_ranks, rank, n_xchg, pad_x;
+  float* xchg_peer[kMaxRanks];             // [2][n_ranks][dim] buffer of rank q (q == rank: the local one)
+  unsigned* xflag_peer[kMaxRanks];         // n_ranks flags of rank q: flag[r] = sequence number of rank r's last finished store
   long long* route_prof;                   // profiling: 4 phase durations of the last routing (cycles)
   unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
   Stage stage[1];                          // n_stages entries follow
@@ -977,6 +985,22 @@ __device__ __forceinline__ void consume_down_tile(const Program& P, const Stage&
     if (lane == 0) res[lr * np + pc] = v[0];
   }
 }
+// ---- multi-GPU partial sums -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_partial(const Program& P, const Stage& st, int i, float acc) {
+  if (P.n_xchg > 0) {   // peer-memory mode: straight into every rank's exchange buffer (parity by sequence number)
+    const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
+    const size_t off = ((size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank) * (size_t)P.dim + (size_t)i;
+    for (int q = 0; q < P.n_ranks; q++) P.xchg_peer[q][off] = acc;
+    __threadfence_system();
+  } else {
+    P.partial[i] = acc;
+  }
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 // x[i] += sum_k w_k * dot_k + dot_shared in the reference's order (src/infer.cpp:873-877, 899-903, 926-930)
 __device__ __forceinline__ void down_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, const float* actw_smem,
                                                    const int* act_smem, float xres) {
@@ -998,7 +1022,7 @@ __device__ __forceinline__ void down_tile_epilogue(const Program& P, const Stage
       acc += v;
     }
   }
-  if (to_partial) P.partial[i] = acc; else P.x[i] = acc;
+  if (to_partial) store_partial(P, st, i, acc); else P.x[i] = acc;
 }
 
 // ---- attention stage (one head per CTA; body of attn_kernel with consumer-only barriers) ---------------------------
@@ -1124,6 +1148,32 @@ __device__ __forceinline__ void c_attention(const Program& P, const Stage& st, c
   csync();
 }
 
+// ST_XCHG (after the grid barrier that follows the DOWN stage: every CTA's peer stores are issued and fenced):
+// CTA 0 raises this rank's flag on every peer; every CTA waits for the N local flags, then x += sum of the N partials in
+// rank order (identical on every rank, so the replicated residual stream stays bit-identical across GPUs).
+__device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const MegaSmem& sm) {
+  const int tid = threadIdx.x;
+  const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
+  if (blockIdx.x == 0 && tid < P.n_ranks) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + P.rank), "r"(seq) : "memory");
+  }
+  if (tid < P.n_ranks) {
+    const unsigned long long t0 = gtime();
+    while ((int)(ld_acquire_sys(P.xflag_peer[P.rank] + tid) - seq) < 0) {
+      if (gtime() - t0 > 30000000000ull) __trap();   // a peer is more than 30 s late: fail instead of hanging the GPU
+    }
+  }
+  csync();
+  const int i = (int)blockIdx.x * kConsumers + tid;
+  if (i < P.dim) {
+    const float* b = P.xchg_peer[P.rank] + (size_t)(seq & 1u) * (size_t)P.n_ranks * (size_t)P.dim + (size_t)i;
+    float acc = P.x[i];
+    for (int r = 0; r < P.n_ranks; r++) acc += __ldcg(b + (size_t)r * (size_t)P.dim);
+    P.x[i] = acc;
+  }
+}
+
 // ---- embedding stage (CTA 0): token feed + step counters + dequantised row (body of embed_kernel) ------------------
 __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* s_token) {
   if (threadIdx.x == 0) {
@@ -1137,6 +1187,7 @@ __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* 
       c->kv_pos = sink + (pos - sink) % (P.original_max - sink);
       c->kv_len = pos >= P.original_max ? P.original_max : pos + 1;
       if (P.token_log && P.step) { P.token_log[*P.step] = token; *P.step = *P.step + 1; }
+      c->pad[0] += P.n_xchg;   // peer-memory mode: exchanges completed before this token
     }
     c->argmax_key = 0ull;
     *s_token = token;
@@ -1437,7 +1488,7 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
         if (ee >= 0 && ee < P.expert_count) acc = fmaf(v, sm.actw[kk], acc);
       } else if (st.sw2 != nullptr && st.add_shared) acc += v;
     }
-    if (to_partial) P.partial[i] = acc; else P.x[i] = acc;
+    if (to_partial) store_partial(P, st, i, acc); else P.x[i] = acc;
   }
   __syncwarp();
   if (lane == 0) *cnt = 0;
@@ -1673,7 +1724,7 @@ __device__ __forceinline__ void wp_kq_down_piece(const Program& P, const Stage& 
         if (ee >= 0 && ee < P.expert_count) acc = fmaf(v, sm.actw[kk], acc);
       } else if (st.sw2 != nullptr && st.add_shared) acc += v;
     }
-    if (to_partial) P.partial[i] = acc; else P.x[i] = acc;
+    if (to_partial) store_partial(P, st, i, acc); else P.x[i] = acc;
   }
   __syncwarp();
   if (lane == 0) *cnt = 0;
@@ -2168,6 +2219,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 8 + 0] = gtime(); P.tstamp[s * 8 + 1] = 0; P.tstamp[s * 8 + 4] = 0; P.tstamp[s * 8 + 5] = 0; P.tstamp[s * 8 + 6] = 0; P.tstamp[s * 8 + 7] = 0; }
     if (st.kind == ST_EMBED) {
       if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
+      if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
+    } else if (st.kind == ST_XCHG) {
+      c_xchg(P, st, sm);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else if (st.kind == ST_ATTN) {
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
