@@ -1075,6 +1075,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   g_wp_rows = getenv("DSK_WP_ROWS") ? atoi(getenv("DSK_WP_ROWS")) : 16;
   if (g_wp_rows != 8) g_wp_rows = 16;
   g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : (kq_model ? 16 * 1024 + 512 : kSlotData);   // 16 (or 8) rows x (2048 + 16) B
+  if (q != DSK_F32 && c.n_routed_experts > 0) g_slot_data = std::max(g_slot_data, (int)align_up((size_t)c.dim * 4, 128));   // a whole F32 gate row per slot
   g_slot_scale = kSlotScale;
   std::vector<Stage> S;
   int n_xchg = 0;
@@ -1124,6 +1125,13 @@ static int build_program(dsk_model* m, dsk_state* s) {
         MJob j{}; j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
         st.job[0] = j; st.njobs = 1;
         plan_gemv_stage(st, DSK_F32, G);
+        if (q != DSK_F32) {
+          if ((size_t)c.dim * 4 > (size_t)g_slot_data) return fail(-4, "gate row (%d bytes) does not fit a ring slot", c.dim * 4);
+          // quantised model: the dedicated gate stage (gate_f32_stage) takes one row per tile
+          st.rows_per_tile = 1; st.rpass = 1; st.npieces = 1; st.wp = 0; st.use_mma = 0;
+          st.piece[0] = Piece{0, 0, c.dim / 4, 0};
+          st.job[0].tile_begin = 0; st.ntiles = c.n_routed_experts; st.has_dyn = 0;
+        }
         S.push_back(st);
       }
       {  // S56: routing + shared (static, first: streams before the routing is known) + routed experts

@@ -1875,6 +1875,79 @@ __device__ __forceinline__ void carve_down_q8(unsigned char* p, int K, int mi, i
   carve_x<Q>(p + (K * mi ? xvec_bytes<Q>(K * mi) : 0), sh, dummy, seg[K]);
 }
 
+// ---- MoE gate logits of a quantised model (F32 weights, E rows): a dedicated compact stage --------------------------
+// One row per tile (one 4n-byte TMA copy), one tile per CTA for E <= 148; all eight warps split the columns of the row and
+// a block reduction in a fixed order finishes it.  Deliberately tiny: it replaces a whole second template instantiation of
+// the generic consumer (cold code every layer) for 0.5 MB of weights.
+__device__ __noinline__ int gate_f32_stage(int it, int n_slots, int dep_count, int stage_index) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  const Program& P = *reinterpret_cast<const Program*>(dsk_dyn_smem + 4096 + 2 * kStageSlot);
+  const Stage& st = *reinterpret_cast<const Stage*>(dsk_dyn_smem + 4096);
+  const MegaSmem sm = carve_mega(dsk_dyn_smem, P.xregion_bytes);
+  const int tid = threadIdx.x, n = st.n, nf = n >> 2;
+  if ((int)blockIdx.x >= st.ntiles) {
+    if (tid == 0) dep_signal(sm.dep, dep_count);
+    return it;
+  }
+  float4* xs = reinterpret_cast<float4*>(sm.xregion);
+  {  // x -> RMSNorm -> shared memory (fp32)
+    float sc = 1.0f;
+    if (st.norm_w && nf > 8 * kConsumers) sc = c_rms_scale(st.in, n, P.eps, sm.red);
+#pragma unroll 1
+    for (int c0 = 0; c0 < nf; c0 += 8 * kConsumers) {
+      float4 v[8];
+      float ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int f = c0 + tid + k * kConsumers;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < nf) {
+          v[k] = reinterpret_cast<const float4*>(st.in)[f];
+          ss = fmaf(v[k].x, v[k].x, ss); ss = fmaf(v[k].y, v[k].y, ss); ss = fmaf(v[k].z, v[k].z, ss); ss = fmaf(v[k].w, v[k].w, ss);
+        }
+      }
+      if (st.norm_w && nf <= 8 * kConsumers) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int f = c0 + tid + k * kConsumers;
+        if (f < nf) {
+          float4 o = v[k];
+          if (st.norm_w) {
+            const float4 w = reinterpret_cast<const float4*>(st.norm_w)[f];
+            o.x = __fmul_rn(__fmul_rn(o.x, sc), w.x); o.y = __fmul_rn(__fmul_rn(o.y, sc), w.y);
+            o.z = __fmul_rn(__fmul_rn(o.z, sc), w.z); o.w = __fmul_rn(__fmul_rn(o.w, sc), w.w);
+          }
+          xs[f] = o;
+        }
+      }
+    }
+  }
+  csync();
+  if (tid == 0) dep_signal(sm.dep, dep_count);
+  if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
+  const MJob& jb = st.job[0];
+#pragma unroll 1
+  for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
+    const int sl = it % n_slots;
+    mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+    const uint32_t wrow = sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes + (uint32_t)P.slot_scale;
+    float acc = 0.f;
+#pragma unroll 1
+    for (int f = tid; f < nf; f += kConsumers) {
+      const uint4 wv = lds128(wrow + (uint32_t)f * 16u);
+      const float4 x = xs[f];
+      acc = fmaf(__uint_as_float(wv.x), x.x, acc); acc = fmaf(__uint_as_float(wv.y), x.y, acc);
+      acc = fmaf(__uint_as_float(wv.z), x.z, acc); acc = fmaf(__uint_as_float(wv.w), x.w, acc);
+    }
+    acc = csum(acc, sm.red);          // every warp is done with the slot after this reduction
+    if (tid == 0) {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+      if (t < jb.rows) jb.out[t] = acc;
+    }
+  }
+  return it;
+}
+
 template <int Q>
 __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
                                                unsigned long long& best_key, int dep_count, int stage_index) {
@@ -2227,7 +2300,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else {
-      if (st.quant == Q_F32 && Q != Q_F32) consumer_stage<Q_F32>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
+      if (st.quant == Q_F32 && Q != Q_F32) it = gate_f32_stage(it, n_slots, nstage_seen + 1, s);
       else consumer_stage<Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
       if (st.epi == EPI_LOGITS) {
         unsigned long long b = best_key;
