@@ -193,7 +193,9 @@ static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory pe
 static constexpr size_t kSmemBudget = 200 * 1024;
 static bool g_use_pdl = true;
 static bool g_f8_mma_ok = true;   // f8 scale-block width is a power of two (the tensor-core loop shifts instead of dividing)
-static bool g_coop_small = true, g_kq_small = true;   // DSK_COOP_SMALL=0 / DSK_KQ_SMALL=0: A/B switches of the tile planner
+static bool g_coop_small = false, g_kq_small = true;   // DSK_COOP_SMALL=1 / DSK_KQ_SMALL=0: A/B switches of the tile planner
+// (cooperative tiles for one-tile-per-CTA F8 stages won 2 us per stage in isolation but lose overall: their code is one more
+//  cold path per layer — 393 vs 408 tok/s)
 static bool g_use_mma = true;   // F8E5M2 tiles through mma.sync (DSK_NO_MMA=1: CUDA-core dequant path)
 enum { ENG_MEGA = 0, ENG_STAGE = 1, ENG_V2 = 2 };
 static int g_engine = ENG_MEGA;

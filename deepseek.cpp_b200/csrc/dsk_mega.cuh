@@ -2125,7 +2125,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
 template <int Q>
 __device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
                                                    int dep_count, bool& dep_waited) {
-  const size_t rb = QTraits<Q>::row_bytes(st.n);
+  const size_t rb = (st.quant == Q_F32 && Q != Q_F32) ? (size_t)st.n * 4 : QTraits<Q>::row_bytes(st.n);   // F32 gate rows in a quantised model
   const int RT = st.rows_per_tile, parts = st.epi == EPI_GLU ? 2 : 1;
   const uint32_t part_stride = (uint32_t)align_up((size_t)RT * rb, 128);
   const uint32_t full_bytes = (uint32_t)align_up((size_t)RT * rb, 16);
@@ -2264,8 +2264,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       const Stage& st = *sm.st_p;
       const bool streams = st.kind == ST_GEMV || st.kind == ST_DOWN;
       if (tid == kConsumers && streams) {
-        if (st.quant == Q_F32 && Q != Q_F32) producer_stage<Q_F32>(P, st, sm, it, n_slots, nstage_seen + 1);
-        else producer_stage<Q>(P, st, sm, it, n_slots, nstage_seen + 1);
+        producer_stage<Q>(P, st, sm, it, n_slots, nstage_seen + 1);   // (the F32 gate stage of a quantised model is a GEMV stage without scales)
       } else if (tid == kConsumers) {
         dep_wait(sm.dep, nstage_seen + 1);
       }
