@@ -195,12 +195,12 @@ __device__ __noinline__ void q8_block_nf(float4 va, float4 vb, int b, int8_t* q_
     const float ax = fabsf(v[j]);
     if (ax > amax) { amax = ax; mx = v[j]; idx = lane * 8 + j; }
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    const float oa = __shfl_xor_sync(0xffffffffu, amax, o);
-    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-    if (oa > amax || (oa == amax && oi < idx)) { amax = oa; mx = om; idx = oi; }
+  {  // block arg-max |v| with REDUX (non-negative floats order like their bit patterns); ties -> lowest index, as the scan above
+    const unsigned best = __reduce_max_sync(0xffffffffu, __float_as_uint(amax));
+    const int cand = (__float_as_uint(amax) == best) ? idx : 0x7fffffff;
+    const int bi = __reduce_min_sync(0xffffffffu, cand);
+    mx = __shfl_sync(0xffffffffu, mx, (bi == 0x7fffffff ? 0 : bi) >> 3);
+    amax = __uint_as_float(best);
   }
   int qv[8];
   if (amax == 0.f) {
@@ -283,9 +283,8 @@ __device__ __forceinline__ void x16_store(const X16& x, int f, float4 v);
 __device__ __noinline__ void x16_store_nf(uint32_t xhi, uint32_t xlo, uint32_t xgs, int f, float4 v) {
   X16 x; x.hi = xhi; x.lo = xlo; x.gs = xgs;
   float am = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
-  const unsigned active = __activemask();   // 16-lane groups are always fully in or out (n % 64 == 0)
-#pragma unroll
-  for (int o = 8; o; o >>= 1) am = fmaxf(am, __shfl_xor_sync(active, am, o));
+  // maximum over the 16-lane group (= 64 columns) with one REDUX; groups are always fully in or out (n % 64 == 0)
+  am = __uint_as_float(__reduce_max_sync((threadIdx.x & 16) ? 0xffff0000u : 0x0000ffffu, __float_as_uint(am)));
   const unsigned eb = (__float_as_uint(am) >> 23) & 0xffu;                 // biased exponent of the group maximum
   const unsigned sb = am > 0.f ? min(max(267u - eb, 1u), 254u) : 127u;     // 2^(13 - floor(log2 amax))
   const float sc = __uint_as_float(sb << 23), inv = __uint_as_float((254u - sb) << 23);
