@@ -659,6 +659,7 @@ __device__ __noinline__ void warp_route(const Program* Pp, const Stage* stp, int
     act_smem[lane] = mye; actw_smem[lane] = w;
     if (publish) { P.act[lane] = mye; P.act_w[lane] = w; }
   }
+  if (lane == 0) reinterpret_cast<int*>(dsk_dyn_smem + 512)[14] = st.layer + 1;   // MegaSmem::sel[14]: "routing of layer l is here"
   if (publish) {   // state buffers for the host (CTA 0 only), after the selection so that it is not on anybody's critical path
 #pragma unroll 1
     for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) P.moe_scores[j] = sx[j]; }
@@ -1959,8 +1960,12 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   }
   // routing first (one warp, registers): it unblocks the producer's routed-expert tiles
   if (st.kind == ST_DOWN && st.K > 0) {
-    if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
-    csync();
+    // the routing of this layer is normally still in this CTA's shared memory (left by warp_route in the S56 stage of the same
+    // launch, ordered by that stage's barriers); otherwise (first stage of a launch, CTA without S56 tiles) fetch the published copy
+    if (sm.sel[14] != st.layer + 1) {
+      if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
+      csync();
+    }
     if (tid == 0) dep_signal(sm.dep, dep_count);
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 4] = (gtime() - P.tstamp[stage_index * 8]) * 1000ull;
   }
@@ -2247,6 +2252,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     for (int i = 0; i < 8; i++) reinterpret_cast<uint32_t*>(smem + kHdrZero)[i] = 0u;
     for (int i = 0; i < 4; i++) reinterpret_cast<float*>(smem + kHdrOne)[i] = 1.0f;
     dep_signal(sm.dep, 0);
+    sm.sel[14] = 0;
     fence_proxy_async();
   }
   __syncthreads();
