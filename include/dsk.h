@@ -107,8 +107,15 @@ int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int n_steps, in
 /* Number of kernels one forward launches (for bench.py's gpu_launches) */
 int dsk_launches_per_forward(const dsk_model* m, int mode);
 
-/* ---- multi-GPU: one NCCL all-reduce of the MoE partial sum per MoE layer ---------- */
-/* nccl_unique_id: 128 bytes from dsk_comm_unique_id() on rank 0, broadcast by the launcher. */
+/* ---- multi-GPU: one exchange of the MoE partial sum per MoE layer ------------------
+ * The reference has no distributed path; this is the one real exchange step of the expert-sharded model
+ * (rank r keeps experts [r*ceil(E/N), (r+1)*ceil(E/N)), everything else replicated).
+ * nccl_unique_id: 128 bytes from dsk_comm_unique_id() on rank 0, broadcast by the launcher (one process
+ * per GPU).  dsk_comm_init creates the communicator, then — unless DSK_P2P=0 or a rank lacks peer access —
+ * maps one exchange buffer per rank into every peer through CUDA IPC: the decode kernel then stores its
+ * partial sums straight into the peers' buffers (NVLink) and waits on flags, and a token stays ONE kernel
+ * launch per GPU.  Fallback: ncclAllReduce between kernel segments.  Every rank must make the same
+ * sequence of dsk_forward / dsk_block_forward / dsk_decode_greedy calls. */
 int dsk_comm_unique_id(void* out128);
 int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128);
 
