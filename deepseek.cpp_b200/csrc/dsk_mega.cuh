@@ -1876,6 +1876,8 @@ __device__ __forceinline__ void carve_down_q8(unsigned char* p, int K, int mi, i
 }
 
 // ---- MoE gate logits of a quantised model (F32 weights, E rows): a dedicated compact stage --------------------------
+// replaces: matmul_unscaled(s.moe_weights(), s.xb(), moegate->data, dim, n_routed_experts) on the rmsnorm'ed residual
+// (src/infer.cpp:846-851: the gate is F32 in every quant, src/model.cpp:806-812)
 // One row per tile (one 4n-byte TMA copy), one tile per CTA for E <= 148; all eight warps split the columns of the row and
 // a block reduction in a fixed order finishes it.  Deliberately tiny: it replaces a whole second template instantiation of
 // the generic consumer (cold code every layer) for 0.5 MB of weights.
