@@ -532,9 +532,27 @@ def main():
             kern[label] = {"rows": d_, "cols": n_, "us": ms_k * 1e3, "GB/s": b_k / (ms_k / 1e3) / 1e9, "frac": b_k / (ms_k / 1e3) / 1e9 / peak}
     except Exception as e:
         kern = {"error": str(e)[:120]}
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "gemv_kernel<Q> (all launches of one token; achieved = algorithmic bytes/token x tok/s, i.e. every "
-                      "non-GEMV kernel and launch gap is charged to it)",
+    # DRAM traffic per launch (= per token: the token is one decode_kernel launch) from the committed ncu --set full capture
+    # of this workload (profiles/r01_final_decode_kernel_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); a number
+    # taken under the profiler, reported for the configuration it was captured on and null otherwise
+    traffic = None
+    if a.workload == "v2lite" and a.quant == "f8e5m2" and world == 1 and not a.n_layers:
+        try:
+            rd = wr = None
+            for ln in open(os.path.join(REPO, "profiles", "r01_final_decode_kernel_summary.txt")):
+                f = ln.split()
+                if ln.startswith("dram__bytes_read.sum"):
+                    rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[3]]
+                if ln.startswith("dram__bytes_write.sum"):
+                    wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[3]]
+            if rd is not None and wr is not None:
+                traffic = rd + wr
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_unit": "bytes per launch (= per token), ncu capture in profiles/",
+            "kernel": "decode_kernel<Q> (the whole token is one launch; achieved = algorithmic bytes/token x tok/s, i.e. every "
+                      "barrier, staging phase and attention is charged to the GEMV stream)",
             "algorithmic_bytes_per_token": abytes, "peak_source": peak_src, "isolated_kernels": kern}
 
     out = dict(base)
