@@ -638,7 +638,7 @@ static int kv_ptr(dsk_model* m, int layer, int which, __half** p, size_t* cap) {
 }
 extern "C" int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, size_t n) {
   if (need_device()) return -1;
-  __half* p; size_t cap;
+  __half* p = nullptr; size_t cap = 0;
   if (kv_ptr(m, layer, which, &p, &cap)) return -4;
   if (n > cap) return fail(-4, "kv cache holds %zu halfs", cap);
   CK(cudaDeviceSynchronize());
@@ -647,7 +647,7 @@ extern "C" int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, si
 }
 extern "C" int dsk_kv_write(dsk_model* m, int layer, int which, const uint16_t* src, size_t n) {
   if (need_device()) return -1;
-  __half* p; size_t cap;
+  __half* p = nullptr; size_t cap = 0;
   if (kv_ptr(m, layer, which, &p, &cap)) return -4;
   if (n > cap) return fail(-4, "kv cache holds %zu halfs", cap);
   CK(cudaDeviceSynchronize());
@@ -1762,7 +1762,6 @@ extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos,
   if (!m || !s || !out) return fail(-1, "bad arguments");
   if (g_engine != ENG_V2) {
     // stage-level timeline of the last token from the interpreter's own globaltimer stamps (CTA 0)
-    float* lg = nullptr; (void)lg;
     if (dsk_forward(m, s, token, pos, 1, nullptr, nullptr)) return -2;
     std::vector<unsigned long long> ts((size_t)s->n_stages * 8 + 8);
     CK(cudaMemcpy(ts.data(), s->tstamp, ts.size() * 8, cudaMemcpyDeviceToHost));

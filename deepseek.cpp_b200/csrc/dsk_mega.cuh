@@ -1857,14 +1857,14 @@ __device__ __noinline__ void stage_q8(const Program* Pp, const Stage* stp, const
   if (!routed) stage_route_hook(P, st, route, stage_index);
 }
 // flat activation layout of a DOWN stage: [routed: K*mi values][shared / dense: sh values]; per-segment views by offset
-__host__ __device__ inline size_t down_x16_bytes(int K, int mi, int sh) { return (K * mi ? x16_bytes(K * mi) : 0) + (sh ? x16_bytes(sh) : 0); }
+__host__ __device__ inline size_t down_x16_bytes(int K, int mi, int sh) { return (K * mi != 0 ? x16_bytes(K * mi) : 0) + (sh != 0 ? x16_bytes(sh) : 0); }
 __device__ __forceinline__ void carve_down_x16(unsigned char* p, int K, int mi, int sh, X16* seg) {
   const X16 r = carve_x16(p, K * mi);
   for (int k = 0; k < K; k++) { seg[k].hi = r.hi + (uint32_t)(k * mi) * 2u; seg[k].lo = r.lo + (uint32_t)(k * mi) * 2u; seg[k].gs = r.gs + (uint32_t)(k * (mi >> 6)) * 4u; }
-  seg[K] = carve_x16(p + (K * mi ? x16_bytes(K * mi) : 0), sh);
+  seg[K] = carve_x16(p + (K * mi != 0 ? x16_bytes(K * mi) : 0), sh);
 }
 template <int Q>
-__host__ __device__ inline size_t down_q8_bytes(int K, int mi, int sh) { return (K * mi ? xvec_bytes<Q>(K * mi) : 0) + (sh ? xvec_bytes<Q>(sh) : 0); }
+__host__ __device__ inline size_t down_q8_bytes(int K, int mi, int sh) { return (K * mi != 0 ? xvec_bytes<Q>(K * mi) : 0) + (sh != 0 ? xvec_bytes<Q>(sh) : 0); }
 template <int Q>
 __device__ __forceinline__ void carve_down_q8(unsigned char* p, int K, int mi, int sh, Q8Smem* seg) {
   float* dummy = nullptr;
@@ -1872,7 +1872,7 @@ __device__ __forceinline__ void carve_down_q8(unsigned char* p, int K, int mi, i
   carve_x<Q>(p, K * mi, dummy, r);
   const int nbm = mi >> 8;
   for (int k = 0; k < K; k++) { seg[k].qs = r.qs + k * mi; seg[k].d = r.d + k * nbm; seg[k].bsums = r.bsums + k * nbm * 16; }
-  carve_x<Q>(p + (K * mi ? xvec_bytes<Q>(K * mi) : 0), sh, dummy, seg[K]);
+  carve_x<Q>(p + (K * mi != 0 ? xvec_bytes<Q>(K * mi) : 0), sh, dummy, seg[K]);
 }
 
 // ---- MoE gate logits of a quantised model (F32 weights, E rows): a dedicated compact stage --------------------------
