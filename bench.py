@@ -4,13 +4,20 @@
   python bench.py --gpus N --steps K --warmup W            # this engine (libdsk.so), one rank per GPU
   python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (oracle/_ref)
 
+Workload (every N): DeepSeek-V2 236B shapes, Q2_K, all 60 layers (BASELINE.json configs[3]; 77 GB of weights — fits ONE
+B200, so N = 1, 2, 4, 8 is a legitimate strong-scaling curve of the model north_star says to shard).  The V2-Lite
+configs[1] / configs[2] numbers of round 1 are measured in the same run at N = 1 and reported under `secondary`.
+`--workload v3 --quant q2_k --gpus 8` times the north-star target (220 GB, needs >= 2 GPUs).
+
 A "step" is one fixed 128-token greedy completion (the reference's `-n 128 -t 0`, src/main.cpp:324-335) after a
-16-token prompt has hydrated the KV cache.  `value` is decode-only tok/s with everything resident in HBM (device
-argmax feeds the next token inside one CUDA graph per token, CUDA-event timed); `e2e` is the same completion driven
-through the reference-shaped host call `dsk_forward(token, pos, OUTPUT_LOGITS, host_logits)` per token: control words
-go host->device, the vocab-sized logits come device->host, and the host samples (argmax) — copies inside the timed
-region.  Weights are synthetic (no checkpoints exist offline): N(0,1)/sqrt(fan_in) quantised like convert.py (f8e5m2)
-or random valid K-quant blocks, generated on the GPU and handed to dsk_upload_tensor(src_on_device=1).
+16-token prompt has hydrated the KV cache.  `value` is decode-only tok/s with everything resident in HBM (the token loop
+runs inside ONE persistent kernel launch per completion, device arg-max feeding the next token, CUDA-event timed); `e2e`
+is the same completion driven through the reference-shaped host call `dsk_forward(token, pos, OUTPUT_LOGITS, host_logits)`
+per token: control words go host->device, the vocab-sized logits come device->host, and the host samples (argmax) — copies
+inside the timed region.  Weights are synthetic (no checkpoints exist offline): N(0,1)/sqrt(fan_in) quantised like
+convert.py (f8e5m2) or random valid K-quant blocks, generated on the GPU and handed to dsk_upload_tensor(src_on_device=1).
+The reference arm / cpu_baseline run the UNMODIFIED reference (oracle/_ref) on a full-depth checkpoint of the same shapes
+minted in /dev/shm (bounded by decoding a handful of tokens, not by truncating layers) whenever it fits the host.
 """
 import argparse
 import json
@@ -133,7 +140,8 @@ def mint_on_gpu(dsk, w, rank, n_ranks, device):
         else:
             t = 1.0 + 0.1 * torch.randn(n, device=dev)
         t = t.float().contiguous()
-        m.upload_device(name, "F32", (n,), t.data_ptr(), t.numel() * 4)
+        shape = (w["n_routed_experts"], w["dim"]) if name.endswith("moegate.weight") else (n,)
+        m.upload_device(name, "F32", shape, t.data_ptr(), t.numel() * 4)
     for name, rows, cols, ne in plan:
         lead = max(1, ne)
         seed(name)
@@ -241,20 +249,8 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU reference leg (oracle/_ref = the unmodified reference compiled in the build container)
 # ----------------------------------------------------------------------------------------------------
-def mint_cpu_truncated(w, dirname, n_layers):
-    """Layer-truncated checkpoint of the workload's shapes for the CPU legs: pooled N(0,1) values cast like convert.py."""
-    sys.path.insert(0, os.path.join(REPO, "oracle"))
-    import dseek
-    rng = np.random.default_rng(1234)
-    wt = dict(w)
-    wt["n_layers"] = n_layers
-    plan, f32 = tensor_plan(wt)
+def ckpt_metadata(w, n_layers):
     quant = w["quant"]
-    import torch
-    pool = torch.randn(1 << 24)
-    if quant == "f8e5m2":
-        pool8 = (pool * (57344.0 / 6.0)).clamp(-57344, 57344).to(torch.float8_e5m2).view(torch.uint8).numpy()
-    os.makedirs(dirname, exist_ok=True)
     md = {"arch": w["arch"], "use_mla": "0", "quant": quant, "dim": w["dim"], "hidden_dim": w["hidden_dim"], "n_layers": n_layers,
           "n_heads": w["n_heads"], "vocab_size": w["vocab_size"], "max_seq_len": w["max_seq_len"], "bos_token_id": 0,
           "eos_token_id": 1, "rope_theta": 10000.0, "norm_eps": 1e-6, "norm_type": "rmsnorm", "act_type": "silu",
@@ -271,7 +267,57 @@ def mint_cpu_truncated(w, dirname, n_layers):
     if quant == "f8e5m2":
         md["quantization_block_size_0"] = 128
         md["quantization_block_size_1"] = 128
-    T = {"tokenizer.tokens": ("U8", np.frombuffer(b"\0".join(b"t%d" % i for i in range(w["vocab_size"])) + b"\0", np.uint8).copy())}
+    return md
+
+
+def ckpt_bytes(w, n_layers):
+    """Payload bytes of a .dseek checkpoint of these shapes (weights only)."""
+    wt = dict(w, n_layers=n_layers)
+    plan, f32 = tensor_plan(wt)
+    bpw = {"fp32": 4.0, "fp16": 2.0, "f8e5m2": 1.0 + 4.0 / 16384, "q2_k": 84 / 256, "q3_k": 110 / 256}[w["quant"]]
+    return int(sum(max(1, ne) * rows * cols * bpw for _, rows, cols, ne in plan) + 4 * sum(n for _, n in f32))
+
+
+def mint_cpu_truncated(w, dirname, n_layers):
+    """Synthetic .dseek checkpoint of the workload's shapes with `n_layers` layers (all of them for the full-depth reference
+    arm), written STRAIGHT into a memory-mapped shard: each tensor is tiled from a pool of N(0,1) values cast like
+    convert.py (f8e5m2 / f16 / f32) or of random valid K-quant blocks, so a 77 GB file costs one memcpy pass, not a
+    77 GB random-number run.  (Tiling repeats values across tensors; every page is still a distinct copy in /dev/shm.)"""
+    import json as _json
+    import struct as _struct
+    rng = np.random.default_rng(1234)
+    wt = dict(w, n_layers=n_layers)
+    plan, f32 = tensor_plan(wt)
+    quant = w["quant"]
+    import torch
+    pool = torch.randn(1 << 24)
+    pools = {}
+
+    def payload_pool(cols, embed):
+        key = (cols, embed)
+        if key in pools:
+            return pools[key]
+        if quant == "f8e5m2":
+            a = (pool * (57344.0 / 6.0)).clamp(-57344, 57344).to(torch.float8_e5m2).view(torch.uint8).numpy()
+        elif quant in KBYTES:
+            bb = KBYTES[quant]
+            a = rng.integers(0, 256, size=(1 << 18, bb), dtype=np.uint8)
+            d = np.float16(0.1 / np.sqrt(cols))
+            if quant == "q2_k":
+                a[:, 80:82] = np.frombuffer(d.tobytes(), np.uint8)
+                a[:, 82:84] = np.frombuffer(np.float16(d * 1.5).tobytes(), np.uint8)
+            else:
+                a[:, 108:110] = np.frombuffer(np.float16(d / 8).tobytes(), np.uint8)
+            a = a.reshape(-1)
+        else:
+            sc = np.float32(1.0 if embed else cols ** -0.5)
+            a = (pool.numpy() * sc).astype(np.float16 if quant == "fp16" else np.float32).view(np.uint8).reshape(-1)
+        pools[key] = a
+        return a
+
+    T = []   # (name, dtype, shape, nbytes, filler) in file order
+    tok = np.frombuffer(b"\0".join(b"t%d" % i for i in range(w["vocab_size"])) + b"\0", np.uint8).copy()
+    T.append(("tokenizer.tokens", "U8", tok.shape, tok.nbytes, tok))
     for name, n in f32:
         if name.endswith("moegate.weight"):
             a = (rng.standard_normal(n, dtype=np.float32) * w["dim"] ** -0.5 * 4.0).reshape(w["n_routed_experts"], w["dim"])
@@ -279,154 +325,155 @@ def mint_cpu_truncated(w, dirname, n_layers):
             a = (0.01 * rng.standard_normal(n)).astype(np.float32)
         else:
             a = (1.0 + 0.1 * rng.standard_normal(n)).astype(np.float32)
-        T[name] = ("F32", a)
+        T.append((name, "F32", a.shape, a.nbytes, a))
     for name, rows, cols, ne in plan:
         lead = max(1, ne)
-        shape = (ne, rows, cols) if ne else (rows, cols)
-        numel = lead * rows * cols
+        embed = name == "model.embed"
         if quant == "f8e5m2":
-            off = int(rng.integers(0, pool8.size))
-            a = np.resize(np.roll(pool8, -off), numel).reshape(shape)
-            T[name + ".weight"] = ("F8_E5M2", a)
+            shape = ((ne,) if ne else ()) + (rows, cols)
+            T.append((name + ".weight", "F8_E5M2", shape, lead * rows * cols, ("tile", payload_pool(cols, embed), 1)))
             sshape = ((ne,) if ne else ()) + (-(-rows // 128), -(-cols // 128))
-            sc = 6.0 / 57344.0 * (1.0 if name == "model.embed" else cols ** -0.5)
-            T[name + ".scale"] = ("F32", np.full(sshape, sc, np.float32))
+            sc = 6.0 / 57344.0 * (1.0 if embed else cols ** -0.5)
+            sa = np.full(sshape, sc, np.float32)
+            T.append((name + ".scale", "F32", sshape, sa.nbytes, sa))
         elif quant in KBYTES:
             bb, nb = KBYTES[quant], cols // 256
-            a = rng.integers(0, 256, size=(lead * rows, nb, bb), dtype=np.uint8)
-            d = np.float16(0.1 / np.sqrt(cols))
-            if quant == "q2_k":
-                a[:, :, 80:82] = np.frombuffer(d.tobytes(), np.uint8)
-                a[:, :, 82:84] = np.frombuffer(np.float16(d * 1.5).tobytes(), np.uint8)
-            else:
-                a[:, :, 108:110] = np.frombuffer(np.float16(d / 8).tobytes(), np.uint8)
-            T[name + ".weight"] = ("U8", a.reshape(((ne,) if ne else ()) + (rows, nb * bb)))
+            shape = ((ne,) if ne else ()) + (rows, nb * bb)
+            T.append((name + ".weight", "U8", shape, lead * rows * nb * bb, ("tile", payload_pool(cols, embed), bb)))
         else:
-            a = np.resize(pool.numpy(), numel).reshape(shape) * np.float32(cols ** -0.5)
-            T[name + ".weight"] = ("F16", a.astype(np.float16)) if quant == "fp16" else ("F32", a.astype(np.float32))
-    dseek.write_shard(os.path.join(dirname, "shard_000.dseek"), T, md)
+            isz = 2 if quant == "fp16" else 4
+            shape = ((ne,) if ne else ()) + (rows, cols)
+            T.append((name + ".weight", "F16" if quant == "fp16" else "F32", shape, lead * rows * cols * isz,
+                      ("tile", payload_pool(cols, embed), isz)))
+    T.sort(key=lambda t: t[0])
+    header = {"__metadata__": {str(k): str(v) for k, v in ckpt_metadata(w, n_layers).items()}}
+    off = 0
+    for name, dt, shape, nbytes, _ in T:
+        header[name] = {"dtype": dt, "shape": [int(v) for v in shape], "data_offsets": [off, off + nbytes]}
+        off += nbytes
+    hjson = _json.dumps(header, separators=(",", ":")).encode("utf-8")
+    hjson += b" " * ((-len(hjson)) % 8)
+    os.makedirs(dirname, exist_ok=True)
+    path = os.path.join(dirname, "shard_000.dseek")
+    total = 8 + len(hjson) + off
+    with open(path, "wb") as f:
+        f.truncate(total)
+    mm = np.memmap(path, dtype=np.uint8, mode="r+")
+    mm[:8] = np.frombuffer(_struct.pack("<Q", len(hjson)), np.uint8)
+    mm[8:8 + len(hjson)] = np.frombuffer(hjson, np.uint8)
+    base = 8 + len(hjson)
+    for name, dt, shape, nbytes, fill in T:
+        b0 = base + header[name]["data_offsets"][0]
+        if isinstance(fill, tuple):
+            _, pl, unit = fill
+            start = int(rng.integers(0, pl.size // unit)) * unit      # unit-aligned phase into the pool
+            done = 0
+            while done < nbytes:
+                n = min(nbytes - done, pl.size - start)
+                mm[b0 + done:b0 + done + n] = pl[start:start + n]
+                done += n
+                start = 0
+        else:
+            mm[b0:b0 + nbytes] = np.ascontiguousarray(fill).view(np.uint8).reshape(-1)
+    mm.flush()
+    del mm
+    return total
 
 
-def cpu_reference_leg(w, steps, warmup, tokens_per_step=8):
-    """Times the UNMODIFIED reference (oracle/_ref/libdsref.so) on this box's host cores, on a bounded sample:
-    a 3-layer truncation (first dense layer + 2 MoE layers + LM head) of the workload's shapes, per-block timings
-    extrapolated to the full depth.  Returns (tok/s, description dict)."""
+def host_free_bytes(path):
+    try:
+        st = os.statvfs(path)
+        return st.f_bavail * st.f_frsize
+    except Exception:
+        return 0
+
+
+def cpu_reference_leg(w, steps, warmup, tokens_per_step=6):
+    """Times the UNMODIFIED reference (oracle/_ref/libdsref.so) on this box's host cores.  The sample is bounded by the
+    number of decoded tokens, not by the model: a FULL-DEPTH checkpoint of the workload's shapes is minted in /dev/shm
+    whenever it fits (<= 120 GB and <= 40 % of the free space); otherwise (V3-size) a 3-layer truncation with per-block
+    times extrapolated, labelled as such.  Returns (tok/s, seconds actually spent decoding, description dict)."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import oracle as O
     if O.ref_lib() is None:
         O.port_lib()
         raise RuntimeError("oracle/_ref/libdsref.so is not present")
     nl_full, fk = w["n_layers"], w["first_k_dense_replace"]
-    n_trunc = min(nl_full, fk + 2)
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
+    full_bytes = ckpt_bytes(w, nl_full)
+    full = full_bytes <= 120e9 and full_bytes <= 0.4 * host_free_bytes(base) and os.environ.get("DSK_REF_TRUNCATE", "0") != "1"
+    n_ck = nl_full if full else min(nl_full, fk + 2)
     d = tempfile.mkdtemp(prefix="dsk_ref_", dir=base)
     try:
-        log(f"cpu reference: minting {n_trunc}-layer truncated checkpoint in {d}")
-        mint_cpu_truncated(w, d, n_trunc)
+        t0 = time.time()
+        log(f"cpu reference: minting {'full-depth ' if full else ''}{n_ck}-layer checkpoint ({ckpt_bytes(w, n_ck) / 1e9:.1f} GB) in {d}")
+        mint_cpu_truncated(w, d, n_ck)
+        log(f"cpu reference: minted in {time.time() - t0:.1f} s")
         cores = os.cpu_count() or 1
         best = None
-        for threads in sorted({min(cores, 16), min(cores, 32), max(1, cores // 2)}):
+        cands = sorted({min(cores, 32), max(1, cores // 2)}) if full and full_bytes > 30e9 else sorted({min(cores, 16), min(cores, 32), max(1, cores // 2)})
+        n_tok = max(1, (warmup + steps)) * tokens_per_step
+        for threads in cands:
             log(f"cpu reference: {threads} threads")
             O.ref_lib().ref_set_num_threads(threads)
             s = O.RefSession(d, 0)
             pr = prompt_ids(w["vocab_size"])[:4]
-            for p, t in enumerate(pr):
-                s.forward(t, p, True)
-            pos = len(pr)
-            per_tok = []
-            for it in range((warmup + steps) * tokens_per_step):
-                tok = s.argmax()
-                t0 = time.perf_counter(); s.forward(tok, pos, True); t_f = time.perf_counter() - t0
-                tb = []
-                for l in range(n_trunc):
-                    t0 = time.perf_counter(); s.block(l, pos, 0, pos, pos + 1); tb.append(time.perf_counter() - t0)
-                pos += 1
-                if it >= warmup * tokens_per_step:
-                    t_dense = float(np.mean(tb[:fk])) if fk else 0.0
-                    t_moe = float(np.mean(tb[fk:])) if n_trunc > fk else 0.0
-                    t_rest = max(0.0, t_f - sum(tb))
-                    per_tok.append(t_rest + fk * t_dense + (nl_full - fk) * t_moe)
+            if full:
+                s.timed_decode(pr, 1)                                   # page-touch pass (weights are in tmpfs already)
+                secs, _ = s.timed_decode(pr, n_tok)
+                tps, spent = n_tok / secs, secs
+            else:
+                for p, t in enumerate(pr):
+                    s.forward(t, p, True)
+                pos, per_tok, spent = len(pr), [], 0.0
+                for it in range(n_tok):
+                    tok = s.argmax()
+                    t0 = time.perf_counter(); s.forward(tok, pos, True); t_f = time.perf_counter() - t0
+                    tb = []
+                    for l in range(n_ck):
+                        t0 = time.perf_counter(); s.block(l, pos, 0, pos, pos + 1); tb.append(time.perf_counter() - t0)
+                    pos += 1
+                    spent += t_f + sum(tb)
+                    if it >= warmup * tokens_per_step:
+                        t_dense = float(np.mean(tb[:fk])) if fk else 0.0
+                        t_moe = float(np.mean(tb[fk:])) if n_ck > fk else 0.0
+                        per_tok.append(max(0.0, t_f - sum(tb)) + fk * t_dense + (nl_full - fk) * t_moe)
+                tps = 1.0 / float(np.mean(per_tok))
             s.close()
-            tps = 1.0 / float(np.mean(per_tok))
             if best is None or tps > best[0]:
-                best = (tps, threads)
-        return best[0], {"kind": "reference", "cores": best[1], "host_cpus": cores,
-                         "sample": f"{n_trunc}-layer truncation ({fk} dense + {n_trunc - fk} MoE + LM head) of the workload's shapes, "
-                                   f"{steps * tokens_per_step} decoded tokens, per-block times extrapolated to {nl_full} layers; "
-                                   f"unmodified reference (-O3 -ffast-math -fopenmp -mavx2), best of OMP threads {{16, 32, cores/2}}"}
+                best = (tps, threads, spent)
+        sample = (f"full-depth {nl_full}-layer checkpoint of the workload's shapes ({full_bytes / 1e9:.1f} GB in {base}), {n_tok} greedy tokens "
+                  f"decoded after a 4-token prompt (ref_timed_decode = run_completion's loop), no extrapolation") if full else \
+                 (f"{n_ck}-layer truncation ({fk} dense + {n_ck - fk} MoE + LM head) of the workload's shapes, {n_tok} decoded tokens, "
+                  f"per-block times EXTRAPOLATED to {nl_full} layers (the full checkpoint, {full_bytes / 1e9:.0f} GB, is not minted on the host)")
+        return best[0], best[2], {"kind": "reference", "cores": best[1], "host_cpus": cores, "extrapolated": not full,
+                                  "sample": sample + f"; unmodified reference (-O3 -ffast-math -fopenmp -mavx2), best of OMP threads {cands}"}
     finally:
         import shutil
         shutil.rmtree(d, ignore_errors=True)
 
 
 # ----------------------------------------------------------------------------------------------------
-def main():
-    # stdout carries exactly ONE JSON line: libraries (NCCL banner, the reference's loader chatter) go to stderr
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
+DTYPES = {"f8e5m2": "f8e5m2 weights x f32 activations", "q2_k": "u2 x i8 integer dot (Q2_K x Q8_K), f32 accumulate",
+          "q3_k": "u3 x i8 integer dot (Q3_K x Q8_K), f32 accumulate", "fp16": "f16 weights x f32", "fp32": "f32"}
+NAMES = {"v2lite": "DeepSeek-V2-Lite", "v2": "DeepSeek-V2 236B", "v3": "DeepSeek-V3 671B"}
 
-    def emit(obj):
-        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("DSK_WORKLOAD", "v2lite"))
-    ap.add_argument("--quant", default=os.environ.get("DSK_QUANT", "f8e5m2"))
-    ap.add_argument("--n-layers", type=int, default=int(os.environ.get("DSK_LAYERS", "0")))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-token", action="store_true", help="print a per-launch event profile of one token to stderr")
-    a = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    w = workload_cfg(a.workload, a.quant, a.n_layers or None)
-    wl_name = f"DeepSeek-{a.workload.upper()}-shaped {a.quant} single-batch decode, {PROMPT_LEN}-token prompt + {GEN_TOKENS}-token greedy completion"
-    base = {"metric": "tok/s single-batch decode (128-tok gen)", "unit": "tok/s", "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": {"f8e5m2": "f8e5m2 weights x f32 activations", "q2_k": "u2 x i8 integer dot (Q2_K x Q8_K), f32 accumulate",
-                      "q3_k": "u3 x i8 integer dot (Q3_K x Q8_K), f32 accumulate", "fp16": "f16 weights x f32", "fp32": "f32"}[a.quant],
-            "data": "synthetic (random-init weights of the named architecture; no checkpoints offline)",
-            "config": {"workload": wl_name, "layers": w["n_layers"], "tokens_per_step": GEN_TOKENS,
-                       "parallelism": f"experts sharded over {a.gpus} GPU(s), rest replicated" if a.gpus > 1 else "1 GPU",
-                       "l2": "weights streamed per token (GBs) exceed the 126 MB L2; no flush needed"}}
+def workload_name(workload, quant):
+    return (f"{NAMES.get(workload, workload)}-shaped {quant} single-batch decode, {PROMPT_LEN}-token prompt + {GEN_TOKENS}-token "
+            f"greedy completion")
 
-    if a.impl == "reference":
-        if rank != 0:
-            return 0
-        try:
-            tps, desc = cpu_reference_leg(w, max(1, a.steps), max(1, a.warmup))
-        except Exception as e:  # the oracle always exists in this tier; this only trips if _ref did not travel
-            emit({"impl": "reference", "unavailable": str(e)[:200]})
-            return 0
-        out = dict(base)
-        out.update({"impl": "reference", "value": tps, "ms_per_step": GEN_TOKENS / tps * 1e3, "n_gpus": a.gpus,
-                    "cpu_baseline": dict(desc, value=tps, unit="tok/s"),
-                    "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                    "gpu_launches": 0, "dtype": "reference CPU path (AVX2/F16C, OpenMP)"})
-        emit(out)
-        return 0
 
-    import torch
-    import dsk
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dsk.init(local_rank)
-    log(f"rank {rank}/{world}: minting {a.workload}/{a.quant} on the GPU")
+def measure(dsk, torch, dist, w, rank, world, local_rank, steps, warmup, want_e2e=True, profile=False):
+    """Mints the workload on this rank's GPU and times `steps` completions: returns a dict (rank-local; times are max over ranks)."""
     m = mint_on_gpu(dsk, w, rank, world, local_rank)
-    log(f"minted: {m.resident_bytes() / 1e9:.2f} GB resident, {m.active_bytes_per_token() / 1e9:.3f} GB/token algorithmic")
+    log(f"rank {rank}/{world}: minted {m.resident_bytes() / 1e9:.2f} GB resident, {m.active_bytes_per_token() / 1e9:.3f} GB/token algorithmic")
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             uid = torch.frombuffer(bytearray(dsk.Model.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(uid, 0)
         m.comm_init(bytes(uid.cpu().numpy().tobytes()))
-
     vocab = w["vocab_size"]
     pr = prompt_ids(vocab)
     sharded_check = None
@@ -446,6 +493,7 @@ def main():
             log(f"sharded vs single-GPU logits rel-L2 (max over {len(errs)} positions): {max(errs):.2e}")
 
     def hydrate():
+        am = None
         for p, t in enumerate(pr):
             last = p + 1 == len(pr)
             _, am = m.forward(t, p, dsk.OUTPUT_LOGITS if last else dsk.HYDRATE_KV_CACHE, want_logits=False)
@@ -456,21 +504,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    if a.profile_token and rank == 0:
+    timeline = None
+    if profile and rank == 0 and world == 1:
         hydrate()
         m.profile_token(pr[0], PROMPT_LEN)
-        print(m.profile_token(pr[1], PROMPT_LEN + 1), file=sys.stderr, flush=True)
+        timeline = m.profile_token(pr[1], PROMPT_LEN + 1)
+        print(timeline, file=sys.stderr, flush=True)
 
-    # ---- value: device-resident decode, CUDA events inside dsk_decode_greedy --------------------------
-    for _ in range(a.warmup):
+    # ---- value: device-resident decode, CUDA events inside dsk_decode_greedy (one persistent launch per completion) ----
+    for _ in range(warmup):
         hydrate()
         m.decode_greedy(PROMPT_LEN, GEN_TOKENS)
-    log("warm-up done; timing device-resident decode")
     clocks = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t_wall0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(a.steps):
+    dev_ms, toks = 0.0, None
+    for _ in range(steps):
         hydrate()
         barrier()
         toks, ms = m.decode_greedy(PROMPT_LEN, GEN_TOKENS)
@@ -482,29 +531,120 @@ def main():
         t = torch.tensor([dev_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    value = a.steps * GEN_TOKENS / (dev_ms / 1e3)
-    log(f"value {value:.1f} tok/s ({dev_ms / a.steps / GEN_TOKENS:.3f} ms/token); timing host-driven e2e")
+    value = steps * GEN_TOKENS / (dev_ms / 1e3)
+    log(f"value {value:.1f} tok/s ({dev_ms / steps / GEN_TOKENS:.3f} ms/token)")
 
     # ---- e2e: reference-shaped host loop, host buffers, copies inside the timed region -------------
-    def host_completion():
-        am = hydrate()
-        t0 = time.perf_counter()
-        pos = PROMPT_LEN
-        for _ in range(GEN_TOKENS):
-            logits, _ = m.forward(am, pos)            # H2D control words, D2H vocab logits, sync
-            am = int(np.argmax(logits))               # host sampler (Sampler::sample_argmax)
-            pos += 1
-        return time.perf_counter() - t0
-    for _ in range(max(1, a.warmup // 2)):
-        host_completion()
-    barrier()
-    e2e_s = sum(host_completion() for _ in range(a.steps))
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e = a.steps * GEN_TOKENS / e2e_s
-    log(f"e2e {e2e:.1f} tok/s; isolated kernels + CPU baseline next")
+    e2e = None
+    if want_e2e:
+        def host_completion():
+            am = hydrate()
+            t0 = time.perf_counter()
+            pos = PROMPT_LEN
+            for _ in range(GEN_TOKENS):
+                logits, _ = m.forward(am, pos)            # H2D control words, D2H vocab logits, sync
+                am = int(np.argmax(logits))               # host sampler (Sampler::sample_argmax)
+                pos += 1
+            return time.perf_counter() - t0
+        for _ in range(max(1, warmup // 2)):
+            host_completion()
+        barrier()
+        e2e_s = sum(host_completion() for _ in range(steps))
+        if dist is not None:
+            t = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = steps * GEN_TOKENS / e2e_s
+        log(f"e2e {e2e:.1f} tok/s")
+    res = {"value": value, "dev_ms": dev_ms, "wall": wall, "e2e": e2e, "clocks": clk, "sharded_check": sharded_check,
+           "abytes": m.active_bytes_per_token(), "resident_gb": m.resident_bytes() / 1e9, "tokens": toks[:8].tolist(),
+           "launches_per_forward": m.launches_per_forward(dsk.OUTPUT_LOGITS), "timeline": timeline}
+    m.close()
+    torch.cuda.empty_cache()
+    return res
+
+
+def committed_traffic(workload, quant):
+    """roofline.traffic: dram__bytes_read + dram__bytes_write of the decode kernel, per launch == per token, from the committed
+    `ncu --set full` capture of this workload (profiles/r02_traffic.json).  A number taken under the profiler; it is reported
+    only while the kernel sources still hash to what the capture ran (otherwise null: it would describe another build)."""
+    try:
+        import hashlib
+        rec = json.load(open(os.path.join(REPO, "profiles", "r02_traffic.json")))
+        h = hashlib.sha256()
+        for f in ("dsk_mega.cuh", "dsk_kernels.cuh"):
+            h.update(open(os.path.join(REPO, "deepseek.cpp_b200", "csrc", f), "rb").read())
+        e = rec.get(f"{workload}/{quant}")
+        if e and e.get("kernel_sources_sha256") == h.hexdigest():
+            return float(e["dram_bytes_per_token"]), e.get("capture")
+    except Exception:
+        pass
+    return None, None
+
+
+def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL banner, the reference's loader chatter) go to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DSK_WORKLOAD", "v2"))
+    ap.add_argument("--quant", default=os.environ.get("DSK_QUANT", "q2_k"))
+    ap.add_argument("--n-layers", type=int, default=int(os.environ.get("DSK_LAYERS", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the V2-Lite configs[1]/[2] continuity numbers")
+    ap.add_argument("--profile-token", action="store_true", help="print the per-stage timeline of one token to stderr")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = workload_cfg(a.workload, a.quant, a.n_layers or None)
+    base = {"metric": "tok/s single-batch decode (128-tok gen)", "unit": "tok/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": DTYPES[a.quant],
+            "data": "synthetic (random-init weights of the named architecture; no checkpoints offline)",
+            "config": {"workload": workload_name(a.workload, a.quant), "baseline_config": {"v2lite": "configs[1]/[2]", "v2": "configs[3]", "v3": "configs[4]"}.get(a.workload),
+                       "layers": w["n_layers"], "tokens_per_step": GEN_TOKENS,
+                       "parallelism": f"routed experts sharded over {a.gpus} GPU(s), rest replicated; one in-kernel peer-memory exchange per MoE layer" if a.gpus > 1 else "1 GPU",
+                       "l2": "weights streamed per token (GBs) exceed the 126 MB L2; no flush needed"}}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        try:
+            t0 = time.time()
+            tps, spent, desc = cpu_reference_leg(w, max(1, a.steps), max(1, a.warmup))
+        except Exception as e:  # the oracle always exists in this tier; this only trips if _ref did not travel
+            emit({"impl": "reference", "unavailable": str(e)[:200]})
+            return 0
+        out = dict(base)
+        # a reference "step" is the bounded sample actually decoded (ms_per_step x steps = the CPU time really spent decoding);
+        # `value` is its tok/s — measured on the full-depth model unless cpu_baseline.extrapolated says otherwise
+        out.update({"impl": "reference", "value": tps, "ms_per_step": spent / max(1, a.steps) * 1e3, "n_gpus": a.gpus,
+                    "step_note": "reference arm: one step = 1/steps of the bounded token sample described in cpu_baseline.sample",
+                    "cpu_baseline": dict(desc, value=tps, unit="tok/s", seconds_decoding=spent, seconds_total=time.time() - t0),
+                    "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                    "gpu_launches": 0, "dtype": "reference CPU path (AVX2/F16C, OpenMP)"})
+        emit(out)
+        return 0
+
+    import torch
+    import dsk
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dsk.init(local_rank)
+    log(f"rank {rank}/{world}: workload {a.workload}/{a.quant}")
+    R = measure(dsk, torch, dist, w, rank, world, local_rank, a.steps, a.warmup, want_e2e=True, profile=a.profile_token)
 
     if rank != 0:
         if dist is not None:
@@ -512,7 +652,7 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline: whole-token algorithmic bytes vs measured HBM peak + the dominant kernel alone ----
+    # ---- roofline: whole-token algorithmic bytes vs measured HBM peak + the dominant stage kinds alone ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -520,51 +660,56 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    abytes = m.active_bytes_per_token()
+    abytes, value = R["abytes"], R["value"]
     achieved = abytes * value / 1e9 / a.gpus
     kern = {}
     try:
         hd = w["qk_nope_head_dim"] + w["qk_rope_head_dim"]
-        for label, (d_, n_) in {"lm_head": (w["vocab_size"], w["dim"]), "wq": (w["n_heads"] * hd, w["dim"]),
-                                 "expert_w1": (w["moe_intermediate_size"], w["dim"])}.items():
+        shapes = {"lm_head": (w["vocab_size"], w["dim"]), "wo": (w["dim"], w["n_heads"] * w["v_head_dim"]),
+                  "expert_w1": (w["moe_intermediate_size"], w["dim"])}
+        if w["q_lora_rank"] > 0:
+            shapes["wq_b"] = (w["n_heads"] * hd, w["q_lora_rank"])
+        else:
+            shapes["wq"] = (w["n_heads"] * hd, w["dim"])
+        for label, (d_, n_) in shapes.items():
             n_mats = max(2, int(300e6 // (d_ * n_)) + 1)
             ms_k, b_k = dsk.bench_gemv(a.quant, d_, n_, n_mats=min(n_mats, 64), warmup=3, iters=20)
             kern[label] = {"rows": d_, "cols": n_, "us": ms_k * 1e3, "GB/s": b_k / (ms_k / 1e3) / 1e9, "frac": b_k / (ms_k / 1e3) / 1e9 / peak}
+        kern["note"] = "ONE interpreter GEMV stage per launch (decode_kernel<Q>, production tile plan); launch overhead included"
     except Exception as e:
         kern = {"error": str(e)[:120]}
-    # DRAM traffic per launch (= per token: the token is one decode_kernel launch) from the committed ncu --set full capture
-    # of this workload (profiles/r01_final_decode_kernel_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum); a number
-    # taken under the profiler, reported for the configuration it was captured on and null otherwise
-    traffic = None
-    if a.workload == "v2lite" and a.quant == "f8e5m2" and world == 1 and not a.n_layers:
-        try:
-            rd = wr = None
-            for ln in open(os.path.join(REPO, "profiles", "r01_final_decode_kernel_summary.txt")):
-                f = ln.split()
-                if ln.startswith("dram__bytes_read.sum"):
-                    rd = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[3]]
-                if ln.startswith("dram__bytes_write.sum"):
-                    wr = float(f[2]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[3]]
-            if rd is not None and wr is not None:
-                traffic = rd + wr
-        except Exception:
-            traffic = None
+    traffic, capture = committed_traffic(a.workload, a.quant) if world == 1 and not a.n_layers else (None, None)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-            "traffic_unit": "bytes per launch (= per token), ncu capture in profiles/",
-            "kernel": "decode_kernel<Q> (the whole token is one launch; achieved = algorithmic bytes/token x tok/s, i.e. every "
+            "traffic_unit": "bytes per token (= per launch / tokens per launch), ncu capture in profiles/", "traffic_capture": capture,
+            "kernel": "decode_kernel<Q> (a whole completion is one launch; achieved = algorithmic bytes/token x tok/s / N_gpus, i.e. every "
                       "barrier, staging phase and attention is charged to the GEMV stream)",
-            "algorithmic_bytes_per_token": abytes, "peak_source": peak_src, "isolated_kernels": kern}
+            "algorithmic_bytes_per_token": abytes, "peak_source": peak_src, "isolated_stages": kern}
 
     out = dict(base)
-    out.update({"value": value, "ms_per_step": dev_ms / a.steps, "wall_s": wall,
-                "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": GEN_TOKENS * 48, "d2h_bytes_per_step": GEN_TOKENS * vocab * 4},
-                "gpu_launches": m.launches_per_forward(dsk.OUTPUT_LOGITS) * GEN_TOKENS * a.steps,
-                "launches_per_token": m.launches_per_forward(dsk.OUTPUT_LOGITS),
-                "roofline": roof, "clocks": clk, "sharded_check": sharded_check, "resident_gb": m.resident_bytes() / 1e9, "sample_tokens": toks[:8].tolist()})
+    vocab = w["vocab_size"]
+    out.update({"value": value, "ms_per_step": R["dev_ms"] / a.steps, "wall_s": R["wall"],
+                "e2e": {"value": R["e2e"], "unit": "tok/s", "h2d_bytes_per_step": GEN_TOKENS * 48, "d2h_bytes_per_step": GEN_TOKENS * vocab * 4},
+                "gpu_launches": a.steps * R["launches_per_forward"],
+                "gpu_launches_note": "decode_kernel launches inside the timed region of `value`: one persistent cooperative launch per 128-token "
+                                     "completion (the e2e region launches it once per token: steps x 128)",
+                "roofline": roof, "clocks": R["clocks"], "sharded_check": R["sharded_check"], "resident_gb": R["resident_gb"],
+                "sample_tokens": R["tokens"]})
+    # ---- secondary: the V2-Lite configs of BASELINE.json (round-1 headline), same run, N = 1 only ---------------------
+    if world == 1 and not a.no_secondary and a.workload != "v2lite" and not a.n_layers:
+        sec = {}
+        for sq in ("f8e5m2", "q2_k"):
+            try:
+                ws = workload_cfg("v2lite", sq)
+                r2 = measure(dsk, torch, None, ws, 0, 1, local_rank, max(2, a.steps // 2), max(3, a.warmup), want_e2e=True)
+                sec[f"v2lite/{sq}"] = {"workload": workload_name("v2lite", sq), "value": r2["value"], "e2e": r2["e2e"], "unit": "tok/s",
+                                       "algorithmic_bytes_per_token": r2["abytes"], "roofline_frac": r2["abytes"] * r2["value"] / 1e9 / peak}
+            except Exception as e:
+                sec[f"v2lite/{sq}"] = {"error": str(e)[:160]}
+        out["secondary"] = sec
     if a.gpus == 1 and not a.no_cpu_baseline:
         try:
-            tps, desc = cpu_reference_leg(w, 2, 1)
-            out["cpu_baseline"] = dict(desc, value=tps, unit="tok/s")
+            tps, spent, desc = cpu_reference_leg(w, 1, 1, tokens_per_step=4)
+            out["cpu_baseline"] = dict(desc, value=tps, unit="tok/s", seconds_decoding=spent)
         except Exception as e:
             out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": 0, "kind": "reference", "sample": f"failed: {str(e)[:150]}"}
     emit(out)

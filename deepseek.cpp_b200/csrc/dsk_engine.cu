@@ -25,6 +25,7 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
 #include "dsk_kernels.cuh"
 #include "dsk_mega.cuh"
 
@@ -82,6 +83,7 @@ static int nccl_load() {
   return 0;
 }
 
+
 static int g_device = -1;
 static int g_sm_count = 148;
 static bool g_attrs_set = false;
@@ -110,6 +112,21 @@ struct Layer {
   __half *kcache = nullptr, *vcache = nullptr;
 };
 
+// Host->device weight upload pipeline: the .dseek payload is an mmap of pageable memory, so a plain cudaMemcpy
+// stages every tensor synchronously through the driver's bounce buffer.  Here two pinned staging buffers alternate: while
+// chunk i travels over PCIe (cudaMemcpy2DAsync on the upload stream, which also re-pitches rows), the host thread copies
+// chunk i+1 out of the page cache.  dsk_model_finalize() joins the stream.
+struct Uploader {
+  static constexpr size_t kChunk = 32u << 20;
+  void* pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t st = nullptr;
+  int cur = 0;
+  std::vector<void*> staging;   // device staging buffers (Q3_K repack), freed at finalize
+  size_t bytes = 0;
+  double seconds = 0;
+};
+
 struct dsk_model {
   dsk_config c;
   int head_dim = 0;
@@ -128,6 +145,10 @@ struct dsk_model {
   float* xchg = nullptr;                 // [2 parities][n_ranks][dim] floats, then n_ranks arrival flags
   float* xchg_peer[kMaxRanks] = {};      // the same buffer of every rank, as seen from this process
   unsigned* xflag_peer[kMaxRanks] = {};
+  long long xchg_done = 0;               // exchanges completed so far through this model's buffer (sequence numbers are per model:
+                                         // the buffer and its flags are shared by every dsk_state of the model)
+  int n_states = 0;
+  Uploader up;
   std::vector<void*> allocs;
 };
 
@@ -140,10 +161,11 @@ struct dsk_state {
   Ctrl* h_ctrl = nullptr;     // pinned host mirror
   int* token_log = nullptr;   // device
   int* step = nullptr;        // device
+  float* sample_out = nullptr;   // device: [0] sampled token (as int bits), [1] its probability
   cudaStream_t stream = nullptr;
-  cudaGraphExec_t graph[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [mode][from_argmax]
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int last_pos = -1;
+  bool have_logits = false;   // the last forward ran the LM-head stage: Ctrl::argmax_key / logits are valid
   size_t token_log_cap = 0;
   // persistent interpreter
   Program* prog = nullptr;              // device
@@ -158,7 +180,6 @@ struct dsk_state {
   int built_epoch = 0;                  // m->p2p_epoch the program was built for
   int n_xchg = 0;                       // in-kernel exchanges per token (peer-memory mode)
   std::vector<int> xchg_before;         // exchanges preceding stage i within a token (size n_stages + 1)
-  long long xchg_done = 0;              // exchanges completed so far on this state (host mirror of Ctrl::pad[0] + n_xchg)
 };
 
 static size_t disk_row_bytes(int quant, int cols) {
@@ -176,35 +197,29 @@ static size_t dev_row_bytes(int quant, int cols) {
   if (quant == DSK_F8E5M2) return f8_pitch((size_t)cols);   // re-pitched rows (see f8_pitch)
   return disk_row_bytes(quant, cols);
 }
-// rows of `drb` disk bytes -> device rows of `vrb` bytes (no-op layouts use a flat copy)
-static cudaError_t copy_rows(void* dst, size_t vrb, const void* src, size_t drb, size_t nrows, int on_dev) {
-  const cudaMemcpyKind kind = on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (vrb == drb) return cudaMemcpy(dst, src, drb * nrows, kind);
-  cudaError_t e = cudaMemset(dst, 0, vrb * nrows);
-  if (e != cudaSuccess) return e;
-  return cudaMemcpy2D(dst, vrb, src, drb, drb, nrows, kind);
-}
 static int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------------
 // process / device
 // ---------------------------------------------------------------------------------------------------
 static constexpr int kSmemMax = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
-static constexpr size_t kSmemBudget = 200 * 1024;
-static bool g_use_pdl = true;
 static bool g_f8_mma_ok = true;   // f8 scale-block width is a power of two (the tensor-core loop shifts instead of dividing)
 static bool g_coop_small = false, g_kq_small = true;   // DSK_COOP_SMALL=1 / DSK_KQ_SMALL=0: A/B switches of the tile planner
 // (cooperative tiles for one-tile-per-CTA F8 stages won 2 us per stage in isolation but lose overall: their code is one more
 //  cold path per layer — 393 vs 408 tok/s)
 static bool g_use_mma = true;   // F8E5M2 tiles through mma.sync (DSK_NO_MMA=1: CUDA-core dequant path)
-enum { ENG_MEGA = 0, ENG_STAGE = 1, ENG_V2 = 2 };
+enum { ENG_MEGA = 0, ENG_STAGE = 1 };
 static int g_engine = ENG_MEGA;
 
-template <int Q>
-static cudaError_t set_attrs_q() {
-  cudaError_t e = cudaFuncSetAttribute(gemv_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(moe_down_kernel<Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax);
+typedef void (*DecodeKernel)(const Program*, int, int, int, int);
+static DecodeKernel decode_kernel_for(int quant) {
+  switch (quant) {
+    case DSK_F32: return decode_kernel<Q_F32>;
+    case DSK_F16: return decode_kernel<Q_F16>;
+    case DSK_F8E5M2: return decode_kernel<Q_F8>;
+    case DSK_Q2_K: return decode_kernel<Q_Q2K>;
+    default: return decode_kernel<Q_Q3K>;
+  }
 }
 
 extern "C" int dsk_abi_version(void) { return DSK_ABI_VERSION; }
@@ -221,28 +236,16 @@ extern "C" int dsk_init(int device) {
   cudaDeviceProp p;
   CK(cudaGetDeviceProperties(&p, device));
   g_sm_count = p.multiProcessorCount;
+  int coop = 0;
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return fail(-1, "device %d does not support cooperative launches (the decode kernel's grid barrier needs them)", device);
   if (!g_attrs_set) {
-    CK(set_attrs_q<Q_F32>());
-    CK(set_attrs_q<Q_F16>());
-    CK(set_attrs_q<Q_F8>());
-    CK(set_attrs_q<Q_Q2K>());
-    CK(set_attrs_q<Q_Q3K>());
-    CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    CK(cudaFuncSetAttribute(q8k_export_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-    g_use_pdl = getenv("DSK_NO_PDL") == nullptr;
     g_use_mma = getenv("DSK_NO_MMA") == nullptr;
     if (const char* e = getenv("DSK_COOP_SMALL")) g_coop_small = atoi(e) != 0;
     if (const char* e = getenv("DSK_KQ_SMALL")) g_kq_small = atoi(e) != 0;
-    if (const char* en = getenv("DSK_ENGINE")) {
-      if (!strcmp(en, "stage")) g_engine = ENG_STAGE;
-      else if (!strcmp(en, "v2")) g_engine = ENG_V2;
-      else g_engine = ENG_MEGA;
-    }
-    CK(cudaFuncSetAttribute(decode_kernel<Q_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_F8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_Q2K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
-    CK(cudaFuncSetAttribute(decode_kernel<Q_Q3K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
+    if (const char* en = getenv("DSK_ENGINE")) g_engine = !strcmp(en, "stage") ? ENG_STAGE : ENG_MEGA;
+    for (int q = DSK_F32; q <= DSK_Q3_K; q++)
+      CK(cudaFuncSetAttribute(decode_kernel_for(q), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax - 1024));
     g_attrs_set = true;
   }
   return 0;
@@ -283,11 +286,36 @@ static std::vector<float> rope_table(int rot, float theta) {
   return f;
 }
 
+// Limits of the kernels, checked once here so that a checkpoint outside them fails at load time instead of computing garbage
+// (the reference handles arbitrary values of some of these; see each message).
+static int validate_config(const dsk_config& c) {
+  if (c.dim <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.vocab_size <= 0 || c.max_seq_len <= 0) return fail(-1, "bad model dimensions");
+  if (c.dim % 256 != 0 && (c.quant == DSK_Q2_K || c.quant == DSK_Q3_K)) return fail(-1, "K-quants need dim %% 256 == 0 (src/quant.cpp:617)");
+  if (c.n_routed_experts > 256) return fail(-1, "n_routed_experts > 256 unsupported (src/infer.cpp:527)");
+  if (c.n_active_routed + 1 > kMaxJobs) return fail(-1, "n_active_routed > %d unsupported", kMaxJobs - 1);
+  if (c.n_routed_experts > 0 && c.n_active_routed > c.n_routed_experts) return fail(-1, "n_active_routed > n_routed_experts");
+  if (c.qk_rope_head_dim <= 0 || c.qk_rope_head_dim % 2 != 0 || c.qk_rope_head_dim > 128)
+    return fail(-1, "qk_rope_head_dim %d unsupported: the attention stage rotates one pair per thread in 64-thread groups (needs an even value <= 128)", c.qk_rope_head_dim);
+  if (c.qk_nope_head_dim < 0 || c.v_head_dim <= 0 || c.kv_lora_rank <= 0) return fail(-1, "bad attention dimensions");
+  if (c.topk_method == DSK_TOPK_GROUP_LIMITED_GREEDY && c.n_routed_experts > 0) {
+    if (c.n_group <= 0 || c.n_routed_experts % c.n_group != 0) return fail(-1, "n_routed_experts %d is not a multiple of n_group %d", c.n_routed_experts, c.n_group);
+    if (c.topk_group <= 0 || c.topk_group > c.n_routed_experts / c.n_group) return fail(-1, "topk_group %d does not fit a group of %d experts", c.topk_group, c.n_routed_experts / c.n_group);
+  }
+  if (c.quant == DSK_F8E5M2) {
+    // a weight tile (<= 32 rows, aligned to its height) carries ONE row of block scales: the tile must not straddle a
+    // scale-block boundary.  The reference accepts any block size (src/infer.cpp:238-313); quantization_block_size_0 = 128
+    // is what convert.py writes.
+    if (c.bs0 <= 0 || c.bs1 <= 0) return fail(-1, "f8e5m2 needs quantization_block_size_{0,1} > 0 (got %d, %d)", c.bs0, c.bs1);
+    if (c.bs0 % 32 != 0) return fail(-1, "f8e5m2 quantization_block_size_0 = %d unsupported: must be a multiple of 32 (weight tiles of up to 32 rows share one scale row)", c.bs0);
+  }
+  if (c.original_max_position <= 2) return fail(-1, "rope_scaling_original_max_position_embeddings must exceed the 2 attention sinks");
+  return 0;
+}
+
 extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ranks) {
   if (need_device()) return nullptr;
-  if (!cfg || n_ranks < 1 || rank < 0 || rank >= n_ranks) { fail(-1, "bad arguments"); return nullptr; }
-  if (cfg->n_routed_experts > 256) { fail(-1, "n_routed_experts > 256 unsupported (src/infer.cpp:527)"); return nullptr; }
-  if (cfg->n_active_routed + 1 > kMaxJobs) { fail(-1, "n_active_routed > %d unsupported", kMaxJobs - 1); return nullptr; }
+  if (!cfg || n_ranks < 1 || n_ranks > kMaxRanks || rank < 0 || rank >= n_ranks) { fail(-1, "bad arguments"); return nullptr; }
+  if (validate_config(*cfg)) return nullptr;
   dsk_model* m = new dsk_model();
   m->c = *cfg;
   m->head_dim = cfg->qk_nope_head_dim + cfg->qk_rope_head_dim;
@@ -322,13 +350,67 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
   return m;
 }
 
+static void uploader_release(Uploader& u) {
+  if (u.st) cudaStreamSynchronize(u.st);
+  for (void* p : u.staging) cudaFree(p);
+  u.staging.clear();
+  for (int i = 0; i < 2; i++) {
+    if (u.pin[i]) { cudaFreeHost(u.pin[i]); u.pin[i] = nullptr; }
+    if (u.ev[i]) { cudaEventDestroy(u.ev[i]); u.ev[i] = nullptr; }
+  }
+  if (u.st) { cudaStreamDestroy(u.st); u.st = nullptr; }
+}
+
 extern "C" void dsk_model_destroy(dsk_model* m) {
   if (!m) return;
+  uploader_release(m->up);
   if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
   for (int q = 0; q < kMaxRanks; q++) if (m->xchg_peer[q] && q != m->rank) cudaIpcCloseMemHandle(m->xchg_peer[q]);
   if (m->xchg) cudaFree(m->xchg);
   for (void* p : m->allocs) cudaFree(p);
   delete m;
+}
+
+// rows of `width` payload bytes at `spitch` (source) -> rows at `dpitch` (device).  Host sources go through the pinned
+// double buffer on the upload stream; device sources (GPU-side minting) are copied on the legacy default stream, which
+// keeps them ordered with the minting framework's own work on that stream.
+static int copy_rows(dsk_model* m, void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t nrows, int on_dev) {
+  if (nrows == 0 || width == 0) return 0;
+  if (on_dev) {
+    if (dpitch == spitch && spitch == width) { CK(cudaMemcpy(dst, src, width * nrows, cudaMemcpyDeviceToDevice)); return 0; }
+    if (dpitch != width) CK(cudaMemset(dst, 0, dpitch * nrows));
+    CK(cudaMemcpy2D(dst, dpitch, src, spitch, width, nrows, cudaMemcpyDeviceToDevice));
+    return 0;
+  }
+  Uploader& u = m->up;
+  if (!u.st) {
+    CK(cudaStreamCreateWithFlags(&u.st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) { CK(cudaMallocHost(&u.pin[i], Uploader::kChunk)); CK(cudaEventCreateWithFlags(&u.ev[i], cudaEventDisableTiming)); }
+  }
+  const bool flat = dpitch == width && spitch == width;
+  if (!flat && dpitch != width) CK(cudaMemsetAsync(dst, 0, dpitch * nrows, u.st));
+  if (!flat && width > Uploader::kChunk) return fail(-4, "row of %zu bytes exceeds the upload staging buffer", width);
+  // flat payloads are cut into staging-buffer-sized pieces; pitched ones into whole rows
+  const size_t unit = flat ? 1 : width, total = flat ? width * nrows : nrows;
+  const size_t per = flat ? Uploader::kChunk : std::max<size_t>(1, Uploader::kChunk / width);
+  for (size_t o = 0; o < total; o += per) {
+    const size_t cnt = std::min(per, total - o);
+    CK(cudaEventSynchronize(u.ev[u.cur]));   // the copy that last used this staging buffer has drained
+    if (flat) {
+      memcpy(u.pin[u.cur], (const char*)src + o, cnt);
+      CK(cudaMemcpyAsync((char*)dst + o, u.pin[u.cur], cnt, cudaMemcpyHostToDevice, u.st));
+    } else {
+      const char* s = (const char*)src + o * spitch;
+      if (spitch == width) memcpy(u.pin[u.cur], s, cnt * width);
+      else for (size_t r = 0; r < cnt; r++) memcpy((char*)u.pin[u.cur] + r * width, s + r * spitch, width);
+      CK(cudaMemcpy2DAsync((char*)dst + o * dpitch, dpitch, u.pin[u.cur], width, width, cnt, cudaMemcpyHostToDevice, u.st));
+    }
+    CK(cudaEventRecord(u.ev[u.cur], u.st));
+    u.cur ^= 1;
+  }
+  (void)unit;
+  u.bytes += width * nrows;
+  return 0;
 }
 
 // expected logical shape of a weight by its role
@@ -346,39 +428,70 @@ static bool parse_layer_name(const char* name, int* layer, std::string* rest) {
   return true;
 }
 
-static int upload_f32(dsk_model* m, float** dst, size_t n_expected, const void* data, size_t nbytes, int on_dev,
-                      const char* name) {
-  if (nbytes != n_expected * 4) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, n_expected * 4, nbytes);
-  if (dmalloc(m, (void**)dst, nbytes)) return -2;
-  CK(cudaMemcpy(*dst, data, nbytes, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+static const char* dtype_name(int dt) {
+  switch (dt) { case 0: return "F32"; case 1: return "F16"; case 2: return "BF16"; case 3: return "F8_E5M2"; case 4: return "F8_E4M3";
+                case 5: return "I32"; case 6: return "I16"; case 7: return "I8"; case 8: return "U8"; }
+  return "?";
+}
+// QTensor::from_codec_tensor (src/codec.cpp:166-234): dtype must be the quant's codec dtype; K-quants are checked by byte
+// count (their U8 payload shape is free), everything else by the exact 4-slot shape (unused slots zero).
+static int check_tensor(const char* name, int dtype, const int64_t shape[4], size_t nbytes, int want_dtype, bool kquant,
+                        const int64_t want[4], size_t want_bytes) {
+  if (dtype != want_dtype)
+    return fail(-4, "tensor mismatch for %s: expected dtype=%s, got dtype=%s", name, dtype_name(want_dtype), dtype_name(dtype));
+  if (kquant) {
+    if (nbytes != want_bytes) return fail(-4, "tensor mismatch for %s: expected dtype=U8, size=%zu; got size=%zu", name, want_bytes, nbytes);
+    return 0;
+  }
+  for (int i = 0; i < 4; i++)
+    if (shape[i] != want[i])
+      return fail(-4, "tensor mismatch for %s: expected shape=[%lld,%lld,%lld,%lld], got shape=[%lld,%lld,%lld,%lld]", name,
+                  (long long)want[0], (long long)want[1], (long long)want[2], (long long)want[3],
+                  (long long)shape[0], (long long)shape[1], (long long)shape[2], (long long)shape[3]);
+  if (nbytes != want_bytes) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, want_bytes, nbytes);
   return 0;
 }
 
-static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expert, bool is_scale, const void* data,
-                         size_t nbytes, int on_dev, const char* name) {
+static int upload_f32(dsk_model* m, float** dst, int64_t d0, int64_t d1, int dtype, const int64_t shape[4], const void* data,
+                      size_t nbytes, int on_dev, const char* name) {
+  const int64_t want[4] = {d0, d1, 0, 0};
+  const size_t n_expected = (size_t)d0 * (size_t)(d1 > 0 ? d1 : 1);
+  if (check_tensor(name, dtype, shape, nbytes, DSK_DT_F32, false, want, n_expected * 4)) return -4;
+  if (*dst) return fail(-4, "tensor %s uploaded twice", name);
+  if (dmalloc(m, (void**)dst, nbytes)) return -2;
+  return copy_rows(m, *dst, nbytes, data, nbytes, nbytes, 1, on_dev);
+}
+
+static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expert, bool is_scale, int dtype,
+                         const int64_t shape[4], const void* data, size_t nbytes, int on_dev, const char* name) {
   const dsk_config& c = m->c;
   const int E = expert ? c.n_routed_experts : 0;
   const int first = expert ? m->expert_first : 0;
   const int count = expert ? m->expert_count : 1;
   if (is_scale) {
-    const size_t per = (size_t)cdiv(rows, c.bs0) * cdiv(cols, c.bs1);
+    if (c.quant != DSK_F8E5M2) return fail(-4, "tensor %s: only f8e5m2 checkpoints carry scales (src/model.cpp:191)", name);
+    const int sr = cdiv(rows, c.bs0), sc = cdiv(cols, c.bs1);
+    const size_t per = (size_t)sr * sc;
     const size_t tot = per * (expert ? E : 1);
-    if (nbytes != tot * 4) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, tot * 4, nbytes);
+    const int64_t want_e[4] = {E, sr, sc, 0}, want_p[4] = {sr, sc, 0, 0};
+    if (check_tensor(name, dtype, shape, nbytes, DSK_DT_F32, false, expert ? want_e : want_p, tot * 4)) return -4;
+    if (t.scale) return fail(-4, "tensor %s uploaded twice", name);
     t.scale_expert = per;
     const size_t local = per * count;
     if (dmalloc(m, (void**)&t.scale, local * 4)) return -2;
-    if (local)
-      CK(cudaMemcpy(t.scale, (const char*)data + (size_t)first * per * 4, local * 4,
-                    on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-    return 0;
+    return copy_rows(m, t.scale, local * 4, (const char*)data + (size_t)first * per * 4, local * 4, local * 4, local ? 1 : 0, on_dev);
   }
   const int q = c.quant;
-  if ((q == DSK_Q2_K || q == DSK_Q3_K) && cols % 256 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 256", name, cols);
+  const bool kq = q == DSK_Q2_K || q == DSK_Q3_K;
+  if (kq && cols % 256 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 256", name, cols);
   if ((q == DSK_F16 || q == DSK_F8E5M2) && cols % 16 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 16", name, cols);
   if (q == DSK_F32 && cols % 4 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 4", name, cols);
   const size_t drb = disk_row_bytes(q, cols), vrb = dev_row_bytes(q, cols);
   const size_t tot = drb * rows * (expert ? E : 1);
-  if (nbytes != tot) return fail(-4, "tensor %s: expected %zu bytes, got %zu", name, tot, nbytes);
+  static const int codec_of_quant[5] = {DSK_DT_F32, DSK_DT_F16, DSK_DT_F8E5M2, DSK_DT_U8, DSK_DT_U8};   // quant_to_codec_dtype
+  const int64_t want_e[4] = {E, rows, cols, 0}, want_p[4] = {rows, cols, 0, 0};
+  if (check_tensor(name, dtype, shape, nbytes, codec_of_quant[q], kq, expert ? want_e : want_p, tot)) return -4;
+  if (t.present) return fail(-4, "tensor %s uploaded twice", name);
   t.present = true;
   t.quant = q;
   t.total_experts = E;
@@ -393,49 +506,53 @@ static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expe
   const char* src = (const char*)data + (size_t)first * drb * rows;
   if (local_disk == 0) return 0;
   if (q == DSK_Q3_K) {
-    // stage the 110-byte disk blocks, repack to 112-byte aligned blocks on the device
+    // stage the 110-byte disk blocks, repack to 112-byte aligned blocks on the device (same stream as the staging copy)
     const unsigned char* dsrc = (const unsigned char*)src;
-    void* staging = nullptr;
+    cudaStream_t st = nullptr;
     if (!on_dev) {
+      void* staging = nullptr;
       CK(cudaMalloc(&staging, local_disk));
-      CK(cudaMemcpy(staging, src, local_disk, cudaMemcpyHostToDevice));
+      m->up.staging.push_back(staging);
+      if (copy_rows(m, staging, local_disk, src, local_disk, local_disk, 1, 0)) return -2;
       dsrc = (const unsigned char*)staging;
+      st = m->up.st;
     }
     const size_t nblocks = local_disk / kQ3Disk;
-    q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256>>>(dsrc, t.w, nblocks);
+    q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(dsrc, t.w, nblocks);
     CK(cudaGetLastError());
-    CK(cudaDeviceSynchronize());
-    if (staging) cudaFree(staging);
-  } else {
-    CK(copy_rows(t.w, vrb, src, drb, (size_t)rows * count, on_dev));
+    if (on_dev) CK(cudaDeviceSynchronize());
+    return 0;
   }
-  return 0;
+  return copy_rows(m, t.w, vrb, src, drb, drb, (size_t)rows * count, on_dev);
 }
 
 extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, const int64_t shape[4], const void* data,
                                  size_t nbytes, int src_on_device) {
   if (need_device()) return -1;
-  if (!m || !name || !data) return fail(-1, "bad arguments");
-  (void)dtype; (void)shape;
+  if (!m || !name || !data || !shape) return fail(-1, "bad arguments");
   const dsk_config& c = m->c;
   const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size;
   std::string nm(name);
   if (nm == "tokenizer.tokens") return 0;  // host-side only
-  if (nm == "model.embed.weight") return upload_weight(m, m->embed, c.vocab_size, c.dim, false, false, data, nbytes, src_on_device, name);
-  if (nm == "model.embed.scale") return upload_weight(m, m->embed, c.vocab_size, c.dim, false, true, data, nbytes, src_on_device, name);
-  if (nm == "model.output.weight") { m->has_wcls = true; return upload_weight(m, m->wcls, c.vocab_size, c.dim, false, false, data, nbytes, src_on_device, name); }
-  if (nm == "model.output.scale") return upload_weight(m, m->wcls, c.vocab_size, c.dim, false, true, data, nbytes, src_on_device, name);
-  if (nm == "model.norm.weight") return upload_f32(m, &m->rms_final, c.dim, data, nbytes, src_on_device, name);
+  auto W = [&](DTensor& t, int rows, int cols, bool expert, bool is_scale) {
+    return upload_weight(m, t, rows, cols, expert, is_scale, dtype, shape, data, nbytes, src_on_device, name);
+  };
+  auto F = [&](float** dst, int64_t d0, int64_t d1) { return upload_f32(m, dst, d0, d1, dtype, shape, data, nbytes, src_on_device, name); };
+  if (nm == "model.embed.weight") return W(m->embed, c.vocab_size, c.dim, false, false);
+  if (nm == "model.embed.scale") return W(m->embed, c.vocab_size, c.dim, false, true);
+  if (nm == "model.output.weight") { m->has_wcls = true; return W(m->wcls, c.vocab_size, c.dim, false, false); }
+  if (nm == "model.output.scale") return W(m->wcls, c.vocab_size, c.dim, false, true);
+  if (nm == "model.norm.weight") return F(&m->rms_final, c.dim, 0);
   int l = -1;
   std::string rest;
   if (!parse_layer_name(name, &l, &rest) || l < 0 || l >= c.n_layers) return fail(-4, "unknown tensor name %s", name);
   Layer& L = m->layers[l];
-  if (rest == "attn.norm.weight") return upload_f32(m, &L.rms_att, c.dim, data, nbytes, src_on_device, name);
-  if (rest == "mlp.norm.weight") return upload_f32(m, &L.rms_ffn, c.dim, data, nbytes, src_on_device, name);
-  if (rest == "attn.kv_a_norm.weight") return upload_f32(m, &L.rms_kv_a, c.kv_lora_rank, data, nbytes, src_on_device, name);
-  if (rest == "attn.q_a_norm.weight") return upload_f32(m, &L.rms_q_a, c.q_lora_rank, data, nbytes, src_on_device, name);
-  if (rest == "moegate.weight") return upload_f32(m, &L.gate, (size_t)c.n_routed_experts * c.dim, data, nbytes, src_on_device, name);
-  if (rest == "moegate.bias") return upload_f32(m, &L.gate_bias, c.n_routed_experts, data, nbytes, src_on_device, name);
+  if (rest == "attn.norm.weight") return F(&L.rms_att, c.dim, 0);
+  if (rest == "mlp.norm.weight") return F(&L.rms_ffn, c.dim, 0);
+  if (rest == "attn.kv_a_norm.weight") return F(&L.rms_kv_a, c.kv_lora_rank, 0);
+  if (rest == "attn.q_a_norm.weight") return F(&L.rms_q_a, c.q_lora_rank, 0);
+  if (rest == "moegate.weight") return F(&L.gate, c.n_routed_experts, c.dim);
+  if (rest == "moegate.bias") return F(&L.gate_bias, c.n_routed_experts, 0);
   const size_t dot = rest.rfind('.');
   if (dot == std::string::npos) return fail(-4, "unknown tensor name %s", name);
   const std::string base = rest.substr(0, dot), kind = rest.substr(dot + 1);
@@ -456,7 +573,7 @@ extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, cons
   else if (base == "shared_mlp.w2") r = {&L.sw2, c.dim, sh, false};
   else if (base == "shared_mlp.w3") r = {&L.sw3, sh, c.dim, false};
   else return fail(-4, "unknown tensor name %s (MLA-mode tensors are not part of this path)", name);
-  return upload_weight(m, *r.t, r.rows, r.cols, r.expert, is_scale, data, nbytes, src_on_device, name);
+  return W(*r.t, r.rows, r.cols, r.expert, is_scale);
 }
 
 extern "C" int dsk_model_finalize(dsk_model* m) {
@@ -488,6 +605,13 @@ extern "C" int dsk_model_finalize(dsk_model* m) {
         return -5;
     }
   }
+  // join the upload pipeline and give its pinned staging buffers back
+  if (m->up.st) {
+    cudaError_t e = cudaStreamSynchronize(m->up.st);
+    if (e != cudaSuccess) return fail(-2, "weight upload failed: %s", cudaGetErrorString(e));
+  }
+  uploader_release(m->up);
+  CK(cudaDeviceSynchronize());
   return 0;
 }
 
@@ -565,21 +689,24 @@ extern "C" dsk_state* dsk_state_create(dsk_model* m) {
   cudaMalloc((void**)&s->token_log, s->token_log_cap * sizeof(int));
   cudaMalloc((void**)&s->step, sizeof(int));
   cudaMemset(s->step, 0, sizeof(int));
+  cudaMalloc((void**)&s->sample_out, 4 * sizeof(float));
+  cudaMemset(s->sample_out, 0, 4 * sizeof(float));
   cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   cudaEventCreate(&s->ev0);
   cudaEventCreate(&s->ev1);
   if (cudaGetLastError() != cudaSuccess) { fail(-2, "state allocation failed"); return nullptr; }
   if (build_program(m, s)) { return nullptr; }
+  m->n_states++;
   return s;
 }
 
 extern "C" void dsk_state_destroy(dsk_state* s) {
   if (!s) return;
-  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (s->graph[a][b]) cudaGraphExecDestroy(s->graph[a][b]);
+  if (s->m) s->m->n_states--;
   float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->kv_a, s->kv_b, s->moe_logits, s->moe_scores, s->act_w, s->logits, s->partial};
   for (float* b : bufs) cudaFree(b);
   cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words); cudaFree(s->tstamp);
-  cudaFree(s->act); cudaFree(s->ctrl); cudaFreeHost(s->h_ctrl); cudaFree(s->token_log); cudaFree(s->step);
+  cudaFree(s->sample_out); cudaFree(s->act); cudaFree(s->ctrl); cudaFreeHost(s->h_ctrl); cudaFree(s->token_log); cudaFree(s->step);
   cudaEventDestroy(s->ev0); cudaEventDestroy(s->ev1);
   cudaStreamDestroy(s->stream);
   delete s;
@@ -596,7 +723,7 @@ static float* state_buf(dsk_state* s, const char* name, size_t* cap) {
   if (k == "q") { *cap = (size_t)c.n_heads * s->m->head_dim; return s->q; }
   if (k == "kv_a") { *cap = c.kv_lora_rank + c.qk_rope_head_dim; return s->kv_a; }
   if (k == "kv_b") { *cap = (size_t)c.n_heads * (c.qk_nope_head_dim + c.v_head_dim); return s->kv_b; }
-  if (k == "moe_weights") { *cap = c.n_routed_experts; return g_engine == ENG_V2 ? s->moe_logits : s->moe_scores; }
+  if (k == "moe_weights") { *cap = c.n_routed_experts; return s->moe_scores; }
   if (k == "active_experts_weights") { *cap = c.n_active_routed; return s->act_w; }
   if (k == "logits") { *cap = c.vocab_size; return s->logits; }
   return nullptr;
@@ -655,260 +782,14 @@ extern "C" int dsk_kv_write(dsk_model* m, int layer, int which, const uint16_t* 
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// launch helpers
-// ---------------------------------------------------------------------------------------------------
-static int g_launch_count = 0;
-
-// Every kernel is launched with the programmatic-stream-serialization attribute: inside the token's CUDA graph this
-// becomes a programmatic dependency edge, so kernel N+1 is scheduled while kernel N drains, issues its TMA weight
-// prefetch, and blocks in griddepcontrol.wait until N has completed (all kernels call wait before touching state).
-struct ProfRec { const char* name; int grid; size_t smem; cudaEvent_t e0, e1; };
-static std::vector<ProfRec>* g_prof = nullptr;   // non-null while dsk_profile_token() records
-static const char* g_prof_tag = "";
-
-template <typename Arg>
-static cudaError_t launch_k(void (*kern)(Arg), int grid, int block, size_t smem, cudaStream_t st, const Arg& arg) {
-  if (g_prof) {
-    ProfRec r{g_prof_tag, grid, smem, nullptr, nullptr};
-    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
-    cudaEventRecord(r.e0, st);
-    void* args[] = {(void*)&arg};
-    cudaError_t er = cudaLaunchKernel((const void*)kern, dim3((unsigned)grid), dim3((unsigned)block), args, smem, st);
-    cudaEventRecord(r.e1, st);
-    g_prof->push_back(r);
-    return er;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
-  g_launch_count++;
-  return cudaLaunchKernelEx(&cfg, kern, arg);
-}
-
-static size_t row_bytes_q(int quant, int n) { return dev_row_bytes(quant, n); }
-static size_t xvec_bytes_q(int quant, int n) {
-  return (quant == DSK_Q2_K || quant == DSK_Q3_K) ? xvec_bytes<Q_Q2K>(n) : xvec_bytes<Q_F32>(n);
-}
-
-// Tile plan: rows per CTA (power of two, 4..32), rows per warp pass, CTA ranges per job, dynamic smem bytes.
-struct GemvPlan { int grid; size_t smem; };
-static GemvPlan plan_gemv(GemvArgs& a, int quant) {
-  const size_t rb = row_bytes_q(quant, a.n), xb = xvec_bytes_q(quant, a.n);
-  const int parts = a.epi == EPI_GLU ? 2 : 1;
-  int total_rows = 0;
-  for (int j = 0; j < a.njobs; j++) total_rows += a.job[j].rows;
-  int rpc = 32;
-  while (rpc > 4 && kSmemHdr + xb + align_up((size_t)rpc * rb, 128) * parts > kSmemBudget) rpc >>= 1;
-  while (rpc > 8 && (size_t)rpc * rb * parts > 64 * 1024) rpc >>= 1;            // keep >= 2-3 CTAs per SM resident
-  while (rpc > 8 && cdiv(total_rows, rpc) < 2 * g_sm_count) rpc >>= 1;           // small matrices: spread over the SMs
-  a.rows_per_cta = rpc;
-  const bool kq = quant == DSK_Q2_K || quant == DSK_Q3_K;
-  a.rpass = kq ? 1 : (rpc >= 32 ? 4 : (rpc >= 16 ? 2 : 1));
-  int cta = 0;
-  for (int j = 0; j < a.njobs; j++) { a.cta_begin[j] = cta; cta += cdiv(a.job[j].rows, rpc); }
-  for (int j = a.njobs; j <= kMaxJobs; j++) a.cta_begin[j] = cta;
-  return GemvPlan{cta, kSmemHdr + xb + align_up((size_t)rpc * rb, 128) * parts + 128};
-}
-
-static cudaError_t launch_gemv(int quant, GemvArgs& a, cudaStream_t st) {
-  const GemvPlan p = plan_gemv(a, quant);
-  switch (quant) {
-    case DSK_F32: return launch_k(gemv_kernel<Q_F32>, p.grid, kThreads, p.smem, st, a);
-    case DSK_F16: return launch_k(gemv_kernel<Q_F16>, p.grid, kThreads, p.smem, st, a);
-    case DSK_F8E5M2: return launch_k(gemv_kernel<Q_F8>, p.grid, kThreads, p.smem, st, a);
-    case DSK_Q2_K: return launch_k(gemv_kernel<Q_Q2K>, p.grid, kThreads, p.smem, st, a);
-    default: return launch_k(gemv_kernel<Q_Q3K>, p.grid, kThreads, p.smem, st, a);
-  }
-}
-
-static cudaError_t launch_down(int quant, DownArgs& d, cudaStream_t st) {
-  const size_t rb_mi = row_bytes_q(quant, d.mi), rb_sh = row_bytes_q(quant, d.sh);
-  size_t xb = 0;
-  for (int k = 0; k <= d.K; k++) { const int n = k < d.K ? d.mi : d.sh; if (n) xb += xvec_bytes_q(quant, n); }
-  int rpc = 8;
-  auto need = [&](int r) { return kSmemHdr + xb + align_up((size_t)r * rb_mi, 128) * d.K + align_up((size_t)r * rb_sh, 128) + 128; };
-  while (rpc > 1 && need(rpc) > kSmemBudget + 20 * 1024) rpc >>= 1;
-  d.rows_per_cta = rpc;
-  const int grid = cdiv(d.dim, rpc);
-  const size_t smem = need(rpc);
-  switch (quant) {
-    case DSK_F32: return launch_k(moe_down_kernel<Q_F32>, grid, kThreads, smem, st, d);
-    case DSK_F16: return launch_k(moe_down_kernel<Q_F16>, grid, kThreads, smem, st, d);
-    case DSK_F8E5M2: return launch_k(moe_down_kernel<Q_F8>, grid, kThreads, smem, st, d);
-    case DSK_Q2_K: return launch_k(moe_down_kernel<Q_Q2K>, grid, kThreads, smem, st, d);
-    default: return launch_k(moe_down_kernel<Q_Q3K>, grid, kThreads, smem, st, d);
-  }
-}
-
-static GemvJob plain_job(const DTensor& t, float* out) {
-  GemvJob j{};
-  j.w = t.w; j.scale = t.scale; j.out = out; j.rows = t.rows; j.expert_slot = -1;
-  return j;
-}
-
-static GemvArgs base_args(const dsk_model* m, const dsk_state* s, const float* in, const float* norm_w, int n) {
-  GemvArgs a{};
-  const dsk_config& c = m->c;
-  a.in = in; a.norm_w = norm_w; a.eps = c.norm_eps; a.n = n;
-  a.bs0 = c.bs0 > 0 ? c.bs0 : 1; a.bs1 = c.bs1 > 0 ? c.bs1 : 1;
-  a.act_silu = c.act_silu;
-  a.active_experts = s->act;
-  a.expert_first = m->expert_first; a.expert_count = m->expert_count;
-  a.ctrl = s->ctrl; a.ctrl_rw = s->ctrl;
-  a.epi = EPI_STORE;
-  return a;
-}
-
 #define CKL(call)                                                                                   \
   do {                                                                                              \
     cudaError_t e_ = (call);                                                                        \
     if (e_ != cudaSuccess) return fail(-2, "launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-// One transformer block: Block::_block_cpu (src/infer.cpp:810-932) + BlockMHA::_attention_impl (934-1049).
-static int enqueue_layer(dsk_model* m, dsk_state* s, int l, cudaStream_t st) {
-  const dsk_config& c = m->c;
-  Layer& L = m->layers[l];
-  const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant;
-  // S1: xb = rmsnorm(x) fused; q (or q_a) and kv_a in one launch            infer.cpp:823, 942-954
-  {
-    GemvArgs a = base_args(m, s, s->x, L.rms_att, c.dim);
-    if (c.q_lora_rank > 0) a.job[0] = plain_job(L.wq_a, s->q_a); else a.job[0] = plain_job(L.wq, s->q);
-    a.job[1] = plain_job(L.wkv_a, s->kv_a);
-    a.njobs = 2;
-    g_prof_tag = "S1 q+kv_a gemv";
-    CKL(launch_gemv(q, a, st));
-  }
-  if (c.q_lora_rank > 0) {  // q = wq_b . rmsnorm(q_a)                          infer.cpp:944-950
-    GemvArgs a = base_args(m, s, s->q_a, L.rms_q_a, c.q_lora_rank);
-    a.job[0] = plain_job(L.wq_b, s->q);
-    a.njobs = 1;
-    g_prof_tag = "S1b wq_b gemv";
-    CKL(launch_gemv(q, a, st));
-  }
-  // S2: kv_b = wkv_b . rmsnorm(kv_a[:kv_lora]); epilogue writes fp16 K(nope)/V cache row   infer.cpp:974-1002
-  {
-    GemvArgs a = base_args(m, s, s->kv_a, L.rms_kv_a, c.kv_lora_rank);
-    a.job[0] = plain_job(L.wkv_b, s->kv_b);
-    a.njobs = 1;
-    a.epi = EPI_KVB;
-    g_prof_tag = "S2 kv_b gemv+cache";
-    a.kcache = L.kcache; a.vcache = L.vcache; a.n_heads = c.n_heads; a.nope = nope; a.vh = c.v_head_dim; a.hd = hd;
-    CKL(launch_gemv(q, a, st));
-  }
-  // S3: RoPE(q_pe, k_pe) + sink re-rotation + attention over the fp16 cache               infer.cpp:956-1045
-  {
-    AttnArgs a{};
-    a.q = s->q; a.kv_a = s->kv_a; a.kcache = L.kcache; a.vcache = L.vcache; a.out = s->xb2; a.ctrl = s->ctrl;
-    a.n_heads = c.n_heads; a.hd = hd; a.nope = nope; a.rope = c.qk_rope_head_dim; a.vh = c.v_head_dim;
-    a.kv_lora = c.kv_lora_rank; a.rope_freq = m->rope_freq; a.is_v3 = c.is_v3; a.max_seq = c.max_seq_len; a.do_prologue = 1;
-    g_prof_tag = "S3 rope+attn";
-    CKL(launch_k(attn_kernel, c.n_heads, kThreads, attn_smem_bytes(hd, c.v_head_dim, c.max_seq_len), st, a));
-  }
-  // S4: x += wo . xb2                                                                     infer.cpp:1048, 832-834
-  {
-    GemvArgs a = base_args(m, s, s->xb2, nullptr, c.n_heads * c.v_head_dim);
-    a.job[0] = plain_job(L.wo, s->x);
-    a.njobs = 1;
-    a.epi = EPI_RESID;
-    g_prof_tag = "S4 wo gemv+resid";
-    CKL(launch_gemv(q, a, st));
-  }
-  if (L.is_moe) {
-    // gate logits (F32 weights in every quant)                                           infer.cpp:847
-    {
-      GemvArgs a = base_args(m, s, s->x, L.rms_ffn, c.dim);
-      GemvJob j{};
-      j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
-      a.job[0] = j;
-      a.njobs = 1;
-      g_prof_tag = "gate gemv f32";
-      CKL(launch_gemv(DSK_F32, a, st));
-    }
-    {  // moe_gate                                                                        infer.cpp:848-852
-      GateArgs g{};
-      g.x = s->moe_logits; g.bias = L.gate_bias; g.active = s->act; g.weights = s->act_w;
-      g.E = c.n_routed_experts; g.K = c.n_active_routed; g.norm_topk_prob = c.norm_topk_prob; g.sigmoid = c.scoring_sigmoid;
-      g.method = c.topk_method; g.n_group = std::max(1, c.n_group); g.topk_group = c.topk_group; g.scale = c.routed_scaling_factor;
-      g_prof_tag = "gate topk";
-      CKL(launch_k(gate_topk_kernel, 1, 256, 0, st, g));
-    }
-    // routed + shared up/gate projections with fused act(h1)*h3                           infer.cpp:853-870, 879-897
-    const int sh = c.n_shared_experts * mi;
-    {
-      GemvArgs a = base_args(m, s, s->x, L.rms_ffn, c.dim);
-      int nj = 0, rows = 0;
-      for (int k = 0; k < c.n_active_routed; k++) {
-        GemvJob j{};
-        j.w = L.w1.w; j.scale = L.w1.scale; j.w_b = L.w3.w; j.scale_b = L.w3.scale;
-        j.out = s->hbk + (size_t)k * mi; j.rows = mi; j.expert_slot = k;
-        j.w_stride = (long long)L.w1.expert_bytes; j.s_stride = (long long)L.w1.scale_expert;
-        a.job[nj++] = j; rows += mi;
-      }
-      if (sh > 0) {
-        GemvJob j = plain_job(L.sw1, s->hbs);
-        j.w_b = L.sw3.w; j.scale_b = L.sw3.scale;
-        a.job[nj++] = j; rows += sh;
-      }
-      a.njobs = nj;
-      a.epi = EPI_GLU;
-      g_prof_tag = "S56 experts glu";
-      CKL(launch_gemv(q, a, st));
-    }
-    // down projections + weighted accumulate into the residual stream                     infer.cpp:873-877, 899-903
-    {
-      DownArgs d{};
-      d.w2 = L.w2.w; d.s2 = L.w2.scale; d.w_stride = (long long)L.w2.expert_bytes; d.s_stride = (long long)L.w2.scale_expert;
-      d.sw2 = sh > 0 ? L.sw2.w : nullptr; d.ss2 = sh > 0 ? L.sw2.scale : nullptr;
-      d.hb = s->hbk; d.hb_shared = s->hbs; d.active = s->act; d.weights = s->act_w;
-      d.K = c.n_active_routed; d.mi = mi; d.sh = sh; d.dim = c.dim;
-      d.bs0 = c.bs0 > 0 ? c.bs0 : 1; d.bs1 = c.bs1 > 0 ? c.bs1 : 1;
-      d.expert_first = m->expert_first; d.expert_count = m->expert_count;
-      d.x = s->x;
-      d.partial = m->n_ranks > 1 ? s->partial : nullptr;
-      d.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
-      g_prof_tag = "S7 moe down";
-      CKL(launch_down(q, d, st));
-      if (m->n_ranks > 1) {
-        if (!m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
-        CKN(g_nccl.AllReduce(s->partial, s->partial, c.dim, ncclFloat, ncclSum, m->comm, st));
-        add_vec_kernel<<<cdiv(c.dim, 256), 256, 0, st>>>(s->x, s->partial, c.dim);  // follows a NCCL kernel: plain edge
-        g_launch_count += 2;
-        CKL(cudaGetLastError());
-      }
-    }
-  } else {
-    // dense FFN                                                                          infer.cpp:905-931
-    {
-      GemvArgs a = base_args(m, s, s->x, L.rms_ffn, c.dim);
-      GemvJob j = plain_job(L.w1, s->hbs);
-      j.w_b = L.w3.w; j.scale_b = L.w3.scale;
-      a.job[0] = j;
-      a.njobs = 1;
-      a.epi = EPI_GLU;
-      g_prof_tag = "dense glu";
-      CKL(launch_gemv(q, a, st));
-    }
-    {
-      DownArgs d{};
-      d.sw2 = L.w2.w; d.ss2 = L.w2.scale;
-      d.hb = s->hbk; d.hb_shared = s->hbs; d.active = s->act; d.weights = s->act_w;
-      d.K = 0; d.mi = 0; d.sh = c.hidden_dim; d.dim = c.dim;
-      d.bs0 = c.bs0 > 0 ? c.bs0 : 1; d.bs1 = c.bs1 > 0 ? c.bs1 : 1;
-      d.x = s->x; d.partial = nullptr; d.add_shared = 1;
-      g_prof_tag = "dense down";
-      CKL(launch_down(q, d, st));
-    }
-  }
-  return 0;
+static size_t xvec_bytes_q(int quant, int n) {
+  return (quant == DSK_Q2_K || quant == DSK_Q3_K) ? xvec_bytes<Q_Q2K>(n) : xvec_bytes<Q_F32>(n);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -922,7 +803,7 @@ static bool kq_quant(int q) { return q == DSK_Q2_K || q == DSK_Q3_K; }
 static int g_wp_rows = 16;
 static int g_slot_data = kSlotData, g_slot_scale = kSlotScale;   // set per program: 16 KB tiles for the warp-per-tile tensor-core path
 
-static void plan_gemv_stage(Stage& st, int quant, int G) {
+static int plan_gemv_stage(Stage& st, int quant, int G) {
   const size_t rb = dev_row_bytes(quant, st.n);
   const int parts = st.epi == EPI_GLU ? 2 : 1;
   if (quant == DSK_F8E5M2 && st.n % 64 == 0 && g_use_mma && g_f8_mma_ok) {
@@ -946,11 +827,12 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
     // short stages (at most ~2 tiles per CTA of long rows): one warp per tile would leave 6-7 warps idle behind a single
     // 5 us tile, so all eight warps share each tile instead (column pieces, combined in a fixed order)
     if (g_coop_small && st.ntiles <= 2 * G && st.n >= 1024 && csplit > 1) st.wp = 0;
-    return;
+    return 0;
   }
   int total_rows = 0;
   for (int j = 0; j < st.njobs; j++) total_rows += st.job[j].rows;
-  if (kq_quant(quant) && (st.n / 256) * 4 <= 32 * kKqMaxPass && g_use_mma) {
+  if (kq_quant(quant)) {
+    if ((st.n / 256) * 4 > 32 * kKqMaxPass) return fail(-4, "K-quant row of %d columns exceeds the warp-per-tile limit (%d)", st.n, 8 * 256 * kKqMaxPass);
     // warp-per-tile K-quant tiles: up to 32 rows (lane r keeps row r), as many as fit one slot, TMA-aligned
     const int nb = st.n / 256;
     const int step = quant == DSK_Q2_K ? ((nb % 4 == 0) ? 1 : (nb % 2 == 0 ? 2 : 4)) : 1;
@@ -969,8 +851,9 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
       st.has_dyn = 0;
       for (int j = 0; j < st.njobs; j++) { st.job[j].tile_begin = t; t += cdiv(st.job[j].rows, RT); if (st.job[j].expert_slot >= 0) st.has_dyn = 1; }
       st.ntiles = t;
-      return;
+      return 0;
     }
+    return fail(-4, "K-quant row of %d columns (%zu bytes) does not fit a ring slot", st.n, rb);
   }
   int RT = 32;
   while (RT > 1 && align_up((size_t)RT * rb, 128) * parts > (size_t)g_slot_data) RT >>= 1;
@@ -993,6 +876,7 @@ static void plan_gemv_stage(Stage& st, int quant, int G) {
   st.has_dyn = 0;
   for (int j = 0; j < st.njobs; j++) { st.job[j].tile_begin = t; t += cdiv(st.job[j].rows, RT); if (st.job[j].expert_slot >= 0) st.has_dyn = 1; }
   st.ntiles = t;
+  return 0;
 }
 
 static int plan_down_stage(Stage& st, int quant, int dim) {
@@ -1016,7 +900,8 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
     st.ntiles = cdiv(dim, g_wp_rows) * np;
     return 0;
   }
-  if (kq_quant(quant) && (std::max(st.mi, st.sh) / 256) * 4 <= 32 * kKqMaxPass && g_use_mma) {
+  if (kq_quant(quant)) {
+    if ((std::max(st.mi, st.sh) / 256) * 4 > 32 * kKqMaxPass) return fail(-4, "K-quant down-projection row exceeds the warp-per-tile limit");
     // warp-per-tile K-quant pieces: (segment, rows of a 16-row output group)
     st.wp = 1; st.down_rows = 16; st.rows_per_tile = 16; st.seg_stride = 0;
     int np = 0;
@@ -1031,7 +916,7 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
       if (np < 0) break;
     }
     if (np > 0) { st.npieces = np; st.ntiles = cdiv(dim, 16) * np; return 0; }
-    st.wp = 0; st.down_rows = 0;
+    return fail(-4, "K-quant down-projection rows do not fit a ring slot");
   }
   int RT = 8;
   auto bytes = [&](int r) { return align_up((size_t)r * rb_mi, 128) * st.K + align_up((size_t)r * rb_sh, 128); };
@@ -1062,23 +947,112 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
   return 0;
 }
 
+
 static MJob mjob(const DTensor& t, float* out) {
   MJob j{};
   j.w = t.w; j.scale = t.scale; j.out = out; j.rows = t.rows; j.expert_slot = -1;
   return j;
 }
 
-static int build_program(dsk_model* m, dsk_state* s) {
-  const dsk_config& c = m->c;
-  const int hd = m->head_dim, nope = c.qk_nope_head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
-  g_f8_mma_ok = c.bs1 > 0 && (c.bs1 & (c.bs1 - 1)) == 0;
+// Ring-slot payload size of a program, chosen before its stages are planned: the tensor-core F8 path wants 16 rows of
+// 2048 + 64 bytes, K-quant tiles at least four rows of the longest row any stage streams (a 4-row interleave is the unit of
+// kq_tile_rows), and a quantised MoE model one whole F32 gate row.
+static void choose_slot_geometry(int q, const std::vector<Stage>& S, int gate_dim) {
   const bool wp_model = q == DSK_F8E5M2 && g_use_mma && g_f8_mma_ok;
-  const bool kq_model = kq_quant(q) && g_use_mma;
+  const bool kq_model = kq_quant(q);
   g_wp_rows = getenv("DSK_WP_ROWS") ? atoi(getenv("DSK_WP_ROWS")) : 16;
   if (g_wp_rows != 8) g_wp_rows = 16;
-  g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : (kq_model ? 16 * 1024 + 512 : kSlotData);   // 16 (or 8) rows x (2048 + 16) B
-  if (q != DSK_F32 && c.n_routed_experts > 0) g_slot_data = std::max(g_slot_data, (int)align_up((size_t)c.dim * 4, 128));   // a whole F32 gate row per slot
+  g_slot_data = wp_model ? (g_wp_rows == 16 ? 33 * 1024 + 256 : 16 * 1024 + 512) : (kq_model ? 16 * 1024 + 512 : kSlotData);
+  if (kq_model) {
+    size_t need = 0;
+    for (const Stage& st : S) {
+      if (st.kind == ST_GEMV && kq_quant(st.quant)) need = std::max(need, 4 * dev_row_bytes(st.quant, st.n) * (st.epi == EPI_GLU ? 2 : 1));
+      else if (st.kind == ST_DOWN) need = std::max(need, 4 * dev_row_bytes(st.quant, std::max(st.mi, st.sh)));
+    }
+    if (need <= 48 * 1024) g_slot_data = std::max(g_slot_data, (int)align_up(need, 128));   // longer rows: the generic (cooperative) path
+  }
+  if (gate_dim > 0) g_slot_data = std::max(g_slot_data, (int)align_up((size_t)gate_dim * 4, 128));   // a whole F32 gate row per slot
   g_slot_scale = kSlotScale;
+}
+
+struct Geometry { int n_slots = 0, slot_data = 0, slot_scale = 0, slot_bytes = 0; size_t xreg = 0, smem = 0; };
+
+// shared-memory budget of a planned stage list: activation region = max over stages, the rest is ring slots
+static int program_geometry(const std::vector<Stage>& S, int q, int hd, int max_seq, int bs1_cfg, Geometry* g) {
+  size_t xreg = 8192;
+  bool has_attn = false;
+  for (const Stage& st : S) {
+    if (st.kind == ST_GEMV) xreg = std::max(xreg, st.use_mma ? x16_bytes(st.n) : xvec_bytes_q(st.quant, st.n));
+    else if (st.kind == ST_DOWN) {
+      size_t b = 0;
+      if (st.use_mma) b = down_x16_bytes(st.K, st.mi, st.sh);
+      else if (kq_quant(st.quant)) b = down_q8_bytes<Q_Q2K>(st.K, st.mi, st.sh);
+      else for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += xvec_bytes_q(st.quant, n); }
+      xreg = std::max(xreg, b);
+    } else if (st.kind == ST_ATTN) has_attn = true;
+  }
+  if (has_attn) {
+    const size_t attn_need = (size_t)(512 + ((hd + 3) & ~3) + ((max_seq + 3) & ~3) + kConsumers + 16) * 4;
+    if (attn_need <= 64 * 1024) xreg = std::max(xreg, attn_need);
+    xreg = std::max(xreg, (size_t)(512 + ((hd + 3) & ~3) + 64) * 4);
+  }
+  xreg = align_up(xreg, 128);
+  const size_t budget = (size_t)kSmemMax - 2048;
+  {  // scale-row area of a ring slot: as small as this program's f8 scale rows allow (a 5th 34 KB slot fits for V2-Lite)
+    size_t need = 0;
+    bool generic = false;
+    const int bs1 = bs1_cfg > 0 ? bs1_cfg : 1;
+    for (const Stage& st : S) {
+      if (st.kind == ST_GEMV && st.quant == DSK_F8E5M2) need = std::max(need, (size_t)(cdiv(st.n, bs1) * 4 + 16) * (st.epi == EPI_GLU ? 2 : 1));
+      else if (st.kind == ST_DOWN && st.quant == DSK_F8E5M2) {
+        if (!st.wp) generic = true;
+        need = std::max(need, (size_t)(cdiv(std::max(st.mi, st.sh), bs1) * 4 + 16));
+      }
+    }
+    if (q != DSK_F8E5M2) g_slot_scale = 128;                       // no scale rows at all (F32 / F16 / K-quants)
+    else if (!generic && need <= 512) g_slot_scale = 512;
+    else g_slot_scale = kSlotScale;
+  }
+  const size_t slot_bytes = (size_t)g_slot_data + g_slot_scale;
+  if (kMegaHdr + xreg + 2 * slot_bytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
+  g->n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / slot_bytes);
+  g->slot_data = g_slot_data; g->slot_scale = g_slot_scale; g->slot_bytes = (int)slot_bytes;
+  g->xreg = xreg;
+  g->smem = kMegaHdr + xreg + (size_t)g->n_slots * slot_bytes;
+  // the grid barrier needs every CTA resident: verify that one CTA of this footprint fits an SM (the launch is cooperative,
+  // so anything less would be a launch error, not a hang)
+  int nb = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, decode_kernel_for(q), kMegaThreads, g->smem));
+  if (nb < 1) return fail(-4, "decode kernel (%zu bytes of shared memory) does not fit an SM", g->smem);
+  return 0;
+}
+
+static void plan_stages(std::vector<Stage>& S, int q, int dim, int G, int* err) {
+  *err = 0;
+  for (Stage& st : S) {
+    if (st.kind == ST_GEMV && st.ntiles == 0) { if (plan_gemv_stage(st, st.quant, G)) { *err = -4; return; } }
+    else if (st.kind == ST_DOWN && st.ntiles == 0) { if (plan_down_stage(st, q, dim)) { *err = -4; return; } }
+  }
+}
+
+static void fill_program_header(Program* P, const dsk_config& c, int hd, const Geometry& g) {
+  P->dim = c.dim; P->n_heads = c.n_heads; P->hd = hd; P->nope = c.qk_nope_head_dim; P->rope = c.qk_rope_head_dim; P->vh = c.v_head_dim;
+  P->kv_lora = c.kv_lora_rank; P->is_v3 = c.is_v3; P->bs0 = c.bs0 > 0 ? c.bs0 : 1; P->bs1 = c.bs1 > 0 ? c.bs1 : 1;
+  P->act_silu = c.act_silu; P->max_seq = c.max_seq_len;
+  { int b1 = P->bs1, sh = 0; while ((1 << sh) < b1) sh++; P->bs1_shift = ((1 << sh) == b1) ? sh : -1; }
+  P->E = c.n_routed_experts; P->K = c.n_active_routed;
+  P->norm_topk_prob = c.norm_topk_prob; P->sigmoid = c.scoring_sigmoid; P->topk_method = c.topk_method;
+  P->n_group = std::max(1, c.n_group); P->topk_group = c.topk_group; P->original_max = c.original_max_position;
+  P->eps = c.norm_eps; P->routed_scale = c.routed_scaling_factor;
+  P->n_slots = g.n_slots; P->xregion_bytes = (int)g.xreg;
+  P->slot_data = g.slot_data; P->slot_scale = g.slot_scale; P->slot_bytes = g.slot_bytes;
+  P->n_ranks = 1; P->rank = 0;
+}
+
+static int build_program(dsk_model* m, dsk_state* s) {
+  const dsk_config& c = m->c;
+  const int hd = m->head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
+  g_f8_mma_ok = c.bs1 > 0 && (c.bs1 & (c.bs1 - 1)) == 0;
   std::vector<Stage> S;
   int n_xchg = 0;
   s->cut_after.clear();
@@ -1098,26 +1072,22 @@ static int build_program(dsk_model* m, dsk_state* s) {
       st.job[0] = c.q_lora_rank > 0 ? mjob(L.wq_a, s->q_a) : mjob(L.wq, s->q);
       st.job[1] = mjob(L.wkv_a, s->kv_a);
       st.njobs = 2;
-      plan_gemv_stage(st, q, G);
       S.push_back(st);
     }
     if (c.q_lora_rank > 0) {
       Stage st = gemv(q, s->q_a, L.rms_q_a, c.q_lora_rank, EPI_STORE, l);
       st.job[0] = mjob(L.wq_b, s->q); st.njobs = 1;
-      plan_gemv_stage(st, q, G);
       S.push_back(st);
     }
     {  // S2
       Stage st = gemv(q, s->kv_a, L.rms_kv_a, c.kv_lora_rank, EPI_KVB, l);
       st.job[0] = mjob(L.wkv_b, s->kv_b); st.njobs = 1; st.kcache = L.kcache; st.vcache = L.vcache;
-      plan_gemv_stage(st, q, G);
       S.push_back(st);
     }
     { Stage st{}; st.kind = ST_ATTN; st.quant = q; st.layer = l; st.kcache = L.kcache; st.vcache = L.vcache; S.push_back(st); }
     {  // S4
       Stage st = gemv(q, s->xb2, nullptr, c.n_heads * c.v_head_dim, EPI_RESID, l);
       st.job[0] = mjob(L.wo, s->x); st.njobs = 1;
-      plan_gemv_stage(st, q, G);
       S.push_back(st);
     }
     if (L.is_moe) {
@@ -1126,9 +1096,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
         Stage st = gemv(DSK_F32, s->x, L.rms_ffn, c.dim, EPI_STORE, l);
         MJob j{}; j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
         st.job[0] = j; st.njobs = 1;
-        plan_gemv_stage(st, DSK_F32, G);
         if (q != DSK_F32) {
-          if ((size_t)c.dim * 4 > (size_t)g_slot_data) return fail(-4, "gate row (%d bytes) does not fit a ring slot", c.dim * 4);
           // quantised model: the dedicated gate stage (gate_f32_stage) takes one row per tile
           st.rows_per_tile = 1; st.rpass = 1; st.npieces = 1; st.wp = 0; st.use_mma = 0;
           st.piece[0] = Piece{0, 0, c.dim / 4, 0};
@@ -1149,7 +1117,6 @@ static int build_program(dsk_model* m, dsk_state* s) {
           st.job[nj++] = j;
         }
         st.njobs = nj;
-        plan_gemv_stage(st, q, G);
         S.push_back(st);
       }
       {  // S7
@@ -1159,7 +1126,6 @@ static int build_program(dsk_model* m, dsk_state* s) {
         st.sw2 = sh > 0 ? L.sw2.w : nullptr; st.ss2 = sh > 0 ? L.sw2.scale : nullptr;
         st.K = c.n_active_routed; st.mi = mi; st.sh = sh;
         st.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
-        if (plan_down_stage(st, q, c.dim)) return -4;
         st.xchg_ord = n_xchg;
         S.push_back(st);
         if (m->n_ranks > 1 && m->p2p) {   // in-kernel exchange over peer memory: the token stays ONE kernel
@@ -1173,14 +1139,12 @@ static int build_program(dsk_model* m, dsk_state* s) {
         Stage st = gemv(q, s->x, L.rms_ffn, c.dim, EPI_GLU, l);
         MJob j = mjob(L.w1, s->hbs); j.w_b = L.w3.w; j.scale_b = L.w3.scale;
         st.job[0] = j; st.njobs = 1;
-        plan_gemv_stage(st, q, G);
         S.push_back(st);
       }
       {
         Stage st{};
         st.kind = ST_DOWN; st.quant = q; st.layer = l;
         st.sw2 = L.w2.w; st.ss2 = L.w2.scale; st.K = 0; st.mi = 0; st.sh = c.hidden_dim; st.add_shared = 1;
-        if (plan_down_stage(st, q, c.dim)) return -4;
         S.push_back(st);
       }
     }
@@ -1189,56 +1153,24 @@ static int build_program(dsk_model* m, dsk_state* s) {
   {  // LM head + argmax
     Stage st = gemv(q, s->x, m->rms_final, c.dim, EPI_LOGITS, -1);
     st.job[0] = mjob(m->wcls, s->logits); st.njobs = 1;
-    plan_gemv_stage(st, q, G);
     S.push_back(st);
   }
-  // shared-memory budget: activation region = max over stages, the rest is ring slots
-  size_t xreg = 8192;
-  for (const Stage& st : S) {
-    if (st.kind == ST_GEMV) xreg = std::max(xreg, st.use_mma ? x16_bytes(st.n) : xvec_bytes_q(st.quant, st.n));
-    else if (st.kind == ST_DOWN) {
-      size_t b = 0;
-      if (st.use_mma) b = down_x16_bytes(st.K, st.mi, st.sh);
-      else if (kq_quant(st.quant)) b = down_q8_bytes<Q_Q2K>(st.K, st.mi, st.sh);
-      else for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += xvec_bytes_q(st.quant, n); }
-      xreg = std::max(xreg, b);
-    }
-  }
-  const size_t attn_need = (size_t)(512 + ((hd + 3) & ~3) + ((c.max_seq_len + 3) & ~3) + kConsumers + 16) * 4;
-  if (attn_need <= 64 * 1024) xreg = std::max(xreg, attn_need);
-  xreg = align_up(std::max(xreg, (size_t)(512 + ((hd + 3) & ~3) + 64) * 4), 128);
-  const size_t budget = (size_t)kSmemMax - 2048;
-  {  // scale-row area of a ring slot: as small as this program's f8 scale rows allow (a 5th 34 KB slot fits for V2-Lite)
-    size_t need = 0;
-    bool generic = false;
-    const int bs1 = c.bs1 > 0 ? c.bs1 : 1;
-    for (const Stage& st : S) {
-      if (st.kind == ST_GEMV && st.quant == DSK_F8E5M2) need = std::max(need, (size_t)(cdiv(st.n, bs1) * 4 + 16) * (st.epi == EPI_GLU ? 2 : 1));
-      else if (st.kind == ST_DOWN && st.quant == DSK_F8E5M2) {
-        if (!st.wp) generic = true;
-        need = std::max(need, (size_t)(cdiv(std::max(st.mi, st.sh), bs1) * 4 + 16));
-      }
-    }
-    if (q != DSK_F8E5M2) g_slot_scale = 128;                       // no scale rows at all (F32 / F16 / K-quants)
-    else if (!generic && need <= 512) g_slot_scale = 512;
-    else g_slot_scale = kSlotScale;
-  }
-  const size_t slot_bytes = (size_t)g_slot_data + g_slot_scale;
-  if (kMegaHdr + xreg + 2 * slot_bytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
-  int n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / slot_bytes);
-  s->mega_smem = kMegaHdr + xreg + (size_t)n_slots * slot_bytes;
+  const bool has_gate = q != DSK_F32 && c.n_routed_experts > 0;
+  choose_slot_geometry(q, S, has_gate ? c.dim : 0);
+  if (has_gate && (size_t)c.dim * 4 > (size_t)g_slot_data) return fail(-4, "gate row (%d bytes) does not fit a ring slot", c.dim * 4);
+  int perr = 0;
+  plan_stages(S, q, c.dim, G, &perr);
+  if (perr) return perr;
+  Geometry geo;
+  if (program_geometry(S, q, hd, c.max_seq_len, c.bs1, &geo)) return -4;
+  s->mega_smem = geo.smem;
   s->n_stages = (int)S.size();
 
   std::vector<unsigned char> buf(sizeof(Program) + (S.size() - 1) * sizeof(Stage));
   Program* P = reinterpret_cast<Program*>(buf.data());
   memset(P, 0, sizeof(Program));
-  P->dim = c.dim; P->n_heads = c.n_heads; P->hd = hd; P->nope = nope; P->rope = c.qk_rope_head_dim; P->vh = c.v_head_dim;
-  P->kv_lora = c.kv_lora_rank; P->is_v3 = c.is_v3; P->bs0 = c.bs0 > 0 ? c.bs0 : 1; P->bs1 = c.bs1 > 0 ? c.bs1 : 1;
-  P->act_silu = c.act_silu; P->max_seq = c.max_seq_len;
-  { int b1 = P->bs1, sh = 0; while ((1 << sh) < b1) sh++; P->bs1_shift = ((1 << sh) == b1) ? sh : -1; } P->E = c.n_routed_experts; P->K = c.n_active_routed;
-  P->norm_topk_prob = c.norm_topk_prob; P->sigmoid = c.scoring_sigmoid; P->topk_method = c.topk_method;
-  P->n_group = std::max(1, c.n_group); P->topk_group = c.topk_group; P->original_max = c.original_max_position;
-  P->eps = c.norm_eps; P->routed_scale = c.routed_scaling_factor; P->expert_first = m->expert_first; P->expert_count = m->expert_count;
+  fill_program_header(P, c, hd, geo);
+  P->expert_first = m->expert_first; P->expert_count = m->expert_count;
   P->embed_quant = q; P->n_stages = (int)S.size();
   P->embed_w = m->embed.w; P->embed_scale = m->embed.scale; P->rope_freq = m->rope_freq;
   P->x = s->x; P->q = s->q; P->q_a = s->q_a; P->kv_a = s->kv_a; P->kv_b = s->kv_b; P->xb2 = s->xb2; P->hbk = s->hbk; P->hbs = s->hbs;
@@ -1248,8 +1180,6 @@ static int build_program(dsk_model* m, dsk_state* s) {
   CK(cudaMalloc((void**)&s->sync_words, 64));
   CK(cudaMemset(s->sync_words, 0, 64));
   P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
-  P->n_slots = n_slots; P->xregion_bytes = (int)xreg;
-  P->slot_data = g_slot_data; P->slot_scale = g_slot_scale; P->slot_bytes = (int)slot_bytes;
   CK(cudaMalloc((void**)&s->tstamp, (S.size() * 8 + 8) * sizeof(unsigned long long)));
   CK(cudaMemset(s->tstamp, 0, (S.size() * 8 + 8) * sizeof(unsigned long long)));
   P->n_ranks = m->n_ranks; P->rank = m->rank; P->n_xchg = n_xchg;
@@ -1258,12 +1188,13 @@ static int build_program(dsk_model* m, dsk_state* s) {
   s->xchg_before.assign(S.size() + 1, 0);
   for (size_t i = 0; i < S.size(); i++) s->xchg_before[i + 1] = s->xchg_before[i] + (S[i].kind == ST_XCHG ? 1 : 0);
   s->built_epoch = m->p2p_epoch;
-  P->tstamp = s->tstamp;
+  P->tstamp = getenv("DSK_TSTAMP") ? s->tstamp : nullptr;   // the per-stage timeline costs a few globaltimer reads per stage: opt-in
   P->route_prof = reinterpret_cast<long long*>(s->tstamp + S.size() * 8);
+  s->stage_names.clear();
   for (const Stage& st : S) {
     char nm[96];
     const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_XCHG ? "xchg" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
-    snprintf(nm, sizeof(nm), "%-8s n=%5d tiles=%5d rt=%2d r=%d pieces=%2d", kind, st.kind == ST_DOWN ? st.K * st.mi + st.sh : st.n, st.ntiles, st.rows_per_tile, st.rpass, st.npieces);
+    snprintf(nm, sizeof(nm), "%-8s n=%5d tiles=%5d rt=%2d wp=%d pieces=%2d", kind, st.kind == ST_DOWN ? st.K * st.mi + st.sh : st.n, st.ntiles, st.rows_per_tile, st.wp, st.npieces);
     s->stage_names.push_back(nm);
   }
   memcpy(P->stage, S.data(), S.size() * sizeof(Stage));
@@ -1272,45 +1203,56 @@ static int build_program(dsk_model* m, dsk_state* s) {
   return 0;
 }
 
-static cudaError_t launch_decode(dsk_model* m, dsk_state* s, int s_begin, int s_end, int from_argmax, cudaStream_t st) {
-  if (s_end <= s_begin) return cudaSuccess;
-  void (*kern)(const Program*, int, int, int) = nullptr;
-  switch (m->c.quant) {
-    case DSK_F32: kern = decode_kernel<Q_F32>; break;
-    case DSK_F16: kern = decode_kernel<Q_F16>; break;
-    case DSK_F8E5M2: kern = decode_kernel<Q_F8>; break;
-    case DSK_Q2_K: kern = decode_kernel<Q_Q2K>; break;
-    default: kern = decode_kernel<Q_Q3K>; break;
-  }
+// ---------------------------------------------------------------------------------------------------
+// launches: ONE cooperative launch runs stages [b, e) for n_tokens tokens (cudaLaunchAttributeCooperative: all g_sm_count
+// CTAs are guaranteed co-resident, which the in-kernel grid barrier relies on — a busy device yields a launch error)
+// ---------------------------------------------------------------------------------------------------
+static int g_launch_count = 0;
+
+static cudaError_t launch_decode_raw(int quant, const Program* prog, size_t smem, int s_begin, int s_end, int from_argmax,
+                                     int n_tokens, cudaStream_t st) {
+  if (s_end <= s_begin || n_tokens <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)g_sm_count);
+  cfg.blockDim = dim3((unsigned)kMegaThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
   g_launch_count++;
-  kern<<<g_sm_count, kMegaThreads, s->mega_smem, st>>>(s->prog, s_begin, s_end, from_argmax);
-  return cudaGetLastError();
+  return cudaLaunchKernelEx(&cfg, decode_kernel_for(quant), prog, s_begin, s_end, from_argmax, n_tokens);
+}
+static cudaError_t launch_decode(dsk_model* m, dsk_state* s, int s_begin, int s_end, int from_argmax, int n_tokens, cudaStream_t st) {
+  return launch_decode_raw(m->c.quant, s->prog, s->mega_smem, s_begin, s_end, from_argmax, n_tokens, st);
 }
 
-// stages [b, e): one resident grid (ENG_MEGA) or one launch per stage (ENG_STAGE); multi-GPU cuts at the all-reduce points
 // The state (and its program) may have been created before dsk_comm_init() mapped the peers: rebuild it once.
 static int ensure_program(dsk_model* m, dsk_state* s) {
   if (s->built_epoch == m->p2p_epoch) return 0;
   CK(cudaStreamSynchronize(s->stream));
-  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) if (s->graph[a][b]) { cudaGraphExecDestroy(s->graph[a][b]); s->graph[a][b] = nullptr; }
   cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words); cudaFree(s->tstamp);
   s->prog = nullptr; s->att_scratch = nullptr; s->sync_words = nullptr; s->tstamp = nullptr;
   s->stage_names.clear(); s->layer_begin.clear(); s->layer_end.clear();
   return build_program(m, s);
 }
 // Ctrl::pad[0] = exchanges completed before the token the launch [b, e) belongs to (peer-memory mode)
-static void set_xchg_base(dsk_state* s, int b, int e) {
+static void set_xchg_base(dsk_model* m, dsk_state* s, int b, int e) {
   if (s->n_xchg == 0) return;
-  s->h_ctrl->pad[0] = (int)(s->xchg_done - s->xchg_before[b]);
-  s->xchg_done += s->xchg_before[e] - s->xchg_before[b];
+  s->h_ctrl->pad[0] = (int)(m->xchg_done - s->xchg_before[b]);
+  m->xchg_done += s->xchg_before[e] - s->xchg_before[b];
 }
 
+// stages [b, e) of ONE token: one resident grid (ENG_MEGA) or one launch per stage (ENG_STAGE); the NCCL fallback of the
+// multi-GPU path cuts at the all-reduce points
 static int run_stages(dsk_model* m, dsk_state* s, int b, int e, int from_argmax, cudaStream_t st) {
   const dsk_config& c = m->c;
   int cur = b;
   auto flush = [&](int upto) -> int {
-    if (g_engine == ENG_STAGE) { for (int i = cur; i < upto; i++) CKL(launch_decode(m, s, i, i + 1, from_argmax, st)); }
-    else CKL(launch_decode(m, s, cur, upto, from_argmax, st));
+    if (g_engine == ENG_STAGE) { for (int i = cur; i < upto; i++) CKL(launch_decode(m, s, i, i + 1, from_argmax, 1, st)); }
+    else CKL(launch_decode(m, s, cur, upto, from_argmax, 1, st));
     cur = upto;
     return 0;
   };
@@ -1324,53 +1266,6 @@ static int run_stages(dsk_model* m, dsk_state* s, int b, int e, int from_argmax,
     CKL(cudaGetLastError());
   }
   return flush(e);
-}
-
-static int enqueue_embed(dsk_model* m, dsk_state* s, int from_argmax, cudaStream_t st) {
-  const dsk_config& c = m->c;
-  EmbedArgs e{};
-  e.table = m->embed.w; e.scale = m->embed.scale; e.x = s->x; e.ctrl = s->ctrl;
-  e.quant = c.quant; e.dim = c.dim; e.bs0 = c.bs0 > 0 ? c.bs0 : 1; e.bs1 = c.bs1 > 0 ? c.bs1 : 1;
-  e.from_argmax = from_argmax; e.original_max = c.original_max_position;
-  e.token_log = s->token_log; e.step = s->step;
-  g_prof_tag = "embed";
-  CKL(launch_k(embed_kernel, 1, 256, 0, st, e));
-  return 0;
-}
-
-// Model::_forward_cpu (src/infer.cpp:1265-1317) as one launch sequence
-static int enqueue_forward(dsk_model* m, dsk_state* s, int mode, int from_argmax, cudaStream_t st) {
-  const dsk_config& c = m->c;
-  if (g_engine != ENG_V2 && !g_prof)
-    return run_stages(m, s, 0, mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - 1 : s->n_stages, from_argmax, st);
-  if (enqueue_embed(m, s, from_argmax, st)) return -2;
-  for (int l = 0; l < c.n_layers; l++)
-    if (enqueue_layer(m, s, l, st)) return -2;
-  if (mode == DSK_HYDRATE_KV_CACHE) return 0;
-  // final RMSNorm fused into the LM-head prologue; fused argmax (Sampler::sample_argmax)   infer.cpp:1292-1316
-  GemvArgs a = base_args(m, s, s->x, m->rms_final, c.dim);
-  a.job[0] = plain_job(m->wcls, s->logits);
-  a.njobs = 1;
-  a.epi = EPI_LOGITS;
-  g_prof_tag = "lm_head+argmax";
-  CKL(launch_gemv(c.quant, a, st));
-  return 0;
-}
-
-static int get_graph(dsk_model* m, dsk_state* s, int mode, int from_argmax, cudaGraphExec_t* out) {
-  cudaGraphExec_t& g = s->graph[mode][from_argmax];
-  if (!g) {
-    cudaGraph_t graph;
-    CK(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_forward(m, s, mode, from_argmax, s->stream);
-    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(-2, "graph capture failed: %s", cudaGetErrorString(e));
-    CK(cudaGraphInstantiate(&g, graph, 0));
-    cudaGraphDestroy(graph);
-  }
-  *out = g;
-  return 0;
 }
 
 static void fill_ctrl(Ctrl* h, const dsk_config& c, int token, int pos) {
@@ -1391,48 +1286,54 @@ extern "C" int dsk_forward(dsk_model* m, dsk_state* s, int token, int pos, int m
   if (token < 0 || token >= c.vocab_size) return fail(-4, "token %d out of range", token);
   if (pos < 0) return fail(-4, "negative pos");
   mode = mode ? 1 : 0;
+  if (m->n_ranks > 1 && !m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
   if (ensure_program(m, s)) return -2;
   fill_ctrl(s->h_ctrl, c, token, pos);
   if (s->h_ctrl->kv_pos >= c.max_seq_len || s->h_ctrl->kv_len > c.max_seq_len)
     return fail(-4, "pos %d does not fit the KV cache (max_seq_len %d; the reference would overrun it)", pos, c.max_seq_len);
-  cudaGraphExec_t g;
-  if (get_graph(m, s, mode, 0, &g)) return -2;
-  if (g_engine != ENG_V2) set_xchg_base(s, 0, mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - 1 : s->n_stages);
+  const int e = mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - 1 : s->n_stages;
+  set_xchg_base(m, s, 0, e);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  CK(cudaGraphLaunch(g, s->stream));
+  if (run_stages(m, s, 0, e, 0, s->stream)) return -2;
   if (mode && host_logits) CK(cudaMemcpyAsync(host_logits, s->logits, (size_t)c.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
   if (mode && argmax) CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   if (mode && argmax) *argmax = (int)(0xFFFFFFFFu - (unsigned)(s->h_ctrl->argmax_key & 0xFFFFFFFFull));
   s->last_pos = pos;
+  s->have_logits = mode != 0;
   return 0;
 }
 
 extern "C" int dsk_copy_embedding(dsk_model* m, dsk_state* s, int token) {
   if (need_device()) return -1;
   if (!m || !s) return fail(-1, "null model/state");
+  if (token < 0 || token >= m->c.vocab_size) return fail(-4, "token %d out of range", token);
   if (ensure_program(m, s)) return -2;
   fill_ctrl(s->h_ctrl, m->c, token, 0);
-  if (g_engine != ENG_V2) set_xchg_base(s, 0, 1);
+  set_xchg_base(m, s, 0, 1);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  if (g_engine != ENG_V2) { if (run_stages(m, s, 0, 1, 0, s->stream)) return -2; }
-  else if (enqueue_embed(m, s, 0, s->stream)) return -2;
+  if (run_stages(m, s, 0, 1, 0, s->stream)) return -2;
   CK(cudaStreamSynchronize(s->stream));
+  s->have_logits = false;
   return 0;
 }
 
 extern "C" int dsk_block_forward(dsk_model* m, dsk_state* s, int layer, int pos, int kv_sink, int kv_pos, int kv_len) {
   if (need_device()) return -1;
   if (!m || !s) return fail(-1, "null model/state");
-  if (layer < 0 || layer >= m->c.n_layers) return fail(-4, "bad layer %d", layer);
+  const dsk_config& c = m->c;
+  if (layer < 0 || layer >= c.n_layers) return fail(-4, "bad layer %d", layer);
+  if (pos < 0 || kv_sink < 0 || kv_pos < 0 || kv_pos >= c.max_seq_len || kv_len < 1 || kv_len > c.max_seq_len || kv_sink > kv_len)
+    return fail(-4, "block(pos %d, kv_sink %d, kv_pos %d, kv_len %d) does not fit the KV cache (max_seq_len %d)", pos, kv_sink, kv_pos, kv_len, c.max_seq_len);
+  if (m->n_ranks > 1 && !m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
   if (ensure_program(m, s)) return -2;
   Ctrl* h = s->h_ctrl;
   h->token = 0; h->pos = pos; h->kv_sink = kv_sink; h->kv_pos = kv_pos; h->kv_len = kv_len; h->argmax_key = 0;
-  if (g_engine != ENG_V2) set_xchg_base(s, s->layer_begin[layer], s->layer_end[layer]);
+  set_xchg_base(m, s, s->layer_begin[layer], s->layer_end[layer]);
   CK(cudaMemcpyAsync(s->ctrl, h, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  if (g_engine != ENG_V2) { if (run_stages(m, s, s->layer_begin[layer], s->layer_end[layer], 0, s->stream)) return -2; }
-  else if (enqueue_layer(m, s, layer, s->stream)) return -2;
+  if (run_stages(m, s, s->layer_begin[layer], s->layer_end[layer], 0, s->stream)) return -2;
   CK(cudaStreamSynchronize(s->stream));
+  s->have_logits = false;
   return 0;
 }
 
@@ -1440,46 +1341,151 @@ extern "C" int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int 
                                  float* elapsed_ms) {
   if (need_device()) return -1;
   if (!m || !s) return fail(-1, "null model/state");
+  if (n_steps <= 0) return fail(-4, "n_steps must be positive");
   if (s->last_pos < 0 || start_pos != s->last_pos + 1)
     return fail(-4, "dsk_decode_greedy: start_pos %d must follow the last forward (pos %d)", start_pos, s->last_pos);
+  // the first token is taken from the on-device arg-max of the previous LM-head stage: a hydrate-only forward, a block
+  // call or an embedding copy leaves no such key behind (the reference's run_completion samples from s.logits() here)
+  if (!s->have_logits)
+    return fail(-4, "dsk_decode_greedy: the last forward did not produce logits (mode DSK_HYDRATE_KV_CACHE, block or embedding call) — run dsk_forward(..., DSK_OUTPUT_LOGITS) first");
   if ((size_t)n_steps > s->token_log_cap) return fail(-4, "n_steps too large");
   const dsk_config& c = m->c;
   if (c.original_max_position > c.max_seq_len && start_pos + n_steps > c.max_seq_len)
     return fail(-4, "decode would run past the KV cache (%d)", c.max_seq_len);
+  if (m->n_ranks > 1 && !m->comm) return fail(-3, "n_ranks > 1 but dsk_comm_init() was not called");
   if (ensure_program(m, s)) return -2;
-  cudaGraphExec_t g;
-  if (get_graph(m, s, 1, 1, &g)) return -2;
-  if (s->n_xchg > 0) {   // the embedding stage of every replay advances the exchange base by n_xchg
-    s->h_ctrl->pad[0] = (int)(s->xchg_done - s->n_xchg);
+  if (s->n_xchg > 0) {   // the embedding stage of every token advances the exchange base by n_xchg
+    s->h_ctrl->pad[0] = (int)(m->xchg_done - s->n_xchg);
     CK(cudaMemcpyAsync(&s->ctrl->pad[0], &s->h_ctrl->pad[0], sizeof(int), cudaMemcpyHostToDevice, s->stream));
-    s->xchg_done += (long long)n_steps * s->n_xchg;
+    m->xchg_done += (long long)n_steps * s->n_xchg;
   }
   CK(cudaMemsetAsync(s->step, 0, sizeof(int), s->stream));
   CK(cudaEventRecord(s->ev0, s->stream));
-  for (int i = 0; i < n_steps; i++) CK(cudaGraphLaunch(g, s->stream));
+  if (g_engine == ENG_MEGA && s->cut_after.empty()) {
+    CKL(launch_decode(m, s, 0, s->n_stages, 1, n_steps, s->stream));   // the token loop runs inside the persistent kernel
+  } else {
+    for (int i = 0; i < n_steps; i++) if (run_stages(m, s, 0, s->n_stages, 1, s->stream)) return -2;
+  }
   CK(cudaEventRecord(s->ev1, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   if (elapsed_ms) CK(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
   if (out_tokens) CK(cudaMemcpy(out_tokens, s->token_log, (size_t)n_steps * 4, cudaMemcpyDeviceToHost));
   s->last_pos = start_pos + n_steps - 1;
+  s->have_logits = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// on-device sampling — Sampler::sample / sample_prob (src/sampler.cpp:12-75) over the logits the LM-head stage left in HBM
+// ---------------------------------------------------------------------------------------------------
+// One CTA of 1024 threads; thread t owns the contiguous index range [t*chunk, (t+1)*chunk) so that the running
+// probability sum is formed in vocabulary order like the reference's loop.  The reference accumulates in fp32 (its own
+// result depends on the compiler's -ffast-math vectorisation of that loop); here the per-element probabilities are the same
+// fp32 values expf((l - max) / T) / sum, accumulated in fp64, so the selected index can only differ from a given build of
+// the reference when r lies within fp32 summation error of a bucket edge.
+__global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int vocab, float temperature, float r,
+                                                       int index, float* __restrict__ out) {
+  __shared__ double s_d[1024];
+  __shared__ float s_f[32];
+  __shared__ int s_who;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = (vocab + 1023) / 1024;
+  const int i0 = min(vocab, tid * chunk), i1 = min(vocab, i0 + chunk);
+  float mx = -3.402823466e38f;
+  for (int i = i0; i < i1; i++) mx = fmaxf(mx, logits[i]);
+  mx = warp_max(mx);
+  if (lane == 0) s_f[warp] = mx;
+  if (tid == 0) s_who = 1024;
+  __syncthreads();
+  mx = s_f[0];
+  for (int w = 1; w < 32; w++) mx = fmaxf(mx, s_f[w]);
+  double part = 0.0;
+  for (int i = i0; i < i1; i++) part += (double)expf((logits[i] - mx) / temperature);
+  s_d[tid] = part;
+  __syncthreads();
+  for (int o = 512; o; o >>= 1) { if (tid < o) s_d[tid] += s_d[tid + o]; __syncthreads(); }
+  const float sum = (float)s_d[0];
+  __syncthreads();
+  if (index >= 0) {   // sample_prob
+    if (tid == 0) { out[0] = __int_as_float(index); out[1] = expf((logits[index] - mx) / temperature) / sum; }
+    return;
+  }
+  double loc = 0.0;
+  for (int i = i0; i < i1; i++) loc += (double)(expf((logits[i] - mx) / temperature) / sum);
+  s_d[tid] = loc;
+  __syncthreads();
+  // inclusive scan over the 1024 per-thread sums (Hillis-Steele in shared memory, fp64)
+  for (int o = 1; o < 1024; o <<= 1) {
+    const double add = tid >= o ? s_d[tid - o] : 0.0;
+    __syncthreads();
+    s_d[tid] += add;
+    __syncthreads();
+  }
+  const double incl = s_d[tid], excl = incl - loc;
+  if (incl >= (double)r && i1 > i0) atomicMin(&s_who, tid);
+  __syncthreads();
+  if (s_who == 1024) {   // the running sum never reaches r: the reference returns vocab_size - 1
+    if (tid == 0) { out[0] = __int_as_float(vocab - 1); out[1] = 0.f; }
+    return;
+  }
+  if (tid == s_who) {
+    double cum = excl;
+    int pick = i1 - 1;
+    for (int i = i0; i < i1; i++) {
+      cum += (double)(expf((logits[i] - mx) / temperature) / sum);
+      if (cum >= (double)r) { pick = i; break; }
+    }
+    out[0] = __int_as_float(pick);
+    out[1] = expf((logits[pick] - mx) / temperature) / sum;
+  }
+}
+
+static int need_logits(dsk_state* s, const char* who) {
+  if (!s->have_logits) return fail(-4, "%s: the last forward did not produce logits (run dsk_forward(..., DSK_OUTPUT_LOGITS) first)", who);
+  return 0;
+}
+
+extern "C" int dsk_sample(dsk_model* m, dsk_state* s, float temperature, float top_p, float coin, int* token) {
+  if (need_device()) return -1;
+  if (!m || !s || !token) return fail(-1, "bad arguments");
+  if (need_logits(s, "dsk_sample")) return -4;
+  if (temperature == 0.0f) {   // Sampler::sample_argmax: the LM-head stage already reduced it (lowest index on ties)
+    CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    *token = (int)(0xFFFFFFFFu - (unsigned)(s->h_ctrl->argmax_key & 0xFFFFFFFFull));
+    return 0;
+  }
+  if (!(temperature > 0.0f)) return fail(-4, "temperature must be >= 0");
+  sample_kernel<<<1, 1024, 0, s->stream>>>(s->logits, m->c.vocab_size, temperature, coin * top_p, -1, s->sample_out);
+  CKL(cudaGetLastError());
+  float h[2];
+  CK(cudaMemcpyAsync(h, s->sample_out, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  memcpy(token, &h[0], sizeof(int));
+  return 0;
+}
+
+extern "C" int dsk_sample_prob(dsk_model* m, dsk_state* s, int index, float* prob) {
+  if (need_device()) return -1;
+  if (!m || !s || !prob) return fail(-1, "bad arguments");
+  if (index < 0 || index >= m->c.vocab_size) return fail(-4, "index %d out of range", index);
+  if (need_logits(s, "dsk_sample_prob")) return -4;
+  sample_kernel<<<1, 1024, 0, s->stream>>>(s->logits, m->c.vocab_size, 1.0f, 0.f, index, s->sample_out);
+  CKL(cudaGetLastError());
+  float h[2];
+  CK(cudaMemcpyAsync(h, s->sample_out, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  *prob = h[1];
   return 0;
 }
 
 extern "C" int dsk_launches_per_forward(const dsk_model* m, int mode) {
   if (!m) return 0;
+  (void)mode;
   const dsk_config& c = m->c;
-  if (g_engine == ENG_MEGA) {
-    int cuts = 0;
-    if (m->n_ranks > 1 && !m->p2p) for (int l = 0; l < c.n_layers; l++) cuts += m->layers[l].is_moe ? 1 : 0;   // peer-memory mode: one kernel
-    return 1 + cuts * 3;
-  }
-  int n = 1;  // embed
-  for (int l = 0; l < c.n_layers; l++) {
-    n += 4 + (c.q_lora_rank > 0 ? 1 : 0);
-    if (m->layers[l].is_moe) n += 4 + (m->n_ranks > 1 ? 2 : 0); else n += 2;
-  }
-  if (mode) n += 1;
-  return n;
+  int cuts = 0;
+  if (m->n_ranks > 1 && !m->p2p) for (int l = 0; l < c.n_layers; l++) cuts += m->layers[l].is_moe ? 1 : 0;   // peer-memory mode: one kernel
+  return 1 + cuts * 3;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1545,8 +1551,11 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
   return 0;
 }
 
+
 // ---------------------------------------------------------------------------------------------------
-// kernel-level test hooks
+// kernel-level test hooks.  Every hook builds a one-stage Program and runs it through decode_kernel<Q> — the persistent
+// interpreter that produces every benchmark number — so the bit-exact / index-exact parity tests exercise the hot path
+// itself (stage_q8 / q8_block_nf, kq_tile_rows, mma_rows_f8, route_all, c_attention, c_embed, gate_f32_stage).
 // ---------------------------------------------------------------------------------------------------
 struct Tmp {
   std::vector<void*> p;
@@ -1556,99 +1565,225 @@ struct Tmp {
     if (cudaMalloc((void**)&d, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess) return nullptr;
     p.push_back(d);
     if (host && n) cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    else cudaMemset(d, 0, std::max<size_t>(n * sizeof(T), 16));
     return d;
   }
 };
 
-extern "C" int dsk_gemv(int quant, int d, int n, const void* w, const float* scale, int bs0, int bs1, const float* x,
-                        float* out) {
-  if (need_device()) return -1;
-  if (quant < 0 || quant > 4) return fail(-4, "bad quant");
-  if ((quant >= DSK_Q2_K && n % 256) || (quant == DSK_F8E5M2 && n % 16) || (quant == DSK_F16 && n % 16) || (quant == DSK_F32 && n % 4))
-    return fail(-4, "n=%d not supported for quant %d (src/infer.cpp:169,246; src/quant.cpp:617)", n, quant);
+struct Mini {
   Tmp t;
+  std::vector<Stage> S;
+  dsk_config c{};            // only the fields the stages under test read
+  int hd = 0;
+  Program hdr{};             // extra header fields set by the hook (buffers, taps); geometry filled by run()
+  Program* d_prog = nullptr;
+  size_t smem = 0;
+  Ctrl h_ctrl{};
+  Mini() {
+    memset(&hdr, 0, sizeof(hdr));
+    c.dim = 256; c.n_heads = 1; c.vocab_size = 1; c.max_seq_len = 1; c.norm_eps = 1e-6f; c.act_silu = 1;
+    c.qk_rope_head_dim = 2; c.v_head_dim = 1; c.kv_lora_rank = 1; c.bs0 = 128; c.bs1 = 128; c.original_max_position = 1 << 30;
+    c.routed_scaling_factor = 1.0f; c.n_group = 1;
+  }
+  int prepare() {
+    const int q = c.quant;
+    g_f8_mma_ok = c.bs1 > 0 && (c.bs1 & (c.bs1 - 1)) == 0;
+    int gate_dim = 0;
+    for (const Stage& st : S) if (st.kind == ST_GEMV && st.quant == DSK_F32 && q != DSK_F32) gate_dim = std::max(gate_dim, st.n);
+    choose_slot_geometry(q, S, gate_dim);
+    int perr = 0;
+    plan_stages(S, q, c.dim, g_sm_count, &perr);
+    if (perr) return perr;
+    Geometry geo;
+    if (program_geometry(S, q, hd, c.max_seq_len, c.bs1, &geo)) return -4;
+    smem = geo.smem;
+    std::vector<unsigned char> buf(sizeof(Program) + (S.size() - 1) * sizeof(Stage));
+    Program* P = reinterpret_cast<Program*>(buf.data());
+    *P = hdr;
+    fill_program_header(P, c, hd, geo);
+    P->expert_first = 0; P->expert_count = c.n_routed_experts;
+    P->embed_quant = q; P->n_stages = (int)S.size();
+    P->ctrl = t.up<Ctrl>(&h_ctrl, 1);
+    unsigned* sync = t.up<unsigned>(nullptr, 16);
+    P->sync_counter = sync; P->sync_base = sync + 1;
+    if (!P->ctrl || !sync) return fail(-2, "allocation failed");
+    memcpy(P->stage, S.data(), S.size() * sizeof(Stage));
+    d_prog = (Program*)t.up<unsigned char>(buf.data(), buf.size());
+    if (!d_prog) return fail(-2, "allocation failed");
+    return 0;
+  }
+  int launch(int b, int e) {
+    CKL(launch_decode_raw(c.quant, d_prog, smem, b, e, 0, 1, 0));
+    return 0;
+  }
+  int run() {
+    if (prepare()) return -4;
+    if (launch(0, (int)S.size())) return -2;
+    CK(cudaDeviceSynchronize());
+    return 0;
+  }
+};
+
+static Stage gemv_stage(int quant, const float* in, const float* norm_w, int n, int epi) {
+  Stage st{};
+  st.kind = ST_GEMV; st.quant = quant; st.epi = epi; st.in = in; st.norm_w = norm_w; st.n = n; st.layer = 0;
+  return st;
+}
+// device copy of a (d x n) weight payload in the layout the kernels stream (Q3_K re-pitched to 112-byte blocks, F8 rows padded)
+static uint8_t* upload_test_weight(Tmp& t, int quant, int d, int n, const void* w) {
   const size_t drb = disk_row_bytes(quant, n), vrb = dev_row_bytes(quant, n);
   uint8_t* dw = t.up<uint8_t>(nullptr, vrb * d + 16);
+  if (!dw) return nullptr;
+  if (!w) return dw;
   if (quant == DSK_Q3_K) {
     uint8_t* st = t.up<uint8_t>((const uint8_t*)w, drb * d);
     const size_t nblocks = drb * d / kQ3Disk;
     q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256>>>(st, dw, nblocks);
+  } else if (vrb == drb) {
+    cudaMemcpy(dw, w, drb * d, cudaMemcpyHostToDevice);
   } else {
-    CK(copy_rows(dw, vrb, w, drb, (size_t)d, 0));
+    cudaMemcpy2D(dw, vrb, w, drb, drb, d, cudaMemcpyHostToDevice);
   }
-  float* ds = scale ? t.up<float>(scale, (size_t)cdiv(d, bs0) * cdiv(n, bs1)) : nullptr;
-  float* dx = t.up<float>(x, n);
-  float* dout = t.up<float>(nullptr, d);
-  GemvArgs a{};
-  a.in = dx; a.n = n; a.bs0 = bs0 > 0 ? bs0 : 1; a.bs1 = bs1 > 0 ? bs1 : 1; a.epi = EPI_STORE; a.njobs = 1;
-  GemvJob j{};
-  j.w = dw; j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
-  a.job[0] = j;
-  CKL(launch_gemv(quant, a, 0));
-  CK(cudaDeviceSynchronize());
+  return dw;
+}
+static int check_gemv_shape(int quant, int n) {
+  if (quant < 0 || quant > 4) return fail(-4, "bad quant");
+  if ((quant >= DSK_Q2_K && n % 256) || (quant == DSK_F8E5M2 && n % 16) || (quant == DSK_F16 && n % 16) || (quant == DSK_F32 && n % 4) || n <= 0)
+    return fail(-4, "n=%d not supported for quant %d (src/infer.cpp:169,246; src/quant.cpp:617)", n, quant);
+  return 0;
+}
+
+extern "C" int dsk_gemv(int quant, int d, int n, const void* w, const float* scale, int bs0, int bs1, const float* x,
+                        float* out) {
+  if (need_device()) return -1;
+  if (check_gemv_shape(quant, n)) return -4;
+  if (d <= 0 || !w || !x || !out) return fail(-4, "bad arguments");
+  if (quant == DSK_F8E5M2 && scale && (bs0 <= 0 || bs1 <= 0 || bs0 % 32 != 0)) return fail(-4, "f8e5m2 block size (%d, %d) unsupported (block_size_0 %% 32 != 0)", bs0, bs1);
+  Mini mp;
+  mp.c.quant = quant; mp.c.dim = d; mp.c.bs0 = bs0 > 0 ? bs0 : 128; mp.c.bs1 = bs1 > 0 ? bs1 : 128;
+  uint8_t* dw = upload_test_weight(mp.t, quant, d, n, w);
+  float* ds = scale ? mp.t.up<float>(scale, (size_t)cdiv(d, mp.c.bs0) * cdiv(n, mp.c.bs1)) : nullptr;
+  float* dx = mp.t.up<float>(x, n);
+  float* dout = mp.t.up<float>(nullptr, d);
+  if (!dw || !dx || !dout) return fail(-2, "allocation failed");
+  Stage st = gemv_stage(quant, dx, nullptr, n, EPI_STORE);
+  MJob j{}; j.w = dw; j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
+  st.job[0] = j; st.njobs = 1;
+  mp.S.push_back(st);
+  if (mp.run()) return -2;
   CK(cudaMemcpy(out, dout, (size_t)d * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
-extern "C" int dsk_quantize_q8k(const float* x, int k, void* out) {
+extern "C" int dsk_stage_input(int model_quant, const float* x, const float* norm_w, int n, float eps, float* out_f32, void* out_q8) {
   if (need_device()) return -1;
+  if (check_gemv_shape(model_quant, n)) return -4;
+  if (!x) return fail(-4, "bad arguments");
+  const bool kq = kq_quant(model_quant);
+  if (kq && !out_q8) return fail(-4, "K-quant staging produces Q8_K blocks: out_q8 is required");
+  if (!kq && !out_f32) return fail(-4, "out_f32 is required");
+  Mini mp;
+  mp.c.quant = model_quant; mp.c.dim = 256; mp.c.norm_eps = eps;
+  uint8_t* dw = upload_test_weight(mp.t, model_quant, 16, n, nullptr);   // 16 zero rows: the tile loop runs, its result is unused
+  std::vector<float> ones((size_t)cdiv(n, 128), 1.0f);
+  float* ds = model_quant == DSK_F8E5M2 ? mp.t.up<float>(ones.data(), ones.size()) : nullptr;
+  float* dx = mp.t.up<float>(x, n);
+  float* dn = norm_w ? mp.t.up<float>(norm_w, n) : nullptr;
+  float* dout = mp.t.up<float>(nullptr, 16);
+  unsigned char* dq8 = kq ? mp.t.up<unsigned char>(nullptr, (size_t)(n / 256) * 292) : nullptr;
+  float* dxf = kq ? nullptr : mp.t.up<float>(nullptr, n);
+  if (!dw || !dx || !dout) return fail(-2, "allocation failed");
+  mp.hdr.dbg_q8 = dq8; mp.hdr.dbg_x = dxf;
+  Stage st = gemv_stage(model_quant, dx, dn, n, EPI_STORE);
+  MJob j{}; j.w = dw; j.scale = ds; j.out = dout; j.rows = 16; j.expert_slot = -1;
+  st.job[0] = j; st.njobs = 1;
+  mp.S.push_back(st);
+  if (mp.run()) return -2;
+  if (kq) CK(cudaMemcpy(out_q8, dq8, (size_t)(n / 256) * 292, cudaMemcpyDeviceToHost));
+  else CK(cudaMemcpy(out_f32, dxf, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int dsk_quantize_q8k(const float* x, int k, void* out) {
   if (k <= 0 || k % 256) return fail(-4, "k must be a positive multiple of 256 (src/quant.cpp:617)");
-  Tmp t;
-  float* dx = t.up<float>(x, k);
-  unsigned char* dout = t.up<unsigned char>(nullptr, (size_t)k / 256 * 292);
-  q8k_export_kernel<<<1, kThreads, 512 + xvec_bytes<Q_Q2K>(k)>>>(dx, k, dout);
-  CKL(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, dout, (size_t)k / 256 * 292, cudaMemcpyDeviceToHost));
+  return dsk_stage_input(DSK_Q2_K, x, nullptr, k, 0.f, nullptr, out);
+}
+
+extern "C" int dsk_rmsnorm(const float* x, const float* w, int n, float eps, float* out) {
+  if (n <= 0 || n % 4) return fail(-4, "n must be a positive multiple of 4");
+  return dsk_stage_input(DSK_F32, x, w, n, eps, out, nullptr);
+}
+
+extern "C" int dsk_gate_logits(int model_quant, int n_experts, int n, const float* gate_w, const float* x, const float* norm_w,
+                               float eps, float* out_logits, float* out_xnorm) {
+  if (need_device()) return -1;
+  if (model_quant < 0 || model_quant > 4 || n_experts <= 0 || n <= 0 || n % 4 || !gate_w || !x || !out_logits) return fail(-4, "bad arguments");
+  Mini mp;
+  mp.c.quant = model_quant; mp.c.dim = n; mp.c.norm_eps = eps; mp.c.n_routed_experts = n_experts;
+  float* dw = mp.t.up<float>(gate_w, (size_t)n_experts * n);
+  float* dx = mp.t.up<float>(x, n);
+  float* dn = norm_w ? mp.t.up<float>(norm_w, n) : nullptr;
+  float* dout = mp.t.up<float>(nullptr, n_experts);
+  float* dxf = out_xnorm ? mp.t.up<float>(nullptr, n) : nullptr;
+  if (!dw || !dx || !dout) return fail(-2, "allocation failed");
+  mp.hdr.dbg_x = dxf;
+  Stage st = gemv_stage(DSK_F32, dx, dn, n, EPI_STORE);
+  MJob j{}; j.w = (const uint8_t*)dw; j.out = dout; j.rows = n_experts; j.expert_slot = -1;
+  st.job[0] = j; st.njobs = 1;
+  if (model_quant != DSK_F32) {   // the dedicated gate stage of a quantised model: one row per tile (build_program does the same)
+    st.rows_per_tile = 1; st.rpass = 1; st.npieces = 1; st.wp = 0; st.use_mma = 0;
+    st.piece[0] = Piece{0, 0, n / 4, 0};
+    st.job[0].tile_begin = 0; st.ntiles = n_experts; st.has_dyn = 0;
+  }
+  mp.S.push_back(st);
+  if (mp.run()) return -2;
+  CK(cudaMemcpy(out_logits, dout, (size_t)n_experts * 4, cudaMemcpyDeviceToHost));
+  if (out_xnorm) CK(cudaMemcpy(out_xnorm, dxf, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 extern "C" int dsk_dequantize_row(int quant, const void* blocks, int k, float* out) {
   if (need_device()) return -1;
-  if ((quant != DSK_Q2_K && quant != DSK_Q3_K) || k % 256) return fail(-4, "bad arguments");
-  Tmp t;
-  const size_t drb = disk_row_bytes(quant, k), vrb = dev_row_bytes(quant, k);
-  uint8_t* dw = t.up<uint8_t>(nullptr, vrb + 16);
-  if (quant == DSK_Q3_K) {
-    uint8_t* st = t.up<uint8_t>((const uint8_t*)blocks, drb);
-    q3k_repack_kernel<<<(unsigned)((k / 256 + 7) / 8), 256>>>(st, dw, k / 256);
-  } else {
-    CK(cudaMemcpy(dw, blocks, drb, cudaMemcpyHostToDevice));
-  }
-  float* dx = t.up<float>(nullptr, k);
-  Ctrl* ctrl = t.up<Ctrl>(nullptr, 1);
-  CK(cudaMemset(ctrl, 0, sizeof(Ctrl)));
-  EmbedArgs e{};
-  e.table = dw; e.x = dx; e.ctrl = ctrl; e.quant = quant; e.dim = k; e.bs0 = 1; e.bs1 = 1; e.original_max = 1 << 30;
-  embed_kernel<<<1, 256>>>(e);
-  CKL(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
+  if ((quant != DSK_Q2_K && quant != DSK_Q3_K) || k <= 0 || k % 256 || !blocks || !out) return fail(-4, "bad arguments");
+  Mini mp;
+  mp.c.quant = quant; mp.c.dim = k;
+  uint8_t* dw = upload_test_weight(mp.t, quant, 1, k, blocks);
+  float* dx = mp.t.up<float>(nullptr, k);
+  if (!dw || !dx) return fail(-2, "allocation failed");
+  mp.hdr.embed_w = dw; mp.hdr.x = dx;
+  Stage st{}; st.kind = ST_EMBED; st.quant = quant;
+  mp.S.push_back(st);
+  mp.h_ctrl.token = 0;
+  if (mp.run()) return -2;
   CK(cudaMemcpy(out, dx, (size_t)k * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
-extern "C" int dsk_rmsnorm(const float* x, const float* w, int n, float eps, float* out) {
-  if (need_device()) return -1;
-  Tmp t;
-  float *dx = t.up<float>(x, n), *dw = t.up<float>(w, n), *dout = t.up<float>(nullptr, n);
-  rmsnorm_kernel<<<1, 256>>>(dout, dx, dw, n, eps);
-  CKL(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  return 0;
-}
-
+// rope / rope_v3 on one head's rotary slice (the reference always calls them with d == head_dim == qk_rope_head_dim,
+// src/infer.cpp:956-972): run as the RoPE prologue of the attention stage on a head with no `nope` part
 extern "C" int dsk_rope(float* vec, int d, int head_dim, int pos, float theta, int v3) {
   if (need_device()) return -1;
-  if (d % 2 || d > 2048) return fail(-4, "bad d");
-  Tmp t;
-  float* dv = t.up<float>(vec, d);
-  std::vector<float> fr = rope_table(head_dim, theta);
-  float* df = t.up<float>(fr.data(), fr.size());
-  rope_test_kernel<<<1, 1024, (size_t)d * 4>>>(dv, d, head_dim, pos, df, v3);
-  CKL(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(vec, dv, (size_t)d * 4, cudaMemcpyDeviceToHost));
+  if (!vec || d <= 0 || d % 2 || d > 128 || d != head_dim) return fail(-4, "rope hook: d must equal head_dim, be even and <= 128 (got d=%d, head_dim=%d)", d, head_dim);
+  if (pos < 0) return fail(-4, "negative pos");
+  Mini mp;
+  mp.c.quant = DSK_F32; mp.c.n_heads = 1; mp.c.qk_nope_head_dim = 0; mp.c.qk_rope_head_dim = d; mp.c.v_head_dim = 4;
+  mp.c.kv_lora_rank = 4; mp.c.is_v3 = v3 ? 1 : 0; mp.c.max_seq_len = 1;
+  mp.hd = d;
+  std::vector<float> fr = rope_table(d, theta);
+  float* df = mp.t.up<float>(fr.data(), fr.size());
+  float* dq = mp.t.up<float>(vec, d);
+  float* dkva = mp.t.up<float>(nullptr, 4 + d);
+  float* dout = mp.t.up<float>(nullptr, 4);
+  __half* kc = mp.t.up<__half>(nullptr, d);
+  __half* vc = mp.t.up<__half>(nullptr, 4);
+  float* scratch = mp.t.up<float>(nullptr, 1 + kConsumers + 8);
+  if (!df || !dq || !dkva || !dout || !kc || !vc || !scratch) return fail(-2, "allocation failed");
+  mp.hdr.rope_freq = df; mp.hdr.q = dq; mp.hdr.kv_a = dkva; mp.hdr.xb2 = dout; mp.hdr.att_scratch = scratch;
+  Stage st{}; st.kind = ST_ATTN; st.quant = DSK_F32; st.kcache = kc; st.vcache = vc;
+  mp.S.push_back(st);
+  mp.h_ctrl.pos = pos; mp.h_ctrl.kv_pos = 0; mp.h_ctrl.kv_len = 1; mp.h_ctrl.kv_sink = 0;
+  if (mp.run()) return -2;
+  CK(cudaMemcpy(vec, dq, (size_t)d * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1656,46 +1791,65 @@ extern "C" int dsk_moe_gate(float* logits, const float* bias, int n_routed, int 
                             float routed_scaling_factor, int scoring_sigmoid, int topk_method, int n_group, int topk_group,
                             int32_t* active_experts, float* weights) {
   if (need_device()) return -1;
-  if (n_routed > 256 || n_active > 16) return fail(-4, "E <= 256 (src/infer.cpp:527), K <= 16");
-  Tmp t;
-  float* dx = t.up<float>(logits, n_routed);
-  float* db = bias ? t.up<float>(bias, n_routed) : nullptr;
-  int* da = t.up<int>(nullptr, 16);
-  float* dwt = t.up<float>(nullptr, 16);
-  GateArgs g{};
-  g.x = dx; g.bias = db; g.active = da; g.weights = dwt; g.E = n_routed; g.K = n_active; g.norm_topk_prob = norm_topk_prob;
-  g.sigmoid = scoring_sigmoid; g.method = topk_method; g.n_group = std::max(1, n_group); g.topk_group = topk_group;
-  g.scale = routed_scaling_factor;
-  gate_topk_kernel<<<1, 256>>>(g);
-  CKL(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
-  CK(cudaMemcpy(logits, dx, (size_t)n_routed * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(active_experts, da, (size_t)n_active * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(weights, dwt, (size_t)n_active * 4, cudaMemcpyDeviceToHost));
+  if (!logits || !active_experts || !weights || n_routed <= 0 || n_routed > 256 || n_active <= 0 || n_active > 16 || n_active + 1 > kMaxJobs)
+    return fail(-4, "E <= 256 (src/infer.cpp:527), K <= %d", kMaxJobs - 1);
+  Mini mp;
+  dsk_config& c = mp.c;
+  c.quant = DSK_Q2_K; c.dim = 256; c.n_routed_experts = n_routed; c.n_active_routed = n_active; c.norm_topk_prob = norm_topk_prob;
+  c.routed_scaling_factor = routed_scaling_factor; c.scoring_sigmoid = scoring_sigmoid; c.topk_method = topk_method;
+  c.n_group = std::max(1, n_group); c.topk_group = topk_group;
+  if (topk_method == DSK_TOPK_GROUP_LIMITED_GREEDY && (n_routed % c.n_group != 0 || topk_group <= 0)) return fail(-4, "bad group configuration");
+  float* dl = mp.t.up<float>(logits, n_routed);
+  float* db = bias ? mp.t.up<float>(bias, n_routed) : nullptr;
+  float* dscores = mp.t.up<float>(nullptr, 256);
+  int* dact = mp.t.up<int>(nullptr, 16);
+  float* dactw = mp.t.up<float>(nullptr, 16);
+  // the routing runs in the prologue of the S56 stage: give that stage one (all-zero) shared-expert tile to stream
+  uint8_t* dw = upload_test_weight(mp.t, DSK_Q2_K, 16, 256, nullptr);
+  float* dx = mp.t.up<float>(nullptr, 256);
+  float* dh = mp.t.up<float>(nullptr, 16);
+  if (!dl || !dscores || !dact || !dactw || !dw || !dx || !dh) return fail(-2, "allocation failed");
+  mp.hdr.moe_scores = dscores; mp.hdr.act = dact; mp.hdr.act_w = dactw;
+  Stage st = gemv_stage(DSK_Q2_K, dx, nullptr, 256, EPI_GLU);
+  st.need_topk = 1; st.gate_logits = dl; st.gate_bias = db;
+  MJob j{}; j.w = dw; j.w_b = dw; j.out = dh; j.rows = 16; j.expert_slot = -1;
+  st.job[0] = j; st.njobs = 1;
+  mp.S.push_back(st);
+  if (mp.run()) return -2;
+  CK(cudaMemcpy(logits, dscores, (size_t)n_routed * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(active_experts, dact, (size_t)n_active * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(weights, dactw, (size_t)n_active * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 extern "C" int dsk_attn(const float* q, const uint16_t* kcache, const uint16_t* vcache, int n_heads, int head_dim,
                         int v_head_dim, int kv_len, float* out) {
   if (need_device()) return -1;
-  Tmp t;
-  float* dq = t.up<float>(q, (size_t)n_heads * head_dim);
-  uint16_t* dk = t.up<uint16_t>(kcache, (size_t)kv_len * n_heads * head_dim);
-  uint16_t* dv = t.up<uint16_t>(vcache, (size_t)kv_len * n_heads * v_head_dim);
-  float* dout = t.up<float>(nullptr, (size_t)n_heads * v_head_dim);
-  AttnArgs a{};
-  a.q = dq; a.kcache = (__half*)dk; a.vcache = (__half*)dv; a.out = dout; a.ctrl = nullptr;
-  a.n_heads = n_heads; a.hd = head_dim; a.nope = head_dim; a.rope = 0; a.vh = v_head_dim; a.do_prologue = 0;
-  a.kv_len_fixed = kv_len; a.max_seq = kv_len;
-  attn_kernel<<<n_heads, kThreads, attn_smem_bytes(head_dim, v_head_dim, kv_len)>>>(a);
-  CKL(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
+  if (!q || !kcache || !vcache || !out || n_heads <= 0 || head_dim <= 0 || v_head_dim <= 0 || kv_len <= 0) return fail(-4, "bad arguments");
+  Mini mp;
+  dsk_config& c = mp.c;
+  c.quant = DSK_Q2_K; c.n_heads = n_heads; c.qk_nope_head_dim = head_dim; c.qk_rope_head_dim = 0; c.v_head_dim = v_head_dim;
+  c.kv_lora_rank = 4; c.max_seq_len = kv_len;
+  mp.hd = head_dim;
+  float* dq = mp.t.up<float>(q, (size_t)n_heads * head_dim);
+  uint16_t* dk = mp.t.up<uint16_t>(kcache, (size_t)kv_len * n_heads * head_dim);
+  uint16_t* dv = mp.t.up<uint16_t>(vcache, (size_t)kv_len * n_heads * v_head_dim);
+  float* dout = mp.t.up<float>(nullptr, (size_t)n_heads * v_head_dim);
+  float* dkva = mp.t.up<float>(nullptr, 8);
+  float* df = mp.t.up<float>(nullptr, 4);
+  float* scratch = mp.t.up<float>(nullptr, (size_t)n_heads * (kv_len + kConsumers + 8));
+  if (!dq || !dk || !dv || !dout || !dkva || !df || !scratch) return fail(-2, "allocation failed");
+  mp.hdr.q = dq; mp.hdr.kv_a = dkva; mp.hdr.xb2 = dout; mp.hdr.rope_freq = df; mp.hdr.att_scratch = scratch;
+  Stage st{}; st.kind = ST_ATTN; st.quant = DSK_Q2_K; st.kcache = (__half*)dk; st.vcache = (__half*)dv;
+  mp.S.push_back(st);
+  mp.h_ctrl.pos = kv_len - 1; mp.h_ctrl.kv_pos = kv_len - 1; mp.h_ctrl.kv_len = kv_len; mp.h_ctrl.kv_sink = 0;
+  if (mp.run()) return -2;
   CK(cudaMemcpy(out, dout, (size_t)n_heads * v_head_dim * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
-// measurement hook
+// measurement hook: ONE interpreter GEMV stage (the production tile plan, TMA ring, warp-per-tile reduction) timed alone
 // ---------------------------------------------------------------------------------------------------
 __global__ void fill_pattern_kernel(uint32_t* p, size_t n_words, uint32_t seed, uint32_t and_mask, uint32_t or_mask) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1710,11 +1864,12 @@ __global__ void fill_pattern_kernel(uint32_t* p, size_t n_words, uint32_t seed, 
 extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, int iters, float* avg_ms,
                               double* bytes_per_launch) {
   if (need_device()) return -1;
-  if (quant < 0 || quant > 4 || n_mats < 1) return fail(-4, "bad arguments");
-  Tmp t;
+  if (check_gemv_shape(quant, n) || n_mats < 1 || n_mats > 64 || d <= 0) return fail(-4, "bad arguments");
+  Mini mp;
+  mp.c.quant = quant; mp.c.dim = 256; mp.c.bs0 = 128; mp.c.bs1 = 128;
   const size_t vrb = dev_row_bytes(quant, n);
   const size_t mat = (vrb * d + 255) & ~(size_t)255;
-  uint8_t* w = t.up<uint8_t>(nullptr, mat * n_mats + 256);
+  uint8_t* w = mp.t.up<uint8_t>(nullptr, mat * n_mats + 256);
   if (!w) return fail(-2, "allocation of %zu bytes failed", mat * n_mats);
   // finite synthetic payload: f8/f16 exponent bits kept small; K-quant bytes arbitrary (d/dmin patched by mask)
   uint32_t and_mask = 0xFFFFFFFFu, or_mask = 0;
@@ -1725,22 +1880,24 @@ extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, i
   fill_pattern_kernel<<<1024, 256>>>((uint32_t*)w, mat * n_mats / 4, 12345u, and_mask, or_mask);
   const int srows = cdiv(d, 128), scols = cdiv(n, 128);
   std::vector<float> hs((size_t)srows * scols, 1e-3f);
-  float* ds = quant == DSK_F8E5M2 ? t.up<float>(hs.data(), hs.size()) : nullptr;
+  float* ds = quant == DSK_F8E5M2 ? mp.t.up<float>(hs.data(), hs.size()) : nullptr;
   std::vector<float> hx(n, 0.5f);
-  float* dx = t.up<float>(hx.data(), n);
-  float* dout = t.up<float>(nullptr, d);
-  GemvArgs a{};
-  a.in = dx; a.n = n; a.bs0 = 128; a.bs1 = 128; a.epi = EPI_STORE; a.njobs = 1;
-  GemvJob j{};
-  j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
+  float* dx = mp.t.up<float>(hx.data(), n);
+  float* dout = mp.t.up<float>(nullptr, d);
+  if (!dx || !dout) return fail(-2, "allocation failed");
+  for (int i = 0; i < n_mats; i++) {   // one stage per matrix: consecutive launches never re-read L2-resident weights
+    Stage st = gemv_stage(quant, dx, nullptr, n, EPI_STORE);
+    MJob j{}; j.w = w + (size_t)i * mat; j.scale = ds; j.out = dout; j.rows = d; j.expert_slot = -1;
+    st.job[0] = j; st.njobs = 1;
+    mp.S.push_back(st);
+  }
+  if (mp.prepare()) return -4;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   for (int i = 0; i < warmup + iters; i++) {
     if (i == warmup) CK(cudaEventRecord(e0, 0));
-    j.w = w + (size_t)(i % n_mats) * mat;
-    a.job[0] = j;
-    CKL(launch_gemv(quant, a, 0));
+    if (mp.launch(i % n_mats, i % n_mats + 1)) return -2;
   }
   CK(cudaEventRecord(e1, 0));
   CK(cudaEventSynchronize(e1));
@@ -1755,75 +1912,47 @@ extern "C" int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, i
 }
 
 // ---------------------------------------------------------------------------------------------------
-// per-launch profile of one token (un-graphed, CUDA events around every launch; includes launch gaps)
+// stage-level timeline of one token from the interpreter's own globaltimer stamps (CTA 0)
 // ---------------------------------------------------------------------------------------------------
 extern "C" int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos, char* out, size_t cap) {
   if (need_device()) return -1;
   if (!m || !s || !out) return fail(-1, "bad arguments");
-  if (g_engine != ENG_V2) {
-    // stage-level timeline of the last token from the interpreter's own globaltimer stamps (CTA 0)
-    if (dsk_forward(m, s, token, pos, 1, nullptr, nullptr)) return -2;
-    std::vector<unsigned long long> ts((size_t)s->n_stages * 8 + 8);
-    CK(cudaMemcpy(ts.data(), s->tstamp, ts.size() * 8, cudaMemcpyDeviceToHost));
-    struct Agg { int n = 0; double wait = 0, stage = 0, tiles = 0, arrive = 0, cw = 0, ct = 0, cs = 0, ce = 0; };
-    std::map<std::string, Agg> agg;
-    double total = 0;
-    for (int i = 0; i < s->n_stages; i++) {
-      const double t0 = (double)ts[i * 8], t1 = (double)ts[i * 8 + 1], t2 = (double)ts[i * 8 + 2], t3 = (double)ts[i * 8 + 3];
-      const double prev_end = i > 0 ? (double)ts[(i - 1) * 8 + 3] : t0;
-      Agg& a = agg[s->stage_names[i]];
-      a.n++;
-      a.wait += (t0 - prev_end) / 1e3;                      // grid barrier wait
-      a.stage += (t1 > 0 ? (t1 - t0) : 0) / 1e3;           // routing + activation staging
-      a.tiles += (t2 - (t1 > 0 ? t1 : t0)) / 1e3;          // tile loop (or attention / embed body)
-      a.arrive += (t3 - t2) / 1e3;                         // fence + arrive
-      a.cw += (double)ts[i * 8 + 4]; a.ct += (double)ts[i * 8 + 5]; a.cs += (double)ts[i * 8 + 6]; a.ce += (double)ts[i * 8 + 7];
-      if (i + 1 == s->n_stages) total = ((double)ts[i * 8 + 3] - (double)ts[0]) / 1e3;
-    }
-    size_t off = 0;
-    for (auto& kv : agg) {
-      const Agg& a = kv.second;
-      int n = snprintf(out + off, cap - off, "%s x%3d  barrier %6.2f  stage-in %6.2f  tiles %6.2f  arrive %5.2f us | kcyc/stage: wait %6.1f task %6.1f sync %6.1f epi %6.1f | sum %8.1f us\n",
-                       kv.first.c_str(), a.n, a.wait / a.n, a.stage / a.n, a.tiles / a.n, a.arrive / a.n, a.cw / a.n / 1e3, a.ct / a.n / 1e3, a.cs / a.n / 1e3, a.ce / a.n / 1e3, a.wait + a.stage + a.tiles + a.arrive);
-      if (n < 0 || (size_t)n >= cap - off) break;
-      off += n;
-    }
-    {
-      const unsigned long long* rp = ts.data() + (size_t)s->n_stages * 8;
-      int n = snprintf(out + off, cap - off, "routing phases (cycles, last MoE layer, CTA 0): scores %llu  bias/publish/groups %llu  top-k %llu  finish %llu\n", rp[0], rp[1], rp[2], rp[3]);
-      if (n > 0 && (size_t)n < cap - off) off += n;
-    }
-    snprintf(out + off, cap - off, "token total %.1f us over %d stages (CTA 0 timeline)\n", total, s->n_stages);
-    return 0;
+  if (ensure_program(m, s)) return -2;
+  {  // switch the stamps on for this token only (they cost a few globaltimer reads per stage)
+    unsigned long long* on = s->tstamp;
+    CK(cudaMemcpy(reinterpret_cast<unsigned char*>(s->prog) + offsetof(Program, tstamp), &on, sizeof(on), cudaMemcpyHostToDevice));
   }
-  std::vector<ProfRec> recs;
-  fill_ctrl(s->h_ctrl, m->c, token, pos);
-  CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
-  g_prof = &recs;
-  int rc = enqueue_forward(m, s, 1, 0, s->stream);
-  g_prof = nullptr;
-  CK(cudaStreamSynchronize(s->stream));
-  if (rc) return rc;
-  std::map<std::string, std::pair<int, double>> agg;
-  size_t off = 0;
+  const int rc = dsk_forward(m, s, token, pos, 1, nullptr, nullptr);
+  if (!getenv("DSK_TSTAMP")) {
+    unsigned long long* off = nullptr;
+    CK(cudaMemcpy(reinterpret_cast<unsigned char*>(s->prog) + offsetof(Program, tstamp), &off, sizeof(off), cudaMemcpyHostToDevice));
+  }
+  if (rc) return -2;
+  std::vector<unsigned long long> ts((size_t)s->n_stages * 8 + 8);
+  CK(cudaMemcpy(ts.data(), s->tstamp, ts.size() * 8, cudaMemcpyDeviceToHost));
+  struct Agg { int n = 0; double wait = 0, stage = 0, tiles = 0, arrive = 0, cw = 0, ct = 0, cs = 0, ce = 0; };
+  std::map<std::string, Agg> agg;
   double total = 0;
-  for (auto& r : recs) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, r.e0, r.e1);
-    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
-    char key[128];
-    snprintf(key, sizeof(key), "%-22s grid=%5d smem=%6zu", r.name, r.grid, r.smem);
-    agg[key].first++;
-    agg[key].second += ms * 1e3;
-    total += ms * 1e3;
+  for (int i = 0; i < s->n_stages; i++) {
+    const double t0 = (double)ts[i * 8], t1 = (double)ts[i * 8 + 1], t2 = (double)ts[i * 8 + 2], t3 = (double)ts[i * 8 + 3];
+    const double prev_end = i > 0 ? (double)ts[(i - 1) * 8 + 3] : t0;
+    Agg& a = agg[s->stage_names[i]];
+    a.n++;
+    a.wait += (t0 - prev_end) / 1e3;                      // grid barrier wait
+    a.stage += (t1 > 0 ? (t1 - t0) : 0) / 1e3;           // routing + activation staging
+    a.tiles += (t2 - (t1 > 0 ? t1 : t0)) / 1e3;          // tile loop (or attention / embed body)
+    a.arrive += (t3 - t2) / 1e3;                         // fence + arrive
+    a.cw += (double)ts[i * 8 + 4]; a.ct += (double)ts[i * 8 + 5]; a.cs += (double)ts[i * 8 + 6]; a.ce += (double)ts[i * 8 + 7];
+    if (i + 1 == s->n_stages) total = ((double)ts[i * 8 + 3] - (double)ts[0]) / 1e3;
   }
+  size_t off = 0;
   for (auto& kv : agg) {
-    int n = snprintf(out + off, cap - off, "%s n=%3d avg=%8.2f us sum=%9.1f us\n", kv.first.c_str(), kv.second.first,
-                     kv.second.second / kv.second.first, kv.second.second);
+    const Agg& a = kv.second;
+    int n = snprintf(out + off, cap - off, "%s x%3d  barrier %6.2f  stage-in %6.2f  tiles %6.2f  arrive %5.2f us | kcyc/stage: wait %6.1f task %6.1f sync %6.1f epi %6.1f | sum %8.1f us\n",
+                     kv.first.c_str(), a.n, a.wait / a.n, a.stage / a.n, a.tiles / a.n, a.arrive / a.n, a.cw / a.n / 1e3, a.ct / a.n / 1e3, a.cs / a.n / 1e3, a.ce / a.n / 1e3, a.wait + a.stage + a.tiles + a.arrive);
     if (n < 0 || (size_t)n >= cap - off) break;
     off += n;
   }
-  snprintf(out + off, cap - off, "total %.1f us over %zu launches\n", total, recs.size());
-  s->last_pos = pos;
+  snprintf(out + off, cap - off, "token total %.1f us over %d stages (CTA 0 timeline)\n", total, s->n_stages);
   return 0;
 }

@@ -96,7 +96,10 @@ struct Program {
   float* xchg_peer[kMaxRanks];             // [2][n_ranks][dim] buffer of rank q (q == rank: the local one)
   unsigned* xflag_peer[kMaxRanks];         // n_ranks flags of rank q: flag[r] = sequence number of rank r's last finished store
   long long* route_prof;                   // profiling: 4 phase durations of the last routing (cycles)
-  unsigned long long* tstamp;              // [n_stages][4] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived
+  unsigned long long* tstamp;              // [n_stages][8] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived, ...
+  // test taps (null in production): CTA 0 dumps the activation vector exactly as the tile loop will read it
+  unsigned char* dbg_q8;                   // K-quant stages: block_q8_K records (292 B each, src/quant.h:104-109)
+  float* dbg_x;                            // fp32 staging: the staged vector; F8 tensor-core staging: (hi + lo) * 2^-e
   Stage stage[1];                          // n_stages entries follow
 };
 constexpr int kProgHdrBytes = (int)offsetof(Program, stage);
@@ -120,23 +123,36 @@ __device__ __forceinline__ float cmax(float v, float* red) {
   float t = fmaxf(fmaxf(fmaxf(red[8], red[9]), fmaxf(red[10], red[11])), fmaxf(fmaxf(red[12], red[13]), fmaxf(red[14], red[15])));
   return t;
 }
-// bounded spin: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// bounded waits are TIME based (globaltimer, checked every 4096 polls): a protocol bug must trap, not hang the GPU
+constexpr unsigned long long kSpinLimitNs = 20ull * 1000ull * 1000ull * 1000ull;
+__device__ __noinline__ void spin_check(unsigned long long& t0) {
+  const unsigned long long now = gtime();
+  if (t0 == 0ull) t0 = now;
+  else if (now - t0 > kSpinLimitNs) __trap();
+}
 __device__ __forceinline__ void mbar_wait_guard(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  for (unsigned long long spins = 0; !ok; spins++) {
+  unsigned long long t0 = 0ull;
+  for (unsigned spins = 0; !ok; spins++) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (spins > (1ull << 24)) __trap();
+    if ((spins & 4095u) == 4095u) spin_check(t0);
   }
 }
 // producer side (waiting for a ring slot to be released): same, with a back-off between polls
 __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
-  for (unsigned long long spins = 0; !ok; spins++) {
+  unsigned long long t0 = 0ull;
+  for (unsigned spins = 0; !ok; spins++) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (!ok) __nanosleep(40);
-    if (spins > (1ull << 24)) __trap();
+    if ((spins & 4095u) == 4095u) spin_check(t0);
   }
 }
 // producer <- consumers: "inputs (and routing) of stage k are ready" as a MONOTONIC stage count in shared memory
@@ -146,17 +162,13 @@ __device__ __forceinline__ void dep_signal(uint32_t addr, int stage_count) {
 }
 __device__ __forceinline__ void dep_wait(uint32_t addr, int stage_count) {
   int v = 0;
-  for (unsigned long long spins = 0;; spins++) {
+  unsigned long long t0 = 0ull;
+  for (unsigned spins = 0;; spins++) {
     asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     if (v >= stage_count) break;
     __nanosleep(40);   // the producer shares a sub-partition with two consumer warps: do not spin in their issue slots
-    if (spins > (1ull << 24)) __trap();
+    if ((spins & 4095u) == 4095u) spin_check(t0);
   }
-}
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
 }
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
   unsigned int v;
@@ -566,106 +578,96 @@ __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_
   return m;
 }
 
-// routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599) by ONE warp with the
-// E <= 256 scores in registers (lane holds experts lane, lane+32, ...).  Every CTA computes it redundantly from the gate
-// logits; `publish` (CTA 0) also writes the state buffers.  Ties: lowest index (the reference's strict `>` scans).
-// warp-wide arg-max over (value, index) pairs with REDUX (one instruction per reduction instead of a 5-level shuffle tree):
-// largest value wins, ties go to the lowest index (the reference's strict `>` scans); idx < 0 = this lane has no candidate
-__device__ __forceinline__ void argmax_redux(float& v, int& i) {
-  const unsigned key = i >= 0 ? orderable(v) : 0u;
-  const unsigned best = __reduce_max_sync(0xffffffffu, key);
-  const int cand = (i >= 0 && key == best) ? i : 0x7fffffff;
-  const int bi = __reduce_min_sync(0xffffffffu, cand);
-  const unsigned src = __ballot_sync(0xffffffffu, cand == bi && bi != 0x7fffffff);
-  if (bi == 0x7fffffff) { i = -1; return; }
-  v = __shfl_sync(0xffffffffu, v, __ffs(src) - 1);
-  i = bi;
-}
-__device__ __noinline__ void warp_route(const Program* Pp, const Stage* stp, int* act_smem, float* actw_smem, bool publish) {
-  // Compact on purpose (rolled loops over the scores kept in shared memory): this runs once per MoE layer on ONE warp
-  // with a cold instruction cache, so its cost is its code size and its dependent collectives, not its arithmetic.
+// routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599), computed redundantly by
+// every CTA from the gate logits with ONE THREAD PER EXPERT (E <= 256 = the consumer threads) and no dependent argmax rounds:
+//   * the reference's K x "arg-max with strict >, lowest index wins ties" selection picks, in order, the experts of RANK
+//     0..K-1 where rank(j) = #{j' selectable : x[j'] > x[j] or (x[j'] == x[j] and j' < j)} — every thread counts its own rank;
+//   * GROUP_LIMITED_GREEDY first keeps, inside each group, the topk_group best experts with x > 0 (the reference compares
+//     the first candidate against x[-1], which is 0.0f in its heap layout: SURVEY §8 A7) — the same rank inside the group;
+//   * wsum is accumulated in selection order like the reference (only when norm_topk_prob).
+// `publish` (CTA 0) also writes the state buffers.  A slot with no selectable expert left (the reference then indexes
+// x[-1] / mask[-1]: UB) gets expert -1 and weight 0.
+__device__ __noinline__ void route_all(const Program* Pp, const Stage* stp, bool publish) {
   const Program& P = *Pp; const Stage& st = *stp;
   extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
-  float* sx = reinterpret_cast<float*>(dsk_dyn_smem + 768);   // 256 scores (MegaSmem::sx)
-  const int lane = threadIdx.x & 31;
-  const int E = P.E, ni = (E + 31) >> 5;                      // every lane runs the same ni iterations (uniform control flow)
-  const long long rk0 = clock64();
-  float mx = -3.402823466e38f;
-#pragma unroll 1
-  for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) { const float v = __ldcg(st.gate_logits + j); sx[j] = v; mx = fmaxf(mx, v); } }
+  float* red = reinterpret_cast<float*>(dsk_dyn_smem + 256);
+  int* act_smem = reinterpret_cast<int*>(dsk_dyn_smem + 384);
+  float* actw_smem = reinterpret_cast<float*>(dsk_dyn_smem + 448);
+  unsigned* cmask = reinterpret_cast<unsigned*>(dsk_dyn_smem + 640);   // 8 words: selectable experts (576..624 hold kHdrZero / kHdrOne)
+  float* selv = reinterpret_cast<float*>(dsk_dyn_smem + 672);          // 16 floats: score of selection k
+  float* sx = reinterpret_cast<float*>(dsk_dyn_smem + 768);            // 256 scores (MegaSmem::sx)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, E = P.E;
+  const bool mine = tid < E;
+  const float v = mine ? __ldcg(st.gate_logits + tid) : -3.402823466e38f;
+  float s;
   if (P.sigmoid) {
-#pragma unroll 1
-    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) sx[j] = 1.0f / (1.0f + expf(-sx[j])); }
+    s = 1.0f / (1.0f + expf(-v));
   } else {
-    mx = warp_max(mx);
-    float sum = 0.f;
-#pragma unroll 1
-    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) { const float e = expf(sx[j] - mx); sx[j] = e; sum += e; } }
-    sum = warp_sum(sum);
-#pragma unroll 1
-    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) sx[j] = sx[j] / sum; }
+    const float mx = cmax(v, red);
+    const float e = mine ? expf(v - mx) : 0.f;
+    const float sum = csum(e, red);
+    s = e / sum;
   }
-  const long long rk1 = clock64();
-  if (st.gate_bias) {
-#pragma unroll 1
-    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) sx[j] += st.gate_bias[j]; }
-  }
-  unsigned mask = 0;   // bit i set = expert lane+32*i not selectable (this lane's experts only)
-  if (P.topk_method == 1) {   // keep only the topk_group best (positive) experts of every group
+  if (st.gate_bias && mine) s += st.gate_bias[tid];
+  if (mine) sx[tid] = s;
+  if (tid < 16) { act_smem[tid] = -1; selv[tid] = 0.f; }
+  csync();
+  bool cand = mine;
+  if (P.topk_method == 1) {   // keep only the topk_group best positive experts of every group
     const int gs = E / P.n_group;
-    unsigned cand = 0;
+    int rank = 0x7fffffff;
+    if (mine && s > 0.0f) {
+      const int g0 = (tid / gs) * gs;
+      rank = 0;
 #pragma unroll 1
-    for (int g = 0; g < P.n_group; g++) {
+      for (int j = g0; j < g0 + gs; j++) { const float o = sx[j]; rank += (o > s || (o == s && j < tid)) ? 1 : 0; }
+    }
+    cand = rank < P.topk_group;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, cand);
+  if (lane == 0) cmask[warp] = bal;
+  csync();
+  if (cand) {
+    int rank = 0;
 #pragma unroll 1
-      for (int k = 0; k < P.topk_group; k++) {
-        float bv = 0.f; int bi = -1;
+    for (int w = 0; w < 8; w++) {
+      unsigned m = cmask[w];
 #pragma unroll 1
-        for (int i = 0; i < ni; i++) {
-          const int j = lane + 32 * i;
-          if (j < E) {
-            const float v = sx[j];
-            if (j >= g * gs && j < (g + 1) * gs && !((cand >> i) & 1u) && v > 0.0f && (bi < 0 || v > bv)) { bv = v; bi = j; }
-          }
-        }
-        argmax_redux(bv, bi);
-        if (bi >= 0 && (bi & 31) == lane) cand |= 1u << (bi >> 5);
+      while (m) {
+        const int j = w * 32 + __ffs(m) - 1;
+        m &= m - 1;
+        const float o = sx[j];
+        rank += (o > s || (o == s && j < tid)) ? 1 : 0;
       }
     }
-    mask = ~cand;
+    if (rank < P.K) { act_smem[rank] = tid; selv[rank] = s; }
   }
-  const long long rk2 = clock64();
-  float wsum = 0.f;
-  float myw = 0.f; int mye = -1;   // lane k keeps selection k
+  csync();
+  if (tid < P.K) {
+    float wsum = 1.0f;
+    if (P.norm_topk_prob) {
+      wsum = 0.f;
 #pragma unroll 1
-  for (int k = 0; k < P.K; k++) {
-    float bv = 0.f; int bi = -1;
-#pragma unroll 1
-    for (int i = 0; i < ni; i++) {
-      const int j = lane + 32 * i;
-      if (j < E) {
-        const float v = sx[j];
-        if (!((mask >> i) & 1u) && (bi < 0 || v > bv)) { bv = v; bi = j; }
-      }
+      for (int k = 0; k < P.K; k++) if (act_smem[k] >= 0) wsum += selv[k];
     }
-    argmax_redux(bv, bi);
-    if (bi >= 0 && (bi & 31) == lane) mask |= 1u << (bi >> 5);
-    if (bi >= 0) wsum += bv;
-    if (lane == k) { mye = bi; myw = bi >= 0 ? bv : 0.f; }
+    const int e = act_smem[tid];
+    const float w = e >= 0 ? selv[tid] / wsum * P.routed_scale : 0.f;
+    actw_smem[tid] = w;
+    if (publish) { P.act[tid] = e; P.act_w[tid] = w; }
   }
-  const long long rk3 = clock64();
-  if (!P.norm_topk_prob) wsum = 1.0f;
-  if (lane < P.K) {
-    const float w = mye >= 0 ? myw / wsum * P.routed_scale : 0.f;
-    act_smem[lane] = mye; actw_smem[lane] = w;
-    if (publish) { P.act[lane] = mye; P.act_w[lane] = w; }
+  if (publish && mine) P.moe_scores[tid] = s;   // state buffer for the host (moe_weights after softmax|sigmoid + bias)
+  if (tid == 0) reinterpret_cast<int*>(dsk_dyn_smem + 512)[14] = st.layer + 1;   // MegaSmem::sel[14]: "routing of layer l is here"
+  csync();
+}
+
+__device__ __forceinline__ void stage_route_hook(const Program& P, const Stage& st, int route, int stage_index) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  if (route >= 0) {   // uniform over the consumer threads: every one of them takes part (thread per expert)
+    const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
+    route_all(&P, &st, blockIdx.x == 0);
+    if (threadIdx.x == 0) dep_signal(smem_u32(dsk_dyn_smem) + 192u, route);
+    if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
   }
-  if (lane == 0) reinterpret_cast<int*>(dsk_dyn_smem + 512)[14] = st.layer + 1;   // MegaSmem::sel[14]: "routing of layer l is here"
-  if (publish) {   // state buffers for the host (CTA 0 only), after the selection so that it is not on anybody's critical path
-#pragma unroll 1
-    for (int i = 0; i < ni; i++) { const int j = lane + 32 * i; if (j < E) P.moe_scores[j] = sx[j]; }
-  }
-  __syncwarp();
-  if (P.tstamp && blockIdx.x == 0 && lane == 0 && P.route_prof) { P.route_prof[0] = rk1 - rk0; P.route_prof[1] = rk2 - rk1; P.route_prof[2] = rk3 - rk2; P.route_prof[3] = clock64() - rk3; }
 }
 
 // ---- producer: one tile -> ring slot --------------------------------------------------------------------------
@@ -1165,8 +1167,7 @@ __device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const 
     }
   }
   csync();
-  const int i = (int)blockIdx.x * kConsumers + tid;
-  if (i < P.dim) {
+  for (int i = (int)blockIdx.x * kConsumers + tid; i < P.dim; i += (int)gridDim.x * kConsumers) {
     const float* b = P.xchg_peer[P.rank] + (size_t)(seq & 1u) * (size_t)P.n_ranks * (size_t)P.dim + (size_t)i;
     float acc = P.x[i];
     for (int r = 0; r < P.n_ranks; r++) acc += __ldcg(b + (size_t)r * (size_t)P.dim);
@@ -1180,6 +1181,9 @@ __device__ __forceinline__ void c_embed(const Program& P, int from_argmax, int* 
     Ctrl* c = P.ctrl;
     int token = c->token;
     if (from_argmax) {
+      // key == 0 means "no LM-head stage ran since the key was cleared" (the host rejects that call sequence; never index
+      // the embedding table with it)
+      if (c->argmax_key == 0ull) __trap();
       token = (int)(0xFFFFFFFFu - (unsigned)(c->argmax_key & 0xFFFFFFFFull));
       const int pos = c->pos + 1;
       const int sink = pos >= P.original_max ? 2 : 0;
@@ -1241,12 +1245,7 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
   if (n > 8192) {   // long vectors: two passes through L1/L2
     float sc = 1.0f;
     if (st.norm_w) sc = c_rms_scale(st.in, n, P.eps, sm.red);
-    if (st.need_topk && threadIdx.x < 32) {   // routing by warp 0 while the other warps convert: it releases the producer itself
-      const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
-      warp_route(&P, &st, sm.act, sm.actw, blockIdx.x == 0);
-      if (threadIdx.x == 0) dep_signal(sm.dep, dep_count);
-      if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
-    }
+    if (st.need_topk) stage_route_hook(P, st, dep_count, stage_index);   // thread-per-expert routing; releases the producer
     c_stage_vec<Q>(st.in, n, st.norm_w, sc, xs0, q80);
     return;
   }
@@ -1267,12 +1266,7 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
     }
     float sc = 1.0f;
     if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
-    if (st.need_topk && threadIdx.x < 32) {   // routing by warp 0 while the other warps convert: it releases the producer itself
-      const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
-      warp_route(&P, &st, sm.act, sm.actw, blockIdx.x == 0);
-      if (threadIdx.x == 0) dep_signal(sm.dep, dep_count);
-      if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
-    }
+    if (st.need_topk) stage_route_hook(P, st, dep_count, stage_index);   // thread-per-expert routing; releases the producer
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       const int b = warp + 8 * k;
@@ -1301,12 +1295,7 @@ __device__ __forceinline__ void c_stage_gemv_input(const Program& P, const Stage
     }
     float sc = 1.0f;
     if (st.norm_w) { ss = csum(ss, sm.red); sc = 1.0f / sqrtf(ss / (float)n + P.eps); }
-    if (st.need_topk && threadIdx.x < 32) {   // routing by warp 0 while the other warps convert: it releases the producer itself
-      const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
-      warp_route(&P, &st, sm.act, sm.actw, blockIdx.x == 0);
-      if (threadIdx.x == 0) dep_signal(sm.dep, dep_count);
-      if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
-    }
+    if (st.need_topk) stage_route_hook(P, st, dep_count, stage_index);   // thread-per-expert routing; releases the producer
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int f = tid + k * kConsumers;
@@ -1502,7 +1491,7 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
 // Rows are reduced one after another (integer dp4a per quarter block, exact int32 block sums via 2 shuffles, fp32 across
 // blocks, one warp_sum per row); lane r keeps the result of tile row r, so the epilogue runs 32 rows wide.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kKqMaxPass = 4;   // up to 128 quarter-blocks (n <= 8192) register-resident
+constexpr int kKqMaxPass = 16;  // warp-per-tile K-quant rows up to 512 quarter-blocks (n <= 32768); passes are a rolled loop
 struct YRegs { int4 y[4]; int bs[4]; float d; };
 
 // this lane's slice of the Q8_K activations for pass p (quarter block lane + 32 p): 64 int8, 4 sub-block sums, scale
@@ -1760,15 +1749,6 @@ __device__ __forceinline__ void kq_gemv_loop(const Program& P, const Stage& st, 
 // on a flat layout (routed hidden vectors concatenated: K*mi values, then the shared/dense vector).
 //   n floats at `in` -> RMSNorm (optional) -> fp16 hi/lo split (stage_x16) or Q8_K blocks (stage_q8); `route` >= 0: warp 0
 //   runs the MoE routing between the norm reduction and its share of the conversion and releases the producer (dep count).
-__device__ __forceinline__ void stage_route_hook(const Program& P, const Stage& st, int route, int stage_index) {
-  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
-  if (route >= 0 && threadIdx.x < 32) {
-    const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
-    warp_route(&P, &st, reinterpret_cast<int*>(dsk_dyn_smem + 384), reinterpret_cast<float*>(dsk_dyn_smem + 448), blockIdx.x == 0);
-    if (threadIdx.x == 0) dep_signal(smem_u32(dsk_dyn_smem) + 192u, route);
-    if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
-  }
-}
 __device__ __noinline__ void stage_x16(const Program* Pp, const Stage* stp, const float* __restrict__ in, int n, const float* __restrict__ norm_w,
                                        uint32_t xhi, uint32_t xlo, uint32_t xgs, int route, int stage_index) {
   extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
@@ -1927,6 +1907,9 @@ __device__ __noinline__ int gate_f32_stage(int it, int n_slots, int dep_count, i
   csync();
   if (tid == 0) dep_signal(sm.dep, dep_count);
   if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
+  if (P.dbg_x != nullptr && blockIdx.x == 0) {   // test tap: the RMS-normalised fp32 vector the gate rows are multiplied with
+    for (int i = tid; i < n; i += kConsumers) P.dbg_x[i] = reinterpret_cast<const float*>(xs)[i];
+  }
   const MJob& jb = st.job[0];
 #pragma unroll 1
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
@@ -1950,6 +1933,35 @@ __device__ __noinline__ int gate_f32_stage(int it, int n_slots, int dep_count, i
   return it;
 }
 
+// ---- test taps (Program::dbg_q8 / dbg_x, null in production) ---------------------------------------------------------
+// CTA 0 copies the staged activation vector of a GEMV stage to global memory exactly as the tile loop reads it:
+// mode 0 = fp32 vector (generic path), 1 = Q8_K blocks as block_q8_K records {float d; int8 qs[256]; int16 bsums[16]}
+// (src/quant.h:104-109), 2 = the fp16 hi/lo split of the tensor-core path, reconstructed as (hi + lo) * 2^-e.
+template <int Q>
+__device__ __noinline__ void dbg_tap(const Program* Pp, int n, int mode, const float* xs0, const int8_t* qs, const float* qd,
+                                     const short* qb, uint32_t xhi, uint32_t xlo, uint32_t xgs) {
+  const Program& P = *Pp;
+  const int tid = threadIdx.x;
+  if (mode == 1 && P.dbg_q8) {
+    for (int b = 0; b < (n >> 8); b++) {
+      unsigned char* o = P.dbg_q8 + (size_t)b * 292;
+      if (tid == 0) { const float d = qd[b]; memcpy(o, &d, 4); }
+      o[4 + tid] = (unsigned char)qs[b * 256 + tid];
+      if (tid < 16) { const short v = qb[b * 16 + tid]; memcpy(o + 260 + 2 * tid, &v, 2); }
+    }
+  } else if (mode == 0 && P.dbg_x) {
+    for (int i = tid; i < n; i += kConsumers) P.dbg_x[i] = xs0[(xswz<Q>(i >> 2) << 2) | (i & 3)];
+  } else if (mode == 2 && P.dbg_x) {
+    for (int i = tid; i < n; i += kConsumers) {
+      unsigned short h, l;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(xhi + (uint32_t)i * 2u));
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(l) : "r"(xlo + (uint32_t)i * 2u));
+      const float g = __uint_as_float(lds32(xgs + (uint32_t)(i >> 6) * 4u));
+      P.dbg_x[i] = (h2f(h) + h2f(l)) * g;
+    }
+  }
+}
+
 template <int Q>
 __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
                                                unsigned long long& best_key, int dep_count, int stage_index) {
@@ -1962,7 +1974,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   }
   // routing first (one warp, registers): it unblocks the producer's routed-expert tiles
   if (st.kind == ST_DOWN && st.K > 0) {
-    // the routing of this layer is normally still in this CTA's shared memory (left by warp_route in the S56 stage of the same
+    // the routing of this layer is normally still in this CTA's shared memory (left by route_all in the S56 stage of the same
     // launch, ordered by that stage's barriers); otherwise (first stage of a launch, CTA without S56 tiles) fetch the published copy
     if (sm.sel[14] != st.layer + 1) {
       if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
@@ -1997,6 +2009,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     for (int k = 0; k <= st.K; k++) xs_seg[k] = 0u;
     if (st.K > 0) stage_q8(&P, &st, P.hbk, st.K * st.mi, nullptr, q8_seg[0].qs, q8_seg[0].d, q8_seg[0].bsums, -1, stage_index);
     if (use_shared && st.sh > 0) stage_q8(&P, &st, P.hbs, st.sh, nullptr, q8_seg[st.K].qs, q8_seg[st.K].d, q8_seg[st.K].bsums, -1, stage_index);
+  } else if (KQ) {
+    __trap();   // K-quant stages are always planned warp-per-tile (the planner rejects rows that do not fit a ring slot)
   } else if (st.kind == ST_GEMV) {
     carve_x<Q>(sm.xregion, st.n, xs0, q80);
     c_stage_gemv_input<Q>(P, st, sm, xs0, q80, dep_count, stage_index);
@@ -2019,6 +2033,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   csync();
   if (!(st.need_topk || (st.kind == ST_DOWN && st.K > 0)) && tid == 0) dep_signal(sm.dep, dep_count);
   if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[stage_index * 8 + 1] = gtime();
+  if ((P.dbg_q8 != nullptr || P.dbg_x != nullptr) && blockIdx.x == 0 && st.kind == ST_GEMV)
+    dbg_tap<Q>(&P, st.n, mma ? 2 : (KQ ? 1 : 0), xs0, q80.qs, q80.d, q80.bsums, x16_0.hi, x16_0.lo, x16_0.gs);
   if (KQ && st.wp) {   // warp-per-tile K-quant stage
     const int warp = tid >> 5, lane = tid & 31;
     if (st.kind == ST_GEMV) {
@@ -2085,6 +2101,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     }
     return;
   }
+  if constexpr (KQ) return;   // (generic cooperative tiles below: F32 / F16 / F8 without the tensor-core plan)
   const uint32_t xs = KQ ? 0u : smem_u32(xs0);
   int parity_res = 0;
   long long c_wait = 0, c_task = 0, c_sync = 0, c_epi = 0;
@@ -2216,6 +2233,7 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
     if (!dep_waited) dep_wait(sm.dep, dep_count);
     return;
   }
+  if constexpr (!QTraits<Q>::kq) {
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     bool dyn = dyn_all;
     if (st.kind == ST_GEMV && st.has_dyn) {
@@ -2228,6 +2246,7 @@ __device__ __forceinline__ void producer_stage(const Program& P, const Stage& st
     if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
     produce_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
   }
+  }
   if (!dep_waited) dep_wait(sm.dep, dep_count);   // bounds the run-ahead to one stage
 }
 
@@ -2236,9 +2255,21 @@ __device__ __forceinline__ void copy_desc(void* dst, const void* src, int bytes,
   for (int i = t; i < bytes / 16; i += nthreads) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
 }
 
+// grid barrier wait: acquire-spin on the monotonic arrival counter, bounded in TIME (a CTA that is not resident — the launch is
+// cooperative, so that cannot happen silently — or a protocol bug traps instead of hanging the GPU)
+__device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned int target) {
+  unsigned long long t0 = 0ull;
+  for (unsigned spins = 0; (int)(ld_acquire(counter) - target) < 0; spins++) {
+    if ((spins & 4095u) == 4095u) spin_check(t0);
+  }
+}
+
+// Stages [s_begin, s_end) for n_tokens consecutive tokens in ONE launch (dsk_decode_greedy: the token loop lives inside the
+// persistent kernel; tokens after the first always take their id from the on-device arg-max of the previous LM-head stage).
+// Launched cooperatively with one CTA per SM: co-residency of the grid barrier's participants is guaranteed by the launch.
 template <int Q>
 __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* __restrict__ prog, int s_begin, int s_end,
-                                                                 int from_argmax) {
+                                                                 int from_argmax, int n_tokens) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x;
   const bool producer = tid >= kConsumers;
@@ -2262,7 +2293,11 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
   const unsigned int G = gridDim.x;
   int it = 0;                      // tiles this CTA has pushed through the ring (same sequence on both sides)
   unsigned long long best_key = 0ull;
-  int nstage_seen = 0;
+  int nstage_seen = 0;             // stages executed by this launch so far (all tokens): barrier targets and dep counts
+#pragma unroll 1
+  for (int tok = 0; tok < n_tokens; tok++) {
+  const int feed = (tok > 0) ? 1 : from_argmax;
+#pragma unroll 1
   for (int s = s_begin; s < s_end; s++, nstage_seen++) {
     if (producer) {
       // the producer keeps its own descriptor copy: it may already be one stage ahead of the consumers
@@ -2286,18 +2321,13 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     if (st.kind == ST_GEMV && st.norm_w && (int)blockIdx.x < st.ntiles) {
       for (int i = tid * 32; i < st.n; i += kConsumers * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(st.norm_w + i));
     }
-    if (s > s_begin) {             // grid barrier: every CTA has finished (and released) stage s-1
-      if (tid == 0) {
-        const unsigned int target = base + (unsigned int)(s - s_begin) * G;
-        for (unsigned long long spins = 0; (int)(ld_acquire(P.sync_counter) - target) < 0; spins++) {
-          if (spins > (1ull << 23)) __trap();
-        }
-      }
+    if (nstage_seen > 0) {         // grid barrier: every CTA has finished (and released) the previous stage
+      if (tid == 0) grid_wait(P.sync_counter, base + (unsigned int)nstage_seen * G);
       csync();
     }
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 8 + 0] = gtime(); P.tstamp[s * 8 + 1] = 0; P.tstamp[s * 8 + 4] = 0; P.tstamp[s * 8 + 5] = 0; P.tstamp[s * 8 + 6] = 0; P.tstamp[s * 8 + 7] = 0; }
     if (st.kind == ST_EMBED) {
-      if (blockIdx.x == 0) c_embed(P, from_argmax, &s_token);
+      if (blockIdx.x == 0) c_embed(P, feed, &s_token);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else if (st.kind == ST_XCHG) {
       c_xchg(P, st, sm);
@@ -2319,15 +2349,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     // stage done: the CTA barrier orders every consumer's writes before thread 0's release-add (cumulative)
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 2] = gtime();
     csync();
-    if (s + 1 < s_end && tid == 0) red_release_add(P.sync_counter, 1u);
+    const bool last = (s + 1 == s_end) && (tok + 1 == n_tokens);
+    if (!last && tid == 0) red_release_add(P.sync_counter, 1u);
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 3] = gtime();
   }
+  }
   // last stage of the launch: publish the new barrier base for the next launch (single writer, after all arrivals)
-  if (!producer && blockIdx.x == 0 && tid == 0 && s_end - s_begin > 1) {
-    const unsigned int target = base + (unsigned int)(s_end - s_begin - 1) * G;
-    for (unsigned long long spins = 0; (int)(ld_acquire(P.sync_counter) - target) < 0; spins++) {
-      if (spins > (1ull << 23)) __trap();
-    }
+  if (!producer && blockIdx.x == 0 && tid == 0 && nstage_seen > 1) {
+    const unsigned int target = base + (unsigned int)(nstage_seen - 1) * G;
+    grid_wait(P.sync_counter, target);
     *P.sync_base = target;
   }
 }

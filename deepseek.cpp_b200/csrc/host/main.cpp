@@ -1,9 +1,8 @@
 // main.cpp — `main <checkpoint_dir> [options]`: the reference's CLI surface (src/main.cpp:18-43, 594-691) over libdsk.so.
 // Host side in C++ calling CUDA through the thin C-ABI (include/dsk.h): .dseek loader, trie tokenizer
-// (src/tokenizer.cpp:3-94), sampler (src/sampler.cpp:28-75), completion + perplexity modes.  The forward pass is
-// dsk_forward(); with -t 0 the generated tokens come from the on-device argmax.
+// (src/tokenizer.cpp:3-94), completion + perplexity modes.  The forward pass is dsk_forward(); sampling (greedy, temperature /
+// top-p, perplexity probabilities) runs on the device through dsk_sample / dsk_sample_prob, so no logits cross PCIe.
 #include <algorithm>
-#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -83,26 +82,8 @@ struct Tokenizer {
   }
 };
 
-// ---- sampler on the host logits (src/sampler.cpp:12-75) -------------------------------------------------------
-struct Sampler {
-  int vocab; std::vector<int> idx;
-  Sampler(int v, uint64_t seed) : vocab(v), idx(v) { for (int i = 0; i < v; i++) idx[i] = i; srand((unsigned)seed); }
-  float prob(const float* logits, int index) const {
-    float mx = -FLT_MAX; for (int i = 0; i < vocab; i++) mx = std::max(mx, logits[i]);
-    float sum = 0; for (int i = 0; i < vocab; i++) sum += expf(logits[i] - mx);
-    return expf(logits[index] - mx) / sum;
-  }
-  int sample(const float* logits, float temperature, float top_p) {
-    if (temperature == 0.0f) { int am = 0; float mv = -FLT_MAX; for (int i = 0; i < vocab; i++) if (logits[i] > mv) { mv = logits[i]; am = i; } return am; }
-    float mx = -FLT_MAX; for (int i = 0; i < vocab; i++) mx = std::max(mx, logits[i]);
-    float sum = 0; for (int i = 0; i < vocab; i++) sum += expf((logits[i] - mx) / temperature);
-    if (top_p < 1.0f) std::sort(idx.begin(), idx.end(), [&](int a, int b) { return logits[a] > logits[b]; });
-    float r = rand() / (float)RAND_MAX * top_p, cum = 0;
-    for (int i = 0; i < vocab; i++) { cum += expf((logits[i] - mx) / temperature) / sum; if (cum >= r) return i; }  // as the reference (indexes unsorted logits)
-    return vocab - 1;
-  }
-};
-
+// Sampling runs on the device (dsk_sample / dsk_sample_prob: Sampler::sample / sample_prob, src/sampler.cpp:12-75); the host
+// only draws the random number, with the reference's generator and seed policy (std::srand / std::rand, src/sampler.cpp:7-10,65).
 static int meta_i(const DseekData& d, const char* k, int def, bool required = false) {
   auto it = d.metadata.find(k);
   if (it == d.metadata.end()) { if (required) { fprintf(stderr, "FATAL: missing metadata %s\n", k); exit(1); } return def; }
@@ -178,7 +159,10 @@ int main(int argc, char* argv[]) {
   size_t up = 0;
   for (auto& kv : data.tensors) {
     const DseekTensor& t = kv.second;
-    int dt = t.dtype == "F32" ? DSK_DT_F32 : t.dtype == "F16" ? DSK_DT_F16 : t.dtype == "F8_E5M2" ? DSK_DT_F8E5M2 : DSK_DT_U8;
+    static const char* names[] = {"F32", "F16", "BF16", "F8_E5M2", "F8_E4M3", "I32", "I16", "I8", "U8"};   // CodecDType order
+    int dt = -1;
+    for (int k = 0; k < 9; k++) if (t.dtype == names[k]) dt = k;
+    if (dt < 0) { fprintf(stderr, "FATAL: tensor %s has unknown dtype %s\n", t.name.c_str(), t.dtype.c_str()); return 1; }
     DSK_OK(dsk_upload_tensor(model, t.name.c_str(), dt, t.shape, t.data, t.size, 0));
     up += t.size;
   }
@@ -189,8 +173,7 @@ int main(int argc, char* argv[]) {
   std::cout << "Model active bytes per token (algorithmic): " << dsk_model_active_bytes_per_token(model) << std::endl;
 
   Tokenizer tokenizer(data);
-  Sampler sampler(cfg.vocab_size, (uint64_t)(now_s() * 1000));
-  std::vector<float> logits(cfg.vocab_size);
+  srand((unsigned)(uint64_t)(now_s() * 1000));
   if (num_steps == 0) num_steps = cfg.max_seq_len;
   DSK_OK(dsk_forward(model, state, 0, 0, DSK_OUTPUT_LOGITS, nullptr, nullptr));   // warm-up (graph capture), like src/main.cpp:299-303
   std::vector<int> enc = tokenizer.encode(prompt, true);
@@ -201,8 +184,10 @@ int main(int argc, char* argv[]) {
   if (mode == "perplexity") {  // src/main.cpp:371-431
     double sum_nll = 0, ss = 0; size_t n = 0;
     for (size_t pos = 0; pos + 1 < enc.size(); pos++) {
-      DSK_OK(dsk_forward(model, state, enc[pos], (int)pos, DSK_OUTPUT_LOGITS, logits.data(), nullptr));
-      double lp = std::log((double)sampler.prob(logits.data(), enc[pos + 1]));
+      DSK_OK(dsk_forward(model, state, enc[pos], (int)pos, DSK_OUTPUT_LOGITS, nullptr, nullptr));
+      float pr = 0.f;
+      DSK_OK(dsk_sample_prob(model, state, enc[pos + 1], &pr));
+      double lp = std::log((double)pr);
       sum_nll += -lp; ss += lp * lp; n++;
     }
     double mean = sum_nll / n, var = ss / n - mean * mean;
@@ -210,19 +195,20 @@ int main(int argc, char* argv[]) {
     return 0;
   }
   double start = now_s();
-  int am = -1;
   for (size_t pos = 0; pos < enc.size(); pos++) {   // hydrate (src/main.cpp:312-319)
     bool last = pos + 1 == enc.size();
-    DSK_OK(dsk_forward(model, state, enc[pos], (int)pos, last ? DSK_OUTPUT_LOGITS : DSK_HYDRATE_KV_CACHE, (last && temperature != 0.0f) ? logits.data() : nullptr, last ? &am : nullptr));
+    DSK_OK(dsk_forward(model, state, enc[pos], (int)pos, last ? DSK_OUTPUT_LOGITS : DSK_HYDRATE_KV_CACHE, nullptr, nullptr));
   }
   double end_hydrate = now_s();
   for (int i = 0; i < num_steps || num_steps == -1; i++) {   // src/main.cpp:324-335
-    int tok = temperature == 0.0f ? am : sampler.sample(logits.data(), temperature, top_p);
+    int tok = -1;
+    const float coin = temperature == 0.0f ? 0.f : rand() / (float)RAND_MAX;
+    DSK_OK(dsk_sample(model, state, temperature, top_p, coin, &tok));
     std::cout << tokenizer.decode_one(enc.back(), tok) << std::flush;
     enc.push_back(tok);
     if (tok == tokenizer.eos_id || tok == tokenizer.eot_id) break;
     if ((int)enc.size() - 1 >= cfg.max_seq_len && cfg.original_max_position > cfg.max_seq_len) break;
-    DSK_OK(dsk_forward(model, state, tok, (int)enc.size() - 1, DSK_OUTPUT_LOGITS, temperature != 0.0f ? logits.data() : nullptr, &am));
+    DSK_OK(dsk_forward(model, state, tok, (int)enc.size() - 1, DSK_OUTPUT_LOGITS, nullptr, nullptr));
   }
   double elapsed = now_s() - start;
   std::cout << "\n\nGeneration stats:\n  " << enc.size() << " tokens\n  throughput: " << enc.size() / elapsed << "tok/s\n  latency: " << elapsed / enc.size()

@@ -134,6 +134,10 @@ def lib():
         L.dsk_device_info.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.dsk_gemv.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, f32p, C.c_int, C.c_int, f32p, f32p]
         L.dsk_quantize_q8k.argtypes = [f32p, C.c_int, C.c_void_p]
+        L.dsk_stage_input.argtypes = [C.c_int, f32p, f32p, C.c_int, C.c_float, f32p, C.c_void_p]
+        L.dsk_gate_logits.argtypes = [C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.c_float, f32p, f32p]
+        L.dsk_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_int)]
+        L.dsk_sample_prob.argtypes = [C.c_void_p, C.c_void_p, C.c_int, f32p]
         L.dsk_dequantize_row.argtypes = [C.c_int, C.c_void_p, C.c_int, f32p]
         L.dsk_rmsnorm.argtypes = [f32p, f32p, C.c_int, C.c_float, f32p]
         L.dsk_rope.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int]
@@ -172,7 +176,7 @@ def device_info():
     return name.value.decode(), sm.value, mem.value
 
 
-_DT = {"F32": 0, "F16": 1, "F8_E5M2": 3, "U8": 8}
+_DT = {"F32": 0, "F16": 1, "BF16": 2, "F8_E5M2": 3, "F8_E4M3": 4, "I32": 5, "I16": 6, "I8": 7, "U8": 8}   # CodecDType (src/codec.h:62-72)
 
 
 class Model:
@@ -201,13 +205,15 @@ class Model:
     def upload(self, name: str, dtype: str, shape, data: np.ndarray):
         arr = np.ascontiguousarray(data)
         shp = (C.c_int64 * 4)(*(list(shape) + [0] * 4)[:4])
-        _ck(self.L.dsk_upload_tensor(self.h, name.encode(), _DT.get(dtype, 8), shp, C.c_void_p(arr.ctypes.data),
+        if dtype not in _DT:
+            raise DskError(f"tensor {name}: unknown dtype {dtype}")
+        _ck(self.L.dsk_upload_tensor(self.h, name.encode(), _DT[dtype], shp, C.c_void_p(arr.ctypes.data),
                                      arr.nbytes, 0))
 
     def upload_device(self, name: str, dtype: str, shape, dev_ptr: int, nbytes: int):
         """`dev_ptr` is a CUDA device pointer (e.g. torch tensor .data_ptr()) — GPU-side minting."""
         shp = (C.c_int64 * 4)(*(list(shape) + [0] * 4)[:4])
-        _ck(self.L.dsk_upload_tensor(self.h, name.encode(), _DT.get(dtype, 8), shp, C.c_void_p(dev_ptr), nbytes, 1))
+        _ck(self.L.dsk_upload_tensor(self.h, name.encode(), _DT[dtype], shp, C.c_void_p(dev_ptr), nbytes, 1))
 
     def finalize(self):
         _ck(self.L.dsk_model_finalize(self.h))
@@ -245,6 +251,18 @@ class Model:
         ms = C.c_float(0)
         _ck(self.L.dsk_decode_greedy(self.h, self.s, start_pos, n_steps, out.ctypes.data_as(i32p), C.byref(ms)))
         return out, ms.value
+
+    def sample(self, temperature: float = 1.0, top_p: float = 0.95, coin: float = 0.0) -> int:
+        """Sampler::sample on the device (src/sampler.cpp:41-75); `coin` = the host's rand()/RAND_MAX."""
+        tok = C.c_int(-1)
+        _ck(self.L.dsk_sample(self.h, self.s, C.c_float(temperature), C.c_float(top_p), C.c_float(coin), C.byref(tok)))
+        return tok.value
+
+    def sample_prob(self, index: int) -> float:
+        """Sampler::sample_prob on the device (src/sampler.cpp:12-26)."""
+        pr = C.c_float(0)
+        _ck(self.L.dsk_sample_prob(self.h, self.s, index, C.byref(pr)))
+        return pr.value
 
     def buffer(self, name: str, n: Optional[int] = None) -> np.ndarray:
         sizes = self.buffer_sizes()
@@ -324,6 +342,33 @@ def quantize_q8k(x: np.ndarray) -> np.ndarray:
     out = np.zeros(x.size // 256 * 292, dtype=np.uint8)
     _ck(lib().dsk_quantize_q8k(_fp(x), x.size, C.c_void_p(out.ctypes.data)))
     return out
+
+
+def stage_input(model_quant: str, x: np.ndarray, norm_w: Optional[np.ndarray] = None, eps: float = 1e-6) -> np.ndarray:
+    """The activation vector as the tile loop of a `model_quant` model reads it (RMSNorm fused when norm_w is given):
+    K-quants -> uint8 block_q8_K records; F32/F16 -> fp32 vector; F8E5M2 -> re-assembled fp16 hi/lo split."""
+    init(_inited or 0)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = _fp(np.ascontiguousarray(norm_w, dtype=np.float32)) if norm_w is not None else None
+    if model_quant in ("q2_k", "q3_k"):
+        out = np.zeros(x.size // 256 * 292, dtype=np.uint8)
+        _ck(lib().dsk_stage_input(QUANT_IDS[model_quant], _fp(x), w, x.size, C.c_float(eps), None, C.c_void_p(out.ctypes.data)))
+    else:
+        out = np.zeros(x.size, dtype=np.float32)
+        _ck(lib().dsk_stage_input(QUANT_IDS[model_quant], _fp(x), w, x.size, C.c_float(eps), _fp(out), None))
+    return out
+
+
+def gate_logits(model_quant: str, gate_w: np.ndarray, x: np.ndarray, norm_w: Optional[np.ndarray] = None, eps: float = 1e-6):
+    """MoE gate logits of a `model_quant` model (F32 gate rows on rmsnorm(x)); returns (logits, normalised x)."""
+    init(_inited or 0)
+    gw = np.ascontiguousarray(gate_w, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    E, n = gw.shape
+    w = _fp(np.ascontiguousarray(norm_w, dtype=np.float32)) if norm_w is not None else None
+    out, xn = np.zeros(E, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    _ck(lib().dsk_gate_logits(QUANT_IDS[model_quant], E, n, _fp(gw), _fp(x), w, C.c_float(eps), _fp(out), _fp(xn)))
+    return out, xn
 
 
 def dequantize_row(quant: str, blocks: np.ndarray, k: int) -> np.ndarray:

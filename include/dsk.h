@@ -20,12 +20,13 @@
 extern "C" {
 #endif
 
-#define DSK_ABI_VERSION 1
+#define DSK_ABI_VERSION 2
 
 /* Quant: src/codec.h:79-85 (same numbering) */
 enum { DSK_F32 = 0, DSK_F16 = 1, DSK_F8E5M2 = 2, DSK_Q2_K = 3, DSK_Q3_K = 4 };
-/* CodecDType subset used by .dseek payloads: src/codec.h:62-72 */
-enum { DSK_DT_F32 = 0, DSK_DT_F16 = 1, DSK_DT_F8E5M2 = 3, DSK_DT_U8 = 8 };
+/* CodecDType: src/codec.h:62-72 (same numbering; .dseek payloads use F32, F16, F8E5M2 and U8) */
+enum { DSK_DT_F32 = 0, DSK_DT_F16 = 1, DSK_DT_BF16 = 2, DSK_DT_F8E5M2 = 3, DSK_DT_F8E4M3 = 4, DSK_DT_I32 = 5, DSK_DT_I16 = 6,
+       DSK_DT_I8 = 7, DSK_DT_U8 = 8 };
 /* InferenceMode: src/model.h:40-43 */
 enum { DSK_HYDRATE_KV_CACHE = 0, DSK_OUTPUT_LOGITS = 1 };
 /* TopKMethod / ScoringFunc: src/model.h:25-34 */
@@ -67,7 +68,12 @@ dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ranks);
 void dsk_model_destroy(dsk_model* m);
 /* Upload one .dseek tensor by its on-disk name (src/model.cpp:766-871), raw payload bytes exactly as
  * stored (K-quants: U8 block rows).  Expert stacks (E, rows, cols): only this rank's slice is kept.
- * `src_on_device` != 0 means `data` is already a device pointer (GPU-side minting). */
+ * dtype / shape are validated against the tensor's role like check_tensor / QTensor::from_codec_tensor
+ * (src/model.cpp:129-136, src/codec.cpp:166-234): dtype must be the quant's codec dtype; K-quant payloads are
+ * checked by byte count, everything else by the exact 4-slot shape (unused slots 0).  Host payloads travel
+ * through a pinned double buffer with asynchronous copies (the call returns once the last chunk is staged;
+ * dsk_model_finalize() joins the pipeline).  `src_on_device` != 0 means `data` is already a device pointer
+ * (GPU-side minting). */
 int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, const int64_t shape[4], const void* data,
                       size_t nbytes, int src_on_device);
 /* Checks every tensor the config requires is present (check_tensor, src/model.cpp:129-136). */
@@ -99,13 +105,26 @@ int dsk_copy_embedding(dsk_model* m, dsk_state* s, int token);
 /* Block::block(state, pos, kv_sink, kv_pos, kv_len) — src/model.cpp:290-322 -> _block_cpu src/infer.cpp:810-932. */
 int dsk_block_forward(dsk_model* m, dsk_state* s, int layer, int pos, int kv_sink, int kv_pos, int kv_len);
 /* Device-resident greedy decode (run_completion's sample->forward loop, src/main.cpp:324-335, -t 0):
- * starting from the logits already in `s`, generates n_steps tokens with on-device argmax feeding the
- * next forward; no host round trip per token.  out_tokens (n_steps ints, nullable).  Returns the device
- * time of the loop in milliseconds through *elapsed_ms (CUDA events), nullable. */
+ * starting from the logits already in `s` (the previous call must have been dsk_forward(..., DSK_OUTPUT_LOGITS)
+ * or dsk_decode_greedy — anything else is rejected), generates n_steps tokens with on-device argmax feeding
+ * the next forward.  The token loop runs INSIDE one persistent kernel launch: no host round trip and no
+ * launch per token.  out_tokens (n_steps ints, nullable).  Returns the device time of the loop in milliseconds
+ * through *elapsed_ms (CUDA events), nullable. */
 int dsk_decode_greedy(dsk_model* m, dsk_state* s, int start_pos, int n_steps, int32_t* out_tokens,
                       float* elapsed_ms);
 /* Number of kernels one forward launches (for bench.py's gpu_launches) */
 int dsk_launches_per_forward(const dsk_model* m, int mode);
+
+/* ---- on-device sampling: Sampler (src/sampler.cpp), reading the logits left in `s` by the last forward ----
+ * dsk_sample = Sampler::sample(state, temperature, top_p) (src/sampler.cpp:41-75): temperature == 0 -> arg-max
+ * (28-39); otherwise softmax at `temperature` and the first vocabulary index whose running probability sum
+ * reaches r = coin * top_p — the reference sorts its index array for top_p < 1 but then walks the UNSORTED
+ * logits (59-73), so the sort does not change the result and top_p only scales r; reproduced as is.
+ * `coin` is the caller's std::rand() / (float)RAND_MAX, so the host keeps the reference's random stream.
+ * Only the token id crosses PCIe (8 bytes instead of the vocab-sized logits).
+ * dsk_sample_prob = Sampler::sample_prob(index, state) (12-26), used by the perplexity mode. */
+int dsk_sample(dsk_model* m, dsk_state* s, float temperature, float top_p, float coin, int* token);
+int dsk_sample_prob(dsk_model* m, dsk_state* s, int index, float* prob);
 
 /* ---- multi-GPU: one exchange of the MoE partial sum per MoE layer ------------------
  * The reference has no distributed path; this is the one real exchange step of the expert-sharded model
@@ -119,18 +138,29 @@ int dsk_launches_per_forward(const dsk_model* m, int mode);
 int dsk_comm_unique_id(void* out128);
 int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128);
 
-/* ---- kernel-level test hooks (mirror the statics reached by the reference's tests) -------------- */
+/* ---- kernel-level test hooks (mirror the statics reached by the reference's tests) ----------------
+ * Every hook builds a one-stage program and runs it through the SAME persistent decode kernel that produces the
+ * benchmark numbers (decode_kernel<quant>), so the bit-exact / index-exact parity tests cover the hot path itself. */
 /* matmul / matmul_unscaled — src/infer.cpp:381-421.  w: raw payload (host), scale nullable. */
 int dsk_gemv(int quant, int d, int n, const void* w, const float* scale, int bs0, int bs1, const float* x,
              float* out);
-/* quantize_row_q8_K_ref — src/quant.cpp:616-653.  out: k/256 block_q8_K (292 B each). */
+/* The activation vector exactly as the tile loop of a `model_quant` model reads it, after the fused RMSNorm
+ * (norm_w nullable): K-quants -> out_q8 = n/256 block_q8_K records (292 B each; quantize_row_q8_K_ref,
+ * src/quant.cpp:616-653, bit-exact); F32/F16 -> out_f32 = the fp32 vector (rmsnorm, src/infer.cpp:601-611);
+ * F8E5M2 -> out_f32 = the exact fp16 hi/lo split of the tensor-core path, re-assembled ((hi + lo) * 2^-e). */
+int dsk_stage_input(int model_quant, const float* x, const float* norm_w, int n, float eps, float* out_f32, void* out_q8);
+/* quantize_row_q8_K_ref — src/quant.cpp:616-653 (= dsk_stage_input of a Q2_K model).  out: k/256 block_q8_K. */
 int dsk_quantize_q8k(const float* x, int k, void* out);
-/* dequantize_row_q{2,3}_K — src/quant.cpp:217-247, 384-432 (through the embedding-row kernel). */
+/* dequantize_row_q{2,3}_K — src/quant.cpp:217-247, 384-432 (through the embedding stage). */
 int dsk_dequantize_row(int quant, const void* blocks, int k, float* out);
-/* rmsnorm — src/infer.cpp:601-611 */
+/* rmsnorm — src/infer.cpp:601-611 (= dsk_stage_input of an F32 model) */
 int dsk_rmsnorm(const float* x, const float* w, int n, float eps, float* out);
-/* rope / rope_v3 — src/infer.cpp:648-685 (fp32) */
+/* rope / rope_v3 — src/infer.cpp:648-685 (fp32), as the RoPE prologue of the attention stage; d == head_dim <= 128 */
 int dsk_rope(float* vec, int d, int head_dim, int pos, float theta, int v3);
+/* MoE gate logits of a `model_quant` model: matmul_unscaled(moegate) on rmsnorm(x) — src/infer.cpp:846-851.  gate_w is
+ * F32 (n_experts x n) in every quant; out_xnorm (nullable) receives the normalised vector the rows are multiplied with. */
+int dsk_gate_logits(int model_quant, int n_experts, int n, const float* gate_w, const float* x, const float* norm_w,
+                    float eps, float* out_logits, float* out_xnorm);
 /* moe_gate — src/infer.cpp:493-599.  logits (E) in/out (post-softmax/sigmoid+bias scores). */
 int dsk_moe_gate(float* logits, const float* bias, int n_routed, int n_active, int norm_topk_prob,
                  float routed_scaling_factor, int scoring_sigmoid, int topk_method, int n_group, int topk_group,
@@ -139,14 +169,15 @@ int dsk_moe_gate(float* logits, const float* bias, int n_routed, int n_active, i
 int dsk_attn(const float* q, const uint16_t* kcache, const uint16_t* vcache, int n_heads, int head_dim,
              int v_head_dim, int kv_len, float* out);
 
-/* ---- measurement hook (bench.py roofline): times `iters` back-to-back launches of the GEMV kernel on a
- * (d x n) matrix of synthetic weights resident in HBM, CUDA events on the launching stream, after `warmup`
- * launches.  n_mats >= 1 distinct matrices are cycled so consecutive launches never re-read L2-resident data.
- * Returns average milliseconds per launch and the algorithmic bytes per launch. */
+/* ---- measurement hook (bench.py roofline): times `iters` back-to-back launches of ONE GEMV stage of the decode
+ * interpreter (production tile plan, TMA ring, warp-per-tile reduction) on a (d x n) matrix of synthetic weights
+ * resident in HBM, CUDA events on the launching stream, after `warmup` launches.  n_mats >= 1 distinct matrices
+ * are cycled so consecutive launches never re-read L2-resident data.  Returns average milliseconds per launch
+ * (launch overhead included) and the algorithmic bytes per launch. */
 int dsk_bench_gemv(int quant, int d, int n, int n_mats, int warmup, int iters, float* avg_ms, double* bytes_per_launch);
 
-/* Per-launch profile of one token: runs the forward un-graphed with CUDA events around every launch and writes a
- * text table (kernel, grid, smem, count, avg/sum microseconds) into `out`. */
+/* Stage-level timeline of one token from the decode kernel's own globaltimer stamps (CTA 0): a text table (stage kind,
+ * count, barrier / staging / tiles / arrive microseconds) written into `out`. */
 int dsk_profile_token(dsk_model* m, dsk_state* s, int token, int pos, char* out, size_t cap);
 
 #ifdef __cplusplus

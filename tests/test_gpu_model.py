@@ -145,6 +145,53 @@ def test_e2e_golden(dsk, golden_dir, tmp_path):
         m.close()
 
 
+def _sample_restated(logits, temperature, top_p, coin):
+    """Sampler::sample (src/sampler.cpp:41-75) restated: fp32 sequential sums, the UNSORTED walk, r = coin * top_p."""
+    if temperature == 0.0:
+        return int(np.argmax(logits))
+    l = logits.astype(np.float32)
+    e = np.exp(((l - l.max()) / np.float32(temperature)).astype(np.float32)).astype(np.float32)
+    s = np.float32(0)
+    for v in e:
+        s = np.float32(s + v)
+    p = (e / s).astype(np.float32)
+    cum = np.cumsum(p, dtype=np.float32)          # sequential fp32 accumulation, like the reference's loop
+    r = np.float32(np.float32(coin) * np.float32(top_p))
+    hit = np.nonzero(cum >= r)[0]
+    return int(hit[0]) if hit.size else l.size - 1, cum
+
+
+def test_device_sampling(dsk, ckpt):
+    """dsk_sample / dsk_sample_prob (Sampler::sample / sample_prob on the device, src/sampler.cpp:12-75) against the
+    restated host algorithm on the model's own logits; the picked index may differ only when r falls within fp32
+    summation error of a bucket edge (then it must be the neighbour)."""
+    d = ckpt("tiny_v2lite", "fp32")
+    m = dsk.Model.from_dir(d)
+    rng = np.random.default_rng(8)
+    logits, am = m.forward(7, 0)
+    logits = logits.copy()
+    assert m.sample(0.0, 0.95, 0.3) == am == int(np.argmax(logits))
+    mx = logits.max()
+    pr = np.exp(logits - mx) / np.exp(logits - mx).sum()
+    for idx in (0, 5, int(np.argmax(logits)), logits.size - 1):
+        assert abs(m.sample_prob(idx) - pr[idx]) <= 2e-6 * max(pr[idx], 1e-3)
+    mism = 0
+    for t in range(60):
+        T, top_p, coin = float(rng.choice([0.5, 1.0, 1.7])), float(rng.choice([0.95, 1.0, 0.5])), float(rng.uniform(0, 1))
+        exp, cum = _sample_restated(logits, T, top_p, coin)
+        got = m.sample(T, top_p, coin)
+        if got != exp:
+            mism += 1
+            r = coin * top_p
+            assert abs(got - exp) <= 2 and min(abs(cum[got] - r), abs(cum[exp] - r)) < 1e-4, (t, got, exp)
+    assert mism <= 3
+    assert m.sample(1.0, 1.0, 0.0) == 0                       # r = 0: the first index already satisfies cumsum >= r
+    m.forward(3, 1, dsk.HYDRATE_KV_CACHE)
+    with pytest.raises(dsk.DskError):
+        m.sample(1.0, 0.95, 0.5)                              # a hydrate-only forward leaves no logits to sample from
+    m.close()
+
+
 def test_errors_are_loud(dsk, ckpt):
     d = ckpt("tiny_v2lite", "fp32")
     m = dsk.Model.from_dir(d)
@@ -154,6 +201,13 @@ def test_errors_are_loud(dsk, ckpt):
         m.forward(1, 10 ** 6)          # past the KV cache (the reference would overrun it)
     with pytest.raises(dsk.DskError):
         m.decode_greedy(5, 4)          # must follow a forward
+    m.forward(1, 0, dsk.OUTPUT_LOGITS)
+    m.forward(2, 1, dsk.HYDRATE_KV_CACHE)
+    with pytest.raises(dsk.DskError):
+        m.decode_greedy(2, 4)          # hydrate-only forward: no LM-head stage ran, there is no arg-max to feed the loop
+    m.forward(3, 2, dsk.OUTPUT_LOGITS)
+    toks, _ = m.decode_greedy(3, 2)    # and after a logits forward it works
+    assert toks.size == 2
     m.close()
     import dseek
     md, T = dseek.read_dir(d)
@@ -162,4 +216,20 @@ def test_errors_are_loud(dsk, ckpt):
         m2.finalize()                  # missing tensors (check_tensor, src/model.cpp:129-136)
     with pytest.raises(dsk.DskError):
         m2.upload("model.norm.weight", "F32", (3,), np.zeros(3, np.float32))   # wrong size
+    # dtype / shape validation of check_tensor / QTensor::from_codec_tensor (src/codec.cpp:166-234)
+    dim = m2.cfg.dim
+    with pytest.raises(dsk.DskError):
+        m2.upload("model.norm.weight", "F16", (dim,), np.zeros(dim, np.float16))            # wrong dtype
+    with pytest.raises(dsk.DskError):
+        m2.upload("model.norm.weight", "F32", (dim // 2, 2), np.zeros(dim, np.float32))      # right bytes, wrong shape
+    with pytest.raises(dsk.DskError):
+        m2.upload("model.layers.0.attn.wo.weight", "F32", (m2.cfg.n_heads * m2.cfg.v_head_dim, dim),
+                  np.zeros((m2.cfg.n_heads * m2.cfg.v_head_dim, dim), np.float32))           # transposed shape
+    m2.upload("model.norm.weight", "F32", (dim,), np.ones(dim, np.float32))
+    with pytest.raises(dsk.DskError):
+        m2.upload("model.norm.weight", "F32", (dim,), np.ones(dim, np.float32))              # uploaded twice
     m2.close()
+    bad = dsk.Config.from_metadata(md)
+    bad.qk_rope_head_dim = 192
+    with pytest.raises(dsk.DskError):
+        dsk.Model(bad)                 # limits of the kernels are checked at model creation, not discovered as garbage

@@ -71,19 +71,26 @@ def _gpus():
 
 @pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs on one node")
 @pytest.mark.parametrize("p2p", ["1", "0"])
-@pytest.mark.parametrize("quant,tol", [("fp32", 2e-4), ("f8e5m2", 5e-4)])
-def test_sharded_decode_matches_reference(repo, ckpt, tmp_path, p2p, quant, tol):
+@pytest.mark.parametrize("preset,quant,tol", [("tiny_v2lite", "fp32", 2e-4), ("tiny_v2lite", "f8e5m2", 5e-4),
+                                              ("tiny_v3", "f8e5m2", 5e-4), ("tiny_v2", "q2_k", 8e-2), ("tiny_v3", "q3_k", 8e-2)])
+def test_sharded_decode_matches_reference(repo, ckpt, tmp_path, p2p, preset, quant, tol):
     import json
-    d = ckpt("tiny_v2lite", quant)
+    d = ckpt(preset, quant)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, DSK_P2P=p2p)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541" if p2p == "1" else "29542",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29541 + (hash((preset, quant, p2p)) % 400)),
                         str(script), repo, d], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
     res = json.loads(line[len("RESULT "):])
     assert max(res["errs"]) < tol, res
-    assert res["dev"] == res["host"], res          # greedy tokens identical to the reference for the dense quants
+    if quant in ("fp32", "f8e5m2"):
+        assert res["dev"] == res["host"], res      # greedy tokens identical to the reference for the dense quants
+    else:
+        # K-quants: the sharded sum order differs from the CPU's expert loop, so a Q8_K rounding may flip downstream
+        # (SURVEY §0.4); the bound is the reference-vs-reference floor and the median must sit far below it
+        import numpy as np
+        assert np.median(res["errs"]) < 2e-2, res
     assert res["launches"] == (1 if p2p == "1" else res["launches"])   # peer-memory mode: one kernel per token

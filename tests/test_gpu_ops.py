@@ -1,5 +1,9 @@
 """GPU parity, tier T1: every kernel fed the oracle's exact inputs, through the C-ABI hooks.
-Checker = the unmodified reference (oracle/_ref) when present, else the plain-C port; plus committed goldens."""
+Checker = the unmodified reference (oracle/_ref) when present, else the plain-C port; plus committed goldens.
+
+Every hook runs a one-stage program through the persistent decode kernel itself (decode_kernel<quant>: stage_q8 /
+q8_block_nf, kq_tile_rows, mma_rows_f8, route_all, c_attention, c_embed, gate_f32_stage) — the code that produces the
+benchmark numbers — so the bit-exact (Q8_K blocks) and index-exact (expert ids) assertions below pin the hot path."""
 import os
 
 import numpy as np
@@ -53,11 +57,65 @@ def test_q8k_bit_exact(dsk, chk, ops):
                 assert np.array_equal(a[i, :260], b[i, :260])
 
 
+def test_q8k_bit_exact_production_lengths(dsk, chk):
+    """The activation lengths the V2-Lite / V2-236B / V3 programs actually stage (GEMV inputs and the concatenated DOWN
+    inputs), through the K-quant staging routine of BOTH K-quant kernels: byte-identical to quantize_row_q8_K_ref."""
+    rng = np.random.default_rng(5)
+    for n in (512, 1536, 2048, 3072, 5120, 7168, 11008, 12288, 16384, 18432):
+        x = (rng.standard_normal(n) * 10 ** rng.uniform(-2, 2)).astype(np.float32)
+        exp = chk.quantize_q8k(x)
+        for mq in ("q2_k", "q3_k"):
+            assert np.array_equal(dsk.stage_input(mq, x), exp), (n, mq)
+
+
+def test_staging_with_fused_rmsnorm(dsk, chk):
+    """RMSNorm fused into the staging.  The sum of squares is reduced in a different order than the reference's loop, so
+    the normalised values may differ by an ulp: K-quant blocks then agree except where that ulp flips a rounding (bounded
+    here: <= 0.5 % of the int8 values by +-1, block scales to 1e-6); the fp32 paths to 1e-6; the F8 tensor-core staging
+    (exact fp16 hi/lo split of the fp32 value) reconstructs the vector to 2^-20 of each 64-column group's maximum."""
+    rng = np.random.default_rng(6)
+    for n in (512, 2048, 5120, 7168):
+        x = (rng.standard_normal(n) * 3).astype(np.float32)
+        w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        xn = chk.rmsnorm(x, w, 1e-6)
+        assert rel_l2(dsk.stage_input("fp32", x, w, 1e-6), xn) < 1e-6
+        assert rel_l2(dsk.stage_input("fp16", x, w, 1e-6), xn) < 1e-6
+        got8 = dsk.stage_input("f8e5m2", x, w, 1e-6)
+        gmax = np.abs(xn).reshape(-1, 64).max(axis=1).repeat(64)
+        assert np.max(np.abs(got8 - xn) / gmax) < 2.0 ** -19, n
+        raw = dsk.stage_input("f8e5m2", x)                       # no norm: the split itself, exact to 2^-22 of the group max
+        assert np.max(np.abs(raw - x) / np.abs(x).reshape(-1, 64).max(axis=1).repeat(64)) < 2.0 ** -21
+        exp = chk.quantize_q8k(xn).reshape(-1, 292)
+        got = dsk.stage_input("q2_k", x, w, 1e-6).reshape(-1, 292)
+        dq = got[:, 4:260].view(np.int8).astype(np.int32) - exp[:, 4:260].view(np.int8).astype(np.int32)
+        assert np.abs(dq).max() <= 1 and (dq != 0).mean() < 5e-3, (n, (dq != 0).mean())
+        assert np.allclose(got[:, :4].copy().view(np.float32), exp[:, :4].copy().view(np.float32), rtol=1e-6)
+
+
+@pytest.mark.parametrize("mq", ["fp32", "f8e5m2", "q2_k", "q3_k"])
+@pytest.mark.parametrize("E,n", [(64, 2048), (160, 5120), (256, 7168)])
+def test_gate_logits_stage(dsk, chk, mq, E, n):
+    """The MoE gate of a quantised model is its own compact stage (F32 rows on rmsnorm(x)): logits vs the reference's
+    F32 matmul on the reference's rmsnorm, at the three real gate shapes."""
+    rng = np.random.default_rng(E + n)
+    gw = (rng.standard_normal((E, n)) * n ** -0.5 * 4).astype(np.float32)
+    x = (rng.standard_normal(n) * 2).astype(np.float32)
+    w = (1 + 0.1 * rng.standard_normal(n)).astype(np.float32)
+    xn = chk.rmsnorm(x, w, 1e-6)
+    exp = chk.matmul(xn, gw, "fp32", E, n)
+    got, got_xn = dsk.gate_logits(mq, gw, x, w, 1e-6)
+    assert rel_l2(got_xn, xn) < 1e-6
+    assert rel_l2(got, exp) < 1e-5          # the reference's scalar F32 loop is re-associated by -ffast-math (DESIGN §2)
+
+
 @pytest.mark.parametrize("quant,d,n,tol", [
     ("fp32", 64, 2048, 2e-6), ("fp16", 40, 256, 2e-6), ("fp16", 300, 2048, 2e-6),
     ("f8e5m2", 200, 384, 2e-6), ("f8e5m2", 3072, 2048, 2e-6), ("f8e5m2", 2048, 1408, 2e-6), ("f8e5m2", 576, 512, 2e-6),
     ("q2_k", 24, 768, 2e-6), ("q2_k", 1000, 2048, 2e-6), ("q2_k", 512, 512, 2e-6), ("q2_k", 130, 11008, 2e-6),
-    ("q3_k", 24, 768, 2e-6), ("q3_k", 1000, 2048, 2e-6), ("q3_k", 512, 256, 2e-6), ("q3_k", 64, 7168, 2e-6)])
+    ("q3_k", 24, 768, 2e-6), ("q3_k", 1000, 2048, 2e-6), ("q3_k", 512, 256, 2e-6), ("q3_k", 64, 7168, 2e-6),
+    # production row lengths of V2-236B / V3 (wq_b, wkv_b, wo, expert and dense down projections)
+    ("q2_k", 300, 1536, 2e-6), ("q2_k", 200, 5120, 2e-6), ("q2_k", 96, 7168, 2e-6), ("q2_k", 64, 16384, 2e-6),
+    ("q2_k", 40, 18432, 2e-6), ("q3_k", 48, 16384, 2e-6), ("f8e5m2", 64, 7168, 2e-6), ("f8e5m2", 48, 16384, 2e-6)])
 def test_gemv_vs_oracle(dsk, chk, quant, d, n, tol):
     """_matmul x5 (src/infer.cpp:121-379): fp32 re-association only (integer dots exact) -> rel-L2 <= 2e-6."""
     import mint
