@@ -169,8 +169,9 @@ def mint_on_gpu(dsk, w, rank, n_ranks, device):
             q = torch.cat(chunks_q).contiguous()
             s = torch.cat(chunks_s).float().contiguous()
             shape = (ne, rows, cols) if ne else (rows, cols)
+            sshape = tuple(s.shape) if ne else tuple(s.shape[1:])
             m.upload_device(name + ".weight", "F8_E5M2", shape, q.data_ptr(), q.numel())
-            m.upload_device(name + ".scale", "F32", s.shape, s.data_ptr(), s.numel() * 4)
+            m.upload_device(name + ".scale", "F32", sshape, s.data_ptr(), s.numel() * 4)
             del q, s, chunks_q, chunks_s
         elif quant in KBYTES:
             bb, nb = KBYTES[quant], cols // 256

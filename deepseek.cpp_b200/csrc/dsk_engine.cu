@@ -879,6 +879,15 @@ static int plan_gemv_stage(Stage& st, int quant, int G) {
   return 0;
 }
 
+// partial-sum buffers a warp-per-tile DOWN stage needs: the ring lets at most 8 consecutive pieces be outstanding, which touch
+// up to (8 - 2) / np + 2 row groups; 512 floats of shared memory hold them ([buffer][piece][16 rows])
+static int down_buffers(int np) {
+  const int need = (8 - 2) / np + 2;
+  int nb = 2;
+  while (nb < need) nb <<= 1;
+  return (nb * np * 16 <= 512) ? nb : 0;
+}
+
 static int plan_down_stage(Stage& st, int quant, int dim) {
   const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
   if (quant == DSK_F8E5M2 && st.mi % 64 == 0 && st.sh % 64 == 0 && g_use_mma && g_f8_mma_ok) {
@@ -898,24 +907,37 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
     }
     st.npieces = np;
     st.ntiles = cdiv(dim, g_wp_rows) * np;
+    st.down_nbuf = down_buffers(np);
+    if (!st.down_nbuf) return fail(-4, "down projection: %d pieces per row group exceed the partial-sum buffers", np);
     return 0;
   }
   if (kq_quant(quant)) {
     if ((std::max(st.mi, st.sh) / 256) * 4 > 32 * kKqMaxPass) return fail(-4, "K-quant down-projection row exceeds the warp-per-tile limit");
-    // warp-per-tile K-quant pieces: (segment, rows of a 16-row output group)
-    st.wp = 1; st.down_rows = 16; st.rows_per_tile = 16; st.seg_stride = 0;
+    // warp-per-tile K-quant pieces: (segment, rows of a DR-row output group).  DR = 16 or 8: whichever leaves the busiest
+    // CTA fewer rows (V2-236B: 320 groups of 16 over 148 CTAs = 3 groups = 48 rows, 640 groups of 8 = 5 groups = 40 rows)
+    const int G = g_sm_count;
+    int DR = 16;
+    if (cdiv(cdiv(dim, 8), G) * 8 < cdiv(cdiv(dim, 16), G) * 16) DR = 8;
+    if (const char* e = getenv("DSK_DOWN_ROWS")) { const int v = atoi(e); if (v == 8 || v == 16) DR = v; }
+    st.wp = 1; st.down_rows = DR; st.rows_per_tile = DR; st.seg_stride = 0;
     int np = 0;
     for (int k = 0; k <= st.K; k++) {
       const int n = k < st.K ? st.mi : st.sh;
       if (n == 0) continue;
       const size_t rb = dev_row_bytes(quant, n);
-      int pr = 16;
+      int pr = DR;
       while (pr > 4 && (size_t)pr * rb > (size_t)g_slot_data) pr >>= 1;
       if ((size_t)pr * rb > (size_t)g_slot_data) { np = -1; break; }
-      for (int r0 = 0; r0 < 16; r0 += pr) { if (np >= 16) { np = -1; break; } st.piece[np++] = Piece{k, r0, pr, 0}; }
+      if (quant == DSK_Q2_K && ((size_t)pr * rb) % 16 != 0) { np = -1; break; }   // TMA source / size alignment of a piece
+      for (int r0 = 0; r0 < DR; r0 += pr) { if (np >= 16) { np = -1; break; } st.piece[np++] = Piece{k, r0, pr, 0}; }
       if (np < 0) break;
     }
-    if (np > 0) { st.npieces = np; st.ntiles = cdiv(dim, 16) * np; return 0; }
+    if (np > 0) {
+      st.npieces = np; st.ntiles = cdiv(dim, DR) * np;
+      st.down_nbuf = down_buffers(np);
+      if (!st.down_nbuf) return fail(-4, "down projection: %d pieces per row group exceed the partial-sum buffers", np);
+      return 0;
+    }
     return fail(-4, "K-quant down-projection rows do not fit a ring slot");
   }
   int RT = 8;
@@ -1016,6 +1038,9 @@ static int program_geometry(const std::vector<Stage>& S, int q, int hd, int max_
   const size_t slot_bytes = (size_t)g_slot_data + g_slot_scale;
   if (kMegaHdr + xreg + 2 * slot_bytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
   g->n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / slot_bytes);
+  // warp-per-tile stages: ring slot s is owned by consumer warp kWarpOfSlot[s mod 8] (an mbarrier parity must be awaited by
+  // one warp in order), so 9..15 slots would give the owners of slots 8.. twice the tiles of the others: keep 8
+  if (g->n_slots > 8 && g->n_slots < 16) g->n_slots = 8;
   g->slot_data = g_slot_data; g->slot_scale = g_slot_scale; g->slot_bytes = (int)slot_bytes;
   g->xreg = xreg;
   g->smem = kMegaHdr + xreg + (size_t)g->n_slots * slot_bytes;

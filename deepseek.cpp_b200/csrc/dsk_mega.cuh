@@ -50,7 +50,7 @@ struct Stage {
   int kind, quant, epi, njobs;
   int n, rows_per_tile, rpass, ntiles;
   int need_topk, npieces, layer, has_dyn;
-  int use_mma, wp, down_rows, pad3;   // wp: warp-per-tile stage (tensor-core tiles owned by single warps)          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
+  int use_mma, wp, down_rows, down_nbuf;   // down_nbuf: partial-sum buffers of the warp-per-tile DOWN stage (row groups in flight)   // wp: warp-per-tile stage (tensor-core tiles owned by single warps)          // F8E5M2 tiles through mma.sync (pieces in 64-column units)
   const float* in; const float* norm_w;
   MJob job[kMaxJobs];
   Piece piece[kMaxPieces];
@@ -1432,8 +1432,10 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
   if (routed) { e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
   else live = live && st.sw2 != nullptr && st.add_shared;
   const int np = st.npieces;
-  float* part = sm.res + (size_t)(rg_local & 1) * 256;    // [2 row groups in flight][np <= 16][16 rows]
-  int* cnt = sm.sel + (rg_local & 1);
+  // [row groups in flight][np <= 16][16 rows]: a window of n_slots <= 8 consecutive pieces touches up to (8 - 2) / np + 2 row
+  // groups, each of which needs its own partial sums and completion counter until its last piece has been combined
+  float* part = sm.res + (size_t)(rg_local & (st.down_nbuf - 1)) * (size_t)(np * 16);
+  int* cnt = sm.sel + (rg_local & (st.down_nbuf - 1));
   if (live) {
     const int n = routed ? st.mi : st.sh;
     const float* sc = routed ? st.s2 : st.ss2;
@@ -1492,9 +1494,15 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
 // blocks, one warp_sum per row); lane r keeps the result of tile row r, so the epilogue runs 32 rows wide.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kKqMaxPass = 16;  // warp-per-tile K-quant rows up to 512 quarter-blocks (n <= 32768); passes are a rolled loop
-struct YRegs { int4 y[4]; int bs[4]; float d; };
+struct YRegs { int4 y[4]; int bs[4]; int bs01, bs23; float d; };
 
-// this lane's slice of the Q8_K activations for pass p (quarter block lane + 32 p): 64 int8, 4 sub-block sums, scale
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {   // unsigned bytes x signed bytes
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// this lane's slice of the Q8_K activations for quarter block qb: 64 int8, 4 sub-block sums, scale
 __device__ __forceinline__ void kq_load_y(uint32_t a_qs, uint32_t a_d, uint32_t a_bsums, int nb, int qb, YRegs& yr) {
   const int b = min(qb >> 2, nb - 1), h = (qb >> 1) & 1, c = qb & 1;
   const uint32_t y = a_qs + (uint32_t)(b * 256 + 128 * h + 16 * c);
@@ -1506,10 +1514,12 @@ __device__ __forceinline__ void kq_load_y(uint32_t a_qs, uint32_t a_d, uint32_t 
     asm volatile("ld.shared.s16 %0, [%1];" : "=h"(bsv) : "r"(a_bsums + (uint32_t)(b * 16 + 8 * h + c + 2 * s) * 2u));
     yr.bs[s] = (int)bsv;
   }
+  yr.bs01 = (yr.bs[0] & 0xffff) | (yr.bs[1] << 16);
+  yr.bs23 = (yr.bs[2] & 0xffff) | (yr.bs[3] << 16);
   yr.d = __uint_as_float(lds32(a_d + (uint32_t)b * 4u));
 }
 
-// one row x one pass: this lane's quarter block; returns the block's fp32 contribution in lanes with (lane & 3) == 0
+// one row x one quarter block (64 weights); returns the quarter's fp32 contribution (0 for lanes past the end of the row)
 template <int Q>
 __device__ __forceinline__ float kq_quarter(uint32_t row, int qb, int nqb, const YRegs& yr) {
   // branch-free: lanes past the end of the row (qb >= nqb) read the last block and contribute zero, so the four rows a
@@ -1517,30 +1527,37 @@ __device__ __forceinline__ float kq_quarter(uint32_t row, int qb, int nqb, const
   const bool act = qb < nqb;
   const int qc = act ? qb : nqb - 1;
   const int b = qc >> 2, h = (qc >> 1) & 1, c = qc & 1;
-  int isum = 0, summs = 0;
   float out = 0.f;
   if constexpr (Q == Q_Q2K) {
+    // ggml_vec_dot_q2_K_q8_K (src/quant.cpp:666-783) for sub-blocks j = 8h + 2s + c, s = 0..3.  The 2-bit fields are NOT
+    // shifted down: dp4a of the masked word (u8 = q << 2s) against the int8 activations gives 4^s x the sub-block dot, an
+    // exact multiple, shifted back once per sub-block — one LOP3 per dp4a instead of SHF + LOP3.  The four scale bytes are
+    // gathered with one PRMT; the four (min x block-sum) products are two dp2a.
     const uint32_t blk = row + (uint32_t)b * kQ2Bytes;
     const uint32_t qp = blk + 16 + 32 * h + 16 * c;
     const uint32_t w0 = lds32(qp), w1 = lds32(qp + 4), w2 = lds32(qp + 8), w3 = lds32(qp + 12);
     const uint32_t sA = lds32(blk + 8 * h), sB = lds32(blk + 8 * h + 4);
     const uint32_t dm = lds32(blk + 80);
+    const uint32_t pack = __byte_perm(sA, sB, c ? 0x7531u : 0x6420u);   // scale bytes of s = 0..3
+    const uint32_t sc4 = pack & 0x0F0F0F0Fu, m4 = (pack >> 4) & 0x0F0F0F0Fu;
+    int isum = 0;
 #pragma unroll
     for (int s = 0; s < 4; s++) {
-      int dp = __dp4a((int)((w0 >> (2 * s)) & 0x03030303u), yr.y[s].x, 0);
-      dp = __dp4a((int)((w1 >> (2 * s)) & 0x03030303u), yr.y[s].y, dp);
-      dp = __dp4a((int)((w2 >> (2 * s)) & 0x03030303u), yr.y[s].z, dp);
-      dp = __dp4a((int)((w3 >> (2 * s)) & 0x03030303u), yr.y[s].w, dp);
-      const uint32_t sw = (s < 2) ? sA : sB;
-      const int sc = (sw >> (8 * ((2 * s + c) & 3))) & 0xff;
-      isum += (sc & 0xF) * dp;
-      summs += (sc >> 4) * yr.bs[s];
+      const uint32_t mk = 0x03030303u << (2 * s);
+      int dp = dp4a_us(w0 & mk, yr.y[s].x, 0);
+      dp = dp4a_us(w1 & mk, yr.y[s].y, dp);
+      dp = dp4a_us(w2 & mk, yr.y[s].z, dp);
+      dp = dp4a_us(w3 & mk, yr.y[s].w, dp);
+      isum += (int)__byte_perm(sc4, 0u, 0x4440u + s) * (dp >> (2 * s));   // scale byte s (one PRMT); dp is an exact multiple of 4^s
     }
+    int summs = __dp2a_lo(yr.bs01, (int)m4, 0);
+    summs = __dp2a_hi(yr.bs23, (int)m4, summs);
     // per-quarter fp32 contribution (the integer sums are exact in fp32; the four quarters of a block are added in fp32 by the
-    // row reduction instead of in int32 first: same value up to fp32 re-association, two dependent shuffle pairs fewer)
+    // row reduction instead of in int32 first: same value up to fp32 re-association)
     const float o = (yr.d * h2f((uint16_t)(dm & 0xffff))) * (float)isum - (yr.d * h2f((uint16_t)(dm >> 16))) * (float)summs;
     out = act ? o : 0.f;
   } else {
+    int isum = 0;
     const uint32_t blk = row + (uint32_t)b * kQ3Bytes;
     const uint4 hm = lds128(blk + 16 * c);
     const uint4 qq = lds128(blk + 32 + 32 * h + 16 * c);
@@ -1569,31 +1586,43 @@ __device__ __forceinline__ float kq_quarter(uint32_t row, int qb, int nqb, const
 }
 
 // all rows of a tile: returns in lane r the dot product of tile row r (r < nrows <= 32).  ONE out-of-line copy per
-// quant for every GEMV / DOWN stage (instruction-cache footprint): four rows are interleaved (four independent dp4a /
-// shuffle chains), passes over long rows are a rolled loop that re-reads this lane's activation slice from shared memory.
+// quant for every GEMV / DOWN stage (instruction-cache footprint).
+// Lane mapping: a row of nqb quarter blocks is spread over L = 32 / G lanes, where G = 4, 2 or 1 rows share a warp pass
+// (short rows — kv_b's 512 columns are 8 quarter blocks — would otherwise leave 24 of 32 lanes idle); lane l works on quarter
+// (l mod L) + L*p of row group member l / L.  Four such row groups are interleaved per iteration (independent dp4a chains), so an
+// iteration covers 4 G rows; passes over long rows are a rolled loop that re-reads this lane's activation slice from shared
+// memory (kept in registers across the whole tile when one pass covers the row).
 template <int Q>
 __device__ __noinline__ float kq_tile_rows(uint32_t base, uint32_t rb, int nrows, int nb, uint32_t q_qs, uint32_t q_d, uint32_t q_bsums) {
   const int lane = threadIdx.x & 31;
-  const int nqb = nb * 4, npass = (nqb + 31) >> 5;
+  const int nqb = nb * 4;
+  const int G = nqb <= 8 ? 4 : (nqb <= 16 ? 2 : 1), L = 32 / G;
+  const int sub = lane / L, ql = lane & (L - 1);
+  const int npass = (nqb + L - 1) / L;
   float mine = 0.f;
   YRegs yr;
-  if (npass == 1) kq_load_y(q_qs, q_d, q_bsums, nb, lane, yr);
+  if (npass == 1) kq_load_y(q_qs, q_d, q_bsums, nb, ql, yr);
 #pragma unroll 1
-  for (int r0 = 0; r0 < nrows; r0 += 4) {
+  for (int r0 = 0; r0 < nrows; r0 += 4 * G) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int p = 0; p < npass; p++) {
-      if (npass > 1) kq_load_y(q_qs, q_d, q_bsums, nb, lane + 32 * p, yr);
+      if (npass > 1) kq_load_y(q_qs, q_d, q_bsums, nb, ql + L * p, yr);
 #pragma unroll
-      for (int i = 0; i < 4; i++) acc[i] += kq_quarter<Q>(base + (uint32_t)min(r0 + i, nrows - 1) * rb, lane + 32 * p, nqb, yr);
+      for (int i = 0; i < 4; i++) acc[i] += kq_quarter<Q>(base + (uint32_t)min(r0 + i * G + sub, nrows - 1) * rb, ql + L * p, nqb, yr);
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
+#pragma unroll 1
+    for (int o = L >> 1; o; o >>= 1) {
 #pragma unroll
       for (int i = 0; i < 4; i++) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
     }
+    // lane r keeps row r: row r0 + i G + m was reduced by the lanes [m L, (m + 1) L)
 #pragma unroll
-    for (int i = 0; i < 4; i++) if (lane == r0 + i && r0 + i < nrows) mine = acc[i];
+    for (int i = 0; i < 4; i++) {
+      const int rel = lane - r0 - i * G;
+      const float t = __shfl_sync(0xffffffffu, acc[i], (rel & (G - 1)) * L);
+      if (rel >= 0 && rel < G && lane < nrows) mine = t;
+    }
   }
   return mine;
 }
@@ -1678,8 +1707,10 @@ __device__ __forceinline__ void wp_kq_down_piece(const Program& P, const Stage& 
   if (routed) { const int e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
   else live = live && st.sw2 != nullptr && st.add_shared;
   const int np = st.npieces;
-  float* part = sm.res + (size_t)(rg_local & 1) * 256;
-  int* cnt = sm.sel + (rg_local & 1);
+  // [row groups in flight][np <= 16][16 rows]: a window of n_slots <= 8 consecutive pieces touches up to (8 - 2) / np + 2 row
+  // groups, each of which needs its own partial sums and completion counter until its last piece has been combined
+  float* part = sm.res + (size_t)(rg_local & (st.down_nbuf - 1)) * (size_t)(np * 16);
+  int* cnt = sm.sel + (rg_local & (st.down_nbuf - 1));
   if (live) {
     const int n = routed ? st.mi : st.sh, nb = n >> 8;
     const uint32_t base = slot + (uint32_t)P.slot_scale, rb = (uint32_t)QTraits<Q>::row_bytes(n);
@@ -2040,7 +2071,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     if (st.kind == ST_GEMV) {
       kq_gemv_loop<Q>(P, st, sm, q80, it, n_slots, best_key, stage_index);
     } else {
-      if (tid < 4) sm.sel[tid] = 0;
+      if (tid < 8) sm.sel[tid] = 0;
       csync();
       const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
       int rgl = 0;
@@ -2084,7 +2115,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
         }
       }
     } else {
-      if (tid < 4) sm.sel[tid] = 0;
+      if (tid < 8) sm.sel[tid] = 0;
       csync();
       const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
       int rgl = 0;
@@ -2324,6 +2355,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     if (nstage_seen > 0) {         // grid barrier: every CTA has finished (and released) the previous stage
       if (tid == 0) grid_wait(P.sync_counter, base + (unsigned int)nstage_seen * G);
       csync();
+    }
+    // pull this stage's input vector(s) into L1 with every line in flight at once: the staging loops then take ONE L2 round
+    // trip instead of one per batch of blocks (the acquire above has dropped any stale copy)
+    if (st.kind == ST_GEMV) {
+      if ((int)blockIdx.x < st.ntiles)
+        for (int i = tid * 32; i < st.n; i += kConsumers * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(st.in + i));
+    } else if (st.kind == ST_DOWN) {
+      for (int i = tid * 32; i < st.K * st.mi; i += kConsumers * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.hbk + i));
+      for (int i = tid * 32; i < st.sh; i += kConsumers * 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.hbs + i));
     }
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) { P.tstamp[s * 8 + 0] = gtime(); P.tstamp[s * 8 + 1] = 0; P.tstamp[s * 8 + 4] = 0; P.tstamp[s * 8 + 5] = 0; P.tstamp[s * 8 + 6] = 0; P.tstamp[s * 8 + 7] = 0; }
     if (st.kind == ST_EMBED) {
