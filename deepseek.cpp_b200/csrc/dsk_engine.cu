@@ -879,13 +879,17 @@ static int plan_gemv_stage(Stage& st, int quant, int G) {
   return 0;
 }
 
-// partial-sum buffers a warp-per-tile DOWN stage needs: the ring lets at most 8 consecutive pieces be outstanding, which touch
-// up to (8 - 2) / np + 2 row groups; 512 floats of shared memory hold them ([buffer][piece][16 rows])
-static int down_buffers(int np) {
-  const int need = (8 - 2) / np + 2;
-  int nb = 2;
-  while (nb < need) nb <<= 1;
-  return (nb * np * 16 <= 512) ? nb : 0;
+// partial-sum buffers of a warp-per-tile DOWN stage: with at most W consecutive pieces outstanding in the ring, up to
+// (W - 2) / np + 2 row groups are in flight; 512 floats of shared memory hold their partial sums ([buffer][piece][16 rows]).
+// Picks the largest window (16, 8, 4) whose buffers fit; returns 0 if none does.
+static int down_window(int np, int* nbuf) {
+  for (int W = kRingEntries; W >= 4; W >>= 1) {
+    const int need = (W - 2) / np + 2;
+    int nb = 2;
+    while (nb < need) nb <<= 1;
+    if (nb <= 16 && nb * np * 16 <= 512) { *nbuf = nb; return W; }
+  }
+  return 0;
 }
 
 static int plan_down_stage(Stage& st, int quant, int dim) {
@@ -907,35 +911,30 @@ static int plan_down_stage(Stage& st, int quant, int dim) {
     }
     st.npieces = np;
     st.ntiles = cdiv(dim, g_wp_rows) * np;
-    st.down_nbuf = down_buffers(np);
-    if (!st.down_nbuf) return fail(-4, "down projection: %d pieces per row group exceed the partial-sum buffers", np);
+    st.max_inflight = down_window(np, &st.down_nbuf);
+    if (!st.max_inflight) return fail(-4, "down projection: %d pieces per row group exceed the partial-sum buffers", np);
     return 0;
   }
   if (kq_quant(quant)) {
     if ((std::max(st.mi, st.sh) / 256) * 4 > 32 * kKqMaxPass) return fail(-4, "K-quant down-projection row exceeds the warp-per-tile limit");
-    // warp-per-tile K-quant pieces: (segment, rows of a DR-row output group).  DR = 16 or 8: whichever leaves the busiest
-    // CTA fewer rows (V2-236B: 320 groups of 16 over 148 CTAs = 3 groups = 48 rows, 640 groups of 8 = 5 groups = 40 rows)
+    // K-quants: one tile per row group = DR output rows x all K + 1 segments, reduced by one warp (see kq_down_group).
+    // DR = the smallest of {16, 8, 4} that leaves every CTA at most 8 row groups (one per consumer warp: a single round),
+    // as long as the tile fits the ring comfortably.
     const int G = g_sm_count;
-    int DR = 16;
-    if (cdiv(cdiv(dim, 8), G) * 8 < cdiv(cdiv(dim, 16), G) * 16) DR = 8;
-    if (const char* e = getenv("DSK_DOWN_ROWS")) { const int v = atoi(e); if (v == 8 || v == 16) DR = v; }
-    st.wp = 1; st.down_rows = DR; st.rows_per_tile = DR; st.seg_stride = 0;
-    int np = 0;
-    for (int k = 0; k <= st.K; k++) {
-      const int n = k < st.K ? st.mi : st.sh;
-      if (n == 0) continue;
-      const size_t rb = dev_row_bytes(quant, n);
-      int pr = DR;
-      while (pr > 4 && (size_t)pr * rb > (size_t)g_slot_data) pr >>= 1;
-      if ((size_t)pr * rb > (size_t)g_slot_data) { np = -1; break; }
-      if (quant == DSK_Q2_K && ((size_t)pr * rb) % 16 != 0) { np = -1; break; }   // TMA source / size alignment of a piece
-      for (int r0 = 0; r0 < DR; r0 += pr) { if (np >= 16) { np = -1; break; } st.piece[np++] = Piece{k, r0, pr, 0}; }
-      if (np < 0) break;
+    const size_t rb_mi = dev_row_bytes(quant, st.mi), rb_sh = dev_row_bytes(quant, st.sh);
+    int DR = 0;
+    for (int cand : {4, 8, 16}) {
+      if (cdiv(cdiv(dim, cand), G) > 8 && cand != 16) continue;
+      DR = cand;
+      break;
     }
-    if (np > 0) {
-      st.npieces = np; st.ntiles = cdiv(dim, DR) * np;
-      st.down_nbuf = down_buffers(np);
-      if (!st.down_nbuf) return fail(-4, "down projection: %d pieces per row group exceed the partial-sum buffers", np);
+    if (const char* e = getenv("DSK_DOWN_ROWS")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) DR = v; }
+    while (DR > 4 && (size_t)DR * (rb_mi * st.K + rb_sh) > 64 * 1024) DR >>= 1;
+    if ((size_t)DR * (rb_mi * st.K + rb_sh) <= 64 * 1024) {
+      st.wp = 1; st.down_rows = DR; st.rows_per_tile = DR; st.npieces = 1;
+      st.seg_stride = (int)((size_t)DR * rb_mi);          // 16-byte multiple for every DR >= 4 (84- / 112-byte blocks)
+      st.ntiles = cdiv(dim, DR);
+      st.max_inflight = kRingEntries; st.down_nbuf = 1;
       return 0;
     }
     return fail(-4, "K-quant down-projection rows do not fit a ring slot");
@@ -997,7 +996,7 @@ static void choose_slot_geometry(int q, const std::vector<Stage>& S, int gate_di
   g_slot_scale = kSlotScale;
 }
 
-struct Geometry { int n_slots = 0, slot_data = 0, slot_scale = 0, slot_bytes = 0; size_t xreg = 0, smem = 0; };
+struct Geometry { int ring_bytes = 0, slot_data = 0, slot_scale = 0, slot_bytes = 0; size_t xreg = 0, smem = 0; };
 
 // shared-memory budget of a planned stage list: activation region = max over stages, the rest is ring slots
 static int program_geometry(const std::vector<Stage>& S, int q, int hd, int max_seq, int bs1_cfg, Geometry* g) {
@@ -1036,14 +1035,15 @@ static int program_geometry(const std::vector<Stage>& S, int q, int hd, int max_
     else g_slot_scale = kSlotScale;
   }
   const size_t slot_bytes = (size_t)g_slot_data + g_slot_scale;
-  if (kMegaHdr + xreg + 2 * slot_bytes > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
-  g->n_slots = (int)std::min<size_t>(kMaxSlots, (budget - kMegaHdr - xreg) / slot_bytes);
-  // warp-per-tile stages: ring slot s is owned by consumer warp kWarpOfSlot[s mod 8] (an mbarrier parity must be awaited by
-  // one warp in order), so 9..15 slots would give the owners of slots 8.. twice the tiles of the others: keep 8
-  if (g->n_slots > 8 && g->n_slots < 16) g->n_slots = 8;
+  size_t max_tile = align_up(slot_bytes, 128);
+  for (const Stage& st : S)
+    if (st.kind == ST_DOWN && st.wp && kq_quant(st.quant))
+      max_tile = std::max(max_tile, align_up((size_t)st.K * st.seg_stride + (size_t)st.down_rows * dev_row_bytes(st.quant, st.sh), 128));
+  if (kMegaHdr + xreg + 2 * max_tile > budget) return fail(-4, "activation staging (%zu bytes) leaves no room for the TMA ring", xreg);
+  g->ring_bytes = (int)((budget - kMegaHdr - xreg) / 128 * 128);   // everything left: tiles take what they need out of it
   g->slot_data = g_slot_data; g->slot_scale = g_slot_scale; g->slot_bytes = (int)slot_bytes;
   g->xreg = xreg;
-  g->smem = kMegaHdr + xreg + (size_t)g->n_slots * slot_bytes;
+  g->smem = kMegaHdr + xreg + (size_t)g->ring_bytes;
   // the grid barrier needs every CTA resident: verify that one CTA of this footprint fits an SM (the launch is cooperative,
   // so anything less would be a launch error, not a hang)
   int nb = 0;
@@ -1055,6 +1055,7 @@ static int program_geometry(const std::vector<Stage>& S, int q, int hd, int max_
 static void plan_stages(std::vector<Stage>& S, int q, int dim, int G, int* err) {
   *err = 0;
   for (Stage& st : S) {
+    if (st.max_inflight == 0) st.max_inflight = kRingEntries;
     if (st.kind == ST_GEMV && st.ntiles == 0) { if (plan_gemv_stage(st, st.quant, G)) { *err = -4; return; } }
     else if (st.kind == ST_DOWN && st.ntiles == 0) { if (plan_down_stage(st, q, dim)) { *err = -4; return; } }
   }
@@ -1069,7 +1070,7 @@ static void fill_program_header(Program* P, const dsk_config& c, int hd, const G
   P->norm_topk_prob = c.norm_topk_prob; P->sigmoid = c.scoring_sigmoid; P->topk_method = c.topk_method;
   P->n_group = std::max(1, c.n_group); P->topk_group = c.topk_group; P->original_max = c.original_max_position;
   P->eps = c.norm_eps; P->routed_scale = c.routed_scaling_factor;
-  P->n_slots = g.n_slots; P->xregion_bytes = (int)g.xreg;
+  P->ring_bytes = g.ring_bytes; P->xregion_bytes = (int)g.xreg;
   P->slot_data = g.slot_data; P->slot_scale = g.slot_scale; P->slot_bytes = g.slot_bytes;
   P->n_ranks = 1; P->rank = 0;
 }

@@ -31,7 +31,7 @@ constexpr int kMegaThreads = 288;          // + producer warp 8
 constexpr int kSlotScale = 2048;           // bytes reserved per ring slot for f8 scale rows
 constexpr int kSlotData = 32 * 1024;       // weight bytes per ring slot
 constexpr int kSlotBytes = kSlotScale + kSlotData;
-constexpr int kMaxSlots = 12;
+constexpr int kRingEntries = 16;          // tiles in flight per CTA (mbarrier pairs); their bytes come out of one circular buffer
 constexpr int kMaxPieces = 24;
 constexpr int kMegaHdr = 8192;             // barriers, scratch, partial results, smem copies of Program + 2 Stage descriptors
 constexpr int kStageSlot = 1536;           // bytes reserved per cached Stage descriptor
@@ -63,7 +63,8 @@ struct Stage {
   int K, mi, sh, add_shared;
   int seg_stride;                          // bytes between segments inside a ring slot (ST_DOWN)
   int xchg_ord;                            // peer-memory mode: ordinal (within a token) of the exchange this DOWN / XCHG stage belongs to
-  int pad2[2];
+  int max_inflight;                        // tiles the producer may have outstanding in this stage (<= kRingEntries)
+  int pad2[1];
 } __attribute__((aligned(16)));
 
 static_assert(sizeof(Stage) <= kStageSlot, "Stage descriptor must fit its shared-memory cache slot");
@@ -87,7 +88,7 @@ struct Program {
   unsigned int* sync_counter;              // grid barrier arrivals (monotonic)
   unsigned int* sync_base;                 // value of the counter when this launch started
   int* token_log; int* step;
-  int n_slots, xregion_bytes;
+  int ring_bytes, xregion_bytes;           // circular tile buffer after the activation region
   int slot_data, slot_scale, slot_bytes, pad_s;   // ring slot geometry (bytes): [scale rows | weight tile]
   // multi-GPU, peer-memory mode: every rank stores its MoE partial sums straight into every peer's exchange buffer over
   // NVLink (plain stores to IPC-mapped memory), then raises a flag there; an ST_XCHG stage waits for the N flags and adds the
@@ -540,20 +541,25 @@ __device__ __forceinline__ void piece_rows(const uint32_t (&wa)[NACC], const uin
 }
 
 // ---- shared-memory map of the interpreter -----------------------------------------------------------------------
-// Static ring-slot ownership of the warp-per-tile stages: slot s is consumed by warp kWarpOfSlot[s & 7] = {1,2,3,5,6,7,0,4}.
-// With 4-5 slots (34 KB F8 tiles) the busy warps land on sub-partitions 1-3, away from the producer warp (warp 8 lives on
-// sub-partition 0 with warps 0 and 4): measured 7.3 vs 4.9 kcycles per tile for a consumer sharing the producer's scheduler.
-__device__ __forceinline__ int slot_of_warp(int warp) { return (int)((0x54372106u >> (4 * warp)) & 7u); }
+// The TMA ring.  Tiles are numbered per CTA in issue order (`it`, the same sequence on the producer and consumer side, running
+// across stages).  Tile j uses mbarrier pair (full, empty)[j mod 16]; its BYTES are carved out of one circular buffer by the
+// producer (variable size per tile: small DOWN pieces do not occupy a whole 20 KB slot, so up to 16 of them are in flight and
+// keep the HBM pipe full; large tiles simply use more of the buffer), which publishes the offset in ent_off[] before issuing
+// the copies.  Consumers CLAIM tiles dynamically (shared-memory counter): a warp that finishes early takes the next tile, so
+// the stage ends when the last tile does, not when the most loaded warp of a static assignment does.  A claimer of use k of
+// an entry first waits until use k-1 has been consumed (consumed[] counter) — only then does the full-barrier parity k & 1
+// refer to the right phase (an mbarrier parity wait cannot tell phase k-2 from phase k).
 struct MegaSmem {
-  uint32_t full[kMaxSlots], empty[kMaxSlots], dep;   // shared addresses of the mbarriers
+  uint32_t full0, empty0, dep, claim;   // shared addresses: mbarrier arrays (8 B apart), producer release word, claim counter
+  uint32_t ent_off, consumed, start_abs;   // 16 x u32 each: tile offset in the ring / completed uses per entry / producer bookkeeping
   float* red;          // 32 floats
   int* act; float* actw;   // routing (K <= 16)
-  float* res;          // 2 x 512 partial results
+  float* res;          // 512 floats of partial results
   float* sx;           // 256 gate scores
-  unsigned char* mask; // 256
-  int* sel;            // 16
+  int* sel;            // 16 ints: warp-per-tile DOWN completion counters
+  int* marker;         // "routing of layer l is in this CTA's shared memory"
   unsigned char* xregion;
-  uint32_t ring;       // shared address of slot 0
+  uint32_t ring;       // shared address of the circular tile buffer
   Stage* st_c;         // consumers' copy of the current stage descriptor
   Stage* st_p;         // producer's copy (it may be one stage ahead)
   Program* prog;       // header copy (no stage array)
@@ -561,15 +567,18 @@ struct MegaSmem {
 __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_bytes) {
   MegaSmem m;
   const uint32_t b = smem_u32(smem);
-  for (int i = 0; i < kMaxSlots; i++) { m.full[i] = b + 8 * i; m.empty[i] = b + 96 + 8 * i; }
-  m.dep = b + 192;
+  m.full0 = b; m.empty0 = b + 128;                         // 16 + 16 mbarriers -> 256
   m.red = reinterpret_cast<float*>(smem + 256);            // 32 floats -> 384
   m.act = reinterpret_cast<int*>(smem + 384);              // 16 ints -> 448
   m.actw = reinterpret_cast<float*>(smem + 448);           // 16 floats -> 512
-  m.sel = reinterpret_cast<int*>(smem + 512);              // 16 ints: warp-per-tile DOWN completion counters -> 576
-  m.mask = smem + 576;                                     // 192 B spare -> 768
-  m.sx = reinterpret_cast<float*>(smem + 768);             // 256 floats: warp-per-tile DOWN partial sums [8][pieces<=4..] -> 1792
-  m.res = reinterpret_cast<float*>(smem + 1792);           // 2 x 256 floats -> 3840
+  m.sel = reinterpret_cast<int*>(smem + 512);              // 16 ints -> 576
+  //                                                          576..624: kHdrZero / kHdrOne
+  m.dep = b + 624; m.claim = b + 628;
+  m.marker = reinterpret_cast<int*>(smem + 632);
+  //                                                          640..736: routing scratch (cmask, selv)
+  m.sx = reinterpret_cast<float*>(smem + 768);             // 256 floats -> 1792
+  m.res = reinterpret_cast<float*>(smem + 1792);           // 512 floats -> 3840
+  m.ent_off = b + 3840; m.consumed = b + 3904; m.start_abs = b + 3968;   // -> 4032
   m.st_c = reinterpret_cast<Stage*>(smem + 4096);
   m.st_p = reinterpret_cast<Stage*>(smem + 4096 + kStageSlot);
   m.prog = reinterpret_cast<Program*>(smem + 4096 + 2 * kStageSlot);
@@ -577,6 +586,60 @@ __device__ __forceinline__ MegaSmem carve_mega(unsigned char* smem, int xregion_
   m.ring = b + kMegaHdr + (uint32_t)xregion_bytes;
   return m;
 }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// ---- producer side: reserve `need` bytes (multiple of 128) for tile `it`; returns the tile's shared address -------------
+struct RingProd { uint32_t head; int oldest; };   // absolute byte counter (mod 2^32) / oldest tile not yet known released
+__device__ __forceinline__ uint32_t ring_acquire(const Program& P, const MegaSmem& sm, RingProd& rp, int it, uint32_t need, int max_inflight,
+                                                 uint32_t& full) {
+  const uint32_t R = (uint32_t)P.ring_bytes;
+  uint32_t pos = rp.head % R;
+  if (pos + need > R) { rp.head += R - pos; pos = 0; }    // a tile is contiguous: skip the tail of the buffer
+  // wait (in issue order) for old tiles to be released until the mbarrier pair is free, the in-flight cap holds and the
+  // bytes [start of the oldest live tile, head) leave room for this one
+  while (rp.oldest < it) {
+    const bool pair_busy = rp.oldest + max_inflight <= it;
+    const uint32_t used = rp.head - lds32(sm.start_abs + 4u * (uint32_t)(rp.oldest & (kRingEntries - 1)));
+    if (!pair_busy && used + need <= R) break;
+    mbar_wait_backoff(sm.empty0 + 8u * (uint32_t)(rp.oldest & (kRingEntries - 1)), (uint32_t)((rp.oldest / kRingEntries) & 1));
+    rp.oldest++;
+  }
+  const uint32_t e = (uint32_t)(it & (kRingEntries - 1));
+  sts32(sm.start_abs + 4u * e, rp.head);
+  sts32(sm.ent_off + 4u * e, pos);
+  rp.head += need;
+  full = sm.full0 + 8u * e;
+  return sm.ring + pos;
+}
+// ---- consumer side -----------------------------------------------------------------------------------------------
+// next tile of this CTA (warp-uniform; lane 0 takes the ticket)
+__device__ __forceinline__ int ring_claim(const MegaSmem& sm) {
+  int j = 0;
+  if ((threadIdx.x & 31) == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(j) : "r"(sm.claim) : "memory");
+  return __shfl_sync(0xffffffffu, j, 0);
+}
+// wait until tile j has landed; returns its shared address
+__device__ __forceinline__ uint32_t ring_wait(const MegaSmem& sm, int j) {
+  const uint32_t e = (uint32_t)(j & (kRingEntries - 1));
+  const uint32_t k = (uint32_t)(j / kRingEntries);
+  unsigned long long t0 = 0ull;
+  for (unsigned spins = 0;; spins++) {   // use k-1 of this entry fully consumed?  (then the parity below cannot alias)
+    uint32_t c;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(c) : "r"(sm.consumed + 4u * e) : "memory");
+    if (c >= k) break;
+    if ((spins & 4095u) == 4095u) spin_check(t0);
+  }
+  mbar_wait_guard(sm.full0 + 8u * e, k & 1u);
+  return sm.ring + lds32(sm.ent_off + 4u * e);
+}
+// one thread per tile, after every reader of the tile is done with it
+__device__ __forceinline__ void ring_release(const MegaSmem& sm, int j) {
+  const uint32_t e = (uint32_t)(j & (kRingEntries - 1));
+  asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(sm.consumed + 4u * e), "r"((uint32_t)(j / kRingEntries) + 1u) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty0 + 8u * e) : "memory");
+}
+// tiles of a stage that land on this CTA (tile t = blockIdx.x + i * gridDim.x < n)
+__device__ __forceinline__ int my_tile_count(int n) { return (int)blockIdx.x < n ? (n - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0; }
 
 // routing: softmax|sigmoid(+bias) and greedy / group-limited top-K (moe_gate, src/infer.cpp:493-599), computed redundantly by
 // every CTA from the gate logits with ONE THREAD PER EXPERT (E <= 256 = the consumer threads) and no dependent argmax rounds:
@@ -656,7 +719,7 @@ __device__ __noinline__ void route_all(const Program* Pp, const Stage* stp, bool
     if (publish) { P.act[tid] = e; P.act_w[tid] = w; }
   }
   if (publish && mine) P.moe_scores[tid] = s;   // state buffer for the host (moe_weights after softmax|sigmoid + bias)
-  if (tid == 0) reinterpret_cast<int*>(dsk_dyn_smem + 512)[14] = st.layer + 1;   // MegaSmem::sel[14]: "routing of layer l is here"
+  if (tid == 0) *reinterpret_cast<int*>(dsk_dyn_smem + 632) = st.layer + 1;   // MegaSmem::marker: "routing of layer l is here"
   csync();
 }
 
@@ -665,7 +728,7 @@ __device__ __forceinline__ void stage_route_hook(const Program& P, const Stage& 
   if (route >= 0) {   // uniform over the consumer threads: every one of them takes part (thread per expert)
     const unsigned long long tr0 = (P.tstamp && blockIdx.x == 0) ? gtime() : 0ull;
     route_all(&P, &st, blockIdx.x == 0);
-    if (threadIdx.x == 0) dep_signal(smem_u32(dsk_dyn_smem) + 192u, route);
+    if (threadIdx.x == 0) dep_signal(smem_u32(dsk_dyn_smem) + 624u, route);
     if (P.tstamp && blockIdx.x == 0 && threadIdx.x == 0) { P.tstamp[stage_index * 8 + 6] = (tr0 - P.tstamp[stage_index * 8]) * 1000ull; P.tstamp[stage_index * 8 + 7] = (gtime() - tr0) * 1000ull; }
   }
 }
@@ -1674,100 +1737,80 @@ __device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& s
   }
 }
 
-// ST_DOWN piece (segment k, rows [g0, g0+g1) of a row group) for K-quants; producer side = wp_produce_down_piece_q
+// ST_DOWN for K-quants: ONE tile = a row group of DR = st.down_rows output rows x ALL segments (the K routed experts' w2 rows, then
+// the shared / dense rows), K + 1 bulk copies on one mbarrier, reduced by ONE warp: lane r accumulates output row r over the
+// segments in the reference's order (src/infer.cpp:873-877, 899-903, 926-930) — no cross-warp partial sums, no completion
+// counters, and a handful of tiles per CTA instead of (row groups x segments) small pieces, whose per-tile cost on the single
+// producer thread (~0.5 us each) used to bound the stage.  Segment k lives at k * st.seg_stride inside the tile.
 template <int Q>
-__device__ __forceinline__ void wp_produce_down_piece_q(const Program& P, const Stage& st, int rg, int pc, uint32_t slot, uint32_t full,
-                                                        const int* act_smem) {
-  const Piece pcd = st.piece[pc];
-  const int k = pcd.seg, i0 = rg * st.down_rows + pcd.g0;
-  const int nrows = min(pcd.g1, P.dim - i0);
-  const bool routed = k < st.K;
-  int e = 0;
-  if (routed) {
-    e = act_smem[k] - P.expert_first;
-    if (e < 0 || e >= P.expert_count) { mbar_expect_tx(full, 0); return; }
-  } else if (!(st.sw2 != nullptr && st.add_shared)) { mbar_expect_tx(full, 0); return; }
-  if (nrows <= 0) { mbar_expect_tx(full, 0); return; }
-  const size_t rb = QTraits<Q>::row_bytes(routed ? st.mi : st.sh);
-  const uint32_t bytes = (uint32_t)align_up((size_t)nrows * rb, 16);
-  const uint8_t* src = routed ? st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * rb : st.sw2 + (size_t)i0 * rb;
-  mbar_expect_tx(full, bytes);
-  bulk_g2s(slot + (uint32_t)P.slot_scale, src, bytes, full);
+__device__ __forceinline__ void kq_produce_down_group(const Program& P, const Stage& st, int rg, uint32_t slot, uint32_t full,
+                                                      const int* act_smem) {
+  const int i0 = rg * st.down_rows;
+  const int nrows = min(st.down_rows, P.dim - i0);
+  const uint32_t rb_mi = (uint32_t)QTraits<Q>::row_bytes(st.mi), rb_sh = (uint32_t)QTraits<Q>::row_bytes(st.sh);
+  const uint32_t b_mi = (uint32_t)align_up((size_t)nrows * rb_mi, 16), b_sh = (uint32_t)align_up((size_t)nrows * rb_sh, 16);
+  const bool use_shared = st.sw2 != nullptr && st.add_shared && st.sh > 0;
+  uint32_t live = 0, total = 0;
+  for (int k = 0; k < st.K; k++) {
+    const int e = act_smem[k] - P.expert_first;
+    if (e >= 0 && e < P.expert_count) { live |= 1u << k; total += b_mi; }
+  }
+  if (use_shared) total += b_sh;
+  mbar_expect_tx(full, total);
+  for (int k = 0; k < st.K; k++) {
+    if (!((live >> k) & 1u)) continue;
+    const int e = act_smem[k] - P.expert_first;
+    bulk_g2s(slot + (uint32_t)k * (uint32_t)st.seg_stride, st.w2 + (size_t)e * st.w2_stride + (size_t)i0 * rb_mi, b_mi, full);
+  }
+  if (use_shared) bulk_g2s(slot + (uint32_t)st.K * (uint32_t)st.seg_stride, st.sw2 + (size_t)i0 * rb_sh, b_sh, full);
 }
 
 template <int Q>
-__device__ __forceinline__ void wp_kq_down_piece(const Program& P, const Stage& st, const MegaSmem& sm, int rg, int rg_local, int pc,
-                                                 uint32_t slot, const Q8Smem* q8_seg) {
+__device__ __forceinline__ void kq_down_group(const Program& P, const Stage& st, const MegaSmem& sm, int rg, uint32_t slot,
+                                              const Q8Smem* q8_seg) {
   const int lane = threadIdx.x & 31;
-  const Piece pcd = st.piece[pc];
-  const int k = pcd.seg, i0 = rg * st.down_rows + pcd.g0;
-  const int nrows = min(pcd.g1, P.dim - i0);
-  const bool routed = k < st.K;
-  bool live = nrows > 0;
-  if (routed) { const int e = sm.act[k] - P.expert_first; live = live && e >= 0 && e < P.expert_count; }
-  else live = live && st.sw2 != nullptr && st.add_shared;
-  const int np = st.npieces;
-  // [row groups in flight][np <= 16][16 rows]: a window of n_slots <= 8 consecutive pieces touches up to (8 - 2) / np + 2 row
-  // groups, each of which needs its own partial sums and completion counter until its last piece has been combined
-  float* part = sm.res + (size_t)(rg_local & (st.down_nbuf - 1)) * (size_t)(np * 16);
-  int* cnt = sm.sel + (rg_local & (st.down_nbuf - 1));
-  if (live) {
-    const int n = routed ? st.mi : st.sh, nb = n >> 8;
-    const uint32_t base = slot + (uint32_t)P.slot_scale, rb = (uint32_t)QTraits<Q>::row_bytes(n);
+  const int i0 = rg * st.down_rows;
+  const int nrows = min(st.down_rows, P.dim - i0);
+  const bool to_partial = P.partial != nullptr && st.K > 0;
+  float acc = 0.f;
+  if (!to_partial && lane < nrows) acc = P.x[i0 + lane];   // residual operand first: its L2 latency hides behind the dots
+  const uint32_t rb_mi = (uint32_t)QTraits<Q>::row_bytes(st.mi);
+#pragma unroll 1
+  for (int k = 0; k < st.K; k++) {
+    const int e = sm.act[k] - P.expert_first;
+    if (e < 0 || e >= P.expert_count) continue;
     const Q8Smem qk = q8_seg[k];
-    const float v = kq_tile_rows<Q>(base, rb, nrows, nb, smem_u32(qk.qs), smem_u32(qk.d), smem_u32(qk.bsums));
-    if (lane < nrows) part[pc * 16 + pcd.g0 + lane] = v;
+    const float v = kq_tile_rows<Q>(slot + (uint32_t)k * (uint32_t)st.seg_stride, rb_mi, nrows, st.mi >> 8, smem_u32(qk.qs), smem_u32(qk.d), smem_u32(qk.bsums));
+    acc = fmaf(v, sm.actw[k], acc);
   }
-  __syncwarp();
-  int last = 0;
-  if (lane == 0) { __threadfence_block(); last = atomicAdd(cnt, 1) == np - 1; }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  __threadfence_block();
-  const int gi0 = rg * st.down_rows;
-  const int grows = min(st.down_rows, P.dim - gi0);
-  if (lane < grows) {
-    const int i = gi0 + lane;
-    const bool to_partial = P.partial != nullptr && st.K > 0;
-    float acc = to_partial ? 0.f : P.x[i];
-    int p2 = 0;
-    for (int kk = 0; kk <= st.K; kk++) {
-      float v = 0.f;
-      bool any = false;
-      for (; p2 < np && st.piece[p2].seg == kk; p2++) {
-        const Piece q = st.piece[p2];
-        if (lane >= q.g0 && lane < q.g0 + q.g1) { v += part[p2 * 16 + lane]; any = true; }
-      }
-      if (!any) continue;
-      if (kk < st.K) {
-        const int ee = sm.act[kk] - P.expert_first;
-        if (ee >= 0 && ee < P.expert_count) acc = fmaf(v, sm.actw[kk], acc);
-      } else if (st.sw2 != nullptr && st.add_shared) acc += v;
-    }
-    if (to_partial) store_partial(P, st, i, acc); else P.x[i] = acc;
+  if (st.sw2 != nullptr && st.add_shared && st.sh > 0) {
+    const Q8Smem qk = q8_seg[st.K];
+    acc += kq_tile_rows<Q>(slot + (uint32_t)st.K * (uint32_t)st.seg_stride, (uint32_t)QTraits<Q>::row_bytes(st.sh), nrows, st.sh >> 8, smem_u32(qk.qs), smem_u32(qk.d), smem_u32(qk.bsums));
   }
-  __syncwarp();
-  if (lane == 0) *cnt = 0;
+  if (lane < nrows) { if (to_partial) store_partial(P, st, i0 + lane, acc); else P.x[i0 + lane] = acc; }
 }
 
 // the tile loop of a warp-per-tile K-quant GEMV stage; this lane's activation slice lives in NP register sets
 template <int Q>
-__device__ __forceinline__ void kq_gemv_loop(const Program& P, const Stage& st, const MegaSmem& sm, const Q8Smem& q80, int& it, int n_slots,
+__device__ __forceinline__ void kq_gemv_loop(const Program& P, const Stage& st, const MegaSmem& sm, const Q8Smem& q80, int& it,
                                              unsigned long long& best_key, int stage_index) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long c_wait = 0, c_task = 0;
   int n_mine = 0;
-  for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
-    const int sl = it % n_slots;
-    if ((sl & 7) != slot_of_warp(warp)) continue;
+  const int it0 = it, cnt = my_tile_count(st.ntiles);
+  for (;;) {
+    const int j = ring_claim(sm);
+    if (j >= it0 + cnt) break;
+    const int t = (int)blockIdx.x + (j - it0) * (int)gridDim.x;
     const long long k0 = clock64();
-    mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+    const uint32_t slot = ring_wait(sm, j);
     const long long k1 = clock64();
-    wp_kq_gemv_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, q80, sm.act, best_key);
+    wp_kq_gemv_tile<Q>(P, st, t, slot, q80, sm.act, best_key);
     __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+    if (lane == 0) ring_release(sm, j);
     c_wait += k1 - k0; c_task += clock64() - k1; n_mine++;
   }
+  it = it0 + cnt;
   if (lane == 0 && blockIdx.x == 0 && P.tstamp && n_mine && !st.need_topk) {   // profiling: cycles per tile waiting / reducing
     if (warp == 0) { P.tstamp[stage_index * 8 + 4] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 5] = (unsigned long long)(c_task / n_mine); }
     if (warp == 1) { P.tstamp[stage_index * 8 + 6] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 7] = (unsigned long long)(c_task / n_mine); }
@@ -1892,7 +1935,7 @@ __device__ __forceinline__ void carve_down_q8(unsigned char* p, int K, int mi, i
 // One row per tile (one 4n-byte TMA copy), one tile per CTA for E <= 148; all eight warps split the columns of the row and
 // a block reduction in a fixed order finishes it.  Deliberately tiny: it replaces a whole second template instantiation of
 // the generic consumer (cold code every layer) for 0.5 MB of weights.
-__device__ __noinline__ int gate_f32_stage(int it, int n_slots, int dep_count, int stage_index) {
+__device__ __noinline__ int gate_f32_stage(int it, int dep_count, int stage_index) {
   extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
   const Program& P = *reinterpret_cast<const Program*>(dsk_dyn_smem + 4096 + 2 * kStageSlot);
   const Stage& st = *reinterpret_cast<const Stage*>(dsk_dyn_smem + 4096);
@@ -1944,9 +1987,7 @@ __device__ __noinline__ int gate_f32_stage(int it, int n_slots, int dep_count, i
   const MJob& jb = st.job[0];
 #pragma unroll 1
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
-    const int sl = it % n_slots;
-    mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
-    const uint32_t wrow = sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes + (uint32_t)P.slot_scale;
+    const uint32_t wrow = ring_wait(sm, it) + (uint32_t)P.slot_scale;
     float acc = 0.f;
 #pragma unroll 1
     for (int f = tid; f < nf; f += kConsumers) {
@@ -1957,7 +1998,7 @@ __device__ __noinline__ int gate_f32_stage(int it, int n_slots, int dep_count, i
     }
     acc = csum(acc, sm.red);          // every warp is done with the slot after this reduction
     if (tid == 0) {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+      ring_release(sm, it);
       if (t < jb.rows) jb.out[t] = acc;
     }
   }
@@ -1994,7 +2035,7 @@ __device__ __noinline__ void dbg_tap(const Program* Pp, int n, int mode, const f
 }
 
 template <int Q>
-__device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
+__device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it,
                                                unsigned long long& best_key, int dep_count, int stage_index) {
   constexpr bool KQ = QTraits<Q>::kq;
   const int tid = threadIdx.x;
@@ -2007,7 +2048,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   if (st.kind == ST_DOWN && st.K > 0) {
     // the routing of this layer is normally still in this CTA's shared memory (left by route_all in the S56 stage of the same
     // launch, ordered by that stage's barriers); otherwise (first stage of a launch, CTA without S56 tiles) fetch the published copy
-    if (sm.sel[14] != st.layer + 1) {
+    if (*sm.marker != st.layer + 1) {
       if (tid < st.K) { sm.act[tid] = P.act[tid]; sm.actw[tid] = P.act_w[tid]; }
       csync();
     }
@@ -2067,45 +2108,43 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   if ((P.dbg_q8 != nullptr || P.dbg_x != nullptr) && blockIdx.x == 0 && st.kind == ST_GEMV)
     dbg_tap<Q>(&P, st.n, mma ? 2 : (KQ ? 1 : 0), xs0, q80.qs, q80.d, q80.bsums, x16_0.hi, x16_0.lo, x16_0.gs);
   if (KQ && st.wp) {   // warp-per-tile K-quant stage
-    const int warp = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
     if (st.kind == ST_GEMV) {
-      kq_gemv_loop<Q>(P, st, sm, q80, it, n_slots, best_key, stage_index);
+      kq_gemv_loop<Q>(P, st, sm, q80, it, best_key, stage_index);
     } else {
-      if (tid < 8) sm.sel[tid] = 0;
-      csync();
       const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
-      int rgl = 0;
-      for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
-        for (int pc = 0; pc < st.npieces; pc++, it++) {
-          const int sl = it % n_slots;
-          if ((sl & 7) != slot_of_warp(warp)) continue;
-          mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
-          wp_kq_down_piece<Q>(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, q8_seg);
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
-        }
+      const int it0 = it, cnt = my_tile_count(nrg);
+      for (;;) {
+        const int j = ring_claim(sm);
+        if (j >= it0 + cnt) break;
+        const uint32_t slot = ring_wait(sm, j);
+        kq_down_group<Q>(P, st, sm, (int)blockIdx.x + (j - it0) * (int)gridDim.x, slot, q8_seg);
+        __syncwarp();
+        if (lane == 0) ring_release(sm, j);
       }
+      it = it0 + cnt;
     }
     return;
   }
-  if (mma && st.wp) {   // warp-per-tile: every consumer warp owns the tiles whose local index is congruent to its id
+  if (mma && st.wp) {   // warp-per-tile tensor-core stage: warps claim tiles dynamically
     const int warp = tid >> 5, lane = tid & 31;
     if (st.kind == ST_GEMV) {
-      // ring slot s is always consumed by warp (s mod 8): every slot's uses are awaited in order by ONE warp, so an
-      // mbarrier parity can never be mistaken for an earlier use of the same slot
       long long c_wait = 0, c_task = 0, c_mma = 0;
       int n_mine = 0;
-      for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
-        const int sl = it % n_slots;
-        if ((sl & 7) != slot_of_warp(warp)) continue;
+      const int it0 = it, cnt = my_tile_count(st.ntiles);
+      for (;;) {
+        const int j = ring_claim(sm);
+        if (j >= it0 + cnt) break;
+        const int t = (int)blockIdx.x + (j - it0) * (int)gridDim.x;
         const long long k0 = clock64();
-        mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+        const uint32_t slot = ring_wait(sm, j);
         const long long k1 = clock64();
-        wp_gemv_tile(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_0, sm.act, best_key, c_mma);
+        wp_gemv_tile(P, st, t, slot, x16_0, sm.act, best_key, c_mma);
         __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+        if (lane == 0) ring_release(sm, j);
         c_wait += k1 - k0; c_task += clock64() - k1; n_mine++;
       }
+      it = it0 + cnt;
       if (lane == 0 && blockIdx.x == 0 && P.tstamp) {   // CTA 0: cycles per tile waiting for TMA / reducing, warp 0 (shares its
         if (warp == 0 && n_mine) {                        // sub-partition with the producer warp) and warp 1 (does not)
           P.tstamp[stage_index * 8 + 4] = (unsigned long long)(c_wait / n_mine); P.tstamp[stage_index * 8 + 5] = (unsigned long long)(c_task / n_mine);
@@ -2115,20 +2154,20 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
         }
       }
     } else {
-      if (tid < 8) sm.sel[tid] = 0;
+      if (tid < 16) sm.sel[tid] = 0;
       csync();
       const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
-      int rgl = 0;
-      for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, rgl++) {
-        for (int pc = 0; pc < st.npieces; pc++, it++) {
-          const int sl = it % n_slots;
-          if ((sl & 7) != slot_of_warp(warp)) continue;
-          mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
-          wp_down_piece(P, st, sm, rg, rgl, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, x16_seg);
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
-        }
+      const int it0 = it, cnt = my_tile_count(nrg) * st.npieces;
+      for (;;) {
+        const int j = ring_claim(sm);
+        if (j >= it0 + cnt) break;
+        const int rgl = (j - it0) / st.npieces, pc = (j - it0) - rgl * st.npieces;
+        const uint32_t slot = ring_wait(sm, j);
+        wp_down_piece(P, st, sm, (int)blockIdx.x + rgl * (int)gridDim.x, rgl, pc, slot, x16_seg);
+        __syncwarp();
+        if (lane == 0) ring_release(sm, j);
       }
+      it = it0 + cnt;
     }
     return;
   }
@@ -2138,10 +2177,8 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
   long long c_wait = 0, c_task = 0, c_sync = 0, c_epi = 0;
   const bool timing = tid == 0 && blockIdx.x == 0 && P.tstamp;
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
-    const int sl = it % n_slots;
-    const uint32_t slot = sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes;
     const long long k0 = clock64();
-    mbar_wait_guard(sm.full[sl], (uint32_t)((it / n_slots) & 1));
+    const uint32_t slot = ring_wait(sm, it);
     const long long k1 = clock64();
     float* res = sm.res + parity_res * 256;
     bool skip = false;
@@ -2159,7 +2196,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     else consume_down_tile<Q>(P, st, t, slot, xs_seg, q8_seg, res, sm.act);
     const long long k2 = clock64();
     csync();                       // every warp is done with the slot -> one arrival frees it
-    if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sm.empty[sl]) : "memory");
+    if (tid == 0) ring_release(sm, it);
     const long long k3 = clock64();
     if (!skip) {
       if (st.kind == ST_GEMV) gemv_tile_epilogue(P, st, t, res, best_key, xres);
@@ -2177,15 +2214,15 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
 // Producer loop of a GEMV stage with everything tile-invariant hoisted into registers: per tile it only advances the
 // source pointers, waits for the slot, posts the byte count and issues the bulk copies.
 template <int Q>
-__device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
+__device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage& st, const MegaSmem& sm, int& it, RingProd& rp,
                                                    int dep_count, bool& dep_waited) {
   const size_t rb = (st.quant == Q_F32 && Q != Q_F32) ? (size_t)st.n * 4 : QTraits<Q>::row_bytes(st.n);   // F32 gate rows in a quantised model
   const int RT = st.rows_per_tile, parts = st.epi == EPI_GLU ? 2 : 1;
   const uint32_t part_stride = (uint32_t)align_up((size_t)RT * rb, 128);
   const uint32_t full_bytes = (uint32_t)align_up((size_t)RT * rb, 16);
-  const uint32_t slot_scale = (uint32_t)P.slot_scale, slot_bytes = (uint32_t)P.slot_bytes;
+  const uint32_t slot_scale = (uint32_t)P.slot_scale;
+  const uint32_t tile_need = (uint32_t)align_up((size_t)slot_scale + (size_t)parts * part_stride, 128);
   const int ncb = (st.n + P.bs1 - 1) / P.bs1, bs0 = P.bs0;
-  const uint32_t ring = sm.ring;
   // current job, cached
   int j = -1, j_begin = 0, j_end = 0, j_rows = 0;
   const uint8_t *w = nullptr, *wb = nullptr;
@@ -2214,9 +2251,8 @@ __device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage
         }
       }
     }
-    const int sl = it % n_slots;
-    const uint32_t slot = ring + (uint32_t)sl * slot_bytes, full = sm.full[sl];
-    if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
+    uint32_t full;
+    const uint32_t slot = ring_acquire(P, sm, rp, it, j_live ? tile_need : 0u, st.max_inflight, full);
     if (!j_live) { mbar_expect_tx(full, 0); continue; }
     const int r0 = (t - j_begin) * RT;
     const int nrows = min(RT, j_rows - r0);
@@ -2241,41 +2277,52 @@ __device__ __forceinline__ void producer_gemv_fast(const Program& P, const Stage
 }
 
 template <int Q>
-__device__ __forceinline__ void producer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, int n_slots,
+__device__ __forceinline__ void producer_stage(const Program& P, const Stage& st, const MegaSmem& sm, int& it, RingProd& rp,
                                                int dep_count) {
   bool dep_waited = false;
   const bool dyn_all = st.kind == ST_DOWN && st.K > 0;
+  if (st.kind == ST_DOWN && st.wp && QTraits<Q>::kq) {   // K-quants: one tile per row group (all segments)
+    const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
+    const uint32_t need = (uint32_t)align_up((size_t)st.K * (size_t)st.seg_stride + (size_t)st.down_rows * QTraits<Q>::row_bytes(st.sh), 128);
+    for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x, it++) {
+      if (st.K > 0 && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
+      uint32_t full;
+      const uint32_t slot = ring_acquire(P, sm, rp, it, need, st.max_inflight, full);
+      kq_produce_down_group<Q>(P, st, rg, slot, full, sm.act);
+    }
+    if (!dep_waited) dep_wait(sm.dep, dep_count);
+    return;
+  }
   if (st.kind == ST_DOWN && st.wp) {
     const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
     for (int rg = blockIdx.x; rg < nrg; rg += gridDim.x) {
       for (int pc = 0; pc < st.npieces; pc++, it++) {
-        if (st.piece[pc].seg < st.K && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
-        const int sl = it % n_slots;
-        if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
-        if constexpr (QTraits<Q>::kq) wp_produce_down_piece_q<Q>(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
-        else wp_produce_down_piece(P, st, rg, pc, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
+        const Piece pcd = st.piece[pc];
+        if (pcd.seg < st.K && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
+        size_t rbp;
+        if constexpr (QTraits<Q>::kq) rbp = QTraits<Q>::row_bytes(pcd.seg < st.K ? st.mi : st.sh);
+        else rbp = f8_pitch((size_t)(pcd.seg < st.K ? st.mi : st.sh));
+        const uint32_t need = (uint32_t)align_up((size_t)P.slot_scale + (size_t)pcd.g1 * rbp, 128);
+        uint32_t full;
+        const uint32_t slot = ring_acquire(P, sm, rp, it, need, st.max_inflight, full);
+        if constexpr (!QTraits<Q>::kq) wp_produce_down_piece(P, st, rg, pc, slot, full, sm.act);
       }
     }
     if (!dep_waited) dep_wait(sm.dep, dep_count);
     return;
   }
   if (st.kind == ST_GEMV) {
-    producer_gemv_fast<Q>(P, st, sm, it, n_slots, dep_count, dep_waited);
+    producer_gemv_fast<Q>(P, st, sm, it, rp, dep_count, dep_waited);
     if (!dep_waited) dep_wait(sm.dep, dep_count);
     return;
   }
   if constexpr (!QTraits<Q>::kq) {
   for (int t = blockIdx.x; t < st.ntiles; t += gridDim.x, it++) {
     bool dyn = dyn_all;
-    if (st.kind == ST_GEMV && st.has_dyn) {
-      int j = 0;
-      while (j + 1 < st.njobs && t >= st.job[j + 1].tile_begin) j++;
-      dyn = st.job[j].expert_slot >= 0;
-    }
     if (dyn && !dep_waited) { dep_wait(sm.dep, dep_count); dep_waited = true; }
-    const int sl = it % n_slots;
-    if (it >= n_slots) mbar_wait_backoff(sm.empty[sl], (uint32_t)(((it / n_slots) - 1) & 1));
-    produce_tile<Q>(P, st, t, sm.ring + (uint32_t)sl * (uint32_t)P.slot_bytes, sm.full[sl], sm.act);
+    uint32_t full;
+    const uint32_t slot = ring_acquire(P, sm, rp, it, (uint32_t)align_up((size_t)P.slot_bytes, 128), st.max_inflight, full);
+    produce_tile<Q>(P, st, t, slot, full, sm.act);
   }
   }
   if (!dep_waited) dep_wait(sm.dep, dep_count);   // bounds the run-ahead to one stage
@@ -2310,19 +2357,23 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
   __syncthreads();
   const Program& P = *reinterpret_cast<const Program*>(smem + 4096 + 2 * kStageSlot);
   const MegaSmem sm = carve_mega(smem, P.xregion_bytes);
-  const int n_slots = P.n_slots;
   if (tid == 0) {
-    for (int i = 0; i < n_slots; i++) { mbar_init(sm.full[i], 1); mbar_init(sm.empty[i], 1); }
+    for (int i = 0; i < kRingEntries; i++) {
+      mbar_init(sm.full0 + 8u * i, 1); mbar_init(sm.empty0 + 8u * i, 1);
+      sts32(sm.consumed + 4u * i, 0u); sts32(sm.ent_off + 4u * i, 0u); sts32(sm.start_abs + 4u * i, 0u);
+    }
+    sts32(sm.claim, 0u);
     for (int i = 0; i < 8; i++) reinterpret_cast<uint32_t*>(smem + kHdrZero)[i] = 0u;
     for (int i = 0; i < 4; i++) reinterpret_cast<float*>(smem + kHdrOne)[i] = 1.0f;
     dep_signal(sm.dep, 0);
-    sm.sel[14] = 0;
+    *sm.marker = 0;
     fence_proxy_async();
   }
   __syncthreads();
   const unsigned int base = *P.sync_base;
   const unsigned int G = gridDim.x;
   int it = 0;                      // tiles this CTA has pushed through the ring (same sequence on both sides)
+  RingProd rp{0u, 0};              // producer thread only
   unsigned long long best_key = 0ull;
   int nstage_seen = 0;             // stages executed by this launch so far (all tokens): barrier targets and dep counts
 #pragma unroll 1
@@ -2337,7 +2388,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       const Stage& st = *sm.st_p;
       const bool streams = st.kind == ST_GEMV || st.kind == ST_DOWN;
       if (tid == kConsumers && streams) {
-        producer_stage<Q>(P, st, sm, it, n_slots, nstage_seen + 1);   // (the F32 gate stage of a quantised model is a GEMV stage without scales)
+        producer_stage<Q>(P, st, sm, it, rp, nstage_seen + 1);   // (the F32 gate stage of a quantised model is a GEMV stage without scales)
       } else if (tid == kConsumers) {
         dep_wait(sm.dep, nstage_seen + 1);
       }
@@ -2376,8 +2427,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else {
-      if (st.quant == Q_F32 && Q != Q_F32) it = gate_f32_stage(it, n_slots, nstage_seen + 1, s);
-      else consumer_stage<Q>(P, st, sm, it, n_slots, best_key, nstage_seen + 1, s);
+      if (st.quant == Q_F32 && Q != Q_F32) it = gate_f32_stage(it, nstage_seen + 1, s);
+      else consumer_stage<Q>(P, st, sm, it, best_key, nstage_seen + 1, s);
       if (st.epi == EPI_LOGITS) {
         unsigned long long b = best_key;
 #pragma unroll
@@ -2389,6 +2440,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     // stage done: the CTA barrier orders every consumer's writes before thread 0's release-add (cumulative)
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 2] = gtime();
     csync();
+    if (tid == 0) sts32(sm.claim, (uint32_t)it);   // the claim counter overshoots by up to one ticket per warp at the end of a stage
     const bool last = (s + 1 == s_end) && (tok + 1 == n_tokens);
     if (!last && tid == 0) red_release_add(P.sync_counter, 1u);
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 3] = gtime();
