@@ -2114,15 +2114,23 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     } else {
       const int nrg = (P.dim + st.down_rows - 1) / st.down_rows;
       const int it0 = it, cnt = my_tile_count(nrg);
+      long long c_wait = 0, c_task = 0;
       for (;;) {
         const int j = ring_claim(sm);
         if (j >= it0 + cnt) break;
+        const long long k0 = clock64();
         const uint32_t slot = ring_wait(sm, j);
+        const long long k1 = clock64();
         kq_down_group<Q>(P, st, sm, (int)blockIdx.x + (j - it0) * (int)gridDim.x, slot, q8_seg);
         __syncwarp();
         if (lane == 0) ring_release(sm, j);
+        c_wait += k1 - k0; c_task += clock64() - k1;
       }
       it = it0 + cnt;
+      if (lane == 0 && blockIdx.x == 0 && P.tstamp && c_task) {   // profiling: the busiest warp's cycles waiting for TMA / reducing
+        atomicMax(&P.tstamp[stage_index * 8 + 6], (unsigned long long)c_wait);
+        atomicMax(&P.tstamp[stage_index * 8 + 7], (unsigned long long)c_task);
+      }
     }
     return;
   }
