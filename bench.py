@@ -613,7 +613,7 @@ def main():
             "data": "synthetic (random-init weights of the named architecture; no checkpoints offline)",
             "config": {"workload": workload_name(a.workload, a.quant), "baseline_config": {"v2lite": "configs[1]/[2]", "v2": "configs[3]", "v3": "configs[4]"}.get(a.workload),
                        "layers": w["n_layers"], "tokens_per_step": GEN_TOKENS,
-                       "parallelism": f"routed experts sharded over {a.gpus} GPU(s), rest replicated; one in-kernel peer-memory exchange per MoE layer" if a.gpus > 1 else "1 GPU",
+                       "parallelism": (f"tensor parallel over {a.gpus} GPUs: attention heads, wo columns, shared-expert / dense-FFN hidden units, LM-head rows and routed experts sharded; two in-kernel peer-memory exchanges per layer" if os.environ.get("DSK_TP", "1") != "0" else f"routed experts sharded over {a.gpus} GPU(s), rest replicated; one in-kernel peer-memory exchange per MoE layer") if a.gpus > 1 else "1 GPU",
                        "l2": "weights streamed per token (GBs) exceed the 126 MB L2; no flush needed"}}
 
     if a.impl == "reference":

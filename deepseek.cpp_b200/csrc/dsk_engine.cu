@@ -145,6 +145,16 @@ struct dsk_model {
   float* xchg = nullptr;                 // [2 parities][n_ranks][dim] floats, then n_ranks arrival flags
   float* xchg_peer[kMaxRanks] = {};      // the same buffer of every rank, as seen from this process
   unsigned* xflag_peer[kMaxRanks] = {};
+  // tensor parallelism (n_ranks > 1, peer memory available): attention heads, wo columns, shared-expert / dense-FFN hidden
+  // units and LM-head rows are sharded too; their partial sums / slices travel through the same exchange buffer
+  bool tp = false;
+  int h0 = 0, nh_loc = 0;                // local attention heads [h0, h0 + nh_loc)
+  int sh0 = 0, sh_loc = 0;               // local hidden units of the concatenated shared experts (multiples of 256)
+  int hid0 = 0, hid_loc = 0;             // local hidden units of the dense FFN layers
+  int v0 = 0, v_loc = 0;                 // local LM-head rows
+  float* logits_full = nullptr;          // tp: full-vocabulary logits inside the exchange allocation
+  float* logits_peer[kMaxRanks] = {};
+  unsigned long long* amax_peer[kMaxRanks] = {};
   long long xchg_done = 0;               // exchanges completed so far through this model's buffer (sequence numbers are per model:
                                          // the buffer and its flags are shared by every dsk_state of the model)
   int n_states = 0;
@@ -180,6 +190,8 @@ struct dsk_state {
   int built_epoch = 0;                  // m->p2p_epoch the program was built for
   int n_xchg = 0;                       // in-kernel exchanges per token (peer-memory mode)
   std::vector<int> xchg_before;         // exchanges preceding stage i within a token (size n_stages + 1)
+  int n_tail = 1;                       // stages after the last layer (LM head [+ arg-max exchange]): skipped by HYDRATE_KV_CACHE
+  float* logits_src = nullptr;          // where the full logits of the last forward live (tp: the exchange allocation)
 };
 
 static size_t disk_row_bytes(int quant, int cols) {
@@ -331,12 +343,34 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
     m->allocs.push_back(m->rope_freq);
     if (!fr.empty()) cudaMemcpy(m->rope_freq, fr.data(), fr.size() * 4, cudaMemcpyHostToDevice);
   }
+  {  // tensor-parallel shard of this rank (block splits: rank r keeps blocks [r B / N, (r + 1) B / N))
+    const dsk_config& c = *cfg;
+    auto lo = [&](int B, int r) { return (int)((long long)r * B / n_ranks); };
+    const char* e_tp = getenv("DSK_TP");
+    const char* e_p2p = getenv("DSK_P2P");
+    const int sh = c.n_shared_experts * c.moe_intermediate_size;
+    bool ok = n_ranks > 1 && !(e_tp && atoi(e_tp) == 0) && !(e_p2p && atoi(e_p2p) == 0);
+    ok = ok && c.n_heads % n_ranks == 0 && ((c.n_heads / n_ranks) * c.v_head_dim) % 256 == 0;   // wo column slices: whole 256-blocks
+    ok = ok && sh % 256 == 0 && c.hidden_dim % 256 == 0;
+    if (c.quant == DSK_F8E5M2)                                                                   // slices must not cut a scale block
+      ok = ok && c.bs0 == 128 && c.bs1 == 128 && ((c.n_heads / n_ranks) * (c.qk_nope_head_dim + c.qk_rope_head_dim)) % 128 == 0 &&
+           ((c.n_heads / n_ranks) * (c.qk_nope_head_dim + c.v_head_dim)) % 128 == 0;
+    m->tp = ok;
+    m->h0 = 0; m->nh_loc = c.n_heads; m->sh0 = 0; m->sh_loc = sh; m->hid0 = 0; m->hid_loc = c.hidden_dim; m->v0 = 0; m->v_loc = c.vocab_size;
+    if (ok) {
+      m->nh_loc = c.n_heads / n_ranks; m->h0 = rank * m->nh_loc;
+      m->sh0 = lo(sh / 256, rank) * 256; m->sh_loc = lo(sh / 256, rank + 1) * 256 - m->sh0;
+      m->hid0 = lo(c.hidden_dim / 256, rank) * 256; m->hid_loc = lo(c.hidden_dim / 256, rank + 1) * 256 - m->hid0;
+      const int vb = cdiv(c.vocab_size, 128);
+      m->v0 = lo(vb, rank) * 128; m->v_loc = std::min(c.vocab_size, lo(vb, rank + 1) * 128) - m->v0;
+    }
+  }
   m->layers.resize(cfg->n_layers);
   for (int l = 0; l < cfg->n_layers; l++) {
     Layer& L = m->layers[l];
     L.is_moe = E > 0 && l >= cfg->first_k_dense_replace;
-    const size_t kb = (size_t)cfg->max_seq_len * cfg->n_heads * m->head_dim * sizeof(__half);
-    const size_t vb = (size_t)cfg->max_seq_len * cfg->n_heads * cfg->v_head_dim * sizeof(__half);
+    const size_t kb = (size_t)cfg->max_seq_len * m->nh_loc * m->head_dim * sizeof(__half);
+    const size_t vb = (size_t)cfg->max_seq_len * m->nh_loc * cfg->v_head_dim * sizeof(__half);
     if (cudaMalloc(&L.kcache, kb) != cudaSuccess || cudaMalloc(&L.vcache, vb) != cudaSuccess) {
       fail(-2, "KV cache allocation failed (layer %d, %zu bytes)", l, kb + vb);
       delete m;
@@ -413,8 +447,6 @@ static int copy_rows(dsk_model* m, void* dst, size_t dpitch, const void* src, si
   return 0;
 }
 
-// expected logical shape of a weight by its role
-struct Role { DTensor* t; int rows, cols; bool expert; };
 
 static bool parse_layer_name(const char* name, int* layer, std::string* rest) {
   const char* pre = "model.layers.";
@@ -462,8 +494,14 @@ static int upload_f32(dsk_model* m, float** dst, int64_t d0, int64_t d1, int dty
   return copy_rows(m, *dst, nbytes, data, nbytes, nbytes, 1, on_dev);
 }
 
-static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expert, bool is_scale, int dtype,
-                         const int64_t shape[4], const void* data, size_t nbytes, int on_dev, const char* name) {
+// bytes of `cols` consecutive columns of a disk row (cols: a multiple of the quant's block width)
+static size_t disk_col_bytes(int quant, int cols) { return disk_row_bytes(quant, cols); }
+
+// (rows x cols) logical tensor; this rank keeps rows [r0, r0 + rc) and columns [c0, c0 + cc) of it (tensor-parallel slices;
+// the whole tensor when rc == rows and cc == cols) and, for expert stacks, its expert range.  dtype / shape are checked
+// against the FULL tensor, like the reference does.
+static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expert, bool is_scale, int r0, int rc, int c0, int cc,
+                         int dtype, const int64_t shape[4], const void* data, size_t nbytes, int on_dev, const char* name) {
   const dsk_config& c = m->c;
   const int E = expert ? c.n_routed_experts : 0;
   const int first = expert ? m->expert_first : 0;
@@ -476,46 +514,54 @@ static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expe
     const int64_t want_e[4] = {E, sr, sc, 0}, want_p[4] = {sr, sc, 0, 0};
     if (check_tensor(name, dtype, shape, nbytes, DSK_DT_F32, false, expert ? want_e : want_p, tot * 4)) return -4;
     if (t.scale) return fail(-4, "tensor %s uploaded twice", name);
-    t.scale_expert = per;
-    const size_t local = per * count;
+    // local block range (slices start on scale-block boundaries: validated at model creation)
+    const int sr0 = r0 / c.bs0, src = cdiv(rc, c.bs0), sc0 = c0 / c.bs1, scc = cdiv(cc, c.bs1);
+    const size_t per_loc = (size_t)src * scc;
+    t.scale_expert = per_loc;
+    const size_t local = per_loc * count;
     if (dmalloc(m, (void**)&t.scale, local * 4)) return -2;
-    return copy_rows(m, t.scale, local * 4, (const char*)data + (size_t)first * per * 4, local * 4, local * 4, local ? 1 : 0, on_dev);
+    if (local == 0) return 0;
+    if (src == sr && scc == sc)
+      return copy_rows(m, t.scale, local * 4, (const char*)data + (size_t)first * per * 4, local * 4, local * 4, 1, on_dev);
+    return copy_rows(m, t.scale, (size_t)scc * 4, (const char*)data + ((size_t)sr0 * sc + sc0) * 4, (size_t)sc * 4, (size_t)scc * 4, src, on_dev);
   }
   const int q = c.quant;
   const bool kq = q == DSK_Q2_K || q == DSK_Q3_K;
   if (kq && cols % 256 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 256", name, cols);
   if ((q == DSK_F16 || q == DSK_F8E5M2) && cols % 16 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 16", name, cols);
   if (q == DSK_F32 && cols % 4 != 0) return fail(-4, "tensor %s: cols %d not a multiple of 4", name, cols);
-  const size_t drb = disk_row_bytes(q, cols), vrb = dev_row_bytes(q, cols);
+  const size_t drb = disk_row_bytes(q, cols);
   const size_t tot = drb * rows * (expert ? E : 1);
   static const int codec_of_quant[5] = {DSK_DT_F32, DSK_DT_F16, DSK_DT_F8E5M2, DSK_DT_U8, DSK_DT_U8};   // quant_to_codec_dtype
   const int64_t want_e[4] = {E, rows, cols, 0}, want_p[4] = {rows, cols, 0, 0};
   if (check_tensor(name, dtype, shape, nbytes, codec_of_quant[q], kq, expert ? want_e : want_p, tot)) return -4;
   if (t.present) return fail(-4, "tensor %s uploaded twice", name);
+  const size_t drb_loc = disk_col_bytes(q, cc), vrb = dev_row_bytes(q, cc);
   t.present = true;
   t.quant = q;
   t.total_experts = E;
   t.expert_first = first;
   t.expert_count = count;
-  t.rows = rows;
-  t.cols = cols;
+  t.rows = rc;
+  t.cols = cc;
   t.row_bytes = vrb;
-  t.expert_bytes = vrb * rows;
-  const size_t local_disk = drb * rows * count, local_dev = vrb * rows * count;
+  t.expert_bytes = vrb * rc;
+  const size_t nrows_loc = (size_t)rc * count;
+  const size_t local_disk = drb_loc * nrows_loc, local_dev = vrb * nrows_loc;
   if (dmalloc(m, (void**)&t.w, local_dev + 16)) return -2;
-  const char* src = (const char*)data + (size_t)first * drb * rows;
+  const char* src = (const char*)data + (size_t)first * drb * rows + (size_t)r0 * drb + disk_col_bytes(q, c0);
   if (local_disk == 0) return 0;
   if (q == DSK_Q3_K) {
-    // stage the 110-byte disk blocks, repack to 112-byte aligned blocks on the device (same stream as the staging copy)
+    // stage the 110-byte disk blocks (compacted to the local columns), repack to 112-byte aligned blocks on the device
     const unsigned char* dsrc = (const unsigned char*)src;
     cudaStream_t st = nullptr;
-    if (!on_dev) {
+    if (!on_dev || drb_loc != drb) {
       void* staging = nullptr;
       CK(cudaMalloc(&staging, local_disk));
       m->up.staging.push_back(staging);
-      if (copy_rows(m, staging, local_disk, src, local_disk, local_disk, 1, 0)) return -2;
+      if (copy_rows(m, staging, drb_loc, src, drb, drb_loc, nrows_loc, on_dev)) return -2;
       dsrc = (const unsigned char*)staging;
-      st = m->up.st;
+      st = on_dev ? nullptr : m->up.st;
     }
     const size_t nblocks = local_disk / kQ3Disk;
     q3k_repack_kernel<<<(unsigned)((nblocks + 7) / 8), 256, 0, st>>>(dsrc, t.w, nblocks);
@@ -523,7 +569,7 @@ static int upload_weight(dsk_model* m, DTensor& t, int rows, int cols, bool expe
     if (on_dev) CK(cudaDeviceSynchronize());
     return 0;
   }
-  return copy_rows(m, t.w, vrb, src, drb, drb, (size_t)rows * count, on_dev);
+  return copy_rows(m, t.w, vrb, src, drb, drb_loc, nrows_loc, on_dev);
 }
 
 extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, const int64_t shape[4], const void* data,
@@ -535,13 +581,16 @@ extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, cons
   std::string nm(name);
   if (nm == "tokenizer.tokens") return 0;  // host-side only
   auto W = [&](DTensor& t, int rows, int cols, bool expert, bool is_scale) {
-    return upload_weight(m, t, rows, cols, expert, is_scale, dtype, shape, data, nbytes, src_on_device, name);
+    return upload_weight(m, t, rows, cols, expert, is_scale, 0, rows, 0, cols, dtype, shape, data, nbytes, src_on_device, name);
+  };
+  auto WS = [&](DTensor& t, int rows, int cols, bool is_scale, int r0, int rc, int c0, int cc) {
+    return upload_weight(m, t, rows, cols, false, is_scale, r0, rc, c0, cc, dtype, shape, data, nbytes, src_on_device, name);
   };
   auto F = [&](float** dst, int64_t d0, int64_t d1) { return upload_f32(m, dst, d0, d1, dtype, shape, data, nbytes, src_on_device, name); };
   if (nm == "model.embed.weight") return W(m->embed, c.vocab_size, c.dim, false, false);
   if (nm == "model.embed.scale") return W(m->embed, c.vocab_size, c.dim, false, true);
-  if (nm == "model.output.weight") { m->has_wcls = true; return W(m->wcls, c.vocab_size, c.dim, false, false); }
-  if (nm == "model.output.scale") return W(m->wcls, c.vocab_size, c.dim, false, true);
+  if (nm == "model.output.weight") { m->has_wcls = true; return WS(m->wcls, c.vocab_size, c.dim, false, m->v0, m->v_loc, 0, c.dim); }
+  if (nm == "model.output.scale") return WS(m->wcls, c.vocab_size, c.dim, true, m->v0, m->v_loc, 0, c.dim);
   if (nm == "model.norm.weight") return F(&m->rms_final, c.dim, 0);
   int l = -1;
   std::string rest;
@@ -559,21 +608,30 @@ extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, cons
   const bool is_scale = kind == "scale";
   if (!is_scale && kind != "weight") return fail(-4, "unknown tensor name %s", name);
   const int sh = c.n_shared_experts * mi;
-  Role r{nullptr, 0, 0, false};
-  if (base == "attn.wq") r = {&L.wq, c.n_heads * hd, c.dim, false};
-  else if (base == "attn.wq_a") r = {&L.wq_a, c.q_lora_rank, c.dim, false};
-  else if (base == "attn.wq_b") r = {&L.wq_b, c.n_heads * hd, c.q_lora_rank, false};
-  else if (base == "attn.wkv_a") r = {&L.wkv_a, c.kv_lora_rank + c.qk_rope_head_dim, c.dim, false};
-  else if (base == "attn.wkv_b") r = {&L.wkv_b, c.n_heads * (nope + c.v_head_dim), c.kv_lora_rank, false};
-  else if (base == "attn.wo") r = {&L.wo, c.dim, c.n_heads * c.v_head_dim, false};
-  else if (base == "mlp.w1") r = L.is_moe ? Role{&L.w1, mi, c.dim, true} : Role{&L.w1, c.hidden_dim, c.dim, false};
-  else if (base == "mlp.w2") r = L.is_moe ? Role{&L.w2, c.dim, mi, true} : Role{&L.w2, c.dim, c.hidden_dim, false};
-  else if (base == "mlp.w3") r = L.is_moe ? Role{&L.w3, mi, c.dim, true} : Role{&L.w3, c.hidden_dim, c.dim, false};
-  else if (base == "shared_mlp.w1") r = {&L.sw1, sh, c.dim, false};
-  else if (base == "shared_mlp.w2") r = {&L.sw2, c.dim, sh, false};
-  else if (base == "shared_mlp.w3") r = {&L.sw3, sh, c.dim, false};
-  else return fail(-4, "unknown tensor name %s (MLA-mode tensors are not part of this path)", name);
-  return W(*r.t, r.rows, r.cols, r.expert, is_scale);
+  // tensor-parallel slices (the whole tensor when tp is off: h0 = 0, nh_loc = n_heads, ...)
+  const int per_kv = nope + c.v_head_dim;
+  const int hr0 = m->h0 * hd, hrc = m->nh_loc * hd;                    // wq / wq_b rows of the local heads
+  const int kr0 = m->h0 * per_kv, krc = m->nh_loc * per_kv;            // wkv_b rows
+  const int oc0 = m->h0 * c.v_head_dim, occ = m->nh_loc * c.v_head_dim;   // wo columns
+  if (base == "attn.wq") return WS(L.wq, c.n_heads * hd, c.dim, is_scale, hr0, hrc, 0, c.dim);
+  if (base == "attn.wq_a") return W(L.wq_a, c.q_lora_rank, c.dim, false, is_scale);
+  if (base == "attn.wq_b") return WS(L.wq_b, c.n_heads * hd, c.q_lora_rank, is_scale, hr0, hrc, 0, c.q_lora_rank);
+  if (base == "attn.wkv_a") return W(L.wkv_a, c.kv_lora_rank + c.qk_rope_head_dim, c.dim, false, is_scale);
+  if (base == "attn.wkv_b") return WS(L.wkv_b, c.n_heads * per_kv, c.kv_lora_rank, is_scale, kr0, krc, 0, c.kv_lora_rank);
+  if (base == "attn.wo") return WS(L.wo, c.dim, c.n_heads * c.v_head_dim, is_scale, 0, c.dim, oc0, occ);
+  if (L.is_moe) {
+    if (base == "mlp.w1") return W(L.w1, mi, c.dim, true, is_scale);
+    if (base == "mlp.w2") return W(L.w2, c.dim, mi, true, is_scale);
+    if (base == "mlp.w3") return W(L.w3, mi, c.dim, true, is_scale);
+  } else {
+    if (base == "mlp.w1") return WS(L.w1, c.hidden_dim, c.dim, is_scale, m->hid0, m->hid_loc, 0, c.dim);
+    if (base == "mlp.w2") return WS(L.w2, c.dim, c.hidden_dim, is_scale, 0, c.dim, m->hid0, m->hid_loc);
+    if (base == "mlp.w3") return WS(L.w3, c.hidden_dim, c.dim, is_scale, m->hid0, m->hid_loc, 0, c.dim);
+  }
+  if (base == "shared_mlp.w1") return WS(L.sw1, sh, c.dim, is_scale, m->sh0, m->sh_loc, 0, c.dim);
+  if (base == "shared_mlp.w2") return WS(L.sw2, c.dim, sh, is_scale, 0, c.dim, m->sh0, m->sh_loc);
+  if (base == "shared_mlp.w3") return WS(L.sw3, sh, c.dim, is_scale, m->sh0, m->sh_loc, 0, c.dim);
+  return fail(-4, "unknown tensor name %s (MLA-mode tensors are not part of this path)", name);
 }
 
 extern "C" int dsk_model_finalize(dsk_model* m) {
@@ -616,6 +674,13 @@ extern "C" int dsk_model_finalize(dsk_model* m) {
 }
 
 extern "C" size_t dsk_model_resident_bytes(const dsk_model* m) { return m ? m->resident : 0; }
+extern "C" int dsk_model_sharding(const dsk_model* m, int* tensor_parallel, int* local_heads, int* local_experts) {
+  if (!m) return fail(-1, "null model");
+  if (tensor_parallel) *tensor_parallel = m->tp ? 1 : 0;
+  if (local_heads) *local_heads = m->nh_loc;
+  if (local_experts) *local_experts = m->expert_count;
+  return 0;
+}
 
 // Algorithmic weight bytes per decoded token: sum over executed GEMVs of rows*cols*bpw,
 // bpw = 4 / 2 / 1+4/(bs0*bs1) / 84/256 / 110/256, plus the F32 gate, gate bias and norm weights.
@@ -725,7 +790,7 @@ static float* state_buf(dsk_state* s, const char* name, size_t* cap) {
   if (k == "kv_b") { *cap = (size_t)c.n_heads * (c.qk_nope_head_dim + c.v_head_dim); return s->kv_b; }
   if (k == "moe_weights") { *cap = c.n_routed_experts; return s->moe_scores; }
   if (k == "active_experts_weights") { *cap = c.n_active_routed; return s->act_w; }
-  if (k == "logits") { *cap = c.vocab_size; return s->logits; }
+  if (k == "logits") { *cap = c.vocab_size; return s->logits_src ? s->logits_src : s->logits; }
   return nullptr;
 }
 extern "C" int dsk_state_read(dsk_state* s, const char* buffer, float* dst, size_t n) {
@@ -760,7 +825,7 @@ static int kv_ptr(dsk_model* m, int layer, int which, __half** p, size_t* cap) {
   if (!m || layer < 0 || layer >= m->c.n_layers) return fail(-4, "bad layer");
   Layer& L = m->layers[layer];
   *p = which == 0 ? L.kcache : L.vcache;
-  *cap = (size_t)m->c.max_seq_len * m->c.n_heads * (which == 0 ? m->head_dim : m->c.v_head_dim);
+  *cap = (size_t)m->c.max_seq_len * m->nh_loc * (which == 0 ? m->head_dim : m->c.v_head_dim);
   return 0;
 }
 extern "C" int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, size_t n) {
@@ -1078,6 +1143,7 @@ static void fill_program_header(Program* P, const dsk_config& c, int hd, const G
 static int build_program(dsk_model* m, dsk_state* s) {
   const dsk_config& c = m->c;
   const int hd = m->head_dim, mi = c.moe_intermediate_size, q = c.quant, G = g_sm_count;
+  const bool tp = m->tp && m->p2p;   // slices are decided at model creation; without the peer mapping dsk_comm_init() refuses
   g_f8_mma_ok = c.bs1 > 0 && (c.bs1 & (c.bs1 - 1)) == 0;
   std::vector<Stage> S;
   int n_xchg = 0;
@@ -1111,13 +1177,15 @@ static int build_program(dsk_model* m, dsk_state* s) {
       S.push_back(st);
     }
     { Stage st{}; st.kind = ST_ATTN; st.quant = q; st.layer = l; st.kcache = L.kcache; st.vcache = L.vcache; S.push_back(st); }
-    {  // S4
-      Stage st = gemv(q, s->xb2, nullptr, c.n_heads * c.v_head_dim, EPI_RESID, l);
+    {  // S4: x += wo . xb2.  Tensor parallel: this rank holds the wo columns of its heads -> partial sum, exchanged right after
+      Stage st = gemv(q, s->xb2, nullptr, m->nh_loc * c.v_head_dim, tp ? EPI_PARTIAL : EPI_RESID, l);
       st.job[0] = mjob(L.wo, s->x); st.njobs = 1;
+      st.xchg_ord = n_xchg;
       S.push_back(st);
+      if (tp) { Stage xs{}; xs.kind = ST_XCHG; xs.quant = q; xs.layer = l; xs.xchg_ord = n_xchg++; S.push_back(xs); }
     }
     if (L.is_moe) {
-      const int sh = c.n_shared_experts * mi;
+      const int sh = m->sh_loc;   // (local slice of the concatenated shared experts; all of it without tensor parallelism)
       {  // S5 gate logits (F32 weights in every quant)
         Stage st = gemv(DSK_F32, s->x, L.rms_ffn, c.dim, EPI_STORE, l);
         MJob j{}; j.w = (const uint8_t*)L.gate; j.out = s->moe_logits; j.rows = c.n_routed_experts; j.expert_slot = -1;
@@ -1134,7 +1202,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
         Stage st = gemv(q, s->x, L.rms_ffn, c.dim, EPI_GLU, l);
         st.need_topk = 1; st.gate_logits = s->moe_logits; st.gate_bias = L.gate_bias;
         int nj = 0;
-        if (sh > 0) { MJob j = mjob(L.sw1, s->hbs); j.w_b = L.sw3.w; j.scale_b = L.sw3.scale; st.job[nj++] = j; }
+        if (sh > 0 && L.sw1.rows > 0) { MJob j = mjob(L.sw1, s->hbs); j.w_b = L.sw3.w; j.scale_b = L.sw3.scale; st.job[nj++] = j; }
         for (int k = 0; k < c.n_active_routed; k++) {
           MJob j{};
           j.w = L.w1.w; j.scale = L.w1.scale; j.w_b = L.w3.w; j.scale_b = L.w3.scale;
@@ -1149,9 +1217,9 @@ static int build_program(dsk_model* m, dsk_state* s) {
         Stage st{};
         st.kind = ST_DOWN; st.quant = q; st.layer = l;
         st.w2 = L.w2.w; st.s2 = L.w2.scale; st.w2_stride = (long long)L.w2.expert_bytes; st.s2_stride = (long long)L.w2.scale_expert;
-        st.sw2 = sh > 0 ? L.sw2.w : nullptr; st.ss2 = sh > 0 ? L.sw2.scale : nullptr;
+        st.sw2 = sh > 0 ? L.sw2.w : nullptr; st.ss2 = sh > 0 ? L.sw2.scale : nullptr;   // (sh == 0: this rank holds no slice)
         st.K = c.n_active_routed; st.mi = mi; st.sh = sh;
-        st.add_shared = (m->n_ranks == 1 || m->rank == 0) ? 1 : 0;
+        st.add_shared = (m->n_ranks == 1 || m->rank == 0 || tp) ? 1 : 0;   // tp: every rank adds its slice of the shared experts
         st.xchg_ord = n_xchg;
         S.push_back(st);
         if (m->n_ranks > 1 && m->p2p) {   // in-kernel exchange over peer memory: the token stays ONE kernel
@@ -1170,16 +1238,21 @@ static int build_program(dsk_model* m, dsk_state* s) {
       {
         Stage st{};
         st.kind = ST_DOWN; st.quant = q; st.layer = l;
-        st.sw2 = L.w2.w; st.ss2 = L.w2.scale; st.K = 0; st.mi = 0; st.sh = c.hidden_dim; st.add_shared = 1;
+        st.sw2 = L.w2.w; st.ss2 = L.w2.scale; st.K = 0; st.mi = 0; st.sh = m->hid_loc; st.add_shared = 1;
+        st.xchg_ord = n_xchg;
         S.push_back(st);
+        if (tp) { Stage xs{}; xs.kind = ST_XCHG; xs.quant = q; xs.layer = l; xs.xchg_ord = n_xchg++; S.push_back(xs); }
       }
     }
     s->layer_end[l] = (int)S.size();
   }
-  {  // LM head + argmax
+  s->logits_src = (tp && m->logits_full) ? m->logits_full : s->logits;
+  s->n_tail = 1;
+  {  // LM head + argmax (tensor parallel: this rank's rows; logits and arg-max keys are exchanged by the ST_AMAX stage)
     Stage st = gemv(q, s->x, m->rms_final, c.dim, EPI_LOGITS, -1);
-    st.job[0] = mjob(m->wcls, s->logits); st.njobs = 1;
+    st.job[0] = mjob(m->wcls, s->logits_src + m->v0); st.job[0].row_base = m->v0; st.njobs = 1;
     S.push_back(st);
+    if (tp) { Stage xs{}; xs.kind = ST_AMAX; xs.quant = q; xs.layer = -1; xs.xchg_ord = n_xchg++; S.push_back(xs); s->n_tail = 2; }
   }
   const bool has_gate = q != DSK_F32 && c.n_routed_experts > 0;
   choose_slot_geometry(q, S, has_gate ? c.dim : 0);
@@ -1196,30 +1269,34 @@ static int build_program(dsk_model* m, dsk_state* s) {
   Program* P = reinterpret_cast<Program*>(buf.data());
   memset(P, 0, sizeof(Program));
   fill_program_header(P, c, hd, geo);
+  P->n_heads = m->nh_loc;
   P->expert_first = m->expert_first; P->expert_count = m->expert_count;
   P->embed_quant = q; P->n_stages = (int)S.size();
   P->embed_w = m->embed.w; P->embed_scale = m->embed.scale; P->rope_freq = m->rope_freq;
   P->x = s->x; P->q = s->q; P->q_a = s->q_a; P->kv_a = s->kv_a; P->kv_b = s->kv_b; P->xb2 = s->xb2; P->hbk = s->hbk; P->hbs = s->hbs;
-  P->moe_logits = s->moe_logits; P->moe_scores = s->moe_scores; P->act_w = s->act_w; P->logits = s->logits; P->partial = m->n_ranks > 1 ? s->partial : nullptr;
+  P->moe_logits = s->moe_logits; P->moe_scores = s->moe_scores; P->act_w = s->act_w; P->logits = s->logits_src; P->partial = m->n_ranks > 1 ? s->partial : nullptr;
   P->act = s->act; P->ctrl = s->ctrl; P->token_log = s->token_log; P->step = s->step;
-  CK(cudaMalloc((void**)&s->att_scratch, (size_t)c.n_heads * (c.max_seq_len + kConsumers + 8) * 4));
+  CK(cudaMalloc((void**)&s->att_scratch, (size_t)m->nh_loc * (c.max_seq_len + kConsumers + 8) * 4));
   CK(cudaMalloc((void**)&s->sync_words, 64));
   CK(cudaMemset(s->sync_words, 0, 64));
   P->att_scratch = s->att_scratch; P->sync_counter = s->sync_words; P->sync_base = s->sync_words + 1;
   CK(cudaMalloc((void**)&s->tstamp, (S.size() * 8 + 8) * sizeof(unsigned long long)));
   CK(cudaMemset(s->tstamp, 0, (S.size() * 8 + 8) * sizeof(unsigned long long)));
-  P->n_ranks = m->n_ranks; P->rank = m->rank; P->n_xchg = n_xchg;
-  for (int qq = 0; qq < kMaxRanks; qq++) { P->xchg_peer[qq] = m->xchg_peer[qq]; P->xflag_peer[qq] = m->xflag_peer[qq]; }
+  P->n_ranks = m->n_ranks; P->rank = m->rank; P->n_xchg = n_xchg; P->tp = tp ? 1 : 0;
+  for (int qq = 0; qq < kMaxRanks; qq++) {
+    P->xchg_peer[qq] = m->xchg_peer[qq]; P->xflag_peer[qq] = m->xflag_peer[qq];
+    P->logits_peer[qq] = m->logits_peer[qq]; P->amax_peer[qq] = m->amax_peer[qq];
+  }
   s->n_xchg = n_xchg;
   s->xchg_before.assign(S.size() + 1, 0);
-  for (size_t i = 0; i < S.size(); i++) s->xchg_before[i + 1] = s->xchg_before[i] + (S[i].kind == ST_XCHG ? 1 : 0);
+  for (size_t i = 0; i < S.size(); i++) s->xchg_before[i + 1] = s->xchg_before[i] + ((S[i].kind == ST_XCHG || S[i].kind == ST_AMAX) ? 1 : 0);
   s->built_epoch = m->p2p_epoch;
   P->tstamp = getenv("DSK_TSTAMP") ? s->tstamp : nullptr;   // the per-stage timeline costs a few globaltimer reads per stage: opt-in
   P->route_prof = reinterpret_cast<long long*>(s->tstamp + S.size() * 8);
   s->stage_names.clear();
   for (const Stage& st : S) {
     char nm[96];
-    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_XCHG ? "xchg" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
+    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_XCHG ? "xchg" : st.kind == ST_AMAX ? "amax" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
     snprintf(nm, sizeof(nm), "%-8s n=%5d tiles=%5d rt=%2d wp=%d pieces=%2d", kind, st.kind == ST_DOWN ? st.K * st.mi + st.sh : st.n, st.ntiles, st.rows_per_tile, st.wp, st.npieces);
     s->stage_names.push_back(nm);
   }
@@ -1317,11 +1394,11 @@ extern "C" int dsk_forward(dsk_model* m, dsk_state* s, int token, int pos, int m
   fill_ctrl(s->h_ctrl, c, token, pos);
   if (s->h_ctrl->kv_pos >= c.max_seq_len || s->h_ctrl->kv_len > c.max_seq_len)
     return fail(-4, "pos %d does not fit the KV cache (max_seq_len %d; the reference would overrun it)", pos, c.max_seq_len);
-  const int e = mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - 1 : s->n_stages;
+  const int e = mode == DSK_HYDRATE_KV_CACHE ? s->n_stages - s->n_tail : s->n_stages;
   set_xchg_base(m, s, 0, e);
   CK(cudaMemcpyAsync(s->ctrl, s->h_ctrl, sizeof(Ctrl), cudaMemcpyHostToDevice, s->stream));
   if (run_stages(m, s, 0, e, 0, s->stream)) return -2;
-  if (mode && host_logits) CK(cudaMemcpyAsync(host_logits, s->logits, (size_t)c.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
+  if (mode && host_logits) CK(cudaMemcpyAsync(host_logits, s->logits_src, (size_t)c.vocab_size * 4, cudaMemcpyDeviceToHost, s->stream));
   if (mode && argmax) CK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
   CK(cudaStreamSynchronize(s->stream));
   if (mode && argmax) *argmax = (int)(0xFFFFFFFFu - (unsigned)(s->h_ctrl->argmax_key & 0xFFFFFFFFull));
@@ -1482,7 +1559,7 @@ extern "C" int dsk_sample(dsk_model* m, dsk_state* s, float temperature, float t
     return 0;
   }
   if (!(temperature > 0.0f)) return fail(-4, "temperature must be >= 0");
-  sample_kernel<<<1, 1024, 0, s->stream>>>(s->logits, m->c.vocab_size, temperature, coin * top_p, -1, s->sample_out);
+  sample_kernel<<<1, 1024, 0, s->stream>>>(s->logits_src, m->c.vocab_size, temperature, coin * top_p, -1, s->sample_out);
   CKL(cudaGetLastError());
   float h[2];
   CK(cudaMemcpyAsync(h, s->sample_out, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
@@ -1496,7 +1573,7 @@ extern "C" int dsk_sample_prob(dsk_model* m, dsk_state* s, int index, float* pro
   if (!m || !s || !prob) return fail(-1, "bad arguments");
   if (index < 0 || index >= m->c.vocab_size) return fail(-4, "index %d out of range", index);
   if (need_logits(s, "dsk_sample_prob")) return -4;
-  sample_kernel<<<1, 1024, 0, s->stream>>>(s->logits, m->c.vocab_size, 1.0f, 0.f, index, s->sample_out);
+  sample_kernel<<<1, 1024, 0, s->stream>>>(s->logits_src, m->c.vocab_size, 1.0f, 0.f, index, s->sample_out);
   CKL(cudaGetLastError());
   float h[2];
   CK(cudaMemcpyAsync(h, s->sample_out, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
@@ -1537,9 +1614,15 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
   // buffer and maps every peer's through CUDA IPC; the handles travel through the NCCL communicator just created.
   const char* p2p_env = getenv("DSK_P2P");
   if (p2p_env && atoi(p2p_env) == 0) return 0;
-  if (m->n_ranks > kMaxRanks || !g_nccl.AllGather) return 0;
+  if (m->n_ranks > kMaxRanks || !g_nccl.AllGather) {
+    if (m->tp) return fail(-3, "tensor-parallel model needs the peer-memory exchange (ncclAllGather missing): create it with DSK_TP=0");
+    return 0;
+  }
   const int N = m->n_ranks;
-  const size_t data_bytes = (size_t)2 * N * m->c.dim * sizeof(float), total = data_bytes + 256;
+  // layout: [2 parities][N][dim] partial sums | N flags (256 B) | tp: [2][N] arg-max keys (256 B) | tp: vocab logits
+  const size_t data_bytes = (size_t)2 * N * m->c.dim * sizeof(float);
+  const size_t amax_off = data_bytes + 256, logits_off = amax_off + 256;
+  const size_t total = logits_off + (m->tp ? (size_t)m->c.vocab_size * sizeof(float) : 0);
   cudaIpcMemHandle_t mine;
   unsigned char* d_handles = nullptr;
   std::vector<cudaIpcMemHandle_t> all(N);
@@ -1558,6 +1641,10 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
     if (q != m->rank && cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
     m->xchg_peer[q] = (float*)ptr;
     m->xflag_peer[q] = (unsigned*)((unsigned char*)ptr + data_bytes);
+    if (m->tp) {
+      m->amax_peer[q] = (unsigned long long*)((unsigned char*)ptr + amax_off);
+      m->logits_peer[q] = (float*)((unsigned char*)ptr + logits_off);
+    }
   }
   if (d_handles) cudaFree(d_handles);
   cudaGetLastError();
@@ -1572,6 +1659,9 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
   CK(cudaMemcpy(&bad, flag, sizeof(float), cudaMemcpyDeviceToHost));
   cudaFree(flag);
   m->p2p = bad == 0.f;
+  if (m->p2p && m->tp) m->logits_full = m->logits_peer[m->rank];
+  if (!m->p2p && m->tp)
+    return fail(-3, "tensor-parallel weights were sliced at upload but the peer-memory mapping is unavailable on rank %d: create the model with DSK_TP=0 (expert-only sharding, NCCL exchange)", m->rank);
   if (!m->p2p) { fprintf(stderr, "[dsk] rank %d: peer-memory exchange unavailable, using NCCL all-reduce between kernel segments\n", m->rank); return 0; }
   m->p2p_epoch++;
   return 0;

@@ -11,7 +11,7 @@
 namespace dsk {
 
 enum { Q_F32 = 0, Q_F16 = 1, Q_F8 = 2, Q_Q2K = 3, Q_Q3K = 4 };
-enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GLU = 2, EPI_KVB = 3, EPI_LOGITS = 4 };
+enum { EPI_STORE = 0, EPI_RESID = 1, EPI_GLU = 2, EPI_KVB = 3, EPI_LOGITS = 4, EPI_PARTIAL = 5 };   // PARTIAL: tensor-parallel partial sum -> exchange buffer
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;

@@ -23,7 +23,7 @@
 
 namespace dsk {
 
-enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3, ST_XCHG = 4 };
+enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3, ST_XCHG = 4, ST_AMAX = 5 };
 constexpr int kMaxRanks = 8;
 
 constexpr int kConsumers = 256;            // warps 0..7
@@ -41,7 +41,7 @@ struct MJob {                              // one weight matrix of a GEMV stage
   const uint8_t* w_b; const float* scale_b;  // EPI_GLU: the `up` matrix
   float* out;
   long long w_stride, s_stride;            // per-expert strides (bytes / floats)
-  int rows, expert_slot, tile_begin, pad;
+  int rows, expert_slot, tile_begin, row_base;   // row_base: global index of local row 0 (row-sharded LM head)
 };
 
 struct Piece { int seg, g0, g1, pad; };    // column piece: granules [g0,g1) of segment `seg` (granule = 16 B or a 256-block)
@@ -93,9 +93,11 @@ struct Program {
   // multi-GPU, peer-memory mode: every rank stores its MoE partial sums straight into every peer's exchange buffer over
   // NVLink (plain stores to IPC-mapped memory), then raises a flag there; an ST_XCHG stage waits for the N flags and adds the
   // N partials in rank order — no kernel boundary, no NCCL call on the token path
-  int n_ranks, rank, n_xchg, pad_x;
+  int n_ranks, rank, n_xchg, tp;           // tp: tensor-parallel program (heads / FFN slices / LM-head rows sharded)
   float* xchg_peer[kMaxRanks];             // [2][n_ranks][dim] buffer of rank q (q == rank: the local one)
   unsigned* xflag_peer[kMaxRanks];         // n_ranks flags of rank q: flag[r] = sequence number of rank r's last finished store
+  float* logits_peer[kMaxRanks];           // tp: full-vocabulary logits of rank q (every rank stores its rows into every copy)
+  unsigned long long* amax_peer[kMaxRanks];   // tp: [2][n_ranks] arg-max keys of rank q
   long long* route_prof;                   // profiling: 4 phase durations of the last routing (cycles)
   unsigned long long* tstamp;              // [n_stages][8] globaltimer stamps of CTA 0: start, inputs staged, tiles done, arrived, ...
   // test taps (null in production): CTA 0 dumps the activation vector exactly as the tile loop will read it
@@ -937,6 +939,32 @@ __device__ __forceinline__ void consume_gemv_tile(const Program& P, const Stage&
   (void)best;
 }
 
+// ---- multi-GPU partial sums -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_partial(const Program& P, const Stage& st, int i, float acc) {
+  if (P.n_xchg > 0) {   // peer-memory mode: straight into every rank's exchange buffer (parity by sequence number)
+    const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
+    const size_t off = ((size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank) * (size_t)P.dim + (size_t)i;
+    for (int q = 0; q < P.n_ranks; q++) P.xchg_peer[q][off] = acc;
+    __threadfence_system();
+  } else {
+    P.partial[i] = acc;
+  }
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// LM-head rows are sharded under tensor parallelism: every rank stores its logits into every rank's full-vocabulary buffer
+// (NVLink posted writes), made visible by the ST_AMAX exchange that follows the stage
+__device__ __forceinline__ void store_logit(const Program& P, const MJob& jb, int r, float val) {
+  jb.out[r] = val;
+  if (P.tp && P.n_ranks > 1) {
+    const size_t row = (size_t)jb.row_base + (size_t)r;
+    for (int q = 0; q < P.n_ranks; q++) if (q != P.rank) P.logits_peer[q][row] = val;
+    __threadfence_system();
+  }
+}
 // combine column pieces in a fixed order + epilogue, one thread per row of the tile
 __device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, unsigned long long& best,
                                                    float xres) {
@@ -958,6 +986,7 @@ __device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage
   }
   switch (st.epi) {
     case EPI_RESID: jb.out[r] = xres + val; break;
+    case EPI_PARTIAL: store_partial(P, st, r, val); break;
     case EPI_KVB: {
       jb.out[r] = val;
       const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
@@ -967,8 +996,8 @@ __device__ __forceinline__ void gemv_tile_epilogue(const Program& P, const Stage
       break;
     }
     case EPI_LOGITS: {
-      jb.out[r] = val;
-      const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+      store_logit(P, jb, r, val);
+      const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(jb.row_base + r));
       if (key > best) best = key;
       break;
     }
@@ -1050,22 +1079,6 @@ __device__ __forceinline__ void consume_down_tile(const Program& P, const Stage&
     if (lane == 0) res[lr * np + pc] = v[0];
   }
 }
-// ---- multi-GPU partial sums -----------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_partial(const Program& P, const Stage& st, int i, float acc) {
-  if (P.n_xchg > 0) {   // peer-memory mode: straight into every rank's exchange buffer (parity by sequence number)
-    const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
-    const size_t off = ((size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank) * (size_t)P.dim + (size_t)i;
-    for (int q = 0; q < P.n_ranks; q++) P.xchg_peer[q][off] = acc;
-    __threadfence_system();
-  } else {
-    P.partial[i] = acc;
-  }
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // x[i] += sum_k w_k * dot_k + dot_shared in the reference's order (src/infer.cpp:873-877, 899-903, 926-930)
 __device__ __forceinline__ void down_tile_epilogue(const Program& P, const Stage& st, int t, const float* res, const float* actw_smem,
                                                    const int* act_smem, float xres) {
@@ -1074,7 +1087,7 @@ __device__ __forceinline__ void down_tile_epilogue(const Program& P, const Stage
   const int lr = threadIdx.x;
   if (lr >= nrows) return;
   const int i = i0 + lr, np = st.npieces;
-  const bool to_partial = P.partial != nullptr && st.K > 0;
+  const bool to_partial = P.partial != nullptr && (st.K > 0 || P.tp != 0);
   float acc = to_partial ? 0.f : xres;
   int pc = 0;
   for (int k = 0; k <= st.K; k++) {
@@ -1235,6 +1248,31 @@ __device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const 
     float acc = P.x[i];
     for (int r = 0; r < P.n_ranks; r++) acc += __ldcg(b + (size_t)r * (size_t)P.dim);
     P.x[i] = acc;
+  }
+}
+
+// ST_AMAX (tensor parallel, after the row-sharded LM head): the ranks exchange their local arg-max keys (and thereby publish the
+// logits they stored into each other's buffers); the global key — largest logit, lowest index on ties, as sample_argmax —
+// replaces the local one in Ctrl so the next token's embedding stage and the host read the same token on every rank.
+__device__ __forceinline__ void c_amax(const Program& P, const Stage& st) {
+  if (blockIdx.x != 0) return;
+  const int tid = threadIdx.x;
+  const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
+  if (tid < P.n_ranks) {
+    P.amax_peer[tid][(size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank] = P.ctrl->argmax_key;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + P.rank), "r"(seq) : "memory");
+    const unsigned long long t0 = gtime();
+    while ((int)(ld_acquire_sys(P.xflag_peer[P.rank] + tid) - seq) < 0) {
+      if (gtime() - t0 > 30000000000ull) __trap();
+    }
+  }
+  csync();
+  if (tid == 0) {
+    unsigned long long best = 0ull;
+    const unsigned long long* keys = P.amax_peer[P.rank] + (size_t)(seq & 1u) * (size_t)P.n_ranks;
+    for (int r = 0; r < P.n_ranks; r++) { const unsigned long long k = *reinterpret_cast<const volatile unsigned long long*>(keys + r); if (k > best) best = k; }
+    P.ctrl->argmax_key = best;
   }
 }
 
@@ -1433,6 +1471,7 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
     const float val = half ? v_hi : v_lo;
     switch (st.epi) {
       case EPI_RESID: jb.out[r] = (half ? xres_hi : xres_lo) + val; break;
+      case EPI_PARTIAL: store_partial(P, st, r, val); break;
       case EPI_KVB: {
         jb.out[r] = val;
         const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
@@ -1442,8 +1481,8 @@ __device__ __forceinline__ void wp_gemv_tile(const Program& P, const Stage& st, 
         break;
       }
       case EPI_LOGITS: {
-        jb.out[r] = val;
-        const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+        store_logit(P, jb, r, val);
+        const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(jb.row_base + r));
         if (key > best) best = key;
         break;
       }
@@ -1526,7 +1565,7 @@ __device__ __forceinline__ void wp_down_piece(const Program& P, const Stage& st,
   const int grows = min(st.down_rows, P.dim - gi0);
   if (lane < grows) {
     const int i = gi0 + lane;
-    const bool to_partial = P.partial != nullptr && st.K > 0;
+    const bool to_partial = P.partial != nullptr && (st.K > 0 || P.tp != 0);
     float acc = to_partial ? 0.f : P.x[i];
     int p2 = 0;
     for (int kk = 0; kk <= st.K; kk++) {
@@ -1719,6 +1758,7 @@ __device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& s
   if (glu) val = (P.act_silu ? silu_f(v) : gelu_f(v)) * u;
   switch (st.epi) {
     case EPI_RESID: jb.out[r] = xres + val; break;
+    case EPI_PARTIAL: store_partial(P, st, r, val); break;
     case EPI_KVB: {
       jb.out[r] = val;
       const int per = P.nope + P.vh, hh = r / per, ii = r - hh * per;
@@ -1728,8 +1768,8 @@ __device__ __forceinline__ void wp_kq_gemv_tile(const Program& P, const Stage& s
       break;
     }
     case EPI_LOGITS: {
-      jb.out[r] = val;
-      const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)r);
+      store_logit(P, jb, r, val);
+      const unsigned long long key = ((unsigned long long)orderable(val) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(jb.row_base + r));
       if (key > best) best = key;
       break;
     }
@@ -1771,7 +1811,7 @@ __device__ __forceinline__ void kq_down_group(const Program& P, const Stage& st,
   const int lane = threadIdx.x & 31;
   const int i0 = rg * st.down_rows;
   const int nrows = min(st.down_rows, P.dim - i0);
-  const bool to_partial = P.partial != nullptr && st.K > 0;
+  const bool to_partial = P.partial != nullptr && (st.K > 0 || P.tp != 0);
   float acc = 0.f;
   if (!to_partial && lane < nrows) acc = P.x[i0 + lane];   // residual operand first: its L2 latency hides behind the dots
   const uint32_t rb_mi = (uint32_t)QTraits<Q>::row_bytes(st.mi);
@@ -2194,7 +2234,7 @@ __device__ __forceinline__ void consumer_stage(const Program& P, const Stage& st
     float xres = 0.f;
     if (st.kind == ST_DOWN) {
       const int i = t * st.rows_per_tile + tid;
-      if (tid < st.rows_per_tile && i < P.dim && !(P.partial != nullptr && st.K > 0)) xres = P.x[i];
+      if (tid < st.rows_per_tile && i < P.dim && !(P.partial != nullptr && (st.K > 0 || P.tp != 0))) xres = P.x[i];
     } else if (st.epi == EPI_RESID) {
       const int r = (t - st.job[0].tile_begin) * st.rows_per_tile + tid;
       if (tid < st.rows_per_tile && r < st.job[0].rows) xres = st.job[0].out[r];
@@ -2430,6 +2470,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else if (st.kind == ST_XCHG) {
       c_xchg(P, st, sm);
+      if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
+    } else if (st.kind == ST_AMAX) {
+      c_amax(P, st);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else if (st.kind == ST_ATTN) {
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);

@@ -111,6 +111,7 @@ def lib():
         L.dsk_model_destroy.argtypes = [C.c_void_p]
         L.dsk_upload_tensor.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int64), C.c_void_p, C.c_size_t, C.c_int]
         L.dsk_model_finalize.argtypes = [C.c_void_p]
+        L.dsk_model_sharding.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.dsk_model_resident_bytes.restype = C.c_size_t
         L.dsk_model_resident_bytes.argtypes = [C.c_void_p]
         L.dsk_model_active_bytes_per_token.restype = C.c_double
@@ -304,6 +305,12 @@ class Model:
         buf = C.create_string_buffer(1 << 16)
         _ck(self.L.dsk_profile_token(self.h, self.s, token, pos, buf, len(buf)))
         return buf.value.decode()
+
+    def sharding(self):
+        """(tensor_parallel, local attention heads, local routed experts) of this rank."""
+        tp, nh, ne = C.c_int(0), C.c_int(0), C.c_int(0)
+        _ck(self.L.dsk_model_sharding(self.h, C.byref(tp), C.byref(nh), C.byref(ne)))
+        return bool(tp.value), nh.value, ne.value
 
     def resident_bytes(self) -> int:
         return self.L.dsk_model_resident_bytes(self.h)

@@ -62,9 +62,15 @@ int dsk_sync(void);
 int dsk_device_info(char* name128, int* sm_count, size_t* hbm_bytes);
 
 /* ---- model: replaces Model::Model weight binding (src/model.cpp:756-871) + device upload -------- */
-/* rank/n_ranks: expert-shard placement — routed expert e lives on rank e / ceil(E/n_ranks); everything
- * else is replicated. */
+/* rank/n_ranks: shard placement, decided here so that dsk_upload_tensor() can keep only this rank's slices.
+ * Routed expert e lives on rank e / ceil(E/n_ranks).  With n_ranks > 1 and peer memory (default; DSK_TP=0 or
+ * DSK_P2P=0 switch it off) the model is also TENSOR PARALLEL: attention heads (wq/wq_b/wkv_b rows, wo columns, KV cache),
+ * the hidden units of the shared experts and of the dense FFN layers (256-blocks) and the LM-head rows are split across
+ * the ranks; wq_a / wkv_a / the gate / norms / embedding stay replicated.  Requires n_heads % n_ranks == 0 and
+ * (n_heads / n_ranks) * v_head_dim % 256 == 0, otherwise only the experts are sharded. */
 dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ranks);
+/* What dsk_model_create decided for this rank: tensor_parallel (0/1), local attention heads, local routed experts. */
+int dsk_model_sharding(const dsk_model* m, int* tensor_parallel, int* local_heads, int* local_experts);
 void dsk_model_destroy(dsk_model* m);
 /* Upload one .dseek tensor by its on-disk name (src/model.cpp:766-871), raw payload bytes exactly as
  * stored (K-quants: U8 block rows).  Expert stacks (E, rows, cols): only this rank's slice is kept.
@@ -126,9 +132,11 @@ int dsk_launches_per_forward(const dsk_model* m, int mode);
 int dsk_sample(dsk_model* m, dsk_state* s, float temperature, float top_p, float coin, int* token);
 int dsk_sample_prob(dsk_model* m, dsk_state* s, int index, float* prob);
 
-/* ---- multi-GPU: one exchange of the MoE partial sum per MoE layer ------------------
- * The reference has no distributed path; this is the one real exchange step of the expert-sharded model
- * (rank r keeps experts [r*ceil(E/N), (r+1)*ceil(E/N)), everything else replicated).
+/* ---- multi-GPU ---------------------------------------------------------------------------
+ * The reference has no distributed path.  Expert-only sharding has one real exchange step per MoE layer (the MoE partial
+ * sum); the tensor-parallel model adds one after the wo projection of every layer (partial sums of the column-sharded wo),
+ * one after the dense FFN layers, and one arg-max / logits exchange per token.  All of them run INSIDE the persistent
+ * kernel over CUDA-IPC-mapped peer memory: stores straight into every peer's buffer over NVLink, a flag, a fixed-order sum.
  * nccl_unique_id: 128 bytes from dsk_comm_unique_id() on rank 0, broadcast by the launcher (one process
  * per GPU).  dsk_comm_init creates the communicator, then — unless DSK_P2P=0 or a rank lacks peer access —
  * maps one exchange buffer per rank into every peer through CUDA IPC: the decode kernel then stores its

@@ -1,7 +1,10 @@
-"""Expert-sharded decode on >= 2 GPUs of one node: every rank loads the same checkpoint, keeps its slice of
-the routed experts, and exchanges the MoE partial sums inside the persistent kernel over CUDA-IPC-mapped peer memory
-(DSK_P2P=1, the default) or through ncclAllReduce between kernel segments (DSK_P2P=0).  Rank 0 checks teacher-forced
-logits and the device-resident greedy loop against the reference (or its C restatement) on the full checkpoint.
+"""Sharded decode on >= 2 GPUs of one node: every rank loads the same checkpoint and keeps its slices —
+routed experts always; with peer memory (DSK_P2P=1, the default) and head dims that allow it also the attention heads, wo
+columns, shared-expert / dense-FFN hidden units and LM-head rows (tensor parallel).  Partial sums, logits and arg-max keys
+are exchanged inside the persistent kernel over CUDA-IPC-mapped peer memory; DSK_P2P=0 = expert-only sharding with
+ncclAllReduce between kernel segments.  Rank 0 checks teacher-forced logits and the device-resident greedy loop against
+the reference (or its C restatement) on the full checkpoint; the "_tp" cases use real head dims (128 + 64 / 128) so that
+two heads fill a 256-column K-quant block and assert that the tensor-parallel plan is actually active.
 
 Skipped on a single-GPU box (the round-end driver); run it with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multigpu.py`.
 """
@@ -53,7 +56,7 @@ WORKER = textwrap.dedent("""
             o.forward(int(tok), pos)
             tok = o.argmax()
             pos += 1
-        print("RESULT " + json.dumps({"errs": errs, "dev": [int(x) for x in dev], "host": host,
+        print("RESULT " + json.dumps({"errs": errs, "dev": [int(x) for x in dev], "host": host, "tp": bool(m.sharding()[0]),
                                       "launches": m.launches_per_forward(dsk.OUTPUT_LOGITS)}), flush=True)
     dist.barrier()
     m.close()
@@ -72,10 +75,16 @@ def _gpus():
 @pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs on one node")
 @pytest.mark.parametrize("p2p", ["1", "0"])
 @pytest.mark.parametrize("preset,quant,tol", [("tiny_v2lite", "fp32", 2e-4), ("tiny_v2lite", "f8e5m2", 5e-4),
-                                              ("tiny_v3", "f8e5m2", 5e-4), ("tiny_v2", "q2_k", 8e-2), ("tiny_v3", "q3_k", 8e-2)])
+                                              ("tiny_v3", "f8e5m2", 5e-4), ("tiny_v2", "q2_k", 8e-2), ("tiny_v3", "q3_k", 8e-2),
+                                              ("tiny_v2lite_tp", "fp32", 2e-4), ("tiny_v2_tp", "f8e5m2", 5e-4),
+                                              ("tiny_v3_tp", "f8e5m2", 5e-4), ("tiny_v2_tp", "q2_k", 8e-2), ("tiny_v3_tp", "q2_k", 8e-2)])
 def test_sharded_decode_matches_reference(repo, ckpt, tmp_path, p2p, preset, quant, tol):
     import json
-    d = ckpt(preset, quant)
+    want_tp = preset.endswith("_tp") and p2p == "1"
+    if preset.endswith("_tp"):   # real head dims: 2 local heads x 128 = one 256-column block of wo; f8 scale rows stay aligned
+        d = ckpt(preset[:-3], quant, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128)
+    else:
+        d = ckpt(preset, quant)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     env = dict(os.environ, DSK_P2P=p2p)
@@ -86,6 +95,7 @@ def test_sharded_decode_matches_reference(repo, ckpt, tmp_path, p2p, preset, qua
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("RESULT ")][-1]
     res = json.loads(line[len("RESULT "):])
     assert max(res["errs"]) < tol, res
+    assert res["tp"] == want_tp, res
     if quant in ("fp32", "f8e5m2"):
         assert res["dev"] == res["host"], res      # greedy tokens identical to the reference for the dense quants
     else:
