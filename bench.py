@@ -506,11 +506,12 @@ def measure(dsk, torch, dist, w, rank, world, local_rank, steps, warmup, want_e2
         torch.cuda.synchronize()
 
     timeline = None
-    if profile and rank == 0 and world == 1:
+    if profile:   # every rank takes part (the forward is collective); rank 0 prints its CTA-0 timeline
         hydrate()
         m.profile_token(pr[0], PROMPT_LEN)
         timeline = m.profile_token(pr[1], PROMPT_LEN + 1)
-        print(timeline, file=sys.stderr, flush=True)
+        if rank == 0:
+            print(timeline, file=sys.stderr, flush=True)
 
     # ---- value: device-resident decode, CUDA events inside dsk_decode_greedy (one persistent launch per completion) ----
     for _ in range(warmup):

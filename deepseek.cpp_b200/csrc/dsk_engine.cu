@@ -1254,6 +1254,12 @@ static int build_program(dsk_model* m, dsk_state* s) {
     S.push_back(st);
     if (tp) { Stage xs{}; xs.kind = ST_AMAX; xs.quant = q; xs.layer = -1; xs.xchg_ord = n_xchg++; S.push_back(xs); s->n_tail = 2; }
   }
+  if (m->n_ranks > 1 && m->p2p)
+    for (Stage& st : S) {
+      const bool down_partial = st.kind == ST_DOWN && (st.K > 0 || tp);
+      const bool gemv_partial = st.kind == ST_GEMV && (st.epi == EPI_PARTIAL || (st.epi == EPI_LOGITS && tp));
+      st.peer_stores = (down_partial || gemv_partial) ? 1 : 0;
+    }
   const bool has_gate = q != DSK_F32 && c.n_routed_experts > 0;
   choose_slot_geometry(q, S, has_gate ? c.dim : 0);
   if (has_gate && (size_t)c.dim * 4 > (size_t)g_slot_data) return fail(-4, "gate row (%d bytes) does not fit a ring slot", c.dim * 4);

@@ -64,7 +64,7 @@ struct Stage {
   int seg_stride;                          // bytes between segments inside a ring slot (ST_DOWN)
   int xchg_ord;                            // peer-memory mode: ordinal (within a token) of the exchange this DOWN / XCHG stage belongs to
   int max_inflight;                        // tiles the producer may have outstanding in this stage (<= kRingEntries)
-  int pad2[1];
+  int peer_stores;                         // multi-GPU: the epilogues of this stage store into peer memory (one system fence per thread at stage end)
 } __attribute__((aligned(16)));
 
 static_assert(sizeof(Stage) <= kStageSlot, "Stage descriptor must fit its shared-memory cache slot");
@@ -944,8 +944,7 @@ __device__ __forceinline__ void store_partial(const Program& P, const Stage& st,
   if (P.n_xchg > 0) {   // peer-memory mode: straight into every rank's exchange buffer (parity by sequence number)
     const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
     const size_t off = ((size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank) * (size_t)P.dim + (size_t)i;
-    for (int q = 0; q < P.n_ranks; q++) P.xchg_peer[q][off] = acc;
-    __threadfence_system();
+    for (int q = 0; q < P.n_ranks; q++) P.xchg_peer[q][off] = acc;   // posted NVLink writes; fenced ONCE per thread at stage end
   } else {
     P.partial[i] = acc;
   }
@@ -962,7 +961,6 @@ __device__ __forceinline__ void store_logit(const Program& P, const MJob& jb, in
   if (P.tp && P.n_ranks > 1) {
     const size_t row = (size_t)jb.row_base + (size_t)r;
     for (int q = 0; q < P.n_ranks; q++) if (q != P.rank) P.logits_peer[q][row] = val;
-    __threadfence_system();
   }
 }
 // combine column pieces in a fixed order + epilogue, one thread per row of the tile
@@ -1229,6 +1227,11 @@ __device__ __forceinline__ void c_attention(const Program& P, const Stage& st, c
 // ST_XCHG (after the grid barrier that follows the DOWN stage: every CTA's peer stores are issued and fenced):
 // CTA 0 raises this rank's flag on every peer; every CTA waits for the N local flags, then x += sum of the N partials in
 // rank order (identical on every rank, so the replicated residual stream stays bit-identical across GPUs).
+__device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const MegaSmem& sm) {
   const int tid = threadIdx.x;
   const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
@@ -1236,11 +1239,13 @@ __device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const 
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + P.rank), "r"(seq) : "memory");
   }
+  if ((int)blockIdx.x * kConsumers >= P.dim) return;   // CTAs without elements of x neither poll nor add
   if (tid < P.n_ranks) {
     const unsigned long long t0 = gtime();
-    while ((int)(ld_acquire_sys(P.xflag_peer[P.rank] + tid) - seq) < 0) {
+    while ((int)(ld_relaxed_sys(P.xflag_peer[P.rank] + tid) - seq) < 0) {   // relaxed polls, one acquire fence afterwards
       if (gtime() - t0 > 30000000000ull) __trap();   // a peer is more than 30 s late: fail instead of hanging the GPU
     }
+    __threadfence_system();
   }
   csync();
   for (int i = (int)blockIdx.x * kConsumers + tid; i < P.dim; i += (int)gridDim.x * kConsumers) {
@@ -2490,6 +2495,9 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
     }
     // stage done: the CTA barrier orders every consumer's writes before thread 0's release-add (cumulative)
     if (tid == 0 && blockIdx.x == 0 && P.tstamp) P.tstamp[s * 8 + 2] = gtime();
+    // peer-memory stores of this stage (partial sums / logits into the other ranks' exchange buffers): drain them with one
+    // system-scope fence per thread, before this CTA's arrival on the grid barrier that precedes the exchange stage
+    if (st.peer_stores) __threadfence_system();
     csync();
     if (tid == 0) sts32(sm.claim, (uint32_t)it);   // the claim counter overshoots by up to one ticket per warp at the end of a stage
     const bool last = (s + 1 == s_end) && (tok + 1 == n_tokens);
