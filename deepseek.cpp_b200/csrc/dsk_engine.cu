@@ -1256,9 +1256,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   }
   if (m->n_ranks > 1 && m->p2p)
     for (Stage& st : S) {
-      const bool down_partial = st.kind == ST_DOWN && (st.K > 0 || tp);
-      const bool gemv_partial = st.kind == ST_GEMV && (st.epi == EPI_PARTIAL || (st.epi == EPI_LOGITS && tp));
-      st.peer_stores = (down_partial || gemv_partial) ? 1 : 0;
+      st.peer_stores = (st.kind == ST_GEMV && st.epi == EPI_LOGITS && tp) ? 1 : 0;   // (partial sums go through the local vector)
     }
   const bool has_gate = q != DSK_F32 && c.n_routed_experts > 0;
   choose_slot_geometry(q, S, has_gate ? c.dim : 0);
@@ -1625,9 +1623,11 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
     return 0;
   }
   const int N = m->n_ranks;
-  // layout: [2 parities][N][dim] partial sums | N flags (256 B) | tp: [2][N] arg-max keys (256 B) | tp: vocab logits
+  // layout: [2 parities][N][dim] partial sums | chunk + arg-max flags (4 KB) | tp: [2][N] arg-max keys (256 B) | tp: vocab logits
   const size_t data_bytes = (size_t)2 * N * m->c.dim * sizeof(float);
-  const size_t amax_off = data_bytes + 256, logits_off = amax_off + 256;
+  const size_t flag_bytes = 4096;   // [N][dim / 256] chunk flags, then N arg-max flags (u32 each)
+  if (((size_t)N * (size_t)cdiv(m->c.dim, 256) + (size_t)N) * 4 > flag_bytes) return fail(-4, "dim %d too large for the exchange flag area", m->c.dim);
+  const size_t amax_off = data_bytes + flag_bytes, logits_off = amax_off + 256;
   const size_t total = logits_off + (m->tp ? (size_t)m->c.vocab_size * sizeof(float) : 0);
   cudaIpcMemHandle_t mine;
   unsigned char* d_handles = nullptr;

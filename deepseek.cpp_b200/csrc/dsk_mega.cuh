@@ -940,14 +940,11 @@ __device__ __forceinline__ void consume_gemv_tile(const Program& P, const Stage&
 }
 
 // ---- multi-GPU partial sums -----------------------------------------------------------------------------------------
+// Epilogues write tensor-/expert-parallel partial sums into the LOCAL partial vector; the exchange stage that follows pushes
+// it to the peers in coalesced 1 KB chunks (scattered 32-byte NVLink writes straight from the epilogues cost ~8 us per stage).
 __device__ __forceinline__ void store_partial(const Program& P, const Stage& st, int i, float acc) {
-  if (P.n_xchg > 0) {   // peer-memory mode: straight into every rank's exchange buffer (parity by sequence number)
-    const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
-    const size_t off = ((size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank) * (size_t)P.dim + (size_t)i;
-    for (int q = 0; q < P.n_ranks; q++) P.xchg_peer[q][off] = acc;   // posted NVLink writes; fenced ONCE per thread at stage end
-  } else {
-    P.partial[i] = acc;
-  }
+  (void)st;
+  P.partial[i] = acc;
 }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   unsigned v;
@@ -1224,35 +1221,44 @@ __device__ __forceinline__ void c_attention(const Program& P, const Stage& st, c
   csync();
 }
 
-// ST_XCHG (after the grid barrier that follows the DOWN stage: every CTA's peer stores are issued and fenced):
-// CTA 0 raises this rank's flag on every peer; every CTA waits for the N local flags, then x += sum of the N partials in
-// rank order (identical on every rank, so the replicated residual stream stays bit-identical across GPUs).
 __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// ST_XCHG (after the grid barrier that follows the stage whose epilogues filled P.partial): CTA c owns the 256-element chunk c of
+// the vector.  It pushes this rank's chunk into every rank's exchange buffer (one coalesced 1 KB store per peer over NVLink),
+// fences, raises the per-(rank, chunk) flag on every peer, waits for the N flags of its own chunk and adds the N partial
+// chunks in rank order — identical on every rank, so the replicated residual stream stays bit-identical across GPUs.  No
+// second grid barrier is needed between push and reduce: chunks synchronise independently.
 __device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const MegaSmem& sm) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, N = P.n_ranks;
   const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
-  if (blockIdx.x == 0 && tid < P.n_ranks) {
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + P.rank), "r"(seq) : "memory");
-  }
-  if ((int)blockIdx.x * kConsumers >= P.dim) return;   // CTAs without elements of x neither poll nor add
-  if (tid < P.n_ranks) {
-    const unsigned long long t0 = gtime();
-    while ((int)(ld_relaxed_sys(P.xflag_peer[P.rank] + tid) - seq) < 0) {   // relaxed polls, one acquire fence afterwards
-      if (gtime() - t0 > 30000000000ull) __trap();   // a peer is more than 30 s late: fail instead of hanging the GPU
+  const int nchunk = (P.dim + kConsumers - 1) / kConsumers;
+  for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+    const int i = c * kConsumers + tid;
+    const size_t slot = (size_t)(seq & 1u) * (size_t)N * (size_t)P.dim;
+    if (i < P.dim) {
+      const float v = __ldcg(P.partial + i);
+      for (int q = 0; q < N; q++) P.xchg_peer[q][slot + (size_t)P.rank * (size_t)P.dim + (size_t)i] = v;
     }
     __threadfence_system();
-  }
-  csync();
-  for (int i = (int)blockIdx.x * kConsumers + tid; i < P.dim; i += (int)gridDim.x * kConsumers) {
-    const float* b = P.xchg_peer[P.rank] + (size_t)(seq & 1u) * (size_t)P.n_ranks * (size_t)P.dim + (size_t)i;
-    float acc = P.x[i];
-    for (int r = 0; r < P.n_ranks; r++) acc += __ldcg(b + (size_t)r * (size_t)P.dim);
-    P.x[i] = acc;
+    csync();
+    if (tid < N) {
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + (size_t)P.rank * (size_t)nchunk + (size_t)c), "r"(seq) : "memory");
+      const unsigned long long t0 = gtime();
+      while ((int)(ld_relaxed_sys(P.xflag_peer[P.rank] + (size_t)tid * (size_t)nchunk + (size_t)c) - seq) < 0) {
+        if (gtime() - t0 > 30000000000ull) __trap();   // a peer is more than 30 s late: fail instead of hanging the GPU
+      }
+      __threadfence_system();
+    }
+    csync();
+    if (i < P.dim) {
+      const float* b = P.xchg_peer[P.rank] + slot + (size_t)i;
+      float acc = P.x[i];
+      for (int r = 0; r < N; r++) acc += __ldcg(b + (size_t)r * (size_t)P.dim);
+      P.x[i] = acc;
+    }
   }
 }
 
@@ -1266,9 +1272,10 @@ __device__ __forceinline__ void c_amax(const Program& P, const Stage& st) {
   if (tid < P.n_ranks) {
     P.amax_peer[tid][(size_t)(seq & 1u) * (size_t)P.n_ranks + (size_t)P.rank] = P.ctrl->argmax_key;
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + P.rank), "r"(seq) : "memory");
+    const size_t aflag = (size_t)P.n_ranks * (size_t)((P.dim + kConsumers - 1) / kConsumers);   // after the chunk flags
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + aflag + P.rank), "r"(seq) : "memory");
     const unsigned long long t0 = gtime();
-    while ((int)(ld_acquire_sys(P.xflag_peer[P.rank] + tid) - seq) < 0) {
+    while ((int)(ld_acquire_sys(P.xflag_peer[P.rank] + aflag + tid) - seq) < 0) {
       if (gtime() - t0 > 30000000000ull) __trap();
     }
   }
