@@ -1623,8 +1623,8 @@ extern "C" int dsk_comm_init(dsk_model* m, const void* nccl_unique_id128) {
     return 0;
   }
   const int N = m->n_ranks;
-  // layout: [2 parities][N][dim] partial sums | chunk + arg-max flags (4 KB) | tp: [2][N] arg-max keys (256 B) | tp: vocab logits
-  const size_t data_bytes = (size_t)2 * N * m->c.dim * sizeof(float);
+  // layout: [2 parities][N][dim] {partial, seq} 8-byte words | flags (4 KB) | tp: [2][N] arg-max keys (256 B) | tp: vocab logits
+  const size_t data_bytes = (size_t)2 * N * m->c.dim * sizeof(unsigned long long);   // {value, sequence number} words
   const size_t flag_bytes = 4096;   // [N][dim / 256] chunk flags, then N arg-max flags (u32 each)
   if (((size_t)N * (size_t)cdiv(m->c.dim, 256) + (size_t)N) * 4 > flag_bytes) return fail(-4, "dim %d too large for the exchange flag area", m->c.dim);
   const size_t amax_off = data_bytes + flag_bytes, logits_off = amax_off + 256;

@@ -1226,39 +1226,41 @@ __device__ __forceinline__ unsigned ld_relaxed_sys(const unsigned* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-// ST_XCHG (after the grid barrier that follows the stage whose epilogues filled P.partial): CTA c owns the 256-element chunk c of
-// the vector.  It pushes this rank's chunk into every rank's exchange buffer (one coalesced 1 KB store per peer over NVLink),
-// fences, raises the per-(rank, chunk) flag on every peer, waits for the N flags of its own chunk and adds the N partial
-// chunks in rank order — identical on every rank, so the replicated residual stream stays bit-identical across GPUs.  No
-// second grid barrier is needed between push and reduce: chunks synchronise independently.
+// ST_XCHG (after the grid barrier that follows the stage whose epilogues filled P.partial): an all-to-all of the partial vector
+// in the low-latency "data + flag in one word" style.  Thread i of chunk CTA c packs {partial[i], sequence number} into ONE
+// 8-byte word and stores it into every rank's exchange buffer (slot [parity][this rank][i]; 8-byte stores are single NVLink
+// transactions), then polls the N words [parity][r][i] of its OWN buffer until each carries this exchange's sequence number
+// and adds them to x[i] in rank order — identical on every rank, so the replicated residual stream stays bit-identical across
+// GPUs.  No fences, no separate flags, no second barrier: every word validates itself, so the latency is one NVLink store.
+// Two parities make the reuse safe: a rank cannot get two exchanges ahead of a peer (it needs that peer's words to finish
+// the next one), so slot k & 1 is never overwritten before every reader of exchange k is done with it.
 __device__ __forceinline__ void c_xchg(const Program& P, const Stage& st, const MegaSmem& sm) {
+  (void)sm;
   const int tid = threadIdx.x, N = P.n_ranks;
   const unsigned seq = (unsigned)P.ctrl->pad[0] + (unsigned)st.xchg_ord + 1u;
   const int nchunk = (P.dim + kConsumers - 1) / kConsumers;
   for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
     const int i = c * kConsumers + tid;
+    if (i >= P.dim) continue;
     const size_t slot = (size_t)(seq & 1u) * (size_t)N * (size_t)P.dim;
-    if (i < P.dim) {
-      const float v = __ldcg(P.partial + i);
-      for (int q = 0; q < N; q++) P.xchg_peer[q][slot + (size_t)P.rank * (size_t)P.dim + (size_t)i] = v;
+    const unsigned long long word = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(__ldcg(P.partial + i));
+    for (int q = 0; q < N; q++) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.xchg_peer[q]) + slot + (size_t)P.rank * (size_t)P.dim + (size_t)i;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(word) : "memory");
     }
-    __threadfence_system();
-    csync();
-    if (tid < N) {
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.xflag_peer[tid] + (size_t)P.rank * (size_t)nchunk + (size_t)c), "r"(seq) : "memory");
-      const unsigned long long t0 = gtime();
-      while ((int)(ld_relaxed_sys(P.xflag_peer[P.rank] + (size_t)tid * (size_t)nchunk + (size_t)c) - seq) < 0) {
-        if (gtime() - t0 > 30000000000ull) __trap();   // a peer is more than 30 s late: fail instead of hanging the GPU
+    const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(P.xchg_peer[P.rank]) + slot + (size_t)i;
+    float acc = P.x[i];
+    const unsigned long long t0 = gtime();
+    for (int r = 0; r < N; r++) {
+      unsigned long long w;
+      for (unsigned spins = 0;; spins++) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(mine + (size_t)r * (size_t)P.dim) : "memory");
+        if ((unsigned)(w >> 32) == seq) break;
+        if ((spins & 1023u) == 1023u && gtime() - t0 > 30000000000ull) __trap();   // a peer is more than 30 s late: fail, do not hang
       }
-      __threadfence_system();
+      acc += __uint_as_float((unsigned)(w & 0xffffffffull));
     }
-    csync();
-    if (i < P.dim) {
-      const float* b = P.xchg_peer[P.rank] + slot + (size_t)i;
-      float acc = P.x[i];
-      for (int r = 0; r < N; r++) acc += __ldcg(b + (size_t)r * (size_t)P.dim);
-      P.x[i] = acc;
-    }
+    P.x[i] = acc;
   }
 }
 
