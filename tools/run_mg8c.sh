@@ -1,4 +1,4 @@
-out=gpurun_out/mg8c
+out=gpurun_out/mg8d
 mkdir -p $out
 run() { name=$1; shift
   env $1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port $2 bench.py --gpus 8 --steps 2 --warmup 3 --profile-token ${@:3} > $out/$name.json 2> $out/$name.err
