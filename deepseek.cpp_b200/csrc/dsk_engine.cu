@@ -107,6 +107,7 @@ struct DTensor {
 struct Layer {
   float *rms_att = nullptr, *rms_ffn = nullptr, *rms_q_a = nullptr, *rms_kv_a = nullptr;
   DTensor wq, wq_a, wq_b, wkv_a, wkv_b, wo, w1, w2, w3, sw1, sw2, sw3;
+  DTensor wc, wq_rope_b, wv_b;   // true-MLA blocks (use_mla): absorbed query projection, rope query projection, per-head value up-projection
   float *gate = nullptr, *gate_bias = nullptr;
   bool is_moe = false;
   __half *kcache = nullptr, *vcache = nullptr;
@@ -165,7 +166,7 @@ struct dsk_model {
 struct dsk_state {
   dsk_model* m = nullptr;
   float *x = nullptr, *xb2 = nullptr, *hbk = nullptr, *hbs = nullptr, *q_a = nullptr, *q = nullptr, *kv_a = nullptr,
-        *kv_b = nullptr, *moe_logits = nullptr, *moe_scores = nullptr, *act_w = nullptr, *logits = nullptr, *partial = nullptr;
+        *kv_b = nullptr, *q_c = nullptr, *moe_logits = nullptr, *moe_scores = nullptr, *act_w = nullptr, *logits = nullptr, *partial = nullptr;
   int* act = nullptr;
   Ctrl* ctrl = nullptr;       // device
   Ctrl* h_ctrl = nullptr;     // pinned host mirror
@@ -321,6 +322,16 @@ static int validate_config(const dsk_config& c) {
     if (c.bs0 % 32 != 0) return fail(-1, "f8e5m2 quantization_block_size_0 = %d unsupported: must be a multiple of 32 (weight tiles of up to 32 rows share one scale row)", c.bs0);
   }
   if (c.original_max_position <= 2) return fail(-1, "rope_scaling_original_max_position_embeddings must exceed the 2 attention sinks");
+  if (c.use_mla) {
+    if (c.q_lora_rank <= 0) return fail(-1, "use_mla requires q_lora_rank > 0 (src/infer.cpp:1057)");
+    if (c.kv_lora_rank % 64 != 0) return fail(-1, "use_mla: kv_lora_rank %d must be a multiple of 64", c.kv_lora_rank);
+    if (c.quant == DSK_F8E5M2 && c.bs0 > 0 && c.v_head_dim % c.bs0 != 0)
+      return fail(-1, "use_mla with block scales: v_head_dim %d must be a multiple of block_size[0] %d (matmul_expert's per-head scale offset, src/infer.cpp:437)", c.v_head_dim, c.bs0);
+    if ((c.quant == DSK_Q2_K || c.quant == DSK_Q3_K) && (c.kv_lora_rank % 256 != 0 || ((size_t)c.v_head_dim * dev_row_bytes(c.quant, c.kv_lora_rank)) % 16 != 0))
+      return fail(-1, "use_mla with K-quants: kv_lora_rank %d must be a multiple of 256 and a head's wv_b slab a multiple of 16 bytes", c.kv_lora_rank);
+    if (mla_floats(c.kv_lora_rank, c.qk_rope_head_dim, c.max_seq_len) * 4 > 96 * 1024)
+      return fail(-1, "use_mla: max_seq_len %d does not fit the attention stage's shared memory (scores are kept on chip)", c.max_seq_len);
+  }
   return 0;
 }
 
@@ -349,7 +360,7 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
     const char* e_tp = getenv("DSK_TP");
     const char* e_p2p = getenv("DSK_P2P");
     const int sh = c.n_shared_experts * c.moe_intermediate_size;
-    bool ok = n_ranks > 1 && !(e_tp && atoi(e_tp) == 0) && !(e_p2p && atoi(e_p2p) == 0);
+    bool ok = n_ranks > 1 && !(e_tp && atoi(e_tp) == 0) && !(e_p2p && atoi(e_p2p) == 0) && !c.use_mla;   // (MLA blocks: experts only)
     ok = ok && c.n_heads % n_ranks == 0 && ((c.n_heads / n_ranks) * c.v_head_dim) % 256 == 0;   // wo column slices: whole 256-blocks
     ok = ok && sh % 256 == 0 && c.hidden_dim % 256 == 0;
     if (c.quant == DSK_F8E5M2)                                                                   // slices must not cut a scale block
@@ -369,8 +380,9 @@ extern "C" dsk_model* dsk_model_create(const dsk_config* cfg, int rank, int n_ra
   for (int l = 0; l < cfg->n_layers; l++) {
     Layer& L = m->layers[l];
     L.is_moe = E > 0 && l >= cfg->first_k_dense_replace;
-    const size_t kb = (size_t)cfg->max_seq_len * m->nh_loc * m->head_dim * sizeof(__half);
-    const size_t vb = (size_t)cfg->max_seq_len * m->nh_loc * cfg->v_head_dim * sizeof(__half);
+    // MHA blocks: full K / V rows per head (src/model.cpp:459-460); MLA blocks: one latent row + one rope key per token (618-619)
+    const size_t kb = (size_t)cfg->max_seq_len * (cfg->use_mla ? (size_t)cfg->kv_lora_rank : (size_t)m->nh_loc * m->head_dim) * sizeof(__half);
+    const size_t vb = (size_t)cfg->max_seq_len * (cfg->use_mla ? (size_t)cfg->qk_rope_head_dim : (size_t)m->nh_loc * cfg->v_head_dim) * sizeof(__half);
     if (cudaMalloc(&L.kcache, kb) != cudaSuccess || cudaMalloc(&L.vcache, vb) != cudaSuccess) {
       fail(-2, "KV cache allocation failed (layer %d, %zu bytes)", l, kb + vb);
       delete m;
@@ -613,6 +625,11 @@ extern "C" int dsk_upload_tensor(dsk_model* m, const char* name, int dtype, cons
   const int hr0 = m->h0 * hd, hrc = m->nh_loc * hd;                    // wq / wq_b rows of the local heads
   const int kr0 = m->h0 * per_kv, krc = m->nh_loc * per_kv;            // wkv_b rows
   const int oc0 = m->h0 * c.v_head_dim, occ = m->nh_loc * c.v_head_dim;   // wo columns
+  if (c.use_mla) {   // BlockMLA tensors (src/model.cpp:558-610)
+    if (base == "attn.wc") return W(L.wc, c.n_heads * c.kv_lora_rank, c.q_lora_rank, false, is_scale);
+    if (base == "attn.wq_rope_b") return W(L.wq_rope_b, c.n_heads * c.qk_rope_head_dim, c.q_lora_rank, false, is_scale);
+    if (base == "attn.wv_b") return W(L.wv_b, c.n_heads * c.v_head_dim, c.kv_lora_rank, false, is_scale);
+  }
   if (base == "attn.wq") return WS(L.wq, c.n_heads * hd, c.dim, is_scale, hr0, hrc, 0, c.dim);
   if (base == "attn.wq_a") return W(L.wq_a, c.q_lora_rank, c.dim, false, is_scale);
   if (base == "attn.wq_b") return WS(L.wq_b, c.n_heads * hd, c.q_lora_rank, is_scale, hr0, hrc, 0, c.q_lora_rank);
@@ -650,11 +667,14 @@ extern "C" int dsk_model_finalize(dsk_model* m) {
   for (int l = 0; l < c.n_layers; l++) {
     Layer& L = m->layers[l];
     if (!L.rms_att || !L.rms_ffn || !L.rms_kv_a) return fail(-5, "missing norm weights (layer %d)", l);
-    if (c.q_lora_rank > 0) {
+    if (c.use_mla) {
+      if (!L.rms_q_a) return fail(-5, "missing q_a_norm (layer %d)", l);
+      if (need(L.wq_a, "attn.wq_a", l) || need(L.wc, "attn.wc", l) || need(L.wq_rope_b, "attn.wq_rope_b", l) || need(L.wv_b, "attn.wv_b", l)) return -5;
+    } else if (c.q_lora_rank > 0) {
       if (!L.rms_q_a) return fail(-5, "missing q_a_norm (layer %d)", l);
       if (need(L.wq_a, "attn.wq_a", l) || need(L.wq_b, "attn.wq_b", l)) return -5;
     } else if (need(L.wq, "attn.wq", l)) return -5;
-    if (need(L.wkv_a, "attn.wkv_a", l) || need(L.wkv_b, "attn.wkv_b", l) || need(L.wo, "attn.wo", l)) return -5;
+    if (need(L.wkv_a, "attn.wkv_a", l) || (!c.use_mla && need(L.wkv_b, "attn.wkv_b", l)) || need(L.wo, "attn.wo", l)) return -5;
     if (need(L.w1, "mlp.w1", l) || need(L.w2, "mlp.w2", l) || need(L.w3, "mlp.w3", l)) return -5;
     if (L.is_moe) {
       if (!L.gate) return fail(-5, "missing moegate.weight (layer %d)", l);
@@ -699,10 +719,12 @@ extern "C" double dsk_model_active_bytes_per_token(const dsk_model* m) {
   double total = 0;
   for (int l = 0; l < c.n_layers; l++) {
     double w = 0;
-    if (c.q_lora_rank > 0) w += (double)c.q_lora_rank * dim + (double)c.n_heads * hd * c.q_lora_rank;
+    if (c.use_mla) w += (double)c.q_lora_rank * dim + (double)c.n_heads * (c.kv_lora_rank + c.qk_rope_head_dim) * c.q_lora_rank;   // wq_a, wc, wq_rope_b
+    else if (c.q_lora_rank > 0) w += (double)c.q_lora_rank * dim + (double)c.n_heads * hd * c.q_lora_rank;
     else w += (double)c.n_heads * hd * dim;
     w += (double)(c.kv_lora_rank + c.qk_rope_head_dim) * dim;
-    w += (double)c.n_heads * (nope + c.v_head_dim) * c.kv_lora_rank;
+    if (c.use_mla) w += (double)c.n_heads * c.v_head_dim * c.kv_lora_rank;                                                             // wv_b
+    else w += (double)c.n_heads * (nope + c.v_head_dim) * c.kv_lora_rank;
     w += dim * c.n_heads * c.v_head_dim;
     double f32 = 2 * dim + c.kv_lora_rank + c.q_lora_rank;  // norm weights
     if (m->layers[l].is_moe) {
@@ -732,7 +754,8 @@ extern "C" dsk_state* dsk_state_create(dsk_model* m) {
   auto fa = [&](float** p, size_t n) { cudaMalloc((void**)p, std::max<size_t>(n, 4) * 4); cudaMemset(*p, 0, std::max<size_t>(n, 4) * 4); };
   const int mi = c.moe_intermediate_size;
   fa(&s->x, c.dim);
-  fa(&s->xb2, std::max(c.dim, c.n_heads * c.v_head_dim));
+  fa(&s->xb2, std::max(std::max(c.dim, c.n_heads * c.v_head_dim), c.use_mla ? c.n_heads * c.kv_lora_rank : 0));
+  fa(&s->q_c, c.use_mla ? (size_t)c.n_heads * c.kv_lora_rank : 4);
   fa(&s->hbk, (size_t)std::max(1, c.n_active_routed) * std::max(1, mi));
   fa(&s->hbs, std::max(c.hidden_dim, c.n_shared_experts * mi));
   fa(&s->q_a, std::max(1, c.q_lora_rank));
@@ -768,7 +791,7 @@ extern "C" dsk_state* dsk_state_create(dsk_model* m) {
 extern "C" void dsk_state_destroy(dsk_state* s) {
   if (!s) return;
   if (s->m) s->m->n_states--;
-  float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->kv_a, s->kv_b, s->moe_logits, s->moe_scores, s->act_w, s->logits, s->partial};
+  float* bufs[] = {s->x, s->xb2, s->hbk, s->hbs, s->q_a, s->q, s->q_c, s->kv_a, s->kv_b, s->moe_logits, s->moe_scores, s->act_w, s->logits, s->partial};
   for (float* b : bufs) cudaFree(b);
   cudaFree(s->prog); cudaFree(s->att_scratch); cudaFree(s->sync_words); cudaFree(s->tstamp);
   cudaFree(s->sample_out); cudaFree(s->act); cudaFree(s->ctrl); cudaFreeHost(s->h_ctrl); cudaFree(s->token_log); cudaFree(s->step);
@@ -781,7 +804,8 @@ static float* state_buf(dsk_state* s, const char* name, size_t* cap) {
   const dsk_config& c = s->m->c;
   std::string k(name);
   if (k == "x") { *cap = c.dim; return s->x; }
-  if (k == "xb2") { *cap = std::max(c.dim, c.n_heads * c.v_head_dim); return s->xb2; }
+  if (k == "xb2") { *cap = std::max(std::max(c.dim, c.n_heads * c.v_head_dim), c.use_mla ? c.n_heads * c.kv_lora_rank : 0); return s->xb2; }
+  if (k == "q_c" && c.use_mla) { *cap = (size_t)c.n_heads * c.kv_lora_rank; return s->q_c; }
   if (k == "hb") { *cap = std::max(c.hidden_dim, c.n_shared_experts * c.moe_intermediate_size); return s->hbs; }
   if (k == "hb_routed") { *cap = (size_t)c.n_active_routed * c.moe_intermediate_size; return s->hbk; }
   if (k == "q_a") { *cap = c.q_lora_rank; return s->q_a; }
@@ -825,7 +849,8 @@ static int kv_ptr(dsk_model* m, int layer, int which, __half** p, size_t* cap) {
   if (!m || layer < 0 || layer >= m->c.n_layers) return fail(-4, "bad layer");
   Layer& L = m->layers[layer];
   *p = which == 0 ? L.kcache : L.vcache;
-  *cap = (size_t)m->c.max_seq_len * m->nh_loc * (which == 0 ? m->head_dim : m->c.v_head_dim);
+  *cap = m->c.use_mla ? (size_t)m->c.max_seq_len * (which == 0 ? m->c.kv_lora_rank : m->c.qk_rope_head_dim)
+                      : (size_t)m->c.max_seq_len * m->nh_loc * (which == 0 ? m->head_dim : m->c.v_head_dim);
   return 0;
 }
 extern "C" int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, size_t n) {
@@ -1076,6 +1101,15 @@ static int program_geometry(const std::vector<Stage>& S, int q, int hd, int max_
       else for (int k = 0; k <= st.K; k++) { const int n = k < st.K ? st.mi : st.sh; if (n) b += xvec_bytes_q(st.quant, n); }
       xreg = std::max(xreg, b);
     } else if (st.kind == ST_ATTN) has_attn = true;
+    else if (st.kind == ST_MLA_CACHE) xreg = std::max(xreg, (size_t)4096);
+    else if (st.kind == ST_ATTN_MLA) {   // fp32 scratch (scores stay on chip) + the head's wv_b slab and staged latent
+      const int kvl = st.n, vh = st.job[0].rows;
+      size_t b = align_up(mla_floats(kvl, st.K /* rope dim */, max_seq) * 4, 128);
+      if (st.quant == DSK_Q2_K) b += mla_weight_bytes<Q_Q2K>(kvl, vh);
+      else if (st.quant == DSK_Q3_K) b += mla_weight_bytes<Q_Q3K>(kvl, vh);
+      else if (st.quant == DSK_F8E5M2 && st.use_mma) b += mla_weight_bytes<Q_F8>(kvl, vh);
+      xreg = std::max(xreg, b);
+    }
   }
   if (has_attn) {
     const size_t attn_need = (size_t)(512 + ((hd + 3) & ~3) + ((max_seq + 3) & ~3) + kConsumers + 16) * 4;
@@ -1166,6 +1200,30 @@ static int build_program(dsk_model* m, dsk_state* s) {
       st.njobs = 2;
       S.push_back(st);
     }
+    if (c.use_mla) {
+      // BlockMLA (src/infer.cpp:1051-1141): cache update | q_rope = wq_rope_b . q_a', q_c = wc . q_a' | per-head latent attention + wv_b
+      { Stage st{}; st.kind = ST_MLA_CACHE; st.quant = q; st.layer = l; st.norm_w = L.rms_kv_a; st.kcache = L.kcache; st.vcache = L.vcache; S.push_back(st); }
+      {
+        Stage st = gemv(q, s->q_a, L.rms_q_a, c.q_lora_rank, EPI_STORE, l);
+        st.job[0] = mjob(L.wq_rope_b, s->q); st.job[1] = mjob(L.wc, s->q_c); st.njobs = 2;
+        S.push_back(st);
+      }
+      {
+        Stage st{}; st.kind = ST_ATTN_MLA; st.quant = q; st.layer = l; st.kcache = L.kcache; st.vcache = L.vcache;
+        MJob j{}; j.w = L.wv_b.w; j.scale = L.wv_b.scale; j.rows = c.v_head_dim; j.expert_slot = -1;
+        j.w_stride = (long long)((size_t)c.v_head_dim * L.wv_b.row_bytes);                       // bytes per head
+        j.s_stride = (long long)((size_t)cdiv(c.v_head_dim, c.bs0 > 0 ? c.bs0 : 1) * cdiv(c.kv_lora_rank, c.bs1 > 0 ? c.bs1 : 1));   // scale floats per head (matmul_expert)
+        st.job[0] = j; st.njobs = 1; st.n = c.kv_lora_rank; st.K = c.qk_rope_head_dim;
+        st.use_mma = (q == DSK_F8E5M2 && g_use_mma && g_f8_mma_ok && c.kv_lora_rank % 64 == 0 && c.v_head_dim % 8 == 0 &&
+                      c.bs0 % 16 == 0 && j.s_stride <= 256) ? 1 : 0;
+        S.push_back(st);
+      }
+      {  // wo on the up-projected values (src/infer.cpp:1140)
+        Stage st = gemv(q, s->kv_b, nullptr, c.n_heads * c.v_head_dim, EPI_RESID, l);
+        st.job[0] = mjob(L.wo, s->x); st.njobs = 1;
+        S.push_back(st);
+      }
+    } else {
     if (c.q_lora_rank > 0) {
       Stage st = gemv(q, s->q_a, L.rms_q_a, c.q_lora_rank, EPI_STORE, l);
       st.job[0] = mjob(L.wq_b, s->q); st.njobs = 1;
@@ -1184,6 +1242,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
       S.push_back(st);
       if (tp) { Stage xs{}; xs.kind = ST_XCHG; xs.quant = q; xs.layer = l; xs.xchg_ord = n_xchg++; S.push_back(xs); }
     }
+    }   // (MHA blocks)
     if (L.is_moe) {
       const int sh = m->sh_loc;   // (local slice of the concatenated shared experts; all of it without tensor parallelism)
       {  // S5 gate logits (F32 weights in every quant)
@@ -1277,6 +1336,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   P->expert_first = m->expert_first; P->expert_count = m->expert_count;
   P->embed_quant = q; P->n_stages = (int)S.size();
   P->embed_w = m->embed.w; P->embed_scale = m->embed.scale; P->rope_freq = m->rope_freq;
+  P->q_c = s->q_c;
   P->x = s->x; P->q = s->q; P->q_a = s->q_a; P->kv_a = s->kv_a; P->kv_b = s->kv_b; P->xb2 = s->xb2; P->hbk = s->hbk; P->hbs = s->hbs;
   P->moe_logits = s->moe_logits; P->moe_scores = s->moe_scores; P->act_w = s->act_w; P->logits = s->logits_src; P->partial = m->n_ranks > 1 ? s->partial : nullptr;
   P->act = s->act; P->ctrl = s->ctrl; P->token_log = s->token_log; P->step = s->step;
@@ -1300,7 +1360,7 @@ static int build_program(dsk_model* m, dsk_state* s) {
   s->stage_names.clear();
   for (const Stage& st : S) {
     char nm[96];
-    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_XCHG ? "xchg" : st.kind == ST_AMAX ? "amax" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
+    const char* kind = st.kind == ST_EMBED ? "embed" : st.kind == ST_XCHG ? "xchg" : st.kind == ST_AMAX ? "amax" : st.kind == ST_MLA_CACHE ? "mla_kv" : st.kind == ST_ATTN_MLA ? "attn_mla" : st.kind == ST_ATTN ? "attn" : st.kind == ST_DOWN ? "down" : (st.epi == EPI_GLU ? "glu" : st.epi == EPI_KVB ? "kv_b" : st.epi == EPI_RESID ? "wo" : st.epi == EPI_LOGITS ? "lm_head" : (st.quant == DSK_F32 && q != DSK_F32 ? "gate" : "proj"));
     snprintf(nm, sizeof(nm), "%-8s n=%5d tiles=%5d rt=%2d wp=%d pieces=%2d", kind, st.kind == ST_DOWN ? st.K * st.mi + st.sh : st.n, st.ntiles, st.rows_per_tile, st.wp, st.npieces);
     s->stage_names.push_back(nm);
   }

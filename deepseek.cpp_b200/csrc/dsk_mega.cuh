@@ -23,7 +23,7 @@
 
 namespace dsk {
 
-enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3, ST_XCHG = 4, ST_AMAX = 5 };
+enum { ST_EMBED = 0, ST_GEMV = 1, ST_DOWN = 2, ST_ATTN = 3, ST_XCHG = 4, ST_AMAX = 5, ST_MLA_CACHE = 6, ST_ATTN_MLA = 7 };
 constexpr int kMaxRanks = 8;
 
 constexpr int kConsumers = 256;            // warps 0..7
@@ -83,6 +83,7 @@ struct Program {
   const uint8_t* embed_w; const float* embed_scale;
   const float* rope_freq;
   float *x, *q, *q_a, *kv_a, *kv_b, *xb2, *hbk, *hbs, *moe_logits, *moe_scores, *act_w, *logits, *partial, *att_scratch;
+  float* q_c;                              // true-MLA blocks: absorbed query (n_heads x kv_lora_rank)
   int* act;
   Ctrl* ctrl;
   unsigned int* sync_counter;              // grid barrier arrivals (monotonic)
@@ -2404,6 +2405,207 @@ __device__ __forceinline__ void grid_wait(const unsigned int* counter, unsigned 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// True multi-head latent attention (BlockMLA::_attention_impl, src/infer.cpp:1051-1141; attn_mla 766-804): checkpoints
+// converted with --mla carry wc (the k_nope_b^T . q_nope_b absorb), wq_rope_b and wv_b; the KV cache holds ONE latent row
+// (kv_lora_rank fp16) + ONE rotated rope key (qk_rope_head_dim fp16) per token instead of n_heads full K / V rows.
+//   ST_MLA_CACHE (CTA 0): kv_a -> rmsnorm(latent part) -> fp16 latent cache row kv_pos; rope(k_rope) -> fp16 rope cache row;
+//                         re-rotation of the sink rows (src/infer.cpp:1084-1111).  Its own stage because the caches are
+//                         shared by all heads: every head's CTA of the next stage only READS them.
+//   ST_ATTN_MLA (CTA per head): rope(q_rope[h]); scores over the latent + rope caches; softmax; latent mix; then the head's
+//                         value up-projection v_b[h] = wv_b[h] (v_head_dim x kv_lora_rank) . latent — matmul_expert with
+//                         expert = head (src/infer.cpp:1133-1137) — with the weight quant's own arithmetic (Q8_K latent +
+//                         integer dots for K-quants, exact fp16 split + mma for F8E5M2, fp32 otherwise).
+// ------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t mla_floats(int kv_lora, int rope, int max_seq) {   // fp32 scratch: stage | qc | qr | out | att | part
+  return (size_t)512 + (size_t)kv_lora + (size_t)((rope + 3) & ~3) + (size_t)kv_lora + (size_t)((max_seq + 3) & ~3) + 16;
+}
+template <int Q>
+__host__ __device__ inline size_t mla_weight_bytes(int kv_lora, int vh) {   // the head's wv_b slab + staged latent, in shared memory
+  if (QTraits<Q>::kq) return align_up((size_t)vh * QTraits<Q>::row_bytes(kv_lora), 128) + xvec_bytes<Q>(kv_lora);
+  if (Q == Q_F8) return align_up((size_t)vh * f8_pitch((size_t)kv_lora), 128) + x16_bytes(kv_lora) + 1024;   // + the head's scale rows (<= 256 floats)
+  return 0;   // F32 / F16: straight from global memory
+}
+
+__device__ __forceinline__ void c_mla_cache(const Program& P, const Stage& st, const MegaSmem& sm) {
+  if (blockIdx.x != 0) return;
+  const int tid = threadIdx.x;
+  const Ctrl* c = P.ctrl;
+  const int pos = c->pos, kv_pos = c->kv_pos, kv_sink = c->kv_sink;
+  const int half_r = P.rope >> 1;
+  float* stage = reinterpret_cast<float*>(sm.xregion);
+  // latent part: rmsnorm(kv_a[0:kv_lora]) (src/infer.cpp:1079) -> fp16 row of the latent cache
+  float ss = 0.f;
+  for (int i = tid; i < P.kv_lora; i += kConsumers) { const float v = P.kv_a[i]; ss = fmaf(v, v, ss); }
+  ss = csum(ss, sm.red);
+  const float scale = 1.0f / sqrtf(ss / (float)P.kv_lora + P.eps);
+  for (int i = tid; i < P.kv_lora; i += kConsumers) {
+    const float v = __fmul_rn(__fmul_rn(P.kv_a[i], scale), st.norm_w[i]);
+    P.kv_a[i] = v;                                                       // the reference normalises s.kv_a() in place
+    st.kcache[(size_t)kv_pos * P.kv_lora + i] = __float2half_rn(v);
+  }
+  // rope part of the new key (one shared key per token) and the sink rows, exactly as the MHA stage does per head
+  if (tid < half_r) {
+    float cs, sn; rope_cs(P.rope_freq, tid, pos, cs, sn);
+    const float v0 = P.kv_a[P.kv_lora + 2 * tid], v1 = P.kv_a[P.kv_lora + 2 * tid + 1];
+    const float r0 = v0 * cs - v1 * sn, r1 = v0 * sn + v1 * cs;
+    __half* kr = st.vcache + (size_t)kv_pos * P.rope;
+    if (P.is_v3) { kr[2 * tid] = __float2half_rn(r0); kr[2 * tid + 1] = __float2half_rn(r1); }
+    else { kr[tid] = __float2half_rn(r0); kr[tid + half_r] = __float2half_rn(r1); }
+  } else if (tid >= 128 && tid < 128 + half_r * kv_sink && kv_sink > 0) {
+    const int t = (tid - 128) % half_r, r = (tid - 128) / half_r;
+    float cs, sn; rope_cs(P.rope_freq, t, 1, cs, sn);
+    const __half* kr = st.vcache + (size_t)r * P.rope;
+    const float v0 = __half2float(kr[2 * t]), v1 = __half2float(kr[2 * t + 1]);
+    stage[2 * (r * half_r + t)] = v0 * cs - v1 * sn;
+    stage[2 * (r * half_r + t) + 1] = v0 * sn + v1 * cs;
+  }
+  csync();
+  if (tid >= 128 && tid < 128 + half_r * kv_sink && kv_sink > 0) {
+    const int t = (tid - 128) % half_r, r = (tid - 128) / half_r;
+    __half* kr = st.vcache + (size_t)r * P.rope;
+    const float r0 = stage[2 * (r * half_r + t)], r1 = stage[2 * (r * half_r + t) + 1];
+    if (P.is_v3) { kr[2 * t] = __float2half_rn(r0); kr[2 * t + 1] = __float2half_rn(r1); }
+    else { kr[t] = __float2half_rn(r0); kr[t + half_r] = __float2half_rn(r1); }
+  }
+  csync();
+}
+
+template <int Q>
+__device__ __noinline__ void c_attention_mla(const Program* Pp, const Stage* stp, int h) {
+  extern __shared__ __align__(128) unsigned char dsk_dyn_smem[];
+  const Program& P = *Pp; const Stage& st = *stp;
+  const MegaSmem sm = carve_mega(dsk_dyn_smem, P.xregion_bytes);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Ctrl* c = P.ctrl;
+  const int pos = c->pos, kv_len = c->kv_len;
+  const int L = P.kv_lora, R = P.rope, half_r = R >> 1;
+  float* stage = reinterpret_cast<float*>(sm.xregion);                  // 512 floats (unused here; keeps the MHA layout)
+  float* qc = stage + 512;
+  float* qr = qc + L;
+  float* out = qr + ((R + 3) & ~3);
+  float* att = out + L;
+  unsigned char* wbase = sm.xregion + align_up(mla_floats(L, R, P.max_seq) * 4, 128);
+  const __half* ckv = st.kcache;    // (max_seq, kv_lora)
+  const __half* krc = st.vcache;    // (max_seq, rope)
+  float* qrh = P.q + (size_t)h * R;
+  for (int i = tid; i < L; i += kConsumers) qc[i] = P.q_c[(size_t)h * L + i];
+  if (tid < half_r) {
+    float cs, sn; rope_cs(P.rope_freq, tid, pos, cs, sn);
+    const float v0 = qrh[2 * tid], v1 = qrh[2 * tid + 1];
+    const float r0 = v0 * cs - v1 * sn, r1 = v0 * sn + v1 * cs;
+    if (P.is_v3) { qr[2 * tid] = r0; qr[2 * tid + 1] = r1; }
+    else { qr[tid] = r0; qr[tid + half_r] = r1; }
+  }
+  csync();
+  if (tid < R) qrh[tid] = qr[tid];                                       // the reference rotates s.q_rope(h) in place
+  // scores: one warp per cached position
+  const float inv = sqrtf((float)P.hd);
+  for (int t = warp; t < kv_len; t += 8) {
+    float s = 0.f;
+    const __half* row = ckv + (size_t)t * L;
+    for (int i = lane * 2; i < L; i += 64) {
+      const float2 kk = __half22float2(*reinterpret_cast<const __half2*>(row + i));
+      s = fmaf(qc[i], kk.x, s); s = fmaf(qc[i + 1], kk.y, s);
+    }
+    const __half* rr = krc + (size_t)t * R;
+    for (int i = lane * 2; i < R; i += 64) {
+      const float2 kk = __half22float2(*reinterpret_cast<const __half2*>(rr + i));
+      s = fmaf(qr[i], kk.x, s); s = fmaf(qr[i + 1], kk.y, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) att[t] = s / inv;
+  }
+  csync();
+  float m = -3.402823466e38f;
+  for (int t = tid; t < kv_len; t += kConsumers) m = fmaxf(m, att[t]);
+  m = cmax(m, sm.red);
+  float sum = 0.f;
+  for (int t = tid; t < kv_len; t += kConsumers) { const float e = expf(att[t] - m); att[t] = e; sum += e; }
+  sum = csum(sum, sm.red);
+  for (int t = tid; t < kv_len; t += kConsumers) att[t] = att[t] / sum;
+  csync();
+  // latent mix: out[i] = sum_t att[t] * ckv[t][i]
+  for (int i = tid; i < L; i += kConsumers) {
+    float acc = 0.f;
+    for (int t = 0; t < kv_len; t++) acc = fmaf(att[t], __half2float(ckv[(size_t)t * L + i]), acc);
+    out[i] = acc;
+    P.xb2[(size_t)h * L + i] = acc;
+  }
+  csync();
+  // value up-projection of this head: kv_b[h*vh + r] = wv_b[h][r] . out
+  const MJob& jb = st.job[0];
+  const int vh = P.vh;
+  float* vout = P.kv_b + (size_t)h * vh;
+  const uint8_t* wsrc = jb.w + (size_t)h * (size_t)jb.w_stride;
+  if constexpr (QTraits<Q>::kq) {
+    const uint32_t rb = (uint32_t)QTraits<Q>::row_bytes(L);
+    float* dummy = nullptr;
+    Q8Smem q8{};
+    carve_x<Q>(wbase + align_up((size_t)vh * rb, 128), L, dummy, q8);
+    for (int b = warp; b < (L >> 8); b += 8) {
+      const float4 va = *reinterpret_cast<const float4*>(out + (b << 8) + lane * 8);
+      const float4 vb = *reinterpret_cast<const float4*>(out + (b << 8) + lane * 8 + 4);
+      q8_block_nf(va, vb, b, q8.qs, q8.d, q8.bsums);
+    }
+    for (int i = tid; i < (int)((size_t)vh * rb / 16); i += kConsumers)
+      reinterpret_cast<uint4*>(wbase)[i] = reinterpret_cast<const uint4*>(wsrc)[i];
+    csync();
+    for (int g = warp; g * 16 < vh; g += 8) {
+      const int nrows = min(16, vh - g * 16);
+      const float v = kq_tile_rows<Q>(smem_u32(wbase) + (uint32_t)(g * 16) * rb, rb, nrows, L >> 8, smem_u32(q8.qs), smem_u32(q8.d), smem_u32(q8.bsums));
+      if (lane < nrows) vout[g * 16 + lane] = v;
+    }
+  } else if (Q == Q_F8 && st.use_mma) {
+    const uint32_t pitch = (uint32_t)f8_pitch((size_t)L);
+    unsigned char* xb = wbase + align_up((size_t)vh * pitch, 128);
+    const X16 x16 = carve_x16(xb, L);
+    float* srow = reinterpret_cast<float*>(xb + x16_bytes(L));           // the head's scale row (kv_lora / bs1 floats)
+    if (tid < (L >> 2)) x16_store_nf(x16.hi, x16.lo, x16.gs, tid, *reinterpret_cast<const float4*>(out + 4 * tid));
+    for (int f = kConsumers + tid; f < (L >> 2); f += kConsumers) x16_store_nf(x16.hi, x16.lo, x16.gs, f, *reinterpret_cast<const float4*>(out + 4 * f));
+    for (int i = tid; i < (int)((size_t)vh * pitch / 16); i += kConsumers)
+      reinterpret_cast<uint4*>(wbase)[i] = reinterpret_cast<const uint4*>(wsrc)[i];
+    const int ncb = (L + P.bs1 - 1) / P.bs1;
+    if (jb.scale && tid < (int)jb.s_stride) srow[tid] = jb.scale[(size_t)h * (size_t)jb.s_stride + tid];   // cdiv(vh, bs0) rows of ncb
+    csync();
+    const int gid = lane >> 2;
+    for (int g = warp; g * 16 < vh; g += 8) {
+      const int nrows = min(16, vh - g * 16);
+      const uint32_t base = smem_u32(wbase) + (uint32_t)(g * 16) * pitch;
+      const uint32_t a_lo = base + (uint32_t)min(gid, nrows - 1) * pitch;
+      const uint32_t a_hi = nrows > 8 ? base + (uint32_t)min(gid + 8, nrows - 1) * pitch : 0u;
+      const uint32_t ssm = jb.scale ? smem_u32(srow + (size_t)((g * 16) / P.bs0) * ncb) : 0u;   // bs0 % 16 == 0: one scale row per group
+      const float2 vv = mma_rows_f8(a_lo, a_hi, ssm, ssm, P.bs1_shift, 0, L, x16.hi, x16.lo, x16.gs);
+      if ((lane & 3) == 0) {
+        if (gid < nrows) vout[g * 16 + gid] = vv.x;
+        if (gid + 8 < nrows) vout[g * 16 + gid + 8] = vv.y;
+      }
+    }
+  } else {   // F32 / F16 (and F8 without the tensor-core plan): a warp per row straight from global memory
+    const size_t rb = QTraits<Q>::row_bytes(L);
+    const int ncb = (L + P.bs1 - 1) / P.bs1;
+    for (int r = warp; r < vh; r += 8) {
+      const uint8_t* wr = wsrc + (size_t)r * rb;
+      float acc = 0.f;
+      if constexpr (Q == Q_F8) {
+        const float* sc = jb.scale ? jb.scale + (size_t)h * (size_t)jb.s_stride + (size_t)(r / P.bs0) * ncb : nullptr;
+        for (int b = 0; b < ncb; b++) {
+          float p = 0.f;
+          for (int i = b * P.bs1 + lane; i < min(L, (b + 1) * P.bs1); i += 32) p = fmaf(h2f((uint16_t)((uint16_t)wr[i] << 8)), out[i], p);
+          acc = fmaf(p, sc ? sc[b] : 1.0f, acc);
+        }
+      } else if constexpr (Q == Q_F16) {
+        for (int i = lane; i < L; i += 32) acc = fmaf(__half2float(reinterpret_cast<const __half*>(wr)[i]), out[i], acc);
+      } else if constexpr (Q == Q_F32) {
+        for (int i = lane; i < L; i += 32) acc = fmaf(reinterpret_cast<const float*>(wr)[i], out[i], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) vout[r] = acc;
+    }
+  }
+  csync();
+}
+
 // Stages [s_begin, s_end) for n_tokens consecutive tokens in ONE launch (dsk_decode_greedy: the token loop lives inside the
 // persistent kernel; tokens after the first always take their id from the on-device arg-max of the previous LM-head stage).
 // Launched cooperatively with one CTA per SM: co-residency of the grid barrier's participants is guaranteed by the launch.
@@ -2490,6 +2692,12 @@ __global__ void __launch_bounds__(kMegaThreads, 1) decode_kernel(const Program* 
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else if (st.kind == ST_ATTN) {
       for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention(P, st, sm, h);
+      if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
+    } else if (st.kind == ST_MLA_CACHE) {
+      c_mla_cache(P, st, sm);
+      if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
+    } else if (st.kind == ST_ATTN_MLA) {
+      for (int h = blockIdx.x; h < P.n_heads; h += gridDim.x) c_attention_mla<Q>(&P, &st, h);
       if (tid == 0) dep_signal(sm.dep, nstage_seen + 1);
     } else {
       if (st.quant == Q_F32 && Q != Q_F32) it = gate_f32_stage(it, nstage_seen + 1, s);

@@ -111,7 +111,6 @@ static dsk_config config_from(const DseekData& d, int context) {
   if (tm == "noaux_tc") { fprintf(stderr, "FATAL: topk_method noaux_tc unsupported (src/model.cpp:51-53)\n"); exit(1); }
   c.topk_method = tm == "group_limited_greedy";
   c.is_v3 = meta_s(d, "arch", "") == "DeepseekV3ForCausalLM";
-  if (meta_i(d, "use_mla", 0)) { fprintf(stderr, "FATAL: use_mla=1 checkpoints are not supported by this backend; convert without --mla\n"); exit(1); }
   c.kv_lora_rank = meta_i(d, "kv_lora_rank", 0); c.q_lora_rank = meta_i(d, "q_lora_rank", 0);
   c.qk_nope_head_dim = meta_i(d, "qk_nope_head_dim", 0); c.qk_rope_head_dim = meta_i(d, "qk_rope_head_dim", 0); c.v_head_dim = meta_i(d, "v_head_dim", 0);
   std::string q = meta_s(d, "quant", "");
@@ -120,6 +119,7 @@ static dsk_config config_from(const DseekData& d, int context) {
   else { fprintf(stderr, "FATAL: unsupported quant: %s\n", q.c_str()); exit(1); }
   c.bs0 = meta_i(d, "quantization_block_size_0", 0); c.bs1 = meta_i(d, "quantization_block_size_1", 0);
   c.original_max_position = meta_i(d, "rope_scaling_original_max_position_embeddings", 4096);
+  c.use_mla = meta_i(d, "use_mla", 0) ? 1 : 0;
   return c;
 }
 

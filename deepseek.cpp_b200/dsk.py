@@ -45,7 +45,7 @@ class Config(C.Structure):
                [(n, C.c_int) for n in ("n_group", "norm_topk_prob", "scoring_sigmoid", "topk_group", "topk_method",
                                        "is_v3", "kv_lora_rank", "q_lora_rank", "qk_nope_head_dim",
                                        "qk_rope_head_dim", "v_head_dim", "quant", "bs0", "bs1",
-                                       "original_max_position")]
+                                       "original_max_position", "use_mla")]
 
     @staticmethod
     def from_metadata(md: Dict[str, str], context: int = 0) -> "Config":
@@ -74,8 +74,7 @@ class Config(C.Structure):
         c.kv_lora_rank, c.q_lora_rank = int(g("kv_lora_rank", "0")), int(g("q_lora_rank", "0"))
         c.qk_nope_head_dim, c.qk_rope_head_dim = int(g("qk_nope_head_dim", "0")), int(g("qk_rope_head_dim", "0"))
         c.v_head_dim = int(g("v_head_dim", "0"))
-        if int(g("use_mla", "0")):
-            raise DskError("use_mla=1 checkpoints (BlockMLA) are not on this path; convert without --mla")
+        c.use_mla = 1 if int(g("use_mla", "0")) else 0      # BlockMLA checkpoints (convert.py --mla)
         c.quant = QUANT_IDS[md["quant"]]
         c.bs0, c.bs1 = int(g("quantization_block_size_0", "0")), int(g("quantization_block_size_1", "0"))
         c.original_max_position = int(md["rope_scaling_original_max_position_embeddings"])
@@ -83,6 +82,7 @@ class Config(C.Structure):
 
 
 _lib = None
+ABI_VERSION = 3   # DSK_ABI_VERSION (include/dsk.h)
 
 
 def build(force: bool = False) -> str:
@@ -105,6 +105,8 @@ def lib():
     global _lib
     if _lib is None:
         L = C.CDLL(build())
+        if L.dsk_abi_version() != ABI_VERSION:      # dsk_config's layout is part of the ABI
+            raise DskError(f"libdsk.so speaks ABI {L.dsk_abi_version()}, these bindings ABI {ABI_VERSION}: rebuild (make -C deepseek.cpp_b200)")
         L.dsk_last_error.restype = C.c_char_p
         L.dsk_model_create.restype = C.c_void_p
         L.dsk_model_create.argtypes = [C.POINTER(Config), C.c_int, C.c_int]
@@ -279,7 +281,8 @@ class Model:
     def buffer_sizes(self):
         c = self.cfg
         hd = c.qk_nope_head_dim + c.qk_rope_head_dim
-        return {"x": c.dim, "xb2": max(c.dim, c.n_heads * c.v_head_dim),
+        return {"x": c.dim, "xb2": max(c.dim, c.n_heads * c.v_head_dim, c.n_heads * c.kv_lora_rank if c.use_mla else 0),
+                "q_c": c.n_heads * c.kv_lora_rank if c.use_mla else 0,
                 "hb": max(c.hidden_dim, c.n_shared_experts * c.moe_intermediate_size), "q": c.n_heads * hd,
                 "kv_a": c.kv_lora_rank + c.qk_rope_head_dim, "kv_b": c.n_heads * (c.qk_nope_head_dim + c.v_head_dim),
                 "moe_weights": c.n_routed_experts, "active_experts_weights": c.n_active_routed, "logits": c.vocab_size}
@@ -292,6 +295,8 @@ class Model:
     def kv_cache(self, layer: int, which: int, n: Optional[int] = None) -> np.ndarray:
         c = self.cfg
         hd = c.qk_nope_head_dim + c.qk_rope_head_dim
+        if c.use_mla:   # latent rows / rope keys (BlockMLA, src/model.h:451-452)
+            n = n or c.max_seq_len * (c.kv_lora_rank if which == 0 else c.qk_rope_head_dim)
         n = n or c.max_seq_len * c.n_heads * (hd if which == 0 else c.v_head_dim)
         out = np.zeros(n, dtype=np.uint16)
         _ck(self.L.dsk_kv_read(self.h, layer, which, out.ctypes.data_as(u16p), n))

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DSK_ABI_VERSION 2
+#define DSK_ABI_VERSION 3
 
 /* Quant: src/codec.h:79-85 (same numbering) */
 enum { DSK_F32 = 0, DSK_F16 = 1, DSK_F8E5M2 = 2, DSK_Q2_K = 3, DSK_Q3_K = 4 };
@@ -47,6 +47,7 @@ typedef struct dsk_config {
   int quant;                 /* DSK_* weight quant */
   int bs0, bs1;              /* f8e5m2 scale block (128,128) */
   int original_max_position; /* rope_scaling_original_max_position_embeddings (sinks, src/infer.cpp:1274) */
+  int use_mla;               /* 1: true-MLA blocks (BlockMLA, src/model.h:366-453): wc / wq_rope_b / wv_b tensors, latent KV cache */
 } dsk_config;
 
 typedef struct dsk_model dsk_model;
@@ -92,12 +93,14 @@ double dsk_model_active_bytes_per_token(const dsk_model* m);
 /* ---- state: replaces InferenceState (src/model.h:101-179) -------------------------------------- */
 dsk_state* dsk_state_create(dsk_model* m);
 void dsk_state_destroy(dsk_state* s);
-/* Named buffer access for parity taps: "x","xb2","hb","q","kv_a","kv_b","moe_weights",
+/* Named buffer access for parity taps: "x","xb2","hb","q","q_c" (use_mla),"kv_a","kv_b","moe_weights",
  * "active_experts_weights","logits" (float) and "active_experts" (int32, via the _i32 variant). */
 int dsk_state_read(dsk_state* s, const char* buffer, float* dst, size_t n);
 int dsk_state_write(dsk_state* s, const char* buffer, const float* src, size_t n);
 int dsk_state_read_i32(dsk_state* s, const char* buffer, int32_t* dst, size_t n);
-/* fp16 KV cache rows of one layer (BlockMHA::key_cache/value_cache, src/model.h:344-347). which: 0 K, 1 V. */
+/* fp16 KV cache rows of one layer (BlockMHA::key_cache/value_cache, src/model.h:344-347). which: 0 K, 1 V.
+ * use_mla models: which 0 = kv_nope_cache (max_seq_len x kv_lora_rank), 1 = kv_rope_cache (max_seq_len x qk_rope_head_dim)
+ * (BlockMLA, src/model.h:437-440). */
 int dsk_kv_read(dsk_model* m, int layer, int which, uint16_t* dst, size_t n_halfs);
 int dsk_kv_write(dsk_model* m, int layer, int which, const uint16_t* src, size_t n_halfs);
 

@@ -110,7 +110,8 @@ def tokens_tensor(vocab_size: int) -> np.ndarray:
 
 
 def mint(dirname: str, preset: str = "tiny_v2lite", quant: str = "fp32", seed: int = 1234, fast: bool = False,
-         gate_gain: float = 4.0, original_max_position: int = 4096, **overrides) -> dict:
+         gate_gain: float = 4.0, original_max_position: int = 4096, use_mla: bool = False, **overrides) -> dict:
+    """use_mla: BlockMLA tensors as convert.py --mla writes them (convert.py:384-: wc, wq_rope_b, wv_b instead of wq_b, wkv_b)."""
     cfg = dict(PRESETS[preset])
     cfg.update(overrides)
     if quant in ("q2_k", "q3_k"):
@@ -123,7 +124,7 @@ def mint(dirname: str, preset: str = "tiny_v2lite", quant: str = "fp32", seed: i
     nope, rope, vh = cfg["qk_nope_head_dim"], cfg["qk_rope_head_dim"], cfg["v_head_dim"]
     hd = nope + rope
     md = {
-        "arch": cfg["arch"], "use_mla": "0", "quant": quant, "dim": dim, "hidden_dim": cfg["hidden_dim"],
+        "arch": cfg["arch"], "use_mla": "1" if use_mla else "0", "quant": quant, "dim": dim, "hidden_dim": cfg["hidden_dim"],
         "n_layers": cfg["n_layers"], "n_heads": nh, "vocab_size": cfg["vocab_size"], "max_seq_len": cfg["max_seq_len"],
         "bos_token_id": 0, "eos_token_id": 1, "rope_theta": 10000.0, "norm_eps": 1e-6, "norm_type": "rmsnorm",
         "act_type": "silu", "first_k_dense_replace": cfg["first_k_dense_replace"],
@@ -190,14 +191,24 @@ def mint(dirname: str, preset: str = "tiny_v2lite", quant: str = "fp32", seed: i
         shard[p + "attn.norm.weight"] = norm_w(dim)
         shard[p + "mlp.norm.weight"] = norm_w(dim)
         shard[p + "attn.kv_a_norm.weight"] = norm_w(cfg["kv_lora_rank"])
-        if cfg["q_lora_rank"] > 0:
+        if use_mla:
+            assert cfg["q_lora_rank"] > 0, "BlockMLA requires q_lora_rank > 0 (src/infer.cpp:1057)"
             shard[p + "attn.q_a_norm.weight"] = norm_w(cfg["q_lora_rank"])
             put(shard, p + "attn.wq_a", randw(cfg["q_lora_rank"], dim))
-            put(shard, p + "attn.wq_b", randw(nh * hd, cfg["q_lora_rank"]))
+            # wc = k_nope_b^T . q_nope_b absorbed: (n_heads * kv_lora_rank, q_lora_rank); its entries carry two fan-ins
+            put(shard, p + "attn.wc", randw(nh * cfg["kv_lora_rank"], cfg["q_lora_rank"], std=(cfg["q_lora_rank"] * cfg["kv_lora_rank"]) ** -0.5 * nope ** 0.5))
+            put(shard, p + "attn.wq_rope_b", randw(nh * rope, cfg["q_lora_rank"]))
+            put(shard, p + "attn.wkv_a", randw(cfg["kv_lora_rank"] + rope, dim))
+            put(shard, p + "attn.wv_b", randw(nh * vh, cfg["kv_lora_rank"]))
         else:
-            put(shard, p + "attn.wq", randw(nh * hd, dim))
-        put(shard, p + "attn.wkv_a", randw(cfg["kv_lora_rank"] + rope, dim))
-        put(shard, p + "attn.wkv_b", randw(nh * (nope + vh), cfg["kv_lora_rank"]))
+            if cfg["q_lora_rank"] > 0:
+                shard[p + "attn.q_a_norm.weight"] = norm_w(cfg["q_lora_rank"])
+                put(shard, p + "attn.wq_a", randw(cfg["q_lora_rank"], dim))
+                put(shard, p + "attn.wq_b", randw(nh * hd, cfg["q_lora_rank"]))
+            else:
+                put(shard, p + "attn.wq", randw(nh * hd, dim))
+            put(shard, p + "attn.wkv_a", randw(cfg["kv_lora_rank"] + rope, dim))
+            put(shard, p + "attn.wkv_b", randw(nh * (nope + vh), cfg["kv_lora_rank"]))
         put(shard, p + "attn.wo", randw(dim, nh * vh))
         if E > 0 and l >= cfg["first_k_dense_replace"]:
             shard[p + "moegate.weight"] = ("F32", (rng.standard_normal((E, dim), dtype=np.float32) * dim ** -0.5 * gate_gain))

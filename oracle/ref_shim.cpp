@@ -194,6 +194,8 @@ long ref_state_buffer(void* h, const char* name, float** out) {
   if (k == "hb") { *out = st.hb(); return std::max(c.dim, c.hidden_dim); }
   if (k == "hb2") { *out = st.hb2(); return c.hidden_dim; }
   if (k == "q") { *out = st.q(); return c.n_heads * c.head_dim; }
+  if (k == "q_c" && c.use_mla) { *out = st.q_c(); return c.n_heads * c.kv_lora_rank; }
+  if (k == "q_rope" && c.use_mla) { *out = st.q_rope(); return c.n_heads * c.qk_rope_head_dim; }
   if (k == "kv_a") { *out = st.kv_a(); return c.kv_lora_rank + c.qk_rope_head_dim; }
   if (k == "kv_b") { *out = st.kv_b(); return c.n_heads * (c.head_dim - c.qk_rope_head_dim + c.v_head_dim); }
   if (k == "logits") { *out = st.logits(); return c.vocab_size; }
@@ -208,15 +210,23 @@ int ref_active_experts(void* h, int* out) {
   for (int k = 0; k < c.n_active_routed; k++) out[k] = s->state->active_experts()[k];
   return c.n_active_routed;
 }
-// fp16 KV cache of one MHA block (src/model.h:361-362). which: 0 key, 1 value.
+// fp16 KV cache of one block.  MHA (src/model.h:361-362): which 0 key, 1 value.  MLA (src/model.h:411-414): which 0 the
+// latent rows (kv_nope_cache), 1 the rope keys (kv_rope_cache).
 long ref_kv_cache(void* h, int layer, int which, uint16_t** out) {
   auto* s = (RefSession*)h;
   const Config& c = *s->model->config;
-  auto* b = dynamic_cast<BlockMHA*>(s->model->blocks[layer].get());
-  if (!b) { *out = nullptr; return 0; }
-  if (which == 0) { *out = b->key_cache(); return (long)c.max_seq_len * c.n_heads * c.head_dim; }
-  *out = b->value_cache();
-  return (long)c.max_seq_len * c.n_heads * c.v_head_dim;
+  if (auto* b = dynamic_cast<BlockMHA*>(s->model->blocks[layer].get())) {
+    if (which == 0) { *out = b->key_cache(); return (long)c.max_seq_len * c.n_heads * c.head_dim; }
+    *out = b->value_cache();
+    return (long)c.max_seq_len * c.n_heads * c.v_head_dim;
+  }
+  if (auto* b = dynamic_cast<BlockMLA*>(s->model->blocks[layer].get())) {
+    if (which == 0) { *out = b->kv_nope_cache(); return (long)c.max_seq_len * c.kv_lora_rank; }
+    *out = b->kv_rope_cache();
+    return (long)c.max_seq_len * c.qk_rope_head_dim;
+  }
+  *out = nullptr;
+  return 0;
 }
 
 int ref_num_threads() { return omp_get_max_threads(); }

@@ -201,7 +201,7 @@ def test_cabi_exports_every_declared_symbol(repo):
     L = ctypes.CDLL(dsk.build())
     for n in names:
         assert hasattr(L, n), n
-    assert L.dsk_abi_version() == 2
+    assert L.dsk_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_gpu():
