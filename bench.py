@@ -79,14 +79,21 @@ def tensor_plan(w):
     for l in range(w["n_layers"]):
         p = f"model.layers.{l}."
         f32 += [(p + "attn.norm.weight", dim), (p + "mlp.norm.weight", dim), (p + "attn.kv_a_norm.weight", w["kv_lora_rank"])]
-        if w["q_lora_rank"] > 0:
+        if w.get("use_mla"):   # convert.py --mla (convert.py:384-440): absorbed wc, rope-only wq_rope_b, per-head wv_b
             f32.append((p + "attn.q_a_norm.weight", w["q_lora_rank"]))
-            plan += [(p + "attn.wq_a", w["q_lora_rank"], dim, 0), (p + "attn.wq_b", nh * hd, w["q_lora_rank"], 0)]
+            plan += [(p + "attn.wq_a", w["q_lora_rank"], dim, 0), (p + "attn.wc", nh * w["kv_lora_rank"], w["q_lora_rank"], 0),
+                     (p + "attn.wq_rope_b", nh * w["qk_rope_head_dim"], w["q_lora_rank"], 0),
+                     (p + "attn.wkv_a", w["kv_lora_rank"] + w["qk_rope_head_dim"], dim, 0),
+                     (p + "attn.wv_b", nh * w["v_head_dim"], w["kv_lora_rank"], 0), (p + "attn.wo", dim, nh * w["v_head_dim"], 0)]
         else:
-            plan.append((p + "attn.wq", nh * hd, dim, 0))
-        plan += [(p + "attn.wkv_a", w["kv_lora_rank"] + w["qk_rope_head_dim"], dim, 0),
-                 (p + "attn.wkv_b", nh * (w["qk_nope_head_dim"] + w["v_head_dim"]), w["kv_lora_rank"], 0),
-                 (p + "attn.wo", dim, nh * w["v_head_dim"], 0)]
+            if w["q_lora_rank"] > 0:
+                f32.append((p + "attn.q_a_norm.weight", w["q_lora_rank"]))
+                plan += [(p + "attn.wq_a", w["q_lora_rank"], dim, 0), (p + "attn.wq_b", nh * hd, w["q_lora_rank"], 0)]
+            else:
+                plan.append((p + "attn.wq", nh * hd, dim, 0))
+            plan += [(p + "attn.wkv_a", w["kv_lora_rank"] + w["qk_rope_head_dim"], dim, 0),
+                     (p + "attn.wkv_b", nh * (w["qk_nope_head_dim"] + w["v_head_dim"]), w["kv_lora_rank"], 0),
+                     (p + "attn.wo", dim, nh * w["v_head_dim"], 0)]
         if E > 0 and l >= w["first_k_dense_replace"]:
             f32.append((p + "moegate.weight", E * dim))
             if w["arch"] == "DeepseekV3ForCausalLM":
@@ -114,6 +121,7 @@ def make_config(dsk, w):
     c.quant = QUANT_IDS[w["quant"]]
     c.bs0, c.bs1 = (128, 128) if w["quant"] == "f8e5m2" else (0, 0)
     c.original_max_position = 4096
+    c.use_mla = 1 if w.get("use_mla") else 0
     return c
 
 
@@ -252,7 +260,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 def ckpt_metadata(w, n_layers):
     quant = w["quant"]
-    md = {"arch": w["arch"], "use_mla": "0", "quant": quant, "dim": w["dim"], "hidden_dim": w["hidden_dim"], "n_layers": n_layers,
+    md = {"arch": w["arch"], "use_mla": "1" if w.get("use_mla") else "0", "quant": quant, "dim": w["dim"], "hidden_dim": w["hidden_dim"], "n_layers": n_layers,
           "n_heads": w["n_heads"], "vocab_size": w["vocab_size"], "max_seq_len": w["max_seq_len"], "bos_token_id": 0,
           "eos_token_id": 1, "rope_theta": 10000.0, "norm_eps": 1e-6, "norm_type": "rmsnorm", "act_type": "silu",
           "first_k_dense_replace": w["first_k_dense_replace"], "kv_lora_rank": w["kv_lora_rank"], "q_lora_rank": w["q_lora_rank"],
@@ -600,6 +608,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("DSK_WORKLOAD", "v2"))
     ap.add_argument("--quant", default=os.environ.get("DSK_QUANT", "q2_k"))
     ap.add_argument("--n-layers", type=int, default=int(os.environ.get("DSK_LAYERS", "0")))
+    ap.add_argument("--mla", action="store_true", help="true-MLA blocks (convert.py --mla shapes: wc / wq_rope_b / wv_b, latent KV cache)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the V2-Lite configs[1]/[2] continuity numbers")
     ap.add_argument("--profile-token", action="store_true", help="print the per-stage timeline of one token to stderr")
@@ -608,11 +617,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     w = workload_cfg(a.workload, a.quant, a.n_layers or None)
+    if a.mla:
+        w["use_mla"] = 1
     base = {"metric": "tok/s single-batch decode (128-tok gen)", "unit": "tok/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": DTYPES[a.quant],
             "data": "synthetic (random-init weights of the named architecture; no checkpoints offline)",
-            "config": {"workload": workload_name(a.workload, a.quant), "baseline_config": {"v2lite": "configs[1]/[2]", "v2": "configs[3]", "v3": "configs[4]"}.get(a.workload),
+            "config": {"workload": workload_name(a.workload, a.quant) + (" (true-MLA blocks, use_mla=1)" if a.mla else ""), "baseline_config": {"v2lite": "configs[1]/[2]", "v2": "configs[3]", "v3": "configs[4]"}.get(a.workload),
                        "layers": w["n_layers"], "tokens_per_step": GEN_TOKENS,
                        "parallelism": (f"tensor parallel over {a.gpus} GPUs: attention heads, wo columns, shared-expert / dense-FFN hidden units, LM-head rows and routed experts sharded; two in-kernel peer-memory exchanges per layer" if os.environ.get("DSK_TP", "1") != "0" else f"routed experts sharded over {a.gpus} GPU(s), rest replicated; one in-kernel peer-memory exchange per MoE layer") if a.gpus > 1 else "1 GPU",
                        "l2": "weights streamed per token (GBs) exceed the 126 MB L2; no flush needed"}}
@@ -680,7 +691,7 @@ def main():
         kern["note"] = "ONE interpreter GEMV stage per launch (decode_kernel<Q>, production tile plan); launch overhead included"
     except Exception as e:
         kern = {"error": str(e)[:120]}
-    traffic, capture = committed_traffic(a.workload, a.quant) if world == 1 and not a.n_layers else (None, None)
+    traffic, capture = committed_traffic(a.workload, a.quant) if world == 1 and not a.n_layers and not a.mla else (None, None)
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "traffic_unit": "bytes per token (= per launch / tokens per launch), ncu capture in profiles/", "traffic_capture": capture,
             "kernel": "decode_kernel<Q> (a whole completion is one launch; achieved = algorithmic bytes/token x tok/s / N_gpus, i.e. every "
@@ -707,6 +718,15 @@ def main():
                                        "algorithmic_bytes_per_token": r2["abytes"], "roofline_frac": r2["abytes"] * r2["value"] / 1e9 / peak}
             except Exception as e:
                 sec[f"v2lite/{sq}"] = {"error": str(e)[:160]}
+        if a.workload == "v2" and not a.mla:   # the same model converted with --mla (BlockMLA): absorbed projections, latent KV cache
+            try:
+                wm = dict(w, use_mla=1)
+                r3 = measure(dsk, torch, None, wm, 0, 1, local_rank, max(2, a.steps // 2), max(3, a.warmup), want_e2e=False)
+                sec[f"v2/{a.quant}+mla"] = {"workload": workload_name("v2", a.quant) + " (true-MLA blocks, use_mla=1)", "value": r3["value"],
+                                            "unit": "tok/s", "algorithmic_bytes_per_token": r3["abytes"],
+                                            "roofline_frac": r3["abytes"] * r3["value"] / 1e9 / peak, "resident_gb": r3["resident_gb"]}
+            except Exception as e:
+                sec[f"v2/{a.quant}+mla"] = {"error": str(e)[:160]}
         out["secondary"] = sec
     if a.gpus == 1 and not a.no_cpu_baseline:
         try:

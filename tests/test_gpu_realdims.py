@@ -5,7 +5,7 @@
   * DeepSeek-V3 671B: dim 7168, 128 heads, q_lora 1536, 256 routed experts (sigmoid + bias, 8 groups, top-4 per group,
     top-8, norm_topk_prob), 1 shared, moe_intermediate 2048, vocab 129280, interleaved RoPE, scaling 2.5;
 
-each as 1 dense + 1 MoE layer + LM head (first_k_dense_replace overridden to 1 so both layer kinds appear).  The tiny
+(and, for two cases, the same dims converted with --mla: true-MLA blocks) each as 1 dense + 1 MoE layer + LM head (first_k_dense_replace overridden to 1 so both layer kinds appear).  The tiny
 presets exercise every branch of the algorithm; this file exercises the production TILE SHAPES of the interpreter at these
 dims (K-quant rows of 1536 / 5120 / 7168 / 16384 / 18432 columns, 128-head attention, E = 160 / 256 routing, 0.5-0.9 M-row
 LM heads) against the unmodified reference (oracle/_ref), tiers T2 (re-synchronised layers) and T3 (teacher-forced)."""
@@ -22,8 +22,11 @@ from conftest import rel_l2
 pytestmark = pytest.mark.gpu
 
 TOKENS = [0, 9, 40011, 33, 100201, 77]
-# T3 hard ceilings (the reference-vs-reference floor of SURVEY §0.4 for K-quants) and the tight T2 bound
-T3_CEIL = {"f8e5m2": 5e-4, "q2_k": 8e-2, "q3_k": 8e-2}
+# T3 ceilings.  K-quants: the UNMODIFIED reference against itself with ONE norm vector perturbed by 1 ulp moves the logits of
+# these checkpoints by 2e-2 .. 1.1e-1 (profiles/r02_reference_self_sensitivity.txt, tools/ref_sensitivity.py): Q8_K rounding
+# flips on random K-quant blocks.  T3 is therefore a sanity ceiling at ~2x that floor; the arithmetic is proven by T2's clean
+# pairs (< 1e-5) and by the bit-exact hook tests.  F8E5M2 has no activation quantisation: floor 7e-5, ceiling 5e-4.
+T3_CEIL = {"f8e5m2": 5e-4, "q2_k": 2.5e-1, "q3_k": 2.5e-1}
 T2_TOL = 5e-5
 
 
@@ -34,21 +37,29 @@ def dsk():
     return d
 
 
-def _mint(workload, quant, n_layers=2):
+def _mint(workload, quant, n_layers=2, mla=False):
     import bench
     w = bench.workload_cfg(workload, quant, n_layers=n_layers, max_seq_len=64)
     w["first_k_dense_replace"] = 1
+    if mla:
+        w["use_mla"] = 1
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else tempfile.gettempdir()
     d = tempfile.mkdtemp(prefix=f"dsk_real_{workload}_{quant}_", dir=base)
     bench.mint_cpu_truncated(w, d, n_layers)
     return d
 
 
-@pytest.mark.parametrize("workload,quant", [("v2", "q2_k"), ("v3", "q2_k"), ("v3", "q3_k"), ("v2", "f8e5m2")])
-def test_real_dims_layers_and_logits(dsk, workload, quant):
-    d = _mint(workload, quant)
+@pytest.mark.parametrize("workload,quant,mla", [("v2", "q2_k", False), ("v3", "q2_k", False), ("v3", "q3_k", False),
+                                                ("v2", "f8e5m2", False), ("v2", "q2_k", True), ("v2", "f8e5m2", True)])
+def test_real_dims_layers_and_logits(dsk, workload, quant, mla):
+    """mla=True: the same dims converted with --mla (BlockMLA): 128 heads x (512-wide latent + 64 rope) attention, the
+    65536 x 1536 absorbed projection wc, per-head 128 x 512 wv_b slabs."""
+    if mla and O.ref_lib() is None:
+        pytest.skip("BlockMLA parity needs oracle/_ref")
+    d = _mint(workload, quant, mla=mla)
     try:
         m = dsk.Model.from_dir(d)
+        assert m.cfg.use_mla == (1 if mla else 0)
         o = O.open_session(d)
         kq = quant in ("q2_k", "q3_k")
         # ---- T2: every layer fed the checker's input and KV cache (a rounding flip upstream cannot leak in) ----------
@@ -98,8 +109,8 @@ def test_real_dims_layers_and_logits(dsk, workload, quant):
         print(f"real-dims {workload}/{quant} T3: logits rel-L2 median {np.median(t3):.2e} max {max(t3):.2e}")
         if kq:
             # random K-quant blocks make the LM head ill-conditioned (large +-dmin*m terms cancel): a single-flip residual error of
-            # ~3e-3 shows up as a few 1e-2 on the logits; the hard ceiling above is the bound, the median is reported
-            assert np.median(t3) < 6e-2
+            # ~3e-3 shows up as a few 1e-2 on the logits (the reference against itself: median 2e-2 .. 4e-2)
+            assert np.median(t3) < 1e-1
         # device-resident loop == host-driven loop at these shapes (run-to-run determinism of the engine)
         m2 = dsk.Model.from_dir(d)
         for p, t in enumerate(TOKENS):
