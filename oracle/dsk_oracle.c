@@ -472,6 +472,24 @@ void ork_attn(float* xout, float* atth, const float* qh, const uint16_t* kh, con
   }
 }
 
+/* attn_mla: src/infer.cpp:766-804 — scores over the latent + rope caches, softmax, latent mix */
+void ork_attn_mla(float* xout, float* atth, const float* qh_c, const float* qh_rope, const uint16_t* ckv, const uint16_t* k_rope,
+                  int head_dim, int kv_lora_rank, int qk_rope_head_dim, int kv_len) {
+  for (int t = 0; t < kv_len; ++t) {
+    float score = 0.0f;
+    for (int i = 0; i < kv_lora_rank; ++i) score += qh_c[i] * ork_half_to_float(ckv[(size_t)t * kv_lora_rank + i]);
+    for (int i = 0; i < qk_rope_head_dim; ++i) score += qh_rope[i] * ork_half_to_float(k_rope[(size_t)t * qk_rope_head_dim + i]);
+    score /= sqrtf((float)head_dim);
+    atth[t] = score;
+  }
+  ork_softmax(atth, atth, kv_len);
+  for (int i = 0; i < kv_lora_rank; ++i) {
+    float vi = 0.0f;
+    for (int t = 0; t < kv_len; ++t) vi += atth[t] * ork_half_to_float(ckv[(size_t)t * kv_lora_rank + i]);
+    xout[i] = vi;
+  }
+}
+
 /* ---- model level ------------------------------------------------------------------------------- */
 
 /* Model::_copy_embedding: src/infer.cpp:1217-1263 */
@@ -548,12 +566,52 @@ static void attention_mha(const ork_model* m, ork_state* s, const ork_layer* L, 
   ork_matmul(s->hb, s->xb2, &L->wo, -1, c->bs0, c->bs1);
 }
 
+/* BlockMLA::_attention_impl: src/infer.cpp:1051-1141 */
+static void attention_mla(const ork_model* m, ork_state* s, const ork_layer* L, int pos, int kv_sink, int kv_pos,
+                          int kv_len) {
+  const ork_config* c = &m->cfg;
+  const int R = c->qk_rope_head_dim, KL = c->kv_lora_rank;
+  if (c->q_lora_rank <= 0) abort(); /* assert, 1057 */
+  ork_matmul(s->q_a, s->xb, &L->wq_a, -1, c->bs0, c->bs1);
+  ork_rmsnorm(s->q_a, s->q_a, L->rms_q_a, c->q_lora_rank, c->norm_eps);
+  ork_matmul(s->kv_a, s->xb, &L->wkv_a, -1, c->bs0, c->bs1);
+  ork_matmul(s->q_rope, s->q_a, &L->wq_rope_b, -1, c->bs0, c->bs1);
+  ork_matmul(s->q_c, s->q_a, &L->wc, -1, c->bs0, c->bs1);
+  for (int h = 0; h < c->n_heads; h++) {
+    if (c->is_v3) ork_rope_v3(s->q_rope + (size_t)h * R, R, R, pos, c->rope_theta);
+    else ork_rope(s->q_rope + (size_t)h * R, R, R, pos, c->rope_theta);
+  }
+  float* k_rope = s->kv_a + KL;
+  if (c->is_v3) ork_rope_v3(k_rope, R, R, pos, c->rope_theta);
+  else ork_rope(k_rope, R, R, pos, c->rope_theta);
+  ork_rmsnorm(s->kv_a, s->kv_a, L->rms_kv_a, KL, c->norm_eps); /* latent part only (1079) */
+  uint16_t* nrow = L->key_cache + (size_t)kv_pos * KL;           /* kv_nope_cache(kv_pos) */
+  uint16_t* rrow = L->value_cache + (size_t)kv_pos * R;          /* kv_rope_cache(kv_pos) */
+  for (int i = 0; i < KL; ++i) nrow[i] = ork_float_to_half(s->kv_a[i]);
+  for (int i = 0; i < R; ++i) rrow[i] = ork_float_to_half(k_rope[i]);
+  for (int r = 0; r < kv_sink; r++) { /* sink rope keys move one position per step (1099-1111) */
+    uint16_t* kv = L->value_cache + (size_t)r * R;
+    if (c->is_v3) ork_rope_v3_f16(kv, R, R, 1, c->rope_theta);
+    else ork_rope_f16(kv, R, R, 1, c->rope_theta);
+  }
+#pragma omp parallel for
+  for (int h = 0; h < c->n_heads; h++) {
+    ork_attn_mla(s->xb2 + (size_t)h * KL, s->att + (size_t)h * c->max_seq_len, s->q_c + (size_t)h * KL, s->q_rope + (size_t)h * R,
+                 L->key_cache, L->value_cache, c->head_dim, KL, R, kv_len);
+  }
+  /* per-head value up-projection: matmul_expert with expert = head (1133-1137); kv_b is reused for the outputs */
+  for (int h = 0; h < c->n_heads; h++)
+    ork_matmul(s->kv_b + (size_t)h * c->v_head_dim, s->xb2 + (size_t)h * KL, &L->wv_b, h, c->bs0, c->bs1);
+  ork_matmul(s->hb, s->kv_b, &L->wo, -1, c->bs0, c->bs1);
+}
+
 /* Block::_block_cpu: src/infer.cpp:810-932 */
 void ork_block(const ork_model* m, ork_state* s, int layer, int pos, int kv_sink, int kv_pos, int kv_len) {
   const ork_config* c = &m->cfg;
   const ork_layer* L = &m->layers[layer];
   ork_rmsnorm(s->xb, s->x, L->rms_att, c->dim, c->norm_eps);
-  attention_mha(m, s, L, pos, kv_sink, kv_pos, kv_len);
+  if (c->use_mla) attention_mla(m, s, L, pos, kv_sink, kv_pos, kv_len);
+  else attention_mha(m, s, L, pos, kv_sink, kv_pos, kv_len);
   for (int i = 0; i < c->dim; ++i) s->x[i] += s->hb[i];
   ork_rmsnorm(s->xb, s->x, L->rms_ffn, c->dim, c->norm_eps);
   if (L->is_moe) {

@@ -140,12 +140,12 @@ class OrkConfig(C.Structure):
                [(n, C.c_int) for n in ("n_group", "norm_topk_prob", "scoring_sigmoid", "topk_group", "topk_method",
                                        "is_v3", "kv_lora_rank", "q_lora_rank", "qk_nope_head_dim",
                                        "qk_rope_head_dim", "v_head_dim", "head_dim", "quant", "bs0", "bs1",
-                                       "original_max_position")]
+                                       "original_max_position", "use_mla")]
 
 
 class OrkLayer(C.Structure):
     _fields_ = [("rms_att", f32p), ("rms_ffn", f32p), ("rms_q_a", f32p), ("rms_kv_a", f32p)] + \
-               [(n, OrkTensor) for n in ("wq", "wq_a", "wq_b", "wkv_a", "wkv_b", "wo")] + \
+               [(n, OrkTensor) for n in ("wq", "wq_a", "wq_b", "wkv_a", "wkv_b", "wo", "wc", "wq_rope_b", "wv_b")] + \
                [("is_moe", C.c_int)] + \
                [(n, OrkTensor) for n in ("w1", "w2", "w3", "sw1", "sw2", "sw3")] + \
                [("moegate", f32p), ("moegate_bias", f32p), ("key_cache", u16p), ("value_cache", u16p)]
@@ -158,7 +158,8 @@ class OrkModel(C.Structure):
 
 class OrkState(C.Structure):
     _fields_ = [(n, f32p) for n in ("x", "xb", "xb2", "hb", "hb2", "q_a", "q", "kv_a", "kv_b", "att", "moe_weights",
-                                    "active_experts_weights", "logits")] + [("active_experts", i32p)]
+                                    "active_experts_weights", "logits")] + [("active_experts", i32p)] + \
+               [("q_c", f32p), ("q_rope", f32p)]
 
 
 def port_lib():
@@ -377,6 +378,7 @@ def config_from_metadata(md: Dict[str, str], context: int = 0) -> dict:
         quant=QUANT_IDS[md["quant"]], bs0=int(g("quantization_block_size_0", "0")),
         bs1=int(g("quantization_block_size_1", "0")),
         original_max_position=int(md["rope_scaling_original_max_position_embeddings"]),
+        use_mla=1 if int(g("use_mla", "0")) else 0,
     )
     c["head_dim"] = c["qk_nope_head_dim"] + c["qk_rope_head_dim"]
     if context:
@@ -421,14 +423,21 @@ class PortSession:
             L.rms_att = fptr(p + "attn.norm.weight")
             L.rms_ffn = fptr(p + "mlp.norm.weight")
             L.rms_kv_a = fptr(p + "attn.kv_a_norm.weight")
-            if c["q_lora_rank"] > 0:
+            if c["use_mla"]:    # BlockMLA tensors (src/model.cpp:809-821)
+                L.rms_q_a = fptr(p + "attn.q_a_norm.weight")
+                L.wq_a = tensor(p + "attn.wq_a", c["q_lora_rank"], c["dim"])
+                L.wc = tensor(p + "attn.wc", c["n_heads"] * c["kv_lora_rank"], c["q_lora_rank"])
+                L.wq_rope_b = tensor(p + "attn.wq_rope_b", c["n_heads"] * c["qk_rope_head_dim"], c["q_lora_rank"])
+                L.wv_b = tensor(p + "attn.wv_b", c["v_head_dim"], c["kv_lora_rank"], c["n_heads"])   # 3-D view (model.cpp:580)
+            elif c["q_lora_rank"] > 0:
                 L.rms_q_a = fptr(p + "attn.q_a_norm.weight")
                 L.wq_a = tensor(p + "attn.wq_a", c["q_lora_rank"], c["dim"])
                 L.wq_b = tensor(p + "attn.wq_b", c["n_heads"] * c["head_dim"], c["q_lora_rank"])
             else:
                 L.wq = tensor(p + "attn.wq", c["n_heads"] * c["head_dim"], c["dim"])
             L.wkv_a = tensor(p + "attn.wkv_a", c["kv_lora_rank"] + c["qk_rope_head_dim"], c["dim"])
-            L.wkv_b = tensor(p + "attn.wkv_b", c["n_heads"] * (nope + c["v_head_dim"]), c["kv_lora_rank"])
+            if not c["use_mla"]:
+                L.wkv_b = tensor(p + "attn.wkv_b", c["n_heads"] * (nope + c["v_head_dim"]), c["kv_lora_rank"])
             L.wo = tensor(p + "attn.wo", c["dim"], c["n_heads"] * c["v_head_dim"])
             moe = c["n_routed_experts"] > 0 and l >= c["first_k_dense_replace"]
             L.is_moe = 1 if moe else 0
@@ -449,8 +458,12 @@ class PortSession:
                 L.w1 = tensor(p + "mlp.w1", c["hidden_dim"], c["dim"])
                 L.w2 = tensor(p + "mlp.w2", c["dim"], c["hidden_dim"])
                 L.w3 = tensor(p + "mlp.w3", c["hidden_dim"], c["dim"])
-            kc = np.zeros(c["max_seq_len"] * c["n_heads"] * c["head_dim"], dtype=np.uint16)
-            vc = np.zeros(c["max_seq_len"] * c["n_heads"] * c["v_head_dim"], dtype=np.uint16)
+            if c["use_mla"]:   # latent rows + rope keys (src/model.cpp:618-619)
+                kc = np.zeros(c["max_seq_len"] * c["kv_lora_rank"], dtype=np.uint16)
+                vc = np.zeros(c["max_seq_len"] * c["qk_rope_head_dim"], dtype=np.uint16)
+            else:
+                kc = np.zeros(c["max_seq_len"] * c["n_heads"] * c["head_dim"], dtype=np.uint16)
+                vc = np.zeros(c["max_seq_len"] * c["n_heads"] * c["v_head_dim"], dtype=np.uint16)
             self.kcache.append(kc)
             self.vcache.append(vc)
             L.key_cache = kc.ctypes.data_as(u16p)
@@ -467,7 +480,8 @@ class PortSession:
             q=c["n_heads"] * c["head_dim"], kv_a=c["kv_lora_rank"] + c["qk_rope_head_dim"],
             kv_b=c["n_heads"] * (nope + c["v_head_dim"]), att=c["n_heads"] * c["max_seq_len"],
             moe_weights=max(1, c["n_routed_experts"]), active_experts_weights=max(1, c["n_active_routed"]),
-            logits=c["vocab_size"])
+            logits=c["vocab_size"], q_c=max(1, c["n_heads"] * c["kv_lora_rank"] * c["use_mla"]),
+            q_rope=max(1, c["n_heads"] * c["qk_rope_head_dim"] * c["use_mla"]))
         self.buf = {k: np.zeros(v, dtype=np.float32) for k, v in sz.items()}
         self.active = np.zeros(max(1, c["n_active_routed"]), dtype=np.int32)
         s = OrkState()

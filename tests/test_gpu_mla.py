@@ -111,6 +111,32 @@ def test_mla_layers_caches_and_logits(dsk, preset, quant):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def test_mla_e2e_golden(dsk, golden_dir, tmp_path):
+    """Committed reference outputs (tests/golden/e2e_mla.npz, make_golden_mla.py) on MLA checkpoints mintable without the
+    reference: logits, layer-0 cache rows, the last token's q_c and value up-projection."""
+    from golden.make_golden_mla import CASES
+    g = np.load(os.path.join(golden_dir, "e2e_mla.npz"))
+    tols = {"q2_k": 8e-2, "f8e5m2": 5e-4, "fp32": 2e-3}     # (fp32 case runs past original_max_position: fp16 sink re-rounding)
+    for preset, quant, kw in CASES:
+        key = f"{preset}_{quant}"
+        d = str(tmp_path / key)
+        mint.mint(d, preset, quant, fast=True, seed=78, use_mla=True, **kw)
+        m = dsk.Model.from_dir(d)
+        for p, t in enumerate(g[key + "_tokens"]):
+            logits, _ = m.forward(int(t), p)
+            assert rel_l2(logits, g[key + "_logits"][p]) < tols[quant], (key, p)
+        c, n = m.cfg, len(g[key + "_tokens"])
+        if quant != "q2_k":
+            assert rel_l2(m.buffer("q_c"), g[key + "_q_c_last"]) < 1e-3
+            assert rel_l2(m.buffer("kv_b")[:c.n_heads * c.v_head_dim], g[key + "_kv_b_last"][:c.n_heads * c.v_head_dim]) < 1e-3
+            if "original_max_position" not in kw:
+                for which, name, w in ((0, "_latent_cache_l0", c.kv_lora_rank), (1, "_rope_cache_l0", c.qk_rope_head_dim)):
+                    a = m.kv_cache(0, which)[:n * w].view(np.float16).astype(np.float32)
+                    b = g[key + name].view(np.float16).astype(np.float32)
+                    assert np.allclose(a, b, rtol=2e-3, atol=1e-4), (key, name)
+        m.close()
+
+
 def test_mla_sinks_past_original_max(dsk):
     """pos >= rope_scaling_original_max_position_embeddings: 2 sink rows, ring positions, sink rope keys re-rotated by one
     position per step (src/infer.cpp:1099-1111) — teacher-forced against the reference through 8 steps past the limit."""

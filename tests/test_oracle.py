@@ -118,6 +118,35 @@ def test_e2e_golden_port(golden_dir, tmp_path):
             assert rel_l2(s.buffer("logits"), exp) < tol, (preset, quant, p)
 
 
+def test_e2e_mla_golden_port(golden_dir, tmp_path):
+    """True-MLA blocks (BlockMLA::_attention_impl src/infer.cpp:1051-1141, attn_mla 766-804) of the port vs the reference's
+    committed outputs (tests/golden/e2e_mla.npz, make_golden_mla.py): logits, the latent / rope cache rows of layer 0 and the
+    last token's q_c / value up-projection.  The fp32 case runs past original_max_position (sink re-rotation)."""
+    import mint
+    from golden.make_golden_mla import CASES
+    g = np.load(os.path.join(golden_dir, "e2e_mla.npz"))
+    tols = {"q2_k": 5e-2, "f8e5m2": 1e-3, "fp32": 1e-3}
+    for preset, quant, kw in CASES:
+        key = f"{preset}_{quant}"
+        d = str(tmp_path / key)
+        mint.mint(d, preset, quant, fast=True, seed=78, use_mla=True, **kw)
+        s = O.PortSession(d)
+        assert s.c["use_mla"] == 1
+        for p, t in enumerate(g[key + "_tokens"]):
+            s.forward(int(t), p)
+            assert rel_l2(s.buffer("logits"), g[key + "_logits"][p]) < tols[quant], (key, p)
+        n, c = len(g[key + "_tokens"]), s.c
+        nh, vh = c["n_heads"], c["v_head_dim"]
+        if quant != "q2_k":   # (a Q8_K rounding flip upstream moves these by more than a cache ulp)
+            assert rel_l2(s.buffer("q_c"), g[key + "_q_c_last"]) < 1e-3
+            assert rel_l2(s.buffer("kv_b")[:nh * vh], g[key + "_kv_b_last"][:nh * vh]) < 1e-3
+            if "original_max_position" not in kw:   # (sink rows are re-rounded every step past the limit)
+                for which, name, w in ((0, "_latent_cache_l0", c["kv_lora_rank"]), (1, "_rope_cache_l0", c["qk_rope_head_dim"])):
+                    a = s.kv_cache(0, which)[:n * w].view(np.float16).astype(np.float32)
+                    b = g[key + name].view(np.float16).astype(np.float32)
+                    assert np.allclose(a, b, rtol=2e-3, atol=1e-4), (key, name)
+
+
 # ---- port vs the unmodified reference, live (build container and GPU box both carry oracle/_ref) ----
 @needs_ref
 def test_q8k_bit_exact_vs_ref():
@@ -160,6 +189,53 @@ def test_forward_port_vs_ref(ckpt, preset, quant, tol):
         r.forward(tok, pos)
         p.forward(tok, pos)
         assert rel_l2(p.buffer("logits"), r.buffer("logits")) < tol
+    r.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("preset", ["tiny_v2", "tiny_v3"])
+@pytest.mark.parametrize("quant,tol", [("fp32", 1e-3), ("fp16", 1e-3), ("f8e5m2", 1e-3), ("q2_k", 1.5e-1)])   # (q2_k T3: sanity
+# ceiling only — one Q8_K rounding flip between the two builds moves random-block logits by several 1e-2, see
+# profiles/r02_reference_self_sensitivity.txt; the T2 part below is the proof)
+def test_mla_block_port_vs_ref(ckpt, preset, quant, tol):
+    """BlockMLA, layer by layer on the reference's input and caches (tier T2), then teacher-forced logits (T3)."""
+    kw = {"v_head_dim": 128} if quant == "f8e5m2" else {}
+    d = ckpt(preset, quant, use_mla=True, **kw)
+    r, p = O.RefSession(d), O.PortSession(d)
+    errs = []
+    for pos, tok in enumerate([0, 9, 400, 33]):
+        r.copy_embedding(tok)
+        p.copy_embedding(tok)
+        for l in range(p.c["n_layers"]):
+            p.buffer("x")[:] = r.buffer("x")
+            for which in (0, 1):
+                p.kv_cache(l, which)[:] = r.kv_cache(l, which)
+            r.block(l, pos, 0, pos, pos + 1)
+            p.block(l, pos, 0, pos, pos + 1)
+            errs.append(rel_l2(p.buffer("x"), r.buffer("x")))
+    errs = np.array(errs)
+    if quant == "q2_k":   # Q8_K rounding flips between the two builds (-O3 -ffast-math vs -O2): most pairs clean, flips bounded
+        assert np.median(errs) < 1e-5 and errs.max() < 5e-2, errs
+    else:
+        assert errs.max() < 1e-4, errs
+    r.close()
+    r, p = O.RefSession(d), O.PortSession(d)
+    for pos, tok in enumerate([0, 9, 400, 33, 1001]):
+        r.forward(tok, pos)
+        p.forward(tok, pos)
+        assert rel_l2(p.buffer("logits"), r.buffer("logits")) < tol, (preset, quant, pos)
+    r.close()
+
+
+@needs_ref
+def test_mla_sink_ring_port_vs_ref(ckpt):
+    """MLA past original_max_position: 2 sink rows, ring overwrite, sink rope keys re-rotated (src/infer.cpp:1099-1111)."""
+    d = ckpt("tiny_v3", "fp32", use_mla=True, original_max_position=8)
+    r, p = O.RefSession(d), O.PortSession(d)
+    for pos in range(14):
+        r.forward(pos * 7 % 1024, pos)
+        p.forward(pos * 7 % 1024, pos)
+        assert rel_l2(p.buffer("logits"), r.buffer("logits")) < 1e-3, pos
     r.close()
 
 
