@@ -12,12 +12,12 @@ import oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("quant", ["fp32", "f8e5m2"])
-def test_cli_completion_matches_reference(repo, ckpt, quant):
+@pytest.mark.parametrize("quant,mla", [("fp32", False), ("f8e5m2", False), ("fp32", True)])
+def test_cli_completion_matches_reference(repo, ckpt, quant, mla):
     exe = os.path.join(repo, "deepseek.cpp_b200", "main")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-C", os.path.dirname(exe), "main"])
-    d = ckpt("tiny_v2lite", quant)
+    d = ckpt("tiny_v2", quant, use_mla=True) if mla else ckpt("tiny_v2lite", quant)   # mla: a `convert.py --mla` style checkpoint
     prompt, steps = "hello world", 20
     out = subprocess.run([exe, d, "-i", prompt, "-n", str(steps), "-t", "0"], capture_output=True, text=True, errors="replace", timeout=120)
     assert out.returncode == 0, out.stderr[-2000:]

@@ -4,7 +4,8 @@ columns, shared-expert / dense-FFN hidden units and LM-head rows (tensor paralle
 are exchanged inside the persistent kernel over CUDA-IPC-mapped peer memory; DSK_P2P=0 = expert-only sharding with
 ncclAllReduce between kernel segments.  Rank 0 checks teacher-forced logits and the device-resident greedy loop against
 the reference (or its C restatement) on the full checkpoint; the "_tp" cases use real head dims (128 + 64 / 128) so that
-two heads fill a 256-column K-quant block and assert that the tensor-parallel plan is actually active.
+two heads fill a 256-column K-quant block and assert that the tensor-parallel plan is actually active; the "_mla" case runs a
+true-MLA checkpoint (experts sharded, attention replicated).
 
 Skipped on a single-GPU box (the round-end driver); run it with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multigpu.py`.
 """
@@ -77,11 +78,14 @@ def _gpus():
 @pytest.mark.parametrize("preset,quant,tol", [("tiny_v2lite", "fp32", 2e-4), ("tiny_v2lite", "f8e5m2", 5e-4),
                                               ("tiny_v3", "f8e5m2", 5e-4), ("tiny_v2", "q2_k", 8e-2), ("tiny_v3", "q3_k", 8e-2),
                                               ("tiny_v2lite_tp", "fp32", 2e-4), ("tiny_v2_tp", "f8e5m2", 5e-4),
-                                              ("tiny_v3_tp", "f8e5m2", 5e-4), ("tiny_v2_tp", "q2_k", 8e-2), ("tiny_v3_tp", "q2_k", 8e-2)])
+                                              ("tiny_v3_tp", "f8e5m2", 5e-4), ("tiny_v2_tp", "q2_k", 8e-2), ("tiny_v3_tp", "q2_k", 8e-2),
+                                              ("tiny_v3_mla", "f8e5m2", 5e-4)])
 def test_sharded_decode_matches_reference(repo, ckpt, tmp_path, p2p, preset, quant, tol):
     import json
     want_tp = preset.endswith("_tp") and p2p == "1"
-    if preset.endswith("_tp"):   # real head dims: 2 local heads x 128 = one 256-column block of wo; f8 scale rows stay aligned
+    if preset.endswith("_mla"):  # true-MLA blocks: experts sharded, attention replicated (no tensor-parallel plan for BlockMLA)
+        d = ckpt(preset[:-4], quant, use_mla=True, v_head_dim=128)
+    elif preset.endswith("_tp"):   # real head dims: 2 local heads x 128 = one 256-column block of wo; f8 scale rows stay aligned
         d = ckpt(preset[:-3], quant, qk_nope_head_dim=128, qk_rope_head_dim=64, v_head_dim=128)
     else:
         d = ckpt(preset, quant)
