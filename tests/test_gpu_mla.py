@@ -164,6 +164,37 @@ def test_mla_sinks_past_original_max(dsk):
         shutil.rmtree(d, ignore_errors=True)
 
 
+def test_mla_long_context(dsk):
+    """700 cached positions (several passes of every loop of the attention stage: scores 8 positions per round, softmax and
+    latent mix 256 per round), teacher-forced against the reference; logits compared every 100 tokens and on the last 10."""
+    _need_ref()
+    d = tempfile.mkdtemp(prefix="dsk_mla_long_")
+    try:
+        mint.mint(d, "tiny_v2", "fp16", use_mla=True, fast=True, max_seq_len=1024)
+        m = dsk.Model.from_dir(d)
+        o = O.open_session(d)
+        rng = np.random.default_rng(11)
+        worst, n = 0.0, 700
+        for pos in range(n):
+            tok = int(rng.integers(2, 1000))
+            if pos % 100 == 99 or pos >= n - 10:
+                logits, _ = m.forward(tok, pos)
+                o.forward(tok, pos)
+                worst = max(worst, rel_l2(logits, o.buffer("logits")))
+            else:
+                m.forward(tok, pos, dsk.HYDRATE_KV_CACHE, want_logits=False)
+                o.forward(tok, pos, False)
+        print(f"mla long context: worst logits rel-L2 {worst:.2e} over {n} positions")
+        assert worst < 1e-3
+        for which, w in ((0, m.cfg.kv_lora_rank), (1, m.cfg.qk_rope_head_dim)):   # the whole cache, row by row
+            a = m.kv_cache(2, which)[:n * w].view(np.float16).astype(np.float32)
+            b = o.kv_cache(2, which)[:n * w].view(np.float16).astype(np.float32)
+            assert rel_l2(a, b) < 1e-3, which
+        m.close(); o.close()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def test_mla_rejections(dsk):
     """Configurations the MLA path cannot serve fail at model creation with a message, never silently."""
     d = tempfile.mkdtemp(prefix="dsk_mla_rej_")
