@@ -268,6 +268,32 @@ def test_dseek_roundtrip_and_config(ckpt):
         assert getattr(c, k) == oc[k]
 
 
+def test_cabi_header_is_plain_c_and_config_layout(repo):
+    """include/dsk.h is the drop-in boundary: it must compile as C99 (no C++ or torch types in the signatures) and the ctypes
+    mirror of dsk_config must have the compiler's layout (field order and size are part of the ABI; use_mla was appended in
+    ABI 3)."""
+    import ctypes
+    import subprocess
+    import dsk
+    hdr = os.path.join(repo, "include", "dsk.h")
+    subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Wextra", "-pedantic", "-x", "c", hdr])
+    prog = ('#include <stdio.h>\n#include <stddef.h>\n#include "dsk.h"\nint main(void){printf("%zu %zu %zu %zu %d\\n", sizeof(dsk_config), '
+            'offsetof(dsk_config, rope_theta), offsetof(dsk_config, routed_scaling_factor), offsetof(dsk_config, use_mla), DSK_ABI_VERSION);return 0;}')
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "l.c"), os.path.join(td, "l")
+        open(src, "w").write(prog)
+        subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(repo, "include"), src, "-o", exe])
+        size, o_theta, o_rsf, o_mla, abi = map(int, subprocess.check_output([exe]).split())
+    C = dsk.Config
+    assert (ctypes.sizeof(C), C.rope_theta.offset, C.routed_scaling_factor.offset, C.use_mla.offset) == (size, o_theta, o_rsf, o_mla)
+    assert abi == dsk.ABI_VERSION
+    md = {"arch": "DeepseekV2ForCausalLM", "dim": "8", "hidden_dim": "8", "n_layers": "1", "n_heads": "1", "vocab_size": "8",
+          "max_seq_len": "8", "rope_theta": "1e4", "quant": "fp32", "use_mla": "1", "q_lora_rank": "4",
+          "rope_scaling_original_max_position_embeddings": "4096"}
+    assert dsk.Config.from_metadata(md).use_mla == 1 and dsk.Config.from_metadata(dict(md, use_mla="0")).use_mla == 0
+
+
 def test_cabi_exports_every_declared_symbol(repo):
     """libdsk.so must load on a GPU-less machine and export exactly what include/dsk.h declares."""
     import dsk
