@@ -32,8 +32,10 @@ enum { DSK_HYDRATE_KV_CACHE = 0, DSK_OUTPUT_LOGITS = 1 };
 /* TopKMethod / ScoringFunc: src/model.h:25-34 */
 enum { DSK_TOPK_GREEDY = 0, DSK_TOPK_GROUP_LIMITED_GREEDY = 1 };
 
-/* Config: src/model.h:47-96 (fields the MHA-mode decode path reads; filled from .dseek metadata,
- * src/model.cpp:22-127). */
+/* Config: src/model.h:47-96 (the fields the decode path reads; filled from .dseek metadata, src/model.cpp:22-127).
+ * use_mla models (convert.py --mla) need q_lora_rank > 0 (src/infer.cpp:1057), kv_lora_rank % 64 == 0 (K-quants: % 256) and,
+ * with f8e5m2 block scales, v_head_dim % bs0 == 0 (matmul_expert's per-head scale offset, src/infer.cpp:437); they are not
+ * tensor parallel (routed experts are still sharded).  dsk_model_create() rejects anything else with a message. */
 typedef struct dsk_config {
   int dim, hidden_dim, n_layers, n_heads, vocab_size, max_seq_len;
   float rope_theta, norm_eps;
