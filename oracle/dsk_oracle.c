@@ -2,7 +2,8 @@
  *
  * TEST INFRASTRUCTURE ONLY: loaded by tests/, __graft_entry__.smoke() and bench.py's CPU legs as the
  * checker.  The product never links it.  Pinned against oracle/_ref/libdsref.so (unmodified reference)
- * and tests/golden/*.json — see dsk_oracle.h.  Citations: /root/reference @ 8db9e56.
+ * and the committed vectors under tests/golden (kat.json, ops.npz, e2e.npz, e2e_mla.npz) — see dsk_oracle.h.
+ * MHA blocks and true-MLA blocks (use_mla).  Citations: /root/reference @ 8db9e56.
  */
 #include "dsk_oracle.h"
 
